@@ -1,0 +1,206 @@
+/*
+ * h264_common.h -- shared definitions of the B200 macroblock-encode path.
+ *
+ * The per-macroblock code in this directory is written once, in a "warp-phase"
+ * style, and compiled two ways:
+ *   - by nvcc for sm_100a: one warp encodes one macroblock, FOR_LANES() strides
+ *     the 32 lanes over a phase's work items, WSYNC() separates phases and
+ *     wsum()/wmin() are shuffle reductions (this is the product);
+ *   - by g++ with H264_EMU for the developer-only host emulation used to debug
+ *     bit-exactness without a GPU (tests/_emu): FOR_LANES() is a plain loop and
+ *     the reductions are identities.  The emulation is never linked into the
+ *     product library.
+ *
+ * Rules that keep both builds equivalent: shared ("MBWork") memory is only
+ * written inside FOR_LANES()/IF_LANE0 blocks; a phase never reads what the same
+ * phase writes; everything outside those blocks is warp-uniform control code.
+ *
+ * Reference citations (H:nnn) are to /root/reference/src/h264-lab.h.
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#  define H264_DEVICE 1
+#  define HD __device__ __forceinline__
+#  define HDN __device__ __noinline__
+#  define H264_TAB static __device__ const
+#else
+#  define H264_DEVICE 0
+#  define HD static inline
+#  define HDN static
+#  define H264_TAB static const
+#endif
+
+#if H264_DEVICE
+#  define LANE_ID ((int)(threadIdx.x & 31))
+#  define FOR_LANES(i, n) for (int i = LANE_ID; i < (n); i += 32)
+#  define WSYNC() __syncwarp()
+#  define IF_LANE0 if (LANE_ID == 0)
+HD int wsum(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+HD int wmax(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+HD int wor(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#else
+#  define LANE_ID 0
+#  define FOR_LANES(i, n) for (int i = 0; i < (n); i++)
+#  define WSYNC() ((void)0)
+#  define IF_LANE0
+HD int wsum(int v) { return v; }
+HD int wmax(int v) { return v; }
+HD int wor(int v) { return v; }
+#endif
+
+typedef uint8_t pix_t;
+
+/* ---- constants with the reference's meaning --------------------------------- */
+#define MV_NA 0x8000          /* H:3200: "no motion vector" marker (intra / unavailable) */
+#define AVAIL_T 1             /* H:511-514 */
+#define AVAIL_L 2
+#define AVAIL_TL 4
+#define AVAIL_TR 8
+#define SLICE_P 0             /* H:3203-3204 */
+#define SLICE_I 2
+#define NNZ_NA 64             /* H:3206 */
+#define MV_RANGE_PX 32        /* H:3221 */
+#define QDQ_INTRA4 2          /* H:505-508 */
+#define QDQ_INTER 8
+#define QDQ_INTRA16 9
+#define QDQ_CHROMA 5
+
+/* MB types, H:659: -1 skip, 0 P16x16, 1 P16x8, 2 P8x16, 3 P8x8, 5 I4x4, 6 I16x16 */
+#define MBT_SKIP (-1)
+#define MBT_I4 5
+#define MBT_I16 6
+
+/* ---- motion vectors: two int16 packed in an int32, x in the low half (H:533-541) */
+HD int mv_pack(int x, int y) { return (int)(((uint32_t)y << 16) | ((uint32_t)x & 0xFFFFu)); }
+HD int mv_x(int v) { return (int)(int16_t)(v & 0xFFFF); }
+HD int mv_y(int v) { return (int)(int16_t)((uint32_t)v >> 16); }
+HD int mv_add2(int a, int b) { return mv_pack(mv_x(a) + mv_x(b), mv_y(a) + mv_y(b)); }
+HD int mv_sub2(int a, int b) { return mv_pack(mv_x(a) - mv_x(b), mv_y(a) - mv_y(b)); }
+HD int mv_round_fullpel(int v) { return mv_pack((mv_x(v) + 1) & ~3, (mv_y(v) + 1) & ~3); } /* H:3498 */
+HD int iabs(int x) { return x < 0 ? -x : x; }
+HD int imin(int a, int b) { return a < b ? a : b; }
+HD int imax(int a, int b) { return a > b ? a : b; }
+HD int clip_u8(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
+
+/* ---- per-macroblock record kept for the whole frame (HBM) ---------------------
+ * Replaces the reference's one-row rolling contexts (mv_pred, nnz, i4x4mode,
+ * df.*; H:742-745, H:599-605) with frame-wide arrays so that macroblocks can be
+ * processed in wavefront order and CAVLC / deblocking can run as separate passes. */
+struct MBInfo
+{
+    int32_t mv[16];      /* final MV of each 4x4 block, raster; MV_NA for intra MBs        */
+    int32_t mvd[4];      /* MV difference per partition, partition order (H:4574)         */
+    int8_t  type;        /* MBT_*                                                          */
+    int8_t  i16_mode;    /* luma 16x16 mode 0=V 1=H 2=DC; also selects the chroma mode     */
+    uint8_t cbp;         /* luma 8x8 bits | chroma (0..2) << 4                              */
+    uint8_t flags;       /* bit0: row/frame bookkeeping (unused)                           */
+    uint16_t nz_mask;    /* luma 4x4 blocks with coefficients, bit 15 = block 0 (H:2589)   */
+    uint16_t pad0;
+    int8_t  i4_mode[16]; /* actual I4x4 modes (2 = DC for every other MB type, H:4391)     */
+    int8_t  i4_code[16]; /* coded value: -1 = predicted, else rem_intra4x4_pred_mode       */
+    uint8_t nnz[24];     /* total_coeff of each block as seen by neighbours' CAVLC context:
+                            16 luma (raster), 4 U, 4 V                                     */
+    int32_t cl_used[2];  /* rounded cluster candidates this MB was decided with           */
+    int32_t cand_sig[4]; /* candidate-stage outcome (mv_best, sad_best, cost, pref modes)  */
+};
+
+/* Quantised levels of one macroblock (int16), written by the encode pass and read
+ * by the CAVLC pass. Layout in units of int16. */
+#define COEF_Y     0      /* 16 blocks x 16 levels, block raster, level index v+4u (H:2391) */
+#define COEF_YDC   256    /* 16 luma DC levels (I16x16 only)                                */
+#define COEF_C     272    /* 8 blocks x 16: U0..U3, V0..V3                                  */
+#define COEF_CDC   400    /* 4 U DC + 4 V DC                                                */
+#define COEF_PER_MB 416
+
+/* ---- per-frame parameters (uploaded by the host for every frame) --------------- */
+struct FrameParams
+{
+    int width, height;          /* visible size                                             */
+    int nmbx, nmby;
+    int slice_type;             /* SLICE_P / SLICE_I                                        */
+    int qp;                     /* luma QP of the frame (no per-MB QP: fine RC unsupported) */
+    int speed;                  /* run_param.encode_speed                                   */
+    int disable_deblock;
+    /* per-QP tunables looked up on the host (H:1032-1120) */
+    int lambda_q4, lambda_mv_q4, lambda_i4_q4, lambda_i16_q4, skip_thr_inter, skip_thr_i4x4;
+    /* MV limits, absolute quarter-pel (H:6322-6325) */
+    int mvlim_x0, mvlim_y0, mvlim_x1, mvlim_y1;
+    /* deblocking constants for this QP: [0] luma, [1] chroma (H:944-987, H:5673-5696) */
+    int df_alpha[2], df_beta[2], df_tc0[2][4];
+    uint16_t qdat[2][42];       /* quantiser tables built by the host RC (H:5839-5912)      */
+    /* planes */
+    const pix_t *inp[3]; int inp_stride[3];
+    pix_t *dec[3];              /* reconstruction being built (padded planes, pixel (0,0))  */
+    const pix_t *ref[3];        /* previous reconstruction (deblocked, borders extended)    */
+    int stride[2];              /* luma / chroma stride of dec and ref                      */
+    MBInfo *mbi;
+    int16_t *coef;
+    int32_t *clusters;          /* persistent mv_clusters[2] of this encoder (H:766)        */
+    int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
+    int *row_progress_df;       /* [nmby] same for the deblock pass                         */
+    uint32_t *mb_bits;          /* per-MB bit strings, MB_BITS_WORDS words each             */
+    int *mb_nbits;              /* [nmb + 1]                                                */
+    uint32_t *out_words;        /* packed slice payload                                     */
+    int *out_info;              /* [0] total bits, [1] error flags                          */
+    int hdr_bits;               /* bit offset at which the slice data starts                */
+    int serial_rows;            /* 1: a row waits for the whole previous row (exact P mode) */
+};
+
+#define MB_BITS_WORDS 512       /* 2048 bytes per macroblock */
+
+/* ---- per-macroblock working set (shared memory on the GPU) --------------------- */
+struct MBWork
+{
+    pix_t inp_y[256];            /* input MB, stride 16 (mb_pix_inp, H:566)                 */
+    pix_t inp_c[128];            /* U at +0, V at +8, stride 16                             */
+    pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)   */
+    pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
+    pix_t i4rec[256];            /* I4x4 reconstruction under construction                  */
+    pix_t i4pred[9][16];         /* the nine 4x4 predictions of the current block           */
+    pix_t top_y[24];             /* unfiltered row above: 16 + 4 of the top-right MB        */
+    pix_t left_y[16];
+    pix_t top_c[16];             /* U 0..7, V 8..15                                         */
+    pix_t left_c[16];
+    pix_t tl[4];                 /* top-left Y, U, V                                        */
+    int16_t dq_y[16][16];        /* transform coefficients / dequantised (quant_t.dq)       */
+    int16_t qv_y[16][16];        /* quantised levels (quant_t.qv)                           */
+    int16_t dq_c[8][16];
+    int16_t qv_c[8][16];
+    int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
+    int16_t dc_c[8], qdc_c[8];
+    int16_t hpel[21 * 16];       /* half-pel intermediate rows (H:1992)                     */
+    int32_t i4cost[9];
+    int8_t  i4_mode[16], i4_code[16];
+    int8_t  zflag1[16], zflag2[16];
+    int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */
+    int32_t mvp_save[12];
+    int32_t part_mv[4][4], part_mvd[4][4];        /* per mode, per partition                */
+    int32_t scal[16];            /* scalars produced by lane 0 for the whole warp          */
+};
+
+HD int mb_avail(int mbx, int mby, int nmbx)   /* single slice per frame: H:3605-3622 */
+{
+    int f = 0;
+    if (mby > 0) f |= AVAIL_T;
+    if (mby > 0 && mbx != nmbx - 1) f |= AVAIL_TR;
+    if (mbx > 0) f |= AVAIL_L;
+    if (mby > 0 && mbx > 0) f |= AVAIL_TL;
+    return f;
+}

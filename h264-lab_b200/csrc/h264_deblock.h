@@ -1,0 +1,198 @@
+/*
+ * h264_deblock.h -- in-loop deblocking of one macroblock by one warp
+ * (df_strength H:5535, mb_deblock H:5642,
+ * h264e_deblock_luma H:1505, h264e_deblock_chroma H:1469), then border extension
+ * (a16, h264e_copy_borders H:2232).
+ *
+ * Lanes 0-15 own the 16 luma lines crossing the edges being filtered, lanes 16-23
+ * the 8 U lines and lanes 24-31 the 8 V lines.  The four vertical edges are filtered
+ * left to right on each line held in registers, then the four horizontal edges top
+ * to bottom, exactly the per-macroblock order of the reference; macroblocks follow
+ * an x+2y wavefront so that every neighbour a filter touches is final.
+ */
+#pragma once
+#include "h264_common.h"
+
+HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* one line across a luma edge: p[3..0] = p3..p0 at v[o-4..o-1], q0..q3 at v[o..o+3] */
+HD void df_luma_line(int *v, int o, int bs, int alpha, int beta, int tc0)
+{
+    int p2 = v[o - 3], p1 = v[o - 2], p0 = v[o - 1], q0 = v[o], q1 = v[o + 1], q2 = v[o + 2];
+    if (!bs) return;
+    if (!(iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)) return;
+    int ap = iabs(p2 - p0), aq = iabs(q2 - q0);
+    if (bs < 4)
+    {
+        int delta = (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3;
+        int tc = tc0;
+        if (ap < beta) { v[o - 2] = p1 + clip3(-tc0, tc0, ((p2 + ((p0 + q0 + 1) >> 1)) >> 1) - p1); tc++; }
+        if (aq < beta) { v[o + 1] = q1 + clip3(-tc0, tc0, ((q2 + ((p0 + q0 + 1) >> 1)) >> 1) - q1); tc++; }
+        delta = clip3(-tc, tc, delta);
+        v[o - 1] = clip_u8(p0 + delta);
+        v[o] = clip_u8(q0 - delta);
+    } else
+    {
+        int small = iabs(p0 - q0) < ((alpha >> 2) + 2);
+        if (ap < beta && small)
+        {
+            int p3 = v[o - 4];
+            v[o - 1] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+            v[o - 2] = (p2 + p1 + p0 + q0 + 2) >> 2;
+            v[o - 3] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+        } else v[o - 1] = (2 * p1 + p0 + q1 + 2) >> 2;
+        if (aq < beta && small)
+        {
+            int q3 = v[o + 3];
+            v[o] = (q2 + 2 * q1 + 2 * q0 + 2 * p0 + p1 + 4) >> 3;
+            v[o + 1] = (q2 + q1 + p0 + q0 + 2) >> 2;
+            v[o + 2] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+        } else v[o] = (2 * q1 + q0 + p1 + 2) >> 2;
+    }
+}
+
+/* one line across a chroma edge (deblock_chroma H:1217) */
+HD void df_chroma_line(int *v, int o, int bs, int alpha, int beta, int tc0)
+{
+    int p1 = v[o - 2], p0 = v[o - 1], q0 = v[o], q1 = v[o + 1];
+    if (!bs) return;
+    if (iabs(p0 - q0) >= alpha || iabs(p1 - p0) >= beta || iabs(q1 - q0) >= beta) return;
+    if (bs < 4)
+    {
+        int tc = tc0 + 1;
+        int delta = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+        v[o - 1] = clip_u8(p0 + delta);
+        v[o] = clip_u8(q0 - delta);
+    } else
+    {
+        v[o - 1] = (2 * p1 + p0 + q1 + 2) >> 2;
+        v[o] = (2 * q1 + q0 + p1 + 2) >> 2;
+    }
+}
+
+HD int mv_far(int a, int b) { return iabs(mv_x(a) - mv_x(b)) > 3 || iabs(mv_y(a) - mv_y(b)) > 3; }   /* H:3466 */
+
+/* boundary strength between 4x4 block p (in MB mp, index ip) and q (in MB mq, index iq),
+ * both inter (df_strength H:5594-5611) */
+HD int bs_inter(const MBInfo *mp, int ip, const MBInfo *mq, int iq)
+{
+    if (((mp->nz_mask | 0u) & (0x8000u >> ip)) || (mq->nz_mask & (0x8000u >> iq))) return 2;
+    return mv_far(mp->mv[ip], mq->mv[iq]) ? 1 : 0;
+}
+
+HD void deblock_mb(const FrameParams *fp, int mbx, int mby)
+{
+    const MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
+    const MBInfo *ml = mi - 1, *mt = mi - fp->nmbx;
+    const int intra = mi->type >= 5;
+    const int lane = LANE_ID;
+    (void)lane;
+    FOR_LANES(ln, 32)
+    {
+        const int pl = ln < 16 ? 0 : (ln < 24 ? 1 : 2);
+        const int line = ln < 16 ? ln : ((ln - 16) & 7);
+        const int cr = pl != 0;
+        const int n = cr ? 8 : 16;
+        const int stride = fp->stride[cr];
+        pix_t *base = fp->dec[pl] + (mby * n) * stride + mbx * n;
+        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
+        const int seg = cr ? (line >> 1) : (line >> 2);      /* 4x4 luma block row/col this line crosses */
+        int v[20];
+
+        /* ---- vertical edges: this lane owns row `line` ---- */
+        {
+            pix_t *row = base + line * stride;
+            int lo = mbx > 0 ? -4 : 0;
+            for (int i = lo; i < n; i++) v[4 + i] = row[i];
+            for (int e = 0; e < 4; e++)
+            {
+                int bs;
+                if (e == 0)
+                {
+                    if (mbx == 0) bs = 0;
+                    else if (intra || ml->type >= 5) bs = 4;
+                    else bs = bs_inter(ml, seg * 4 + 3, mi, seg * 4);
+                } else
+                {
+                    if (intra) bs = 3;
+                    else bs = bs_inter(mi, seg * 4 + e - 1, mi, seg * 4 + e);
+                }
+                if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
+                else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+            }
+            for (int i = lo; i < n; i++) row[i] = (pix_t)v[4 + i];
+        }
+    }
+    WSYNC();
+    FOR_LANES(ln, 32)
+    {
+        const int pl = ln < 16 ? 0 : (ln < 24 ? 1 : 2);
+        const int line = ln < 16 ? ln : ((ln - 16) & 7);
+        const int cr = pl != 0;
+        const int n = cr ? 8 : 16;
+        const int stride = fp->stride[cr];
+        pix_t *base = fp->dec[pl] + (mby * n) * stride + mbx * n;
+        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
+        const int seg = cr ? (line >> 1) : (line >> 2);
+        int v[20];
+        /* ---- horizontal edges: this lane owns column `line` ---- */
+        {
+            pix_t *col = base + line;
+            int lo = mby > 0 ? -4 : 0;
+            for (int i = lo; i < n; i++) v[4 + i] = col[i * stride];
+            for (int e = 0; e < 4; e++)
+            {
+                int bs;
+                if (e == 0)
+                {
+                    if (mby == 0) bs = 0;
+                    else if (intra || mt->type >= 5) bs = 4;
+                    else bs = bs_inter(mt, 12 + seg, mi, seg);
+                } else
+                {
+                    if (intra) bs = 3;
+                    else bs = bs_inter(mi, (e - 1) * 4 + seg, mi, e * 4 + seg);
+                }
+                if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
+                else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+            }
+            for (int i = lo; i < n; i++) col[i * stride] = (pix_t)v[4 + i];
+        }
+    }
+    WSYNC();
+}
+
+/* a16: replicate the picture edges into the 16 (luma) / 8 (chroma) sample guard band.
+ * One work item per guard sample; idx enumerates the guard samples of plane pl. */
+HD void extend_border_sample(const FrameParams *fp, int pl, long idx)
+{
+    const int cr = pl != 0;
+    const int g = cr ? 8 : 16;
+    const int w = fp->nmbx * (cr ? 8 : 16), h = fp->nmby * (cr ? 8 : 16);
+    const int stride = fp->stride[cr];
+    pix_t *pic = fp->dec[pl];
+    const long side = (long)2 * g * h;        /* left+right strips of the picture rows */
+    int x, y;
+    if (idx < side)
+    {
+        y = (int)(idx / (2 * g));
+        int k = (int)(idx - (long)y * 2 * g);
+        x = k < g ? k - g : w + (k - g);
+    } else
+    {
+        long r = idx - side;
+        int rw = w + 2 * g;
+        int yy = (int)(r / rw);
+        x = (int)(r - (long)yy * rw) - g;
+        y = yy < g ? yy - g : h + (yy - g);
+    }
+    int sx = x < 0 ? 0 : (x >= w ? w - 1 : x), sy = y < 0 ? 0 : (y >= h ? h - 1 : y);
+    pic[(long)y * stride + x] = pic[(long)sy * stride + sx];
+}
+HD long border_samples(const FrameParams *fp, int pl)
+{
+    const int cr = pl != 0;
+    const int g = cr ? 8 : 16;
+    const int w = fp->nmbx * (cr ? 8 : 16), h = fp->nmby * (cr ? 8 : 16);
+    return (long)2 * g * h + (long)2 * g * (w + 2 * g);
+}

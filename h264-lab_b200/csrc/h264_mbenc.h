@@ -1,0 +1,954 @@
+/*
+ * h264_mbenc.h -- macroblock mode decision, motion estimation, transform /
+ * quantisation / reconstruction for one macroblock, executed by one warp
+ * (SURVEY.md 8(a) rows a4-a12, a17).  Decisions replay the reference's greedy,
+ * order-dependent search exactly (same candidate order, same strict comparisons,
+ * same 16-bit cost cache) -- see the H:nnn citations.
+ */
+#pragma once
+#include "h264_common.h"
+#include "h264_pixel.h"
+
+struct MBState   /* warp-uniform registers of the macroblock being encoded */
+{
+    const FrameParams *fp;
+    MBWork *w;
+    int mbx, mby, avail;
+    int type;            /* MBT_* */
+    int cost;
+    int i16_mode;
+    int mv_skip_pred;    /* H:674 */
+    pix_t *pbest, *ptest;
+};
+
+HD int clz32(uint32_t v)
+{
+#if H264_DEVICE
+    return __clz((int)v);
+#else
+    return __builtin_clz(v);
+#endif
+}
+HD int bitsize_ue(int v) { return 2 * (32 - clz32((uint32_t)(v + 1))) - 1; }          /* H:3402 */
+HD int bits_se(int v) { v = 2 * v - 1; v ^= v >> 31; return bitsize_ue(v); }          /* H:3410 */
+HD int mv_cost(int mv, int mvp, int lambda_mv_q4)                                     /* H:4952 */
+{
+    int nb = bits_se(mv_x(mv) - mv_x(mvp)) + bits_se(mv_y(mv) - mv_y(mvp));
+    return (nb * lambda_mv_q4) >> 4;
+}
+HD int mv_in_rect(int v, int x0, int y0, int x1, int y1)
+{
+    int x = mv_x(v), y = mv_y(v);
+    return y >= y0 && y <= y1 && x >= x0 && x <= x1;
+}
+
+/* ------------------------------------------------------------------------------
+ * loading the macroblock's inputs
+ * ---------------------------------------------------------------------------- */
+HD void mb_load(MBState &s)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    int mbx = s.mbx, mby = s.mby;
+    /* input pixels; samples beyond the visible picture replicate the last column / row
+     * (pix_copy_cropped_mb H:3536) */
+    int wv = fp->width, hv = fp->height;
+    FOR_LANES(i, 64)
+    {
+        int r = i >> 2, c = (i & 3) * 4;
+        int y = imin(mby * 16 + r, hv - 1);
+        const pix_t *row = fp->inp[0] + y * fp->inp_stride[0];
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 16 + c + k, wv - 1)] << (8 * k);
+        *(uint32_t *)(w->inp_y + r * 16 + c) = v;
+    }
+    FOR_LANES(i, 32)
+    {
+        int r = i >> 2, q = i & 3, pl = q >> 1, c = (q & 1) * 4;
+        int y = imin(mby * 8 + r, hv / 2 - 1);
+        const pix_t *row = fp->inp[1 + pl] + y * fp->inp_stride[1 + pl];
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 8 + c + k, wv / 2 - 1)] << (8 * k);
+        *(uint32_t *)(w->inp_c + r * 16 + pl * 8 + c) = v;
+    }
+    /* unfiltered neighbour samples of the picture under construction (the reference's
+     * top_line context, H:4693-4714): row above incl. 4 samples of the top-right MB,
+     * left column, top-left corners */
+    {
+        int sy = fp->stride[0], sc = fp->stride[1];
+        const pix_t *dy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+        const pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8;
+        const pix_t *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
+        int av = s.avail;
+        FOR_LANES(i, 32)
+        {
+            if (i < 20) { if ((av & AVAIL_T) && (i < 16 || (av & AVAIL_TR))) w->top_y[i] = dy[-sy + i]; else w->top_y[i] = 0; }
+            if (i < 16) w->left_y[i] = (av & AVAIL_L) ? dy[i * sy - 1] : 0;
+            if (i < 8)
+            {
+                w->top_c[i] = (av & AVAIL_T) ? du[-sc + i] : 0;
+                w->top_c[8 + i] = (av & AVAIL_T) ? dv[-sc + i] : 0;
+                w->left_c[i] = (av & AVAIL_L) ? du[i * sc - 1] : 0;
+                w->left_c[8 + i] = (av & AVAIL_L) ? dv[i * sc - 1] : 0;
+            }
+            if (i == 31)
+            {
+                w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
+                w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
+                w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
+            }
+        }
+    }
+    /* MV predictor context from the neighbours' final MVs (replaces the rolling
+     * enc->mv_pred row, H:742, H:3696-3715) */
+    if (fp->slice_type == SLICE_P)
+    {
+        const MBInfo *mbi = fp->mbi + mby * fp->nmbx + mbx;
+        int nmbx = fp->nmbx, av = s.avail;
+        FOR_LANES(i, 13)
+        {
+            if (i < 4) w->mvp_left[i] = (av & AVAIL_L) ? mbi[-1].mv[4 * i + 3] : MV_NA;
+            else if (i == 4) w->mvp_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
+            else if (i < 8) w->mvp_tl[i - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (i - 5) + 3] : MV_NA;
+            else if (i < 12) w->mvp_top[i - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (i - 8)] : MV_NA;
+            else w->mvp_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
+        }
+    }
+    WSYNC();
+}
+
+/* ------------------------------------------------------------------------------
+ * a6: median / directional MV predictor on the rolling context
+ * (me_mv_medianpredictor_get H:3720).  x,y,wd,ht in units of 4x4 blocks.
+ * ---------------------------------------------------------------------------- */
+HD int med3(int a, int b, int c) { return imax(imin(imax(a, b), c), imin(a, b)); }
+HD int mvp_get(const MBWork *w, int flag, int x, int y, int wd, int ht)
+{
+    int a = w->mvp_left[y], b = w->mvp_top[x], c = w->mvp_top[x + wd], d = w->mvp_tl[y];
+    if (!x)
+    {
+        if (!(flag & AVAIL_L)) a = MV_NA;
+        if (!(flag & AVAIL_TL)) d = MV_NA;
+    }
+    if (!y)
+    {
+        if (!(flag & AVAIL_T))
+        {
+            b = MV_NA;
+            if (x + wd < 4) c = MV_NA;
+            if (x > 0) d = MV_NA;
+        }
+        if (!(flag & AVAIL_TL) && !x) d = MV_NA;
+        if (!(flag & AVAIL_TR) && x + wd == 4) c = MV_NA;
+    }
+    if (x + wd == 4 && (!(flag & AVAIL_TR) || y)) c = d;
+    int na = a != MV_NA, nb = b != MV_NA, nc = c != MV_NA;
+    int kind = 0;   /* 0 median, 1 left, 2 up, 3 up-right */
+    if (na && !nb && !nc) kind = 1;
+    else if (!na && nb && !nc) kind = 2;
+    else if (!na && !nb && nc) kind = 3;
+    if (wd == 2 && ht == 4) { if (x == 0) { if (na) kind = 1; } else { if (nc) kind = 3; } }
+    else if (wd == 4 && ht == 2) { if (y == 0) { if (nb) kind = 2; } else { if (na) kind = 1; } }
+    switch (kind)
+    {
+    case 1: return na ? a : 0;
+    case 2: return nb ? b : 0;
+    case 3: return nc ? c : 0;
+    default:
+        if (!(nb || nc)) return na ? a : 0;
+        if (!na) a = 0;
+        if (!nb) b = 0;
+        if (!nc) c = 0;
+        return mv_pack(med3(mv_x(a), mv_x(b), mv_x(c)), med3(mv_y(a), mv_y(b), mv_y(c)));
+    }
+}
+
+/* me_mv_medianpredictor_put H:3696 -- must be called by one lane, followed by WSYNC */
+HD void mvp_put(MBWork *w, int x, int y, int wd, int ht, int mv)
+{
+    w->mvp_tl[y] = w->mvp_top[x + wd - 1];
+    for (int i = 1; i < ht; i++) w->mvp_tl[y + i] = mv;
+    for (int i = 0; i < ht; i++) w->mvp_left[y + i] = mv;
+    for (int i = 0; i < wd; i++) w->mvp_top[x + i] = mv;
+}
+
+/* ------------------------------------------------------------------------------
+ * a4: integer-pel greedy diamond + diagonal step + 7-probe sub-pel refinement
+ * (me_search_diamond H:4973-5176).
+ *   refp   : reference luma plane + partition offset
+ *   inp    : input MB + partition offset (stride 16)
+ *   mv     : in/out absolute quarter-pel MV
+ *   rng    : search rectangle x0,y0,x1,y1
+ *   buf[4] : scratch, hpel, hpel1, hpel2 destinations (stride-16 blocks)
+ * Returns the best cost; *pbest receives the buffer holding the best prediction.
+ * ---------------------------------------------------------------------------- */
+HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv, const int *rng,
+                 int mv_pred, int min_sad, int bw, int bh, pix_t *const buf[4], pix_t **pbest)
+{
+    const FrameParams *fp = s.fp;
+    const int stride = fp->stride[0];
+    const int lam = fp->lambda_mv_q4;
+    int mv = *pmv;
+    uint32_t cache[8];
+    int dir, cloop, dir_prev, cost, v;
+
+    for (;;)   /* "restart" loop */
+    {
+        dir = 0; cloop = 4; dir_prev = -1;
+        for (int i = 0; i < 8; i++) cache[i] = 0xffffu;
+        do
+        {
+            int dx = dir == 0 ? 4 : (dir == 1 ? -4 : 0), dy = dir == 2 ? 4 : (dir == 3 ? -4 : 0);
+            v = mv_pack(mv_x(mv) + dx, mv_y(mv) + dy);
+            if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]) && cache[dir] == 0xffffu)
+            {
+                cost = sad_frame_wh(refp + (mv_y(v) >> 2) * stride + (mv_x(v) >> 2), stride, inp, bw, bh);
+                cost += mv_cost(v, mv_pred, lam);
+                cache[dir] = (uint32_t)cost & 0xffffu;
+                if (cost < min_sad)
+                {
+                    uint32_t corner = 0xffffu;
+                    if (dir_prev >= 0) corner = cache[4 + dir];
+                    cache[4] = cache[0]; cache[5] = cache[1]; cache[6] = cache[2]; cache[7] = cache[3];
+                    cache[0] = cache[1] = cache[2] = cache[3] = 0xffffu;
+                    if (dir_prev >= 0) cache[dir_prev ^ 1] = corner;
+                    cache[dir ^ 1] = (uint32_t)min_sad & 0xffffu;
+                    dir_prev = dir;
+                    dir--;
+                    cloop = 4 + 1;
+                    mv = v;
+                    min_sad = cost;
+                }
+            }
+            dir = (dir + 1) & 3;
+        } while (--cloop);
+
+        /* one diagonal probe towards the two cheaper axis neighbours */
+        {
+            int pdy = cache[3] >= cache[2] ? 4 : -4;
+            int sdx = cache[1] >= cache[0] ? 4 : -4;
+            v = mv_pack(mv_x(mv) + sdx, mv_y(mv) + pdy);
+            if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]))
+            {
+                cost = sad_frame_wh(refp + (mv_y(v) >> 2) * stride + (mv_x(v) >> 2), stride, inp, bw, bh);
+                cost += mv_cost(v, mv_pred, lam);
+                if (cost < min_sad) { mv = v; min_sad = cost; continue; }
+            }
+        }
+        break;
+    }
+
+    interp_luma_block(refp, stride, mv_x(mv), mv_y(mv), bw, bh, buf[0]);
+    WSYNC();
+    pix_t *best = buf[0];
+
+    if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
+    {
+        int vbest = mv;
+        pix_t *scratch = buf[0], *hpel = buf[1], *hpel1 = buf[2], *hpel2 = buf[3];
+        uint32_t minsad1 = cache[1], minsad2 = cache[3];
+        int sqx = -1, sqy = 0, pqx = 0, pqy = -1;       /* secondary / primary quarter steps */
+        if (cache[3] >= cache[2]) { pqy = 1; minsad2 = cache[2]; }
+        if (cache[1] >= cache[0]) { sqx = 1; minsad1 = cache[0]; }
+        if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
+        int dgx = pqx + sqx, dgy = pqy + sqy;
+        for (int i = 0; i < 7; i++)
+        {
+            pix_t *ptest;
+            switch (i)
+            {
+            case 0:
+                v = mv_pack(mv_x(mv) + 2 * pqx, mv_y(mv) + 2 * pqy);
+                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel1);
+                break;
+            case 1:
+                v = mv_pack(mv_x(mv) + pqx, mv_y(mv) + pqy);
+                average_block(scratch, hpel1, ptest = hpel, bw, bh);
+                break;
+            case 2:
+                v = mv_pack(mv_x(mv) + 2 * sqx, mv_y(mv) + 2 * sqy);
+                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel2);
+                break;
+            case 3:
+                hpel = buf[1]; if (best == hpel) hpel = scratch;
+                v = mv_pack(mv_x(mv) + sqx, mv_y(mv) + sqy);
+                average_block(scratch, hpel2, ptest = hpel, bw, bh);
+                break;
+            case 4:
+                hpel = buf[1]; if (best == hpel) hpel = scratch;
+                v = mv_pack(mv_x(mv) + dgx, mv_y(mv) + dgy);
+                average_block(hpel1, hpel2, ptest = hpel, bw, bh);
+                break;
+            case 5:
+                if (best == hpel2) { hpel2 = scratch; hpel = buf[1]; }
+                v = mv_pack(mv_x(mv) + 2 * dgx, mv_y(mv) + 2 * dgy);
+                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel2);
+                break;
+            default:
+                hpel = buf[1]; if (best == hpel) hpel = scratch;
+                v = mv_pack(mv_x(mv) + pqx + dgx, mv_y(mv) + pqy + dgy);
+                average_block(hpel2, hpel1, ptest = hpel, bw, bh);
+                break;
+            }
+            WSYNC();
+            int sad_test = sad_sm_wh(ptest, inp, bw, bh) + mv_cost(v, mv_pred, lam);
+            if (sad_test < min_sad) { min_sad = sad_test; vbest = v; best = ptest; }
+        }
+        mv = vbest;
+    }
+    *pmv = mv;
+    *pbest = best;
+    return min_sad;
+}
+
+/* me_mv_set_range H:5181 */
+HD void me_set_range(const FrameParams *fp, int *pnt, int *rng, int mby_q)
+{
+    int x0 = fp->mvlim_x0, x1 = fp->mvlim_x1;
+    int y0 = (int16_t)imax(fp->mvlim_y0, mby_q - 63 * 4), y1 = (int16_t)imin(fp->mvlim_y1, mby_q + 63 * 4);
+    int px = imin(imax(mv_x(*pnt), x0), x1), py = imin(imax(mv_y(*pnt), y0), y1);
+    *pnt = mv_pack(px, py);
+    rng[0] = imin(imax(px - MV_RANGE_PX * 4, x0), x1);
+    rng[1] = imin(imax(py - MV_RANGE_PX * 4, y0), y1);
+    rng[2] = imin(imax(px + MV_RANGE_PX * 4, x0), x1);
+    rng[3] = imin(imax(py + MV_RANGE_PX * 4, y0), y1);
+}
+
+/* mb_inter_partition H:5224: which partition shapes are worth a search */
+HD void inter_partition_hint(const int sad[4], int mode[4])
+{
+    int p00 = sad[0], p01 = sad[1], p10 = sad[2], p11 = sad[3];
+    int sum = p00 + p01 + p10 + p11;
+    int slope = iabs((p00 - p10) + (p01 - p11)) - iabs((p00 - p01) + (p10 - p11));
+    int skew = iabs(p11 - p00) - iabs(p10 - p01);
+    if (slope > (sum >> 4)) mode[1] = 1;
+    if (slope < -(sum >> 4)) mode[2] = 1;
+    if (iabs(skew) > (sum >> 4) && iabs(slope) <= (sum >> 4)) mode[3] = 1;
+}
+
+/* chroma motion compensation for every partition of the current MB type
+ * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB. */
+HD void mc_chroma(const MBState &s, int type, const int32_t *mvs)
+{
+    const FrameParams *fp = s.fp;
+    int bw = (type & 2) ? 4 : 8, bh = (type & 1) ? 4 : 8;
+    if (type == MBT_SKIP) bw = bh = 8;
+    int sc = fp->stride[1];
+    for (int pl = 0; pl < 2; pl++)
+    {
+        int part = 0, x = 0, y = 0;
+        for (;; part++)
+        {
+            int ax = mv_x(mvs[part]) + s.mbx * 64, ay = mv_y(mvs[part]) + s.mby * 64;
+            const pix_t *ref = fp->ref[1 + pl] + ((ay >> 3) + y) * sc + (ax >> 3) + x;
+            interp_chroma_block(ref, sc, ax & 7, ay & 7, bw, bh, s.w->predc + pl * 8 + 16 * y + x);
+            x = (x + bw) & 7;
+            if (!x) { y = (y + bh) & 7; if (!y) break; }
+        }
+    }
+    WSYNC();
+}
+
+/* ------------------------------------------------------------------------------
+ * a5: inter mode decision (inter_choose_mode H:5283-5524).
+ * On return s.type / s.cost / s.pbest are set; w->part_mv / part_mvd of the chosen
+ * type are copied to out_mv/out_mvd.  Returns 1 for an early skip decision.
+ * ---------------------------------------------------------------------------- */
+HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const int stride = fp->stride[0];
+    const pix_t *refy = fp->ref[0];
+    const int mbqx = s.mbx * 64, mbqy = s.mby * 64;
+    int pref[4] = {1, 0, 0, 0};
+    int cand[12], ncand = 0, j = 0;
+    int sad4v[4];
+    int sad_skip = 0x7FFFFFFF, sad_best = 0x7FFFFFFF, cand_cost_best = 0;
+    int mv_best = mv_pack(MV_NA, 0);
+
+    /* skip predictor (me_mv_medianpredictor_get_skip H:3877) */
+    int mvp16 = mvp_get(w, s.avail, 0, 0, 4, 4);
+    int mv_skip = 0;
+    if (!(~s.avail & (AVAIL_L | AVAIL_T)) && w->mvp_left[0] != 0 && w->mvp_top[0] != 0) mv_skip = mvp16;
+    s.mv_skip_pred = mv_skip;
+    int mv_skip_a = mv_pack(mv_x(mv_skip) + mbqx, mv_y(mv_skip) + mbqy);
+
+    if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
+    {
+        interp_luma_block(refy, stride, mv_x(mv_skip_a), mv_y(mv_skip_a), 16, 16, s.ptest);
+        WSYNC();
+        sad_skip = sad_mb_quad(w->inp_y, 16, 0, s.ptest, sad4v);
+        if (imax(imax(sad4v[0], sad4v[1]), imax(sad4v[2], sad4v[3])) < fp->skip_thr_inter)
+        {
+            int32_t one_mv = mv_skip;
+            mc_chroma(s, MBT_SKIP, &one_mv);
+            int ok = 1;
+            for (int pl = 0; pl < 2 && ok; pl++)
+            {
+                int acc = 0;
+                FOR_LANES(i, 16)
+                {
+                    int r = i >> 1, c = (i & 1) * 4;
+                    acc += sad4(ld4_sm(w->inp_c + r * 16 + pl * 8 + c), ld4_sm(w->predc + r * 16 + pl * 8 + c));
+                }
+                acc = wsum(acc);
+                if (acc >= fp->skip_thr_inter) ok = 0;
+            }
+            if (ok)
+            {
+                pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
+                s.type = MBT_SKIP;
+                s.cost = 0;
+                out_mv[0] = mv_skip;
+                out_mvd[0] = 0;
+                return 1;
+            }
+        }
+        if (fp->speed < 1) inter_partition_hint(sad4v, pref);
+        mv_best = cand[ncand++] = mv_round_fullpel(mv_skip);
+        if (!((mv_x(mv_skip) | mv_y(mv_skip)) & 3))
+        {
+            sad_best = sad_skip;
+            cand_cost_best = mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+            j = 1;
+        }
+    }
+
+    /* candidate start points (H:5370-5386) */
+    cand[ncand++] = mvp16;
+    cand[ncand++] = 0;
+    if ((s.avail & AVAIL_L) && w->mvp_left[0] != MV_NA) cand[ncand++] = w->mvp_left[0];
+    if ((s.avail & AVAIL_T) && w->mvp_top[0] != MV_NA) cand[ncand++] = w->mvp_top[0];
+    if ((s.avail & AVAIL_TR) && w->mvp_top[4] != MV_NA) cand[ncand++] = w->mvp_top[4];
+    if (s.mbx <= 0) cand[ncand++] = mv_pack(8 * 4, 0);
+    if (s.mby <= 0) cand[ncand++] = mv_pack(0, 8 * 4);
+    cand[ncand++] = cl[0];
+    cand[ncand++] = cl[1];
+    {   /* round to full-pel and drop duplicates, keeping first occurrences (H:5198) */
+        int k = 1;
+        cand[0] = mv_round_fullpel(cand[0]);
+        for (int a = 1; a < ncand; a++)
+        {
+            int m = mv_round_fullpel(cand[a]), i;
+            for (i = 0; i < k; i++) if (m == cand[i]) break;
+            if (i == k) cand[k++] = m;
+        }
+        ncand = k;
+    }
+    for (; j < ncand; j++)
+    {
+        int mva = mv_pack(mv_x(cand[j]) + mbqx, mv_y(cand[j]) + mbqy);
+        if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
+        {
+            int cc = mv_cost(cand[j], mvp16, fp->lambda_mv_q4);
+            int sad = sad_mb_quad(refy + (mv_y(mva) >> 2) * stride + (mv_x(mva) >> 2), stride, 1, w->inp_y, sad4v);
+            if (fp->speed < 1) inter_partition_hint(sad4v, pref);
+            if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
+        }
+    }
+    if (cand_sig)
+    {
+        cand_sig[0] = mv_best; cand_sig[1] = sad_best; cand_sig[2] = cand_cost_best;
+        cand_sig[3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
+    }
+    sad_best += mv_cost(mv_best, mvp16, fp->lambda_mv_q4);
+
+    /* partition modes (H:5416-5510) */
+    pix_t *store = w->store[0];
+    pix_t *pred_best = store, *pred_test = store + 256;
+    int best_type = 0;
+    IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_save[3 * i] = w->mvp_left[i]; w->mvp_save[3 * i + 1] = w->mvp_tl[i]; w->mvp_save[3 * i + 2] = w->mvp_top[i]; } }
+    WSYNC();
+    s.cost = 0xffffff;
+    for (int mb_type = 0; mb_type < 4; mb_type++)
+    {
+        const int nbits = mb_type == 0 ? 1 : (mb_type == 3 ? 12 : 4);
+        int imv = 0;
+        int part_sad = (nbits * fp->lambda_q4) >> 4;
+        if (!pref[mb_type]) continue;
+        int bw = (mb_type & 2) ? 8 : 16, bh = (mb_type & 1) ? 8 : 16;
+        int px = 0, py = 0;
+        for (;;)
+        {
+            int rng[4];
+            int mvabs = mv_pack(mv_x(mv_best) + mbqx, mv_y(mv_best) + mbqy);
+            me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+            int mv_pred = mvp_get(w, s.avail, px >> 2, py >> 2, bw >> 2, bh >> 2);
+            int mv_pred_a = mv_pack(mv_x(mv_pred) + mbqx, mv_y(mv_pred) + mbqy);
+            if (mb_type)
+            {
+                mvabs = mv_round_fullpel(mv_pred_a);
+                me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+                sad_best = sad_frame_wh(refy + ((mv_y(mvabs) >> 2) + py) * stride + (mv_x(mvabs) >> 2) + px, stride,
+                                        w->inp_y + py * 16 + px, bw, bh)
+                         + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
+            }
+            int sb = mb_type ? (mb_type == 2 ? 8 : 128) : 256;
+            pix_t *bufs[4];
+            bufs[0] = store; bufs[1] = store + sb; bufs[2] = store + (sb == 8 ? 256 : 2 * sb); bufs[3] = bufs[2] + sb;
+            pix_t *dout;
+            part_sad += me_search(s, refy + py * stride + px, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
+                                  bw, bh, bufs, &dout);
+            if (!mb_type)
+            {
+                pred_test = dout;
+                if (pred_test < store + 2 * 256)
+                {
+                    pred_best = (pred_test == store ? store + 256 : store);
+                    store += 2 * 256;
+                } else
+                {
+                    pred_best = (pred_test == (store + 512) ? store + 512 + 256 : store + 512);
+                }
+            } else
+            {
+                int wq = bw >> 2;
+                FOR_LANES(i, wq * bh)
+                {
+                    int r = i / wq, c = (i - r * wq) * 4;
+                    *(uint32_t *)(pred_test + (py + r) * 16 + px + c) = ld4_sm(dout + r * 16 + c);
+                }
+            }
+            int mv = mv_pack(mv_x(mvabs) - mbqx, mv_y(mvabs) - mbqy);
+            IF_LANE0
+            {
+                w->part_mvd[mb_type][imv] = mv_sub2(mv, mv_pred);
+                w->part_mv[mb_type][imv] = mv;
+                mvp_put(w, px >> 2, py >> 2, bw >> 2, bh >> 2, mv);
+            }
+            imv++;
+            WSYNC();
+            px = (px + bw) & 15;
+            if (!px) { py = (py + bh) & 15; if (!py) break; }
+        }
+        IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_left[i] = w->mvp_save[3 * i]; w->mvp_tl[i] = w->mvp_save[3 * i + 1]; w->mvp_top[i] = w->mvp_save[3 * i + 2]; } }
+        WSYNC();
+        if (part_sad < s.cost)
+        {
+            pix_t *t = pred_best; pred_best = pred_test; pred_test = t;
+            s.cost = part_sad;
+            best_type = mb_type;
+        }
+    }
+    s.type = best_type;
+    s.pbest = pred_best;
+    s.ptest = pred_test;
+    for (int i = 0; i < 4; i++) { out_mv[i] = w->part_mv[best_type][i]; out_mvd[i] = w->part_mvd[best_type][i]; }
+
+    if (s.cost > sad_skip)     /* P16x16 at the skip vector is cheaper (H:5512) */
+    {
+        s.type = 0;
+        s.cost = sad_skip + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+        out_mv[0] = mv_skip;
+        out_mvd[0] = mv_sub2(mv_skip, mvp16);
+        interp_luma_block(refy, stride, mv_x(mv_skip_a), mv_y(mv_skip_a), 16, 16, s.pbest);
+        WSYNC();
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------
+ * a8: Intra4x4 decision + reconstruction of the 16 blocks in raster order
+ * (intra_choose_4x4 H:4723, h264e_intra_choose_4x4 H:1810).  Returns the cost;
+ * leaves recon in w->i4rec, levels in w->qv_y/dq_y, modes in w->i4_mode/i4_code and
+ * the non-zero mask in *nz_mask_out.
+ * ---------------------------------------------------------------------------- */
+HD int intra4_choose(MBState &s, int *nz_mask_out)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const int avail = s.avail;
+    int cost = fp->lambda_i4_q4;
+    int nz_mask = 0;
+    const int penalty = (3 * fp->lambda_q4) >> 4;
+    const MBInfo *mbi = fp->mbi + s.mby * fp->nmbx + s.mbx;
+
+    for (int n = 0; n < 16; n++)
+    {
+        /* which neighbours exist for block n: bits that depend on the MB's own
+         * neighbours / bits that are always there (block2avail H:4750) */
+        const int r = n >> 2, c = n & 3;
+        int a = 0;
+        if (c > 0 || (avail & AVAIL_L)) a |= AVAIL_L;
+        if (r > 0 || (avail & AVAIL_T)) a |= AVAIL_T;
+        if (r > 0 && c > 0) a |= AVAIL_TL;
+        else if (r == 0 && c == 0) a |= avail & AVAIL_TL;
+        else if (r == 0) a |= (avail & AVAIL_T) ? AVAIL_TL : 0;
+        else a |= (avail & AVAIL_L) ? AVAIL_TL : 0;
+        if (r == 0) { if (c < 3) a |= (avail & AVAIL_T) ? AVAIL_TR : 0; else a |= avail & AVAIL_TR; }
+        else if (c < 3 && !((r & 1) && (c & 1))) a |= AVAIL_TR;     /* raster blocks 4,6,8,9,10,12,14 */
+
+        int ctx_l = c > 0 ? w->i4_mode[n - 1] : ((avail & AVAIL_L) ? mbi[-1].i4_mode[4 * r + 3] : -1);
+        int ctx_t = r > 0 ? w->i4_mode[n - 4] : ((avail & AVAIL_T) ? mbi[-fp->nmbx].i4_mode[12 + c] : -1);
+        int mpred = imin(ctx_l, ctx_t);
+        if (mpred < 0) mpred = 2;
+
+        const pix_t *blockin = w->inp_y + (c + r * 16) * 4;
+        pix_t *block = w->i4rec + (c + r * 16) * 4;
+
+        /* evaluation order of the reference: DC, V, DDL, VL, H, HU, DDR, HD, VR */
+        FOR_LANES(k, 9)
+        {
+            const int order[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
+            int mode = order[k];
+            int ok = k == 0 ? 1 : (k < 4 ? (a & AVAIL_T) : (k < 6 ? (a & AVAIL_L) : ((a & 7) == 7)));
+            int cst = 0x7FFFFFFF;
+            if (ok)
+            {
+                int e[13];
+                for (int jj = 0; jj < 4; jj++)
+                    e[3 - jj] = c > 0 ? w->i4rec[(r * 4 + jj) * 16 + c * 4 - 1] : w->left_y[r * 4 + jj];
+                if (r > 0 && c > 0) e[4] = w->i4rec[(r * 4 - 1) * 16 + c * 4 - 1];
+                else if (r > 0) e[4] = w->left_y[r * 4 - 1];
+                else if (c > 0) e[4] = w->top_y[c * 4 - 1];
+                else e[4] = w->tl[0];
+                for (int jj = 0; jj < 8; jj++)
+                {
+                    int x = c * 4 + jj;
+                    e[5 + jj] = r > 0 ? (x < 16 ? w->i4rec[(r * 4 - 1) * 16 + x] : 0) : w->top_y[x < 20 ? x : 19];
+                }
+                if (!(a & AVAIL_TR)) e[9] = e[10] = e[11] = e[12] = e[8];
+                pix_t pr[16];
+                intra4_predict(mode, e, a, pr);
+                int sad = 0;
+                for (int y = 0; y < 4; y++)
+                    for (int x = 0; x < 4; x++) sad += iabs((int)blockin[y * 16 + x] - pr[y * 4 + x]);
+                if (mode != mpred) sad += penalty;
+                cst = sad;
+                for (int q = 0; q < 4; q++) *(uint32_t *)(w->i4pred[k] + 4 * q) = (uint32_t)pr[4 * q] | ((uint32_t)pr[4 * q + 1] << 8) | ((uint32_t)pr[4 * q + 2] << 16) | ((uint32_t)pr[4 * q + 3] << 24);
+            }
+            w->i4cost[k] = cst;
+        }
+        WSYNC();
+        int bk = 0, best_sad = w->i4cost[0];
+        for (int k = 1; k < 9; k++) if (w->i4cost[k] < best_sad) { best_sad = w->i4cost[k]; bk = k; }
+        const int order2[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
+        int mode = order2[bk];
+
+        IF_LANE0
+        {
+            w->i4_mode[n] = (int8_t)mode;
+            w->i4_code[n] = (int8_t)(mode == mpred ? -1 : (mode > mpred ? mode - 1 : mode));
+            for (int y = 0; y < 4; y++) *(uint32_t *)(block + y * 16) = *(const uint32_t *)(w->i4pred[bk] + 4 * y);
+            int nzb = 0;
+            if (best_sad > fp->skip_thr_i4x4)
+            {
+                fwd4x4(blockin, 16, block, w->dq_y[n]);
+                nzb = quant4x4(w->dq_y[n], w->qv_y[n], 0, fp->qdat[0]);
+                if (nzb) inv4x4_add(w->dq_y[n], block, block, 16);
+            } else
+            {
+                for (int i = 0; i < 16; i++) { w->qv_y[n][i] = 0; w->dq_y[n][i] = 0; }
+            }
+            w->scal[0] = nzb;
+        }
+        WSYNC();
+        nz_mask = (nz_mask << 1) | w->scal[0];
+        cost += best_sad;
+        WSYNC();
+    }
+    *nz_mask_out = nz_mask;
+    return cost;
+}
+
+/* ------------------------------------------------------------------------------
+ * a9-a11: luma transform / quant / reconstruction of a non-I4x4 macroblock
+ * (mb_write H:4423-4434 with h264e_transform_sub_quant_dequant H:2619).
+ * Returns the 16-bit block mask (bit 15 = block 0).
+ * ---------------------------------------------------------------------------- */
+HD int luma_tq_recon(MBState &s, int intra16)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const uint16_t *qdat = fp->qdat[0];
+    pix_t *dec = fp->dec[0] + (s.mby * 16) * fp->stride[0] + s.mbx * 16;
+    FOR_LANES(b, 16)
+    {
+        int off = (b & 3) * 4 + (b >> 2) * 64;
+        fwd4x4(w->inp_y + off, 16, s.pbest + off, w->dq_y[b]);
+        if (intra16) w->dc_y[b] = w->dq_y[b][0];
+        else
+        {
+            w->zflag1[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 10);
+            w->zflag2[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 18);
+        }
+    }
+    WSYNC();
+    int zmask = 0;
+    if (!intra16)       /* zero_smallq H:2512: drop isolated small blocks / 8x8 groups */
+    {
+        for (int b = 0; b < 16; b++) if (w->zflag1[b]) zmask |= 1 << b;
+        const int g0[4] = {0, 2, 8, 10};
+        for (int g = 0; g < 4; g++)
+        {
+            int m = 0x33 << g0[g];
+            int b0 = g0[g];
+            if ((~zmask & m) && w->zflag2[b0] && w->zflag2[b0 + 1] && w->zflag2[b0 + 4] && w->zflag2[b0 + 5]) zmask |= m;
+        }
+    }
+    int nzbits = 0;
+    FOR_LANES(b, 16)
+    {
+        int nz = 0;
+        if (zmask & (1 << b)) { for (int i = 0; i < 16; i++) w->qv_y[b][i] = 0; }
+        else nz = quant4x4(w->dq_y[b], w->qv_y[b], intra16, qdat);
+        if (nz) nzbits |= 0x8000 >> b;
+    }
+    nzbits = wor(nzbits);
+    WSYNC();
+    int recon_mask = nzbits;
+    if (intra16)
+    {
+        IF_LANE0
+        {
+            int16_t dq0[16];
+            luma_dc_quant(w->dc_y, w->qdc_y, dq0, qdat);
+            for (int b = 0; b < 16; b++) w->dq_y[b][0] = dq0[b];
+        }
+        WSYNC();
+        recon_mask = 0xFFFF;
+    }
+    FOR_LANES(b, 16)
+    {
+        int off = (b & 3) * 4 + (b >> 2) * 64;
+        pix_t *o = dec + (b & 3) * 4 + (b >> 2) * 4 * fp->stride[0];
+        if (recon_mask & (0x8000 >> b)) inv4x4_add(w->dq_y[b], s.pbest + off, o, fp->stride[0]);
+        else copy4x4(s.pbest + off, o, fp->stride[0]);
+    }
+    return nzbits;
+}
+
+/* chroma transform / quant / recon of both planes (mb_write H:4443-4491).
+ * Returns cbpc (0..2). */
+HD int chroma_tq_recon(MBState &s)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const uint16_t *qdat = fp->qdat[1];
+    int sc = fp->stride[1];
+    /* forward transform + DC extraction + small-coefficient flags, 8 blocks */
+    FOR_LANES(b, 8)
+    {
+        int pl = b >> 2, k = b & 3;
+        int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64;
+        fwd4x4(w->inp_c + off, 16, w->predc + off, w->dq_c[b]);
+        w->dc_c[b] = w->dq_c[b][0];
+        w->zflag1[b] = (int8_t)coefs_small(w->dq_c[b], 1, qdat + 10);
+    }
+    WSYNC();
+    int nzbits = 0;     /* bit (7 - b) */
+    FOR_LANES(b, 8)
+    {
+        int nz = 0;
+        if (w->zflag1[b]) { for (int i = 0; i < 16; i++) w->qv_c[b][i] = 0; }
+        else nz = quant4x4(w->dq_c[b], w->qv_c[b], 1, qdat);
+        if (nz) nzbits |= 0x80 >> b;
+    }
+    nzbits = wor(nzbits);
+    WSYNC();
+    IF_LANE0
+    {
+        for (int pl = 0; pl < 2; pl++)
+        {
+            int16_t dq0[4];
+            int dcf = chroma_dc_quant(w->dc_c + 4 * pl, w->qdc_c + 4 * pl, dq0, qdat);
+            for (int k = 0; k < 4; k++) w->dq_c[pl * 4 + k][0] = dq0[k];
+            w->scal[1 + pl] = dcf;
+        }
+    }
+    WSYNC();
+    int cbpc = 0;
+    for (int pl = 0; pl < 2; pl++)
+    {
+        int nzm = (nzbits >> (4 * (1 - pl))) & 15;
+        int dcf = w->scal[1 + pl];
+        if (nzm) cbpc = 2;
+        cbpc |= dcf;
+        pix_t *dec = fp->dec[1 + pl] + (s.mby * 8) * sc + s.mbx * 8;
+        FOR_LANES(k, 4)
+        {
+            int b = pl * 4 + k;
+            int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64;
+            pix_t *o = dec + (k & 1) * 4 + (k >> 1) * 4 * sc;
+            if (!(dcf | nzm)) copy4x4(w->predc + off, o, sc);
+            else if (dcf)
+            {
+                if (!(nzm & (8 >> k))) for (int i = 1; i < 16; i++) w->dq_c[b][i] = 0;
+                inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
+            } else
+            {
+                if (nzm & (8 >> k)) inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
+                else copy4x4(w->predc + off, o, sc);
+            }
+        }
+    }
+    WSYNC();
+    return imin(cbpc, 2);
+}
+
+HD int count_nz(const int16_t *q, int i0)
+{
+    int n = 0;
+    for (int i = i0; i < 16; i++) n += q[i] != 0;
+    return n;
+}
+
+/* mv_clusters_update H:5263 */
+HD void clusters_update(int32_t cl[2], int mv)
+{
+    int x = mv_x(mv), y = mv_y(mv);
+    int norm = x * x + y * y;
+    int c0x = mv_x(cl[0]), c0y = mv_y(cl[0]), c1x = mv_x(cl[1]), c1y = mv_y(cl[1]);
+    int n0 = c0x * c0x + c0y * c0y, n1 = c1x * c1x + c1y * c1y;
+    if (norm < n1) cl[0] = mv_pack((63 * c0x + x + 32) >> 6, (63 * c0y + y + 32) >> 6);
+    if (norm >= n0) cl[1] = mv_pack((63 * c1x + x + 32) >> 6, (63 * c1y + y + 32) >> 6);
+}
+
+/* ------------------------------------------------------------------------------
+ * a17: encode one macroblock (mb_encode H:5724 + the pixel/coefficient half of
+ * mb_write H:4378).  cl[] = mv_clusters as seen by this MB; updated in place.
+ * Writes the MB's record, quantised levels and unfiltered reconstruction.
+ * ---------------------------------------------------------------------------- */
+HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, int32_t cl[2])
+{
+    MBState s;
+    s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
+    s.avail = mb_avail(mbx, mby, fp->nmbx);
+    s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
+    s.pbest = w->store[0]; s.ptest = w->store[1];
+    MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
+    int16_t *coef = fp->coef + (size_t)(mby * fp->nmbx + mbx) * COEF_PER_MB;
+    int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
+    int32_t cand_sig[4] = {0, 0, 0, 0};
+    int32_t cl_in0 = mv_round_fullpel(cl[0]), cl_in1 = mv_round_fullpel(cl[1]);
+
+    mb_load(s);
+
+    if (fp->slice_type == SLICE_P) inter_choose(s, pmv, pmvd, cl, cand_sig);
+
+    int nz_mask = 0;
+    if (s.type >= 0)
+    {
+        const pix_t *left = (s.avail & AVAIL_L) ? w->left_y : 0;
+        const pix_t *top = (s.avail & AVAIL_T) ? w->top_y : 0;
+        /* Intra16x16: heuristic mode, one prediction, SAD cost (intra_choose_16x16 H:4876) */
+        s.i16_mode = intra16_estimate(w->inp_y, s.avail, fp->qp);
+        intra16_pred(s.ptest, left, top, s.i16_mode);
+        WSYNC();
+        int cost16 = sad_sm_wh(w->inp_y, s.ptest, 16, 16)
+                   + ((bitsize_ue(s.i16_mode + 1) * fp->lambda_q4) >> 4) + fp->lambda_i16_q4;
+        if (cost16 < s.cost)
+        {
+            s.cost = cost16; s.type = MBT_I16;
+            pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
+        }
+        if (fp->speed < 2 || fp->slice_type != SLICE_P)
+        {
+            int nz4;
+            int cost4 = intra4_choose(s, &nz4);
+            if (cost4 < s.cost) { s.cost = cost4; s.type = MBT_I4; nz_mask = nz4; }
+        }
+    }
+
+    if (s.type < 5) clusters_update(cl, pmv[0]);
+
+    if (s.type >= 5)
+    {
+        intra_chroma_pred(w->predc, (s.avail & AVAIL_L) ? w->left_c : 0, (s.avail & AVAIL_T) ? w->top_c : 0, s.i16_mode);
+        WSYNC();
+    } else
+    {
+        mc_chroma(s, s.type, pmv);
+    }
+
+    /* ---- transform, quantisation, reconstruction ---- */
+    int cbpl = 0, cbpc = 0;
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    pix_t *decy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+    if (s.type != MBT_SKIP)
+    {
+        if (s.type != MBT_I4) nz_mask = luma_tq_recon(s, s.type == MBT_I16);
+        else
+        {
+            FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(w->i4rec + r * 16 + c); }
+        }
+        if (nz_mask & 0xCC00) cbpl |= 1;
+        if (nz_mask & 0x3300) cbpl |= 2;
+        if (nz_mask & 0x00CC) cbpl |= 4;
+        if (nz_mask & 0x0033) cbpl |= 8;
+        cbpc = chroma_tq_recon(s);
+        if (!(s.type | cbpl | cbpc) && pmv[0] == s.mv_skip_pred) s.type = MBT_SKIP;   /* rollback H:4494 */
+    }
+    if (s.type == MBT_SKIP)
+    {
+        /* reconstruction = prediction (H:4417-4420) */
+        pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8, *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
+        FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(s.pbest + r * 16 + c); }
+        FOR_LANES(i, 32)
+        {
+            int r = i >> 2, q = i & 3;
+            pix_t *d = (q < 2 ? du : dv) + r * sc + (q & 1) * 4;
+            *(uint32_t *)d = ld4_sm(w->predc + r * 16 + q * 4);
+        }
+        nz_mask = 0; cbpl = cbpc = 0;
+    }
+    WSYNC();
+
+    /* ---- macroblock record ---- */
+    const int type = s.type;
+    if (type == MBT_I16 && cbpl) cbpl = 15;
+    FOR_LANES(i, 32)
+    {
+        if (i < 16)
+        {
+            int v;
+            if (type >= 5) v = MV_NA;
+            else if (type <= 0) v = pmv[0];
+            else
+            {
+                int bx = i & 3, by = i >> 2;
+                int part = type == 1 ? (by >> 1) : (type == 2 ? (bx >> 1) : (by >> 1) * 2 + (bx >> 1));
+                v = pmv[part];
+            }
+            mi->mv[i] = v;
+            mi->i4_mode[i] = type == MBT_I4 ? w->i4_mode[i] : 2;
+            mi->i4_code[i] = type == MBT_I4 ? w->i4_code[i] : 0;
+            /* total_coeff as the neighbours' CAVLC context will see it (H:4630-4647) */
+            int grp = (i >> 3) * 2 + ((i & 3) >> 1);
+            int n = 0;
+            if (type != MBT_SKIP && (cbpl & (1 << grp))) n = count_nz(w->qv_y[i], type == MBT_I16);
+            mi->nnz[i] = (uint8_t)n;
+        } else if (i < 24)
+        {
+            int b = i - 16;
+            mi->nnz[i] = (uint8_t)((type != MBT_SKIP && cbpc == 2) ? count_nz(w->qv_c[b], 1) : 0);
+        } else if (i < 28)
+        {
+            mi->mvd[i - 24] = pmvd[i - 24];
+        } else if (i == 28)
+        {
+            mi->type = (int8_t)type;
+            mi->i16_mode = (int8_t)s.i16_mode;
+            mi->cbp = (uint8_t)(cbpl | (cbpc << 4));
+            mi->flags = 0;
+            mi->nz_mask = (uint16_t)(type == MBT_SKIP ? 0 : nz_mask);
+            mi->cl_used[0] = cl_in0; mi->cl_used[1] = cl_in1;
+            for (int k = 0; k < 4; k++) mi->cand_sig[k] = cand_sig[k];
+        }
+    }
+    if (type != MBT_SKIP)
+    {
+        FOR_LANES(i, COEF_PER_MB / 2)      /* two int16 per item */
+        {
+            int k = i * 2;
+            uint32_t v;
+            if (k < COEF_YDC) v = *(const uint32_t *)(&w->qv_y[0][0] + k);
+            else if (k < COEF_C) v = *(const uint32_t *)(w->qdc_y + (k - COEF_YDC));
+            else if (k < COEF_CDC) v = *(const uint32_t *)(&w->qv_c[0][0] + (k - COEF_C));
+            else v = *(const uint32_t *)(w->qdc_c + (k - COEF_CDC));
+            *(uint32_t *)(coef + k) = v;
+        }
+    }
+    WSYNC();
+}

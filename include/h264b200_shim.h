@@ -1,0 +1,91 @@
+/*
+ * h264b200_shim.h -- the thin C-ABI between the host C encoder (rate control,
+ * parameter sets, slice headers, NAL assembly; h264-lab_b200/host/) and the sm_100a
+ * CUDA implementation of the macroblock hot path (h264-lab_b200/csrc/).
+ *
+ * Plain C types only (pointers and sizes, no CUDA or torch types).  The boundary
+ * sits between the reference's H264E_encode_one() (H:6477: RC + headers, host) and
+ * the body of encode_slice()'s macroblock loop (H:6414-6449, device): everything the
+ * loop does -- mb_encode (H:5724), mb_write (H:4378), mb_deblock (H:5642) and the
+ * reference-frame border extension (H:3580-3596) -- runs on the GPU.
+ *
+ * H:nnn = /root/reference/src/h264-lab.h line nnn.
+ */
+#ifndef H264B200_SHIM_H
+#define H264B200_SHIM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h264b200_ctx h264b200_ctx;   /* device-side state of one encoder instance */
+
+/* Per-frame parameters computed by the host (replaces the fields of h264e_enc_t that
+ * the macroblock loop reads: rc.qp / rc.qdat H:686-729, slice.type, speed, run_param). */
+typedef struct
+{
+    int slice_type;          /* 0 = P, 2 = I                       (H:3203-3204)        */
+    int qp;                  /* frame QP                            (H:688)              */
+    int speed;               /* run_param.encode_speed              (H:181)              */
+    int disable_deblock;     /* speed == 8 || speed == 10           (H:6717)             */
+    /* per-QP tunables (H:1032-1120) */
+    int lambda_q4, lambda_mv_q4, lambda_i4_q4, lambda_i16_q4, skip_thr_inter, skip_thr_i4x4;
+    /* deblocking constants, [0] luma QP, [1] chroma QP (H:944-987, H:5663-5696) */
+    int df_alpha[2], df_beta[2], df_tc0[2][4];
+    unsigned short qdat[2][42];   /* quantiser tables of rc_set_qp  (H:5839-5912)        */
+    int hdr_bits;            /* bit position inside the NAL at which slice_data() starts */
+} h264b200_frame_params;
+
+/* One frame of one encoder instance. */
+typedef struct
+{
+    h264b200_ctx *ctx;
+    h264b200_frame_params p;
+    const unsigned char *yuv[3];     /* HOST input planes                                  */
+    int stride[3];
+    int update_ref;                  /* 0: droppable frame, the reference picture is kept  */
+    unsigned char *recon[3];         /* optional HOST buffers that receive the              */
+    int recon_stride[3];             /*   reconstruction (NULL: it stays on the device)     */
+    /* results */
+    const unsigned int *out_words;   /* [out] HOST (pinned, owned by ctx) slice payload as 32-bit words,
+                                        MSB first; slice_data() starts at bit p.hdr_bits, the bits
+                                        before it are zero.  Valid until the next call on this ctx. */
+    int out_bits;                    /* [out] end of the payload incl. the trailing mb_skip_run */
+    int trailing_skip_run;           /* [out] skipped macroblocks at the end of the slice   */
+    int status;                      /* [out] 0 = ok, -1 no device, -2 payload overflow, -3 CUDA error */
+} h264b200_job;
+
+/* Create / destroy the device state for a width x height encoder.  device = CUDA
+ * ordinal, or -1 for the current device.  Returns 0 or a negative error. */
+int h264b200_ctx_create(h264b200_ctx **out, int width, int height, int device);
+void h264b200_ctx_destroy(h264b200_ctx *ctx);
+/* Reset cross-frame state (mv_clusters, H:766) -- what H264E_init's memset does. */
+void h264b200_ctx_reset(h264b200_ctx *ctx);
+
+/* Encode one frame for each of n independent encoder instances concurrently
+ * (host->device copy of the inputs, macroblock pass, deblocking, CAVLC + pack,
+ * device->host copy of the payload).  Blocks until every job has finished.
+ * Returns 0, or the first failing job's negative status. */
+int h264b200_encode_frames(int n, h264b200_job *jobs);
+
+/* Timing of the kernels of the last h264b200_encode_frames call, in milliseconds,
+ * measured with CUDA events on the launch stream: [0] whole call on device,
+ * [1] macroblock pass, [2] deblock + border, [3] CAVLC + pack.  */
+void h264b200_last_timing(float out_ms[4]);
+
+/* Device-resident variant for kernel-only measurements: inputs already uploaded with
+ * h264b200_upload_input(); runs the same kernels without host<->device copies.      */
+int h264b200_upload_input(h264b200_ctx *ctx, const unsigned char *const yuv[3], const int stride[3]);
+int h264b200_encode_frames_resident(int n, h264b200_job *jobs);
+
+/* Copy the most recent reconstruction (W16 x H16 luma, W16/2 x H16/2 chroma) to host. */
+int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const int strides[3]);
+
+/* Number of kernel launches issued since the library was loaded. */
+long h264b200_launch_count(void);
+const char *h264b200_backend_name(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

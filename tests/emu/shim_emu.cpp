@@ -1,0 +1,162 @@
+/*
+ * tests/emu/shim_emu.cpp -- DEVELOPER / TEST TOOL, NOT PART OF THE PRODUCT.
+ *
+ * Host emulation of the C-ABI shim (include/h264b200_shim.h): compiles the very same
+ * macroblock code that nvcc compiles for sm_100a (h264-lab_b200/csrc/h264_*.h) with
+ * g++, running every "warp" as a sequential loop, macroblocks in raster order.  It
+ * exists so that bit-exactness against the reference can be debugged in a container
+ * without a GPU and so that the host C layer (rate control, headers, NAL) can be
+ * tested on CPU.  The product library (libh264lab_b200.so) never links this file
+ * and has no CPU fallback.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../h264-lab_b200/csrc/h264_common.h"
+#include "../../h264-lab_b200/csrc/h264_pixel.h"
+#include "../../h264-lab_b200/csrc/h264_mbenc.h"
+#include "../../h264-lab_b200/csrc/h264_cavlc.h"
+#include "../../h264-lab_b200/csrc/h264_deblock.h"
+#include "../../include/h264b200_shim.h"
+
+struct h264b200_ctx
+{
+    int width, height, nmbx, nmby;
+    int stride[2];
+    std::vector<pix_t> frame[2];     /* two padded frames: [cur] = dec, [cur^1] = ref */
+    size_t plane_off[3];
+    int cur;
+    std::vector<MBInfo> mbi;
+    std::vector<int16_t> coef;
+    std::vector<uint32_t> mb_bits;
+    std::vector<int> mb_nbits;
+    std::vector<uint32_t> out_words;
+    int32_t clusters[2];
+};
+
+static long g_launches = 0;
+
+extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, int device)
+{
+    (void)device;
+    h264b200_ctx *c = new h264b200_ctx();
+    c->width = width; c->height = height;
+    c->nmbx = (width + 15) >> 4; c->nmby = (height + 15) >> 4;
+    int w = c->nmbx * 16, h = c->nmby * 16;
+    c->stride[0] = w + 32; c->stride[1] = (w + 32) / 2;
+    size_t ysz = (size_t)c->stride[0] * (h + 32), csz = (size_t)c->stride[1] * (h / 2 + 16);
+    c->plane_off[0] = (size_t)c->stride[0] * 16 + 16;
+    c->plane_off[1] = ysz + (size_t)c->stride[1] * 8 + 8;
+    c->plane_off[2] = ysz + csz + (size_t)c->stride[1] * 8 + 8;
+    for (int i = 0; i < 2; i++) c->frame[i].assign(ysz + 2 * csz + 64, 0);
+    int nmb = c->nmbx * c->nmby;
+    c->mbi.resize(nmb);
+    c->coef.resize((size_t)nmb * COEF_PER_MB);
+    c->mb_bits.resize((size_t)(nmb + 1) * MB_BITS_WORDS);
+    c->mb_nbits.resize(nmb + 2);
+    c->out_words.resize((size_t)nmb * 160 + 1024);
+    c->cur = 0;
+    c->clusters[0] = c->clusters[1] = 0;
+    *out = c;
+    return 0;
+}
+extern "C" void h264b200_ctx_destroy(h264b200_ctx *c) { delete c; }
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; }
+
+static void run_job(h264b200_job *job)
+{
+    h264b200_ctx *c = job->ctx;
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    const h264b200_frame_params &p = job->p;
+    fp.width = c->width; fp.height = c->height; fp.nmbx = c->nmbx; fp.nmby = c->nmby;
+    fp.slice_type = p.slice_type; fp.qp = p.qp; fp.speed = p.speed; fp.disable_deblock = p.disable_deblock;
+    fp.lambda_q4 = p.lambda_q4; fp.lambda_mv_q4 = p.lambda_mv_q4; fp.lambda_i4_q4 = p.lambda_i4_q4;
+    fp.lambda_i16_q4 = p.lambda_i16_q4; fp.skip_thr_inter = p.skip_thr_inter; fp.skip_thr_i4x4 = p.skip_thr_i4x4;
+    fp.mvlim_x0 = -14 * 4; fp.mvlim_y0 = -14 * 4;
+    fp.mvlim_x1 = (c->nmbx * 16 - 2) * 4; fp.mvlim_y1 = (c->nmby * 16 - 2) * 4;
+    for (int i = 0; i < 2; i++)
+    {
+        fp.df_alpha[i] = p.df_alpha[i]; fp.df_beta[i] = p.df_beta[i];
+        for (int k = 0; k < 4; k++) fp.df_tc0[i][k] = p.df_tc0[i][k];
+    }
+    memcpy(fp.qdat, p.qdat, sizeof(fp.qdat));
+    for (int i = 0; i < 3; i++)
+    {
+        fp.inp[i] = job->yuv[i]; fp.inp_stride[i] = job->stride[i];
+        fp.dec[i] = c->frame[c->cur].data() + c->plane_off[i];
+        fp.ref[i] = c->frame[c->cur ^ 1].data() + c->plane_off[i];
+    }
+    fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
+    fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
+    fp.clusters = c->clusters;
+    fp.mb_bits = c->mb_bits.data(); fp.mb_nbits = c->mb_nbits.data();
+    fp.out_words = c->out_words.data();
+    job->out_words = c->out_words.data();
+    const int out_cap_words = (int)c->out_words.size();
+    fp.hdr_bits = p.hdr_bits;
+    const int nmb = c->nmbx * c->nmby;
+
+    MBWork *w = new MBWork();
+    for (int y = 0; y < c->nmby; y++)
+        for (int x = 0; x < c->nmbx; x++) encode_mb(&fp, w, x, y, c->clusters);
+    delete w;
+    g_launches++;
+
+    memset(c->out_words.data(), 0, c->out_words.size() * 4);
+    int bo = p.hdr_bits;
+    for (int n = 0; n <= nmb; n++)
+    {
+        int nb = cavlc_mb(&fp, n);
+        if (bo + nb + 64 > out_cap_words * 32) { job->status = -2; return; }
+        pack_mb(&fp, n, nb, bo);
+        bo += nb;
+    }
+    {
+        int run = 0;
+        if (p.slice_type == SLICE_P) for (int k = nmb - 1; k >= 0 && fp.mbi[k].type == MBT_SKIP; k--) run++;
+        job->trailing_skip_run = run;
+    }
+    job->out_bits = bo;
+    g_launches++;
+
+    if (!p.disable_deblock)
+        for (int y = 0; y < c->nmby; y++)
+            for (int x = 0; x < c->nmbx; x++) deblock_mb(&fp, x, y);
+    for (int pl = 0; pl < 3; pl++)
+    {
+        long ns = border_samples(&fp, pl);
+        for (long i = 0; i < ns; i++) extend_border_sample(&fp, pl, i);
+    }
+    g_launches++;
+    for (int pl = 0; pl < 3; pl++)
+        if (job->recon[pl])
+        {
+            int ww = c->nmbx * (pl ? 8 : 16), hh = c->nmby * (pl ? 8 : 16);
+            for (int r = 0; r < hh; r++) memcpy(job->recon[pl] + (size_t)r * job->recon_stride[pl], fp.dec[pl] + (size_t)r * fp.stride[pl != 0], ww);
+        }
+    if (job->update_ref) c->cur ^= 1;
+    job->status = 0;
+}
+
+extern "C" int h264b200_encode_frames(int n, h264b200_job *jobs)
+{
+    int rc = 0;
+    for (int i = 0; i < n; i++) { run_job(jobs + i); if (jobs[i].status && !rc) rc = jobs[i].status; }
+    return rc;
+}
+extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3], const int strides[3])
+{
+    for (int pl = 0; pl < 3; pl++)
+    {
+        int ww = c->nmbx * (pl ? 8 : 16), hh = c->nmby * (pl ? 8 : 16);
+        const pix_t *src = c->frame[c->cur ^ 1].data() + c->plane_off[pl];
+        for (int r = 0; r < hh; r++) memcpy(planes[pl] + (size_t)r * strides[pl], src + (size_t)r * c->stride[pl != 0], ww);
+    }
+    return 0;
+}
+extern "C" int h264b200_upload_input(h264b200_ctx *, const unsigned char *const[3], const int[3]) { return -1; }
+extern "C" int h264b200_encode_frames_resident(int, h264b200_job *) { return -1; }
+extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
+extern "C" long h264b200_launch_count(void) { return g_launches; }
+extern "C" const char *h264b200_backend_name(void) { return "host-emulation (test only)"; }
