@@ -157,8 +157,9 @@ struct FrameParams
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */
     uint32_t *mb_bits;          /* per-MB bit strings, MB_BITS_WORDS words each             */
     int *mb_nbits;              /* [nmb + 1]                                                */
+    int *mb_bitoff;             /* [nmb + 1] exclusive prefix sum of mb_nbits + hdr_bits    */
     uint32_t *out_words;        /* packed slice payload                                     */
-    int *out_info;              /* [0] total bits, [1] error flags                          */
+    int *out_info;              /* [0] total bits, [1] error flags, [2] trailing skip run   */
     int hdr_bits;               /* bit offset at which the slice data starts                */
     int serial_rows;            /* 1: a row waits for the whole previous row (exact P mode) */
 };

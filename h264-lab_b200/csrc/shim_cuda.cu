@@ -1,0 +1,448 @@
+/*
+ * shim_cuda.cu -- sm_100a kernels + the C-ABI shim (include/h264b200_shim.h).
+ *
+ * One submission encodes one frame for each of n independent encoder instances
+ * (closed-GOP segments or streams).  Per submission, on one CUDA stream:
+ *
+ *   H2D inputs -> k_encode_rows  : macroblock decisions + transform/quant/recon.
+ *                                  Persistent-style wavefront: one warp per macroblock
+ *                                  ROW; rows are claimed from an atomic ticket so that a
+ *                                  claimed row's predecessor is always running; a row may
+ *                                  process macroblock x when the row above has finished
+ *                                  x+2 macroblocks (acquire/release on per-row counters).
+ *              -> k_deblock_rows : in-loop filter, same wavefront on its own counters.
+ *              -> k_borders      : guard-band replication of the new reference picture.
+ *              -> k_cavlc        : one thread per macroblock: syntax + CAVLC bit strings.
+ *              -> k_scan         : per frame, exclusive prefix sum of the bit lengths.
+ *              -> k_pack         : scatter the strings into the slice payload.
+ *   D2H payload.
+ *
+ * The per-macroblock code is in h264_*.h (shared with the test-only host emulation).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "h264_common.h"
+#include "h264_pixel.h"
+#include "h264_mbenc.h"
+#include "h264_cavlc.h"
+#include "h264_deblock.h"
+#include "../../include/h264b200_shim.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "h264b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -3; } } while (0)
+
+/* ------------------------------------------------------------------------------ */
+/* wavefront helpers                                                                */
+/* ------------------------------------------------------------------------------ */
+__device__ __forceinline__ void wait_row(const int *progress_above, int need)
+{
+    if (LANE_ID == 0)
+    {
+        const volatile int *p = progress_above;
+        while (*p < need) { __nanosleep(64); }
+    }
+    __syncwarp();
+    __threadfence();
+}
+__device__ __forceinline__ void publish_row(int *progress, int done)
+{
+    __threadfence();
+    __syncwarp();
+    if (LANE_ID == 0) *(volatile int *)progress = done;
+}
+
+/* sync area layout per submission: [0] ticket of k_encode_rows, [1] ticket of k_deblock_rows */
+__global__ void __launch_bounds__(32) k_encode_rows(const FrameParams *fps, int njobs, int max_rows, int *tickets)
+{
+    __shared__ MBWork work;
+    __shared__ int s_item;
+    if (threadIdx.x == 0) s_item = atomicAdd(&tickets[0], 1);
+    __syncwarp();
+    const int item = s_item;
+    const int job = item % njobs, row = item / njobs;
+    (void)max_rows;
+    const FrameParams *fp = fps + job;
+    if (row >= fp->nmby) return;
+    const int nmbx = fp->nmbx;
+    int *progress = fp->row_progress;
+    int32_t cl[2] = {0, 0};
+    for (int x = 0; x < nmbx; x++)
+    {
+        if (row > 0)
+        {
+            int need = fp->serial_rows ? nmbx : min(x + 2, nmbx);
+            if (x == 0 || !fp->serial_rows) wait_row(progress + row - 1, need);
+        }
+        if (fp->slice_type == SLICE_P) { cl[0] = ((volatile int32_t *)fp->clusters)[0]; cl[1] = ((volatile int32_t *)fp->clusters)[1]; }
+        encode_mb(fp, &work, x, row, cl);
+        if (fp->slice_type == SLICE_P && threadIdx.x == 0) { fp->clusters[0] = cl[0]; fp->clusters[1] = cl[1]; }
+        publish_row(progress + row, x + 1);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int njobs, int *tickets)
+{
+    __shared__ int s_item;
+    if (threadIdx.x == 0) s_item = atomicAdd(&tickets[1], 1);
+    __syncwarp();
+    const int item = s_item;
+    const int job = item % njobs, row = item / njobs;
+    const FrameParams *fp = fps + job;
+    if (row >= fp->nmby || fp->disable_deblock) return;
+    const int nmbx = fp->nmbx;
+    int *progress = fp->row_progress_df;
+    for (int x = 0; x < nmbx; x++)
+    {
+        if (row > 0) wait_row(progress + row - 1, min(x + 2, nmbx));
+        deblock_mb(fp, x, row);
+        publish_row(progress + row, x + 1);
+    }
+}
+
+__global__ void k_borders(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        long n = border_samples(fp, pl);
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+            extend_border_sample(fp, pl, i);
+    }
+}
+
+__global__ void k_cavlc(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    const int nmb = fp->nmbx * fp->nmby;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > nmb) return;
+    fp->mb_nbits[n] = cavlc_mb(fp, n);
+}
+
+/* one block per frame: exclusive scan of mb_nbits -> mb_bitoff, totals, and zero the payload */
+__global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs, int out_cap_words)
+{
+    const FrameParams *fp = fps + blockIdx.x;
+    const int cnt = fp->nmbx * fp->nmby + 1;
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int chunk = (cnt + 1023) / 1024;
+    const int lo = tid * chunk, hi = min(lo + chunk, cnt);
+    int s = 0, maxb = 0;
+    for (int i = lo; i < hi; i++) { int b = fp->mb_nbits[i]; s += b; maxb = max(maxb, b); }
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1)
+    {
+        int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int base = fp->hdr_bits + part[tid] - s;
+    for (int i = lo; i < hi; i++) { int b = fp->mb_nbits[i]; fp->mb_bitoff[i] = base; base += b; }
+    const int total = fp->hdr_bits + part[1023];
+    if (maxb > MB_BITS_WORDS * 32 - 64) atomicOr(&fp->out_info[1], 1);
+    if ((total + 95) / 32 > out_cap_words) atomicOr(&fp->out_info[1], 2);
+    if (tid == 0)
+    {
+        fp->out_info[0] = total;
+        int run = 0;
+        if (fp->slice_type == SLICE_P) for (int k = cnt - 2; k >= 0 && fp->mbi[k].type == MBT_SKIP; k--) run++;
+        fp->out_info[2] = run;
+    }
+    const int nw = min((total + 95) / 32, out_cap_words);
+    for (int i = tid; i < nw; i += 1024) fp->out_words[i] = 0;
+}
+
+__global__ void k_pack(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    const int nmb = fp->nmbx * fp->nmby;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > nmb || fp->out_info[1]) return;
+    int nb = fp->mb_nbits[n];
+    if (nb) pack_mb(fp, n, nb, fp->mb_bitoff[n]);
+}
+
+/* ------------------------------------------------------------------------------ */
+/* host side                                                                        */
+/* ------------------------------------------------------------------------------ */
+struct h264b200_ctx
+{
+    int device;
+    int width, height, nmbx, nmby, nmb;
+    int stride[2];
+    int inp_stride[3];
+    pix_t *d_frames[2];
+    size_t plane_off[3];
+    pix_t *d_inp[3];
+    pix_t *d_clip; int clip_frames;
+    int cur;
+    MBInfo *d_mbi;
+    int16_t *d_coef;
+    uint32_t *d_mb_bits;
+    int *d_mb_nbits, *d_mb_bitoff;
+    uint32_t *d_out_words;
+    int out_cap_words;
+    int *d_out_info;
+    int32_t *d_clusters;
+    int *d_progress;              /* 2 * nmby */
+    uint32_t *h_out_words;        /* pinned */
+    int *h_out_info;              /* pinned */
+};
+
+static long g_launches = 0;
+static cudaStream_t g_stream = 0;
+static FrameParams *g_d_fps = NULL, *g_h_fps = NULL;
+static int g_fps_cap = 0;
+static int *g_d_tickets = NULL;
+static cudaEvent_t g_ev[6];
+static int g_ev_ok = 0;
+static float g_last_ms[4];
+
+static int ensure_globals(int njobs)
+{
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
+    if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ok = 1; }
+    if (njobs > g_fps_cap)
+    {
+        if (g_d_fps) cudaFree(g_d_fps);
+        if (g_h_fps) cudaFreeHost(g_h_fps);
+        int cap = njobs < 16 ? 16 : njobs * 2;
+        CK(cudaMalloc(&g_d_fps, sizeof(FrameParams) * cap));
+        CK(cudaMallocHost(&g_h_fps, sizeof(FrameParams) * cap));
+        g_fps_cap = cap;
+    }
+    return 0;
+}
+
+extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, int device)
+{
+    int ndev = 0;
+    *out = NULL;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return -1;
+    if (device >= 0) CK(cudaSetDevice(device));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    h264b200_ctx *c = (h264b200_ctx *)calloc(1, sizeof(*c));
+    if (!c) return -3;
+    c->device = dev;
+    c->width = width; c->height = height;
+    c->nmbx = (width + 15) >> 4; c->nmby = (height + 15) >> 4; c->nmb = c->nmbx * c->nmby;
+    const int w = c->nmbx * 16, h = c->nmby * 16;
+    c->stride[0] = w + 32; c->stride[1] = (w + 32) / 2;
+    const size_t ysz = (size_t)c->stride[0] * (h + 32), csz = (size_t)c->stride[1] * (h / 2 + 16);
+    c->plane_off[0] = (size_t)c->stride[0] * 16 + 16;
+    c->plane_off[1] = ysz + (size_t)c->stride[1] * 8 + 8;
+    c->plane_off[2] = ysz + csz + (size_t)c->stride[1] * 8 + 8;
+    for (int i = 0; i < 2; i++)
+    {
+        CK(cudaMalloc(&c->d_frames[i], ysz + 2 * csz + 256));
+        CK(cudaMemset(c->d_frames[i], 0, ysz + 2 * csz + 256));
+    }
+    c->inp_stride[0] = (width + 63) & ~63;
+    c->inp_stride[1] = c->inp_stride[2] = (width / 2 + 63) & ~63;
+    CK(cudaMalloc(&c->d_inp[0], (size_t)c->inp_stride[0] * height + 256));
+    CK(cudaMalloc(&c->d_inp[1], (size_t)c->inp_stride[1] * (height / 2) + 256));
+    CK(cudaMalloc(&c->d_inp[2], (size_t)c->inp_stride[2] * (height / 2) + 256));
+    CK(cudaMalloc(&c->d_mbi, sizeof(MBInfo) * c->nmb));
+    CK(cudaMemset(c->d_mbi, 0, sizeof(MBInfo) * c->nmb));
+    CK(cudaMalloc(&c->d_coef, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
+    CK(cudaMemset(c->d_coef, 0, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
+    CK(cudaMalloc(&c->d_mb_bits, sizeof(uint32_t) * MB_BITS_WORDS * (size_t)(c->nmb + 1)));
+    CK(cudaMalloc(&c->d_mb_nbits, sizeof(int) * (c->nmb + 2)));
+    CK(cudaMalloc(&c->d_mb_bitoff, sizeof(int) * (c->nmb + 2)));
+    c->out_cap_words = c->nmb * 160 + 1024;
+    CK(cudaMalloc(&c->d_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
+    CK(cudaMalloc(&c->d_out_info, 64));
+    CK(cudaMalloc(&c->d_clusters, 16));
+    CK(cudaMemset(c->d_clusters, 0, 16));
+    CK(cudaMalloc(&c->d_progress, sizeof(int) * 2 * c->nmby));
+    CK(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
+    CK(cudaMallocHost(&c->h_out_info, 64));
+    *out = c;
+    return 0;
+}
+
+extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 2; i++) cudaFree(c->d_frames[i]);
+    for (int i = 0; i < 3; i++) cudaFree(c->d_inp[i]);
+    if (c->d_clip) cudaFree(c->d_clip);
+    cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
+    cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
+    cudaFreeHost(c->h_out_words); cudaFreeHost(c->h_out_info);
+    free(c);
+}
+
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
+{
+    if (!c) return;
+    cudaMemset(c->d_clusters, 0, 16);
+    c->cur = 0;
+}
+
+static void build_fp(const h264b200_job *job, FrameParams *fp)
+{
+    h264b200_ctx *c = job->ctx;
+    const h264b200_frame_params &p = job->p;
+    memset(fp, 0, sizeof(*fp));
+    fp->width = c->width; fp->height = c->height; fp->nmbx = c->nmbx; fp->nmby = c->nmby;
+    fp->slice_type = p.slice_type; fp->qp = p.qp; fp->speed = p.speed; fp->disable_deblock = p.disable_deblock;
+    fp->lambda_q4 = p.lambda_q4; fp->lambda_mv_q4 = p.lambda_mv_q4; fp->lambda_i4_q4 = p.lambda_i4_q4;
+    fp->lambda_i16_q4 = p.lambda_i16_q4; fp->skip_thr_inter = p.skip_thr_inter; fp->skip_thr_i4x4 = p.skip_thr_i4x4;
+    fp->mvlim_x0 = -14 * 4; fp->mvlim_y0 = -14 * 4;                                /* H:6322-6324 */
+    fp->mvlim_x1 = (c->nmbx * 16 - 2) * 4; fp->mvlim_y1 = (c->nmby * 16 - 2) * 4;
+    for (int i = 0; i < 2; i++)
+    {
+        fp->df_alpha[i] = p.df_alpha[i]; fp->df_beta[i] = p.df_beta[i];
+        for (int k = 0; k < 4; k++) fp->df_tc0[i][k] = p.df_tc0[i][k];
+    }
+    memcpy(fp->qdat, p.qdat, sizeof(fp->qdat));
+    for (int i = 0; i < 3; i++)
+    {
+        if (job->preloaded_index >= 0)
+        {
+            size_t fs = (size_t)c->width * c->height * 3 / 2, ys = (size_t)c->width * c->height;
+            const pix_t *b = c->d_clip + fs * job->preloaded_index;
+            fp->inp[i] = i == 0 ? b : (i == 1 ? b + ys : b + ys + ys / 4);
+            fp->inp_stride[i] = i ? c->width / 2 : c->width;
+        } else { fp->inp[i] = c->d_inp[i]; fp->inp_stride[i] = c->inp_stride[i]; }
+        fp->dec[i] = c->d_frames[c->cur] + c->plane_off[i];
+        fp->ref[i] = c->d_frames[c->cur ^ 1] + c->plane_off[i];
+    }
+    fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
+    fp->mbi = c->d_mbi; fp->coef = c->d_coef;
+    fp->clusters = c->d_clusters;
+    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby;
+    fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
+    fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
+    fp->hdr_bits = p.hdr_bits;
+    fp->serial_rows = p.slice_type == SLICE_P;
+}
+
+extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
+{
+    if (ensure_globals(1)) return -3;
+    size_t fs = (size_t)c->width * c->height * 3 / 2;
+    if (c->d_clip) { cudaFree(c->d_clip); c->d_clip = NULL; c->clip_frames = 0; }
+    CK(cudaMalloc(&c->d_clip, fs * nframes + 256));
+    CK(cudaMemcpy(c->d_clip, frames, fs * nframes, cudaMemcpyHostToDevice));
+    c->clip_frames = nframes;
+    return 0;
+}
+
+static int encode_impl(int n, h264b200_job *jobs)
+{
+    if (n <= 0) return 0;
+    if (ensure_globals(n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
+    cudaStream_t st = g_stream;
+    int max_rows = 0, max_nmb = 0;
+    for (int i = 0; i < n; i++)
+    {
+        h264b200_ctx *c = jobs[i].ctx;
+        jobs[i].status = 0;
+        build_fp(&jobs[i], &g_h_fps[i]);
+        max_rows = c->nmby > max_rows ? c->nmby : max_rows;
+        max_nmb = c->nmb > max_nmb ? c->nmb : max_nmb;
+    }
+    CK(cudaEventRecord(g_ev[0], st));
+    for (int i = 0; i < n; i++)
+        {
+            h264b200_ctx *c = jobs[i].ctx;
+            if (jobs[i].preloaded_index >= 0)
+            {
+                if (jobs[i].preloaded_index >= c->clip_frames) { jobs[i].status = -3; return -3; }
+                continue;
+            }
+            for (int pl = 0; pl < 3; pl++)
+            {
+                int w = pl ? c->width / 2 : c->width, h = pl ? c->height / 2 : c->height;
+                CK(cudaMemcpy2DAsync(c->d_inp[pl], c->inp_stride[pl], jobs[i].yuv[pl], jobs[i].stride[pl], w, h,
+                                     cudaMemcpyHostToDevice, st));
+            }
+        }
+    CK(cudaMemcpyAsync(g_d_fps, g_h_fps, sizeof(FrameParams) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(g_d_tickets, 0, 64, st));
+    for (int i = 0; i < n; i++)
+    {
+        h264b200_ctx *c = jobs[i].ctx;
+        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 2 * c->nmby, st));
+        CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
+    }
+    CK(cudaEventRecord(g_ev[1], st));
+    k_encode_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, max_rows, g_d_tickets);
+    CK(cudaEventRecord(g_ev[2], st));
+    k_deblock_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, g_d_tickets);
+    k_borders<<<dim3(64, n), 256, 0, st>>>(g_d_fps, n);
+    CK(cudaEventRecord(g_ev[3], st));
+    k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, st>>>(g_d_fps, n);
+    {
+        int cap = jobs[0].ctx->out_cap_words;
+        for (int i = 1; i < n; i++) cap = jobs[i].ctx->out_cap_words < cap ? jobs[i].ctx->out_cap_words : cap;
+        k_scan<<<n, 1024, 0, st>>>(g_d_fps, n, cap);
+    }
+    k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, st>>>(g_d_fps, n);
+    g_launches += 6;
+    CK(cudaEventRecord(g_ev[4], st));
+    for (int i = 0; i < n; i++)
+        CK(cudaMemcpyAsync(jobs[i].ctx->h_out_info, jobs[i].ctx->d_out_info, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    int rc = 0;
+    for (int i = 0; i < n; i++)
+    {
+        h264b200_ctx *c = jobs[i].ctx;
+        jobs[i].out_bits = c->h_out_info[0];
+        jobs[i].trailing_skip_run = c->h_out_info[2];
+        jobs[i].out_words = c->h_out_words;
+        if (c->h_out_info[1]) { jobs[i].status = -2; if (!rc) rc = -2; continue; }
+        CK(cudaMemcpyAsync(c->h_out_words, c->d_out_words, (size_t)((jobs[i].out_bits + 95) / 32) * 4, cudaMemcpyDeviceToHost, st));
+        for (int pl = 0; pl < 3; pl++)
+            if (jobs[i].recon[pl])
+            {
+                int w = c->nmbx * (pl ? 8 : 16), h = c->nmby * (pl ? 8 : 16);
+                /* in-place mode hands us the caller's planes: copy only the visible area */
+                int cw = pl ? c->width / 2 : c->width, chh = pl ? c->height / 2 : c->height;
+                (void)w; (void)h;
+                CK(cudaMemcpy2DAsync(jobs[i].recon[pl], jobs[i].recon_stride[pl],
+                                     c->d_frames[c->cur] + c->plane_off[pl], c->stride[pl != 0], cw, chh,
+                                     cudaMemcpyDeviceToHost, st));
+            }
+    }
+    CK(cudaEventRecord(g_ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) if (jobs[i].update_ref && jobs[i].status == 0) jobs[i].ctx->cur ^= 1;
+    cudaEventElapsedTime(&g_last_ms[0], g_ev[0], g_ev[5]);
+    cudaEventElapsedTime(&g_last_ms[1], g_ev[1], g_ev[2]);
+    cudaEventElapsedTime(&g_last_ms[2], g_ev[2], g_ev[3]);
+    cudaEventElapsedTime(&g_last_ms[3], g_ev[3], g_ev[4]);
+    return rc;
+}
+
+extern "C" int h264b200_encode_frames(int n, h264b200_job *jobs) { return encode_impl(n, jobs); }
+
+extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3], const int strides[3])
+{
+    if (ensure_globals(1)) return -3;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        int w = c->nmbx * (pl ? 8 : 16), h = c->nmby * (pl ? 8 : 16);
+        CK(cudaMemcpy2DAsync(planes[pl], strides[pl], c->d_frames[c->cur ^ 1] + c->plane_off[pl], c->stride[pl != 0], w, h,
+                             cudaMemcpyDeviceToHost, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+extern "C" void h264b200_last_timing(float out_ms[4]) { for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
+extern "C" long h264b200_launch_count(void) { return g_launches; }
+extern "C" const char *h264b200_backend_name(void) { return "cuda-sm_100a"; }

@@ -628,8 +628,9 @@ static int plan_frame(h264e_host_t *e, H264E_scratch_t *scratch, const H264E_run
     job->ctx = e->ctx;
     fill_frame_params(e, &job->p, pl->slice_type, hb_bits(&pl->hdr));
     for (i = 0; i < 3; i++) { job->yuv[i] = in->yuv[i]; job->stride[i] = in->stride[i]; }
+    job->preloaded_index = in->yuv[0] ? -1 : in->stride[0];
     job->update_ref = pl->long_term_idx_update != -1;
-    if (!e->param.const_input_flag)
+    if (!e->param.const_input_flag && in->yuv[0])
     {   /* the reference reconstructs in place over the caller's frame (H:6719-6723) */
         for (i = 0; i < 3; i++) { job->recon[i] = in->yuv[i]; job->recon_stride[i] = in->stride[i]; }
     }
@@ -651,7 +652,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
      * add the RBSP stop bit and convert MSB-first words to escaped bytes */
     nbits = job->out_bits + 1;
     nbytes = (nbits + 7) >> 3;
-    if ((int)e->out_pos + 4 + nbytes + nbytes / 2 + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+    if ((int)e->out_pos + 4 + nbytes + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
     d = e->out + e->out_pos;
     d[0] = d[1] = d[2] = 0; d[3] = 1;
     nal = d + 4;
@@ -669,6 +670,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
             if (zeros == 2 && byte <= 3) { nal[j++] = 3; zeros = 0; }
             zeros = byte ? 0 : zeros + 1;
             nal[j++] = byte;
+            if ((int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
         }
     }
     if (e->run.nalu_callback) e->run.nalu_callback(nal, j, e->run.nalu_callback_token);
@@ -754,6 +756,13 @@ int H264E_get_recon(H264E_persist_t *penc, unsigned char *y, unsigned char *u, u
     planes[0] = y; planes[1] = u; planes[2] = v;
     strides[0] = e->w16; strides[1] = strides[2] = e->w16 / 2;
     return h264b200_get_recon(e->ctx, planes, strides) ? H264E_STATUS_DEVICE_ERROR : H264E_STATUS_SUCCESS;
+}
+
+int H264E_preload(H264E_persist_t *penc, int nframes, const unsigned char *frames)
+{
+    h264e_host_t *e = (h264e_host_t *)penc;
+    if (!e || e->magic != H264E_MAGIC || !e->ctx || nframes <= 0 || !frames) return H264E_STATUS_BAD_ARGUMENT;
+    return h264b200_preload(e->ctx, nframes, frames) ? H264E_STATUS_DEVICE_ERROR : H264E_STATUS_SUCCESS;
 }
 
 /* device context of a session, for the bench / tests (kernel-only timing) */

@@ -124,6 +124,11 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
                        const H264E_run_param_t *const *run_param, H264E_io_yuv_t *const *frame,
                        unsigned char **coded_data, int *sizeof_coded_data);
 
+/* Device-resident input: upload nframes tightly packed I420 frames (stride == width) to the
+ * session's GPU; a frame whose io_yuv has yuv[0] == NULL is then taken from clip frame
+ * number stride[0].  Used to measure the hot path with inputs already in HBM. */
+int H264E_preload(H264E_persist_t *enc, int nframes, const unsigned char *frames);
+
 /* Copy the reconstruction of the last encoded frame (W16 x H16, planes tightly packed
  * with strides W16, W16/2, W16/2) to host memory. */
 int H264E_get_recon(H264E_persist_t *enc, unsigned char *y, unsigned char *u, unsigned char *v);

@@ -43,6 +43,8 @@ typedef struct
     h264b200_frame_params p;
     const unsigned char *yuv[3];     /* HOST input planes                                  */
     int stride[3];
+    int preloaded_index;             /* >= 0: take the input from frame #index of the clip uploaded with
+                                        h264b200_preload() instead of the host planes (yuv may be NULL) */
     int update_ref;                  /* 0: droppable frame, the reference picture is kept  */
     unsigned char *recon[3];         /* optional HOST buffers that receive the              */
     int recon_stride[3];             /*   reconstruction (NULL: it stays on the device)     */
@@ -73,10 +75,10 @@ int h264b200_encode_frames(int n, h264b200_job *jobs);
  * [1] macroblock pass, [2] deblock + border, [3] CAVLC + pack.  */
 void h264b200_last_timing(float out_ms[4]);
 
-/* Device-resident variant for kernel-only measurements: inputs already uploaded with
- * h264b200_upload_input(); runs the same kernels without host<->device copies.      */
-int h264b200_upload_input(h264b200_ctx *ctx, const unsigned char *const yuv[3], const int stride[3]);
-int h264b200_encode_frames_resident(int n, h264b200_job *jobs);
+/* Upload a clip of nframes tightly packed I420 frames (stride == width) to device memory
+ * owned by ctx; jobs with preloaded_index >= 0 then read their input from HBM (no
+ * host->device copy inside the call).  Replaces any previously preloaded clip. */
+int h264b200_preload(h264b200_ctx *ctx, int nframes, const unsigned char *frames);
 
 /* Copy the most recent reconstruction (W16 x H16 luma, W16/2 x H16/2 chroma) to host. */
 int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const int strides[3]);

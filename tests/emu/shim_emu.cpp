@@ -31,6 +31,7 @@ struct h264b200_ctx
     std::vector<uint32_t> mb_bits;
     std::vector<int> mb_nbits;
     std::vector<uint32_t> out_words;
+    std::vector<pix_t> clip;
     int32_t clusters[2];
 };
 
@@ -83,7 +84,13 @@ static void run_job(h264b200_job *job)
     memcpy(fp.qdat, p.qdat, sizeof(fp.qdat));
     for (int i = 0; i < 3; i++)
     {
-        fp.inp[i] = job->yuv[i]; fp.inp_stride[i] = job->stride[i];
+        if (job->preloaded_index >= 0)
+        {
+            size_t fs = (size_t)c->width * c->height * 3 / 2, ys = (size_t)c->width * c->height;
+            const pix_t *b = c->clip.data() + fs * job->preloaded_index;
+            fp.inp[i] = i == 0 ? b : (i == 1 ? b + ys : b + ys + ys / 4);
+            fp.inp_stride[i] = i ? c->width / 2 : c->width;
+        } else { fp.inp[i] = job->yuv[i]; fp.inp_stride[i] = job->stride[i]; }
         fp.dec[i] = c->frame[c->cur].data() + c->plane_off[i];
         fp.ref[i] = c->frame[c->cur ^ 1].data() + c->plane_off[i];
     }
@@ -155,8 +162,12 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
     }
     return 0;
 }
-extern "C" int h264b200_upload_input(h264b200_ctx *, const unsigned char *const[3], const int[3]) { return -1; }
-extern "C" int h264b200_encode_frames_resident(int, h264b200_job *) { return -1; }
+extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
+{
+    size_t fs = (size_t)c->width * c->height * 3 / 2;
+    c->clip.assign(frames, frames + fs * nframes);
+    return 0;
+}
 extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "host-emulation (test only)"; }

@@ -1,0 +1,109 @@
+"""GPU suite (pytest -m gpu): the product library (host C + sm_100a kernels), called
+through its C ABI (H264E_sizeof / H264E_init / H264E_encode / H264E_encode_batch), must
+reproduce the compiled reference (oracle/_ref) byte for byte -- bit stream, per-frame
+sizes, reconstruction planes -- and the committed golden digests (tests/golden)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "manifest.json")
+
+
+def _check(case, binding, cuda_lib, ref):
+    name, kind, w, h, n, gop, kw = case
+    frames = cases.make(kind, w, h, n)
+    rbs, rsizes, rrec, _ = ref.encode_sequence(frames, w, h, gop, **kw)
+    bs, sizes, rec = binding.encode_sequence(cuda_lib, frames, w, h, gop, **kw)
+    assert cuda_lib.backend() == "cuda-sm_100a"
+    assert list(sizes) == list(rsizes), "per-frame sizes differ"
+    assert bs == rbs, "bit stream differs"
+    assert np.array_equal(rec, rrec), "reconstruction differs"
+    return bs, rec
+
+
+@pytest.mark.parametrize("case", cases.SMALL, ids=lambda c: c[0])
+def test_small_cases(case, binding, cuda_lib, ref):
+    _check(case, binding, cuda_lib, ref)
+
+
+@pytest.mark.parametrize("case", cases.CIF_FOREMAN_SUBSTITUTE, ids=lambda c: c[0])
+def test_cif_reference_script_qps(case, binding, cuda_lib, ref):
+    _check(case, binding, cuda_lib, ref)
+
+
+@pytest.mark.parametrize("case", cases.LARGE, ids=lambda c: c[0])
+def test_large_cases(case, binding, cuda_lib, ref):
+    _check(case, binding, cuda_lib, ref)
+
+
+def test_golden_digests(binding, cuda_lib):
+    """Committed digests of reference output (made by tests/golden/make_golden.py where
+    /root/reference exists): independent of oracle/_ref being present on the box."""
+    man = json.load(open(GOLDEN))
+    for g in man["cases"]:
+        frames = cases.make(g["kind"], g["width"], g["height"], g["frames"])
+        assert hashlib.md5(frames.tobytes()).hexdigest() == g["input_md5"]
+        bs, sizes, rec = binding.encode_sequence(cuda_lib, frames, g["width"], g["height"], g["gop"], **g["kw"])
+        assert hashlib.md5(bs).hexdigest() == g["bitstream_md5"], g["name"]
+        assert hashlib.md5(rec.tobytes()).hexdigest() == g["recon_md5"], g["name"]
+
+
+def test_batch_equals_sequential(binding, cuda_lib, ref):
+    """Closed-GOP segments encoded concurrently in one submission == each segment on its own
+    (and == the reference run once per segment)."""
+    w, h, seglen, nseg = 352, 288, 5, 4
+    frames = cases.make("panning", w, h, seglen * nseg)
+    encs = [binding.Encoder(cuda_lib, w, h, seglen) for _ in range(nseg)]
+    rps = [e.run_param(qp=28) for e in encs]
+    outs = [b"" for _ in range(nseg)]
+    for t in range(seglen):
+        fr = [frames[s * seglen + t].copy() for s in range(nseg)]
+        res = binding.encode_batch(cuda_lib, encs, fr, rps)
+        for s in range(nseg):
+            outs[s] += res[s]
+    for s in range(nseg):
+        rbs, _, rrec, _ = ref.encode_sequence(frames[s * seglen:(s + 1) * seglen], w, h, seglen, qp=28)
+        assert outs[s] == rbs, "segment %d" % s
+        assert np.array_equal(encs[s].recon(), rrec[-1])
+    for e in encs:
+        e.close()
+
+
+def test_round_trip_decodes(binding, cuda_lib, tmp_path):
+    """Size-independent property at a BASELINE size: the 1080p stream parses in a real
+    decoder (FFmpeg through cv2) into the right number of frames of the cropped size."""
+    cv2 = pytest.importorskip("cv2")
+    w, h, n = 1920, 1080, 3
+    frames = cases.make("panning", w, h, n)
+    bs, sizes, rec = binding.encode_sequence(cuda_lib, frames, w, h, 3, qp=28)
+    p = tmp_path / "o.264"
+    p.write_bytes(bs)
+    cap = cv2.VideoCapture(str(p), cv2.CAP_FFMPEG)
+    cnt = 0
+    while True:
+        ok, img = cap.read()
+        if not ok:
+            break
+        assert img.shape[0] == h and img.shape[1] == w
+        cnt += 1
+    assert cnt == n
+
+
+def test_in_place_recon_and_errors(binding, cuda_lib, ref):
+    """const_input_flag = 0 overwrites the caller's planes with the reconstruction (H:6719-6723)."""
+    w, h = 352, 288
+    frames = cases.make("panning", w, h, 2)
+    enc = binding.Encoder(cuda_lib, w, h, 2, const_input=0)
+    rp = enc.run_param(qp=30)
+    _, _, rrec, _ = ref.encode_sequence(frames, w, h, 2, qp=30)
+    for i in range(2):
+        f = frames[i].copy()
+        enc.encode(f, rp)
+        assert np.array_equal(f, rrec[i])
+    enc.close()
