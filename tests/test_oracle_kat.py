@@ -1,0 +1,262 @@
+"""CPU suite: known-answer tests that PIN the plain-C restatement (oracle/h264_oracle.c)
+against the compiled, unmodified reference (oracle/_ref) function by function, on seeded
+random and adversarial inputs ("kernel KATs")."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def orc():
+    path = os.path.join(ROOT, "oracle", "libh264oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return C.CDLL(path)
+
+
+@pytest.fixture(scope="module")
+def rl(ref):
+    return ref.lib()
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def frame(rng, h=64, w=64, kind="rand"):
+    if kind == "rand":
+        return rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    if kind == "zero":
+        return np.zeros((h, w), np.uint8)
+    if kind == "max":
+        return np.full((h, w), 255, np.uint8)
+    a = np.zeros((h, w), np.uint8)
+    a[::2, ::2] = 255
+    a[1::2, 1::2] = 255
+    return a
+
+
+def test_sad(orc, rl):
+    rng = np.random.default_rng(1)
+    for kind in ("rand", "zero", "max", "checker"):
+        a = frame(rng, kind=kind)
+        b = rng.integers(0, 256, size=256, dtype=np.uint8)
+        for (w, h) in ((16, 16), (16, 8), (8, 16), (8, 8)):
+            for off in (0, 1, 7, 65, 130):
+                pa = a.ctypes.data + off
+                assert orc.orc_sad(C.c_void_p(pa), 64, P(b), 16, w, h) == rl.ref_sad_block(C.c_void_p(pa), 64, P(b), 16, w, h)
+        s1 = (C.c_int * 4)()
+        s2 = (C.c_int * 4)()
+        assert orc.orc_sad_mb_quadrants(P(a), 64, P(b), s1) == rl.ref_sad_mb_8x8(P(a), 64, P(b), s2)
+        assert list(s1) == list(s2)
+
+
+def test_qpel_luma_all_positions(orc, rl):
+    rng = np.random.default_rng(2)
+    for kind in ("rand", "checker", "max"):
+        a = frame(rng, 48, 64, kind)
+        base = a.ctypes.data + 8 * 64 + 8
+        for dy in range(4):
+            for dx in range(4):
+                for (w, h) in ((16, 16), (16, 8), (8, 16), (8, 8)):
+                    if (w, h) != (16, 16) and (dx & 1 or dy & 1):
+                        continue            # the reference only produces quarter positions for 16x16 (H:2114)
+                    d1 = np.zeros(256, np.uint8)
+                    d2 = np.zeros(256, np.uint8)
+                    orc.orc_qpel_luma(C.c_void_p(base), 64, P(d1), w, h, dx, dy)
+                    rl.ref_qpel_luma(C.c_void_p(base), 64, P(d2), w, h, dx, dy)
+                    assert np.array_equal(d1, d2), (kind, dx, dy, w, h)
+
+
+def test_qpel_chroma_all_positions(orc, rl):
+    rng = np.random.default_rng(3)
+    a = frame(rng, 32, 32)
+    base = a.ctypes.data + 4 * 32 + 4
+    for dy in range(8):
+        for dx in range(8):
+            for (w, h) in ((8, 8), (8, 4), (4, 8), (4, 4)):
+                d1 = np.zeros(128, np.uint8)
+                d2 = np.zeros(128, np.uint8)
+                orc.orc_qpel_chroma(C.c_void_p(base), 32, P(d1), w, h, dx, dy)
+                rl.ref_qpel_chroma(C.c_void_p(base), 32, P(d2), w, h, dx, dy)
+                assert np.array_equal(d1, d2)
+
+
+def test_intra16_and_chroma(orc, rl):
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        left = rng.integers(0, 256, 32, dtype=np.uint8)
+        top = rng.integers(0, 256, 32, dtype=np.uint8)
+        for mode in range(3):
+            for av in range(4):
+                hl, ht = av & 2, av & 1
+                if (mode == 0 and not ht) or (mode == 1 and not hl):
+                    continue
+                d1 = np.zeros(256, np.uint8)
+                d2 = np.zeros(256, np.uint8)
+                orc.orc_intra16(P(d1), P(left) if hl else None, P(top) if ht else None, mode)
+                rl.ref_intra16(P(d2), P(left) if hl else None, P(top) if ht else None, mode)
+                assert np.array_equal(d1, d2)
+                c1 = np.zeros(128, np.uint8)
+                c2 = np.zeros(128, np.uint8)
+                lc = left[16:].copy()
+                tc = top[16:].copy()
+                orc.orc_intra_chroma(P(c1), P(lc) if hl else None, P(tc) if ht else None, mode)
+                rl.ref_intra_chroma(P(c2), P(left) if hl else None, P(top) if ht else None, mode)
+                assert np.array_equal(c1, c2), (mode, av)
+    for qp in (10, 28, 51):
+        for _ in range(50):
+            mb = rng.integers(0, 256, 256, dtype=np.uint8)
+            if rng.integers(0, 2):
+                mb = np.sort(mb)
+            for av in range(8):
+                assert orc.orc_intra16_estimate(P(mb), av, qp) == rl.ref_intra16_estimate(P(mb), 16, av, qp)
+
+
+def test_intra4_choose_every_avail(orc, rl):
+    rng = np.random.default_rng(5)
+    for it in range(300):
+        blk = rng.integers(0, 256, 64, dtype=np.uint8)
+        if it % 3 == 0:
+            blk[:] = np.repeat(rng.integers(0, 256, 4, dtype=np.uint8), 16)
+        buf = rng.integers(0, 256, 32, dtype=np.uint8)
+        for avail in range(16):
+            mpred = int(rng.integers(0, 9))
+            pen = int(rng.integers(0, 40))
+            p1 = np.zeros(64, np.uint8)
+            p2 = np.zeros(64, np.uint8)
+            b1 = buf.copy()
+            b2 = buf.copy()
+            r1 = orc.orc_intra4_choose(P(blk), P(p1), avail, C.c_void_p(b1.ctypes.data + 16), mpred, pen)
+            r2 = rl.ref_intra4_choose(P(blk), P(p2), avail, C.c_void_p(b2.ctypes.data + 16), mpred, pen)
+            assert r1 == r2, (avail, mpred)
+            assert np.array_equal(p1, p2)
+
+
+@pytest.mark.parametrize("mode", [2, 8, 9, 5])
+def test_transform_quant_recon(mode, orc, rl):
+    rng = np.random.default_rng(6)
+    n = mode >> 1
+    for qp in (10, 17, 24, 28, 33, 40, 51):
+        for is_p in (0, 1):
+            qdat = np.zeros(84, np.uint16)
+            rl.ref_make_qdat(qp, is_p, P(qdat))
+            q = qdat[42:] if mode == 5 else qdat[:42]
+            q = np.ascontiguousarray(q)
+            for kind in range(6):
+                inp = rng.integers(0, 256, 256, dtype=np.uint8)
+                pred = rng.integers(0, 256, 256, dtype=np.uint8)
+                if kind == 1:
+                    pred = np.clip(inp.astype(int) + rng.integers(-3, 4, 256), 0, 255).astype(np.uint8)
+                if kind == 2:
+                    inp[:] = 255
+                    pred[:] = 0
+                if kind == 3:
+                    inp[:] = 0
+                    pred[:] = 255
+                if kind == 4:
+                    pred = inp.copy()
+                if kind == 5:
+                    pred = np.clip(inp.astype(int) + rng.integers(-12, 13, 256), 0, 255).astype(np.uint8)
+                q1 = np.zeros(16 * 32, np.int16)
+                q2 = np.zeros(16 * 32, np.int16)
+                dc1 = np.zeros(16, np.int16)
+                dc2 = np.zeros(16, np.int16)
+                m1 = orc.orc_transform_quant(P(inp), P(pred), 16, mode, P(q1), P(dc1), P(q))
+                m2 = rl.ref_transform_quant(P(inp), P(pred), 16, mode, P(q2), P(dc2), P(q))
+                assert m1 == m2, (mode, qp, kind)
+                a1 = q1.reshape(16, 2, 16)[:n * n]
+                a2 = q2.reshape(16, 2, 16)[:n * n]
+                i0 = mode & 1
+                assert np.array_equal(a1[:, 0, i0:], a2[:, 0, i0:])       # levels
+                nzmask = m2 & 0xFF if mode == 5 else m2
+                for b in range(n * n):                                    # dequantised values of coded blocks
+                    if (nzmask >> (n * n - 1 - b)) & 1:
+                        assert np.array_equal(a1[b, 1], a2[b, 1])
+                if mode & 1:
+                    k = 16 if mode == 9 else 4
+                    assert np.array_equal(dc1[:k], dc2[:k])
+                    assert np.array_equal(a1[:, 1, 0], a2[:, 1, 0])
+                # reconstruction of the coded blocks
+                for b in range(n * n):
+                    if (nzmask >> (n * n - 1 - b)) & 1:
+                        o1 = np.zeros(64, np.uint8)
+                        o2 = np.zeros(64, np.uint8)
+                        blk = np.ascontiguousarray(a2[b, 1])
+                        blk2 = np.ascontiguousarray(a2[b])
+                        orc.orc_inv4x4_add(P(blk), P(pred), P(o1), 16)
+                        rl.ref_transform_add(P(o2), 16, P(pred), P(blk2), 1, -1)
+                        assert np.array_equal(o1, o2)
+
+
+def test_cavlc_block(orc, rl):
+    rng = np.random.default_rng(7)
+    for it in range(3000):
+        n = (4, 15, 16)[it % 3]
+        dens = rng.random()
+        mag = (1, 2, 5, 40, 3000)[it % 5]
+        c = np.zeros(16, np.int16)
+        m = rng.random(16) < dens
+        c[m] = rng.integers(-mag, mag + 1, int(m.sum()))
+        if n == 4:
+            nA = nB = 17
+            c[4:] = 0
+        else:
+            nA = int(rng.choice([0, 1, 2, 3, 5, 8, 12, 16, 64]))
+            nB = int(rng.choice([0, 1, 2, 4, 7, 9, 16, 64]))
+        o1 = np.zeros(128, np.uint8)
+        o2 = np.zeros(128, np.uint8)
+        t1, t2 = C.c_int(), C.c_int()
+        first = c[1:] if n == 15 else c
+        first = np.ascontiguousarray(first)
+        b1 = orc.orc_cavlc_block(P(first), n, nA, nB, P(o1), C.byref(t1))
+        b2 = rl.ref_vlc_encode(P(c), n, nA, nB, P(o2), C.byref(t2))
+        assert b1 == b2, (n, list(c), nA, nB)
+        assert t1.value == t2.value
+        nb = (b1 + 7) // 8
+        # the reference writes 32-bit big-endian words via SWAP32 -> same byte order
+        assert np.array_equal(o1[:nb - 1], o2[:nb - 1])
+        if b1 % 8:
+            mask = (0xFF << (8 - b1 % 8)) & 0xFF
+            assert (o1[nb - 1] & mask) == (o2[nb - 1] & mask)
+        elif nb:
+            assert o1[nb - 1] == o2[nb - 1]
+
+
+def test_deblock(orc, rl):
+    rng = np.random.default_rng(8)
+    for it in range(400):
+        base = rng.integers(0, 256, size=(32, 32), dtype=np.uint8)
+        if it % 2:
+            base = (base // 16 + 100 + rng.integers(0, 6, size=(32, 32))).astype(np.uint8)   # smooth: filters fire
+        st = rng.integers(0, 4, 32).astype(np.uint8)
+        if it % 3 == 0:
+            st[0:4] = 4
+        if it % 5 == 0:
+            st[16:20] = 4
+        alpha = rng.integers(0, 60, 4).astype(np.uint8)
+        beta = rng.integers(0, 18, 4).astype(np.uint8)
+        tc0 = rng.integers(0, 10, 32).astype(np.uint8)
+        for fn in ("luma", "chroma"):
+            a1 = base.copy()
+            a2 = base.copy()
+            off = 8 * 32 + 8
+            getattr(orc, "orc_deblock_" + fn)(C.c_void_p(a1.ctypes.data + off), 32, P(st), P(tc0), P(alpha), P(beta))
+            getattr(rl, "ref_deblock_" + fn)(C.c_void_p(a2.ctypes.data + off), 32, P(st), P(tc0), P(alpha), P(beta))
+            assert np.array_equal(a1, a2), (fn, it)
+
+
+def test_borders(orc, rl):
+    rng = np.random.default_rng(9)
+    for (w, h, g) in ((32, 16, 16), (16, 16, 8), (48, 32, 16)):
+        a = rng.integers(0, 256, size=((h + 2 * g) * (w + 2 * g)), dtype=np.uint8)
+        b = a.copy()
+        off = g * (w + 2 * g) + g
+        orc.orc_extend_borders(C.c_void_p(a.ctypes.data + off), w, h, g)
+        rl.ref_copy_borders(C.c_void_p(b.ctypes.data + off), w, h, g)
+        assert np.array_equal(a, b)
