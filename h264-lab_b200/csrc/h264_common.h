@@ -67,6 +67,15 @@ HD int wor(int v) { return v; }
 
 typedef uint8_t pix_t;
 
+HD void atomic_add_stat(int *p)
+{
+#if H264_DEVICE
+    atomicAdd(p, 1);
+#else
+    (*p)++;
+#endif
+}
+
 /* ---- constants with the reference's meaning --------------------------------- */
 #define MV_NA 0x8000          /* H:3200: "no motion vector" marker (intra / unavailable) */
 #define AVAIL_T 1             /* H:511-514 */
@@ -117,9 +126,35 @@ struct MBInfo
     int8_t  i4_code[16]; /* coded value: -1 = predicted, else rem_intra4x4_pred_mode       */
     uint8_t nnz[24];     /* total_coeff of each block as seen by neighbours' CAVLC context:
                             16 luma (raster), 4 U, 4 V                                     */
-    int32_t cl_used[2];  /* rounded cluster candidates this MB was decided with           */
-    int32_t cand_sig[4]; /* candidate-stage outcome (mv_best, sad_best, cost, pref modes)  */
 };
+
+/* Speculation record of one macroblock (P frames).  The reference feeds two running MV
+ * averages ("mv_clusters", H:766, H:5263-5278, H:5382-5383) from macroblock to macroblock in
+ * RASTER order, which no wavefront can honour directly.  Macroblocks are therefore decided
+ * with speculated cluster candidates; this record keeps what a sequential replay of the
+ * cluster trajectory needs to verify the speculation and to repair it (h264_wave.h). */
+struct MBSpec
+{
+    int32_t mv0;         /* mb.mv[0] fed to mv_clusters_update                              */
+    int32_t flags;       /* SPEC_UPDATES: MB updates the clusters (final type < 5);
+                            SPEC_USED_CL: the decision consumed the cluster candidates       */
+    int32_t cl_used[2];  /* rounded cluster candidates the decision was made with           */
+    int32_t cand_sig[4]; /* candidate-stage outcome: mv_best, sad_best, cost_best, partition hints */
+};
+#define SPEC_UPDATES 1
+#define SPEC_USED_CL 2
+
+/* per-frame synchronisation words of the wavefront / verification passes */
+#define FS_ARRIVE 0       /* rows that finished the current pass (monotonic)                 */
+#define FS_STATE 1        /* 0..n: pass to run, FS_DONE when the frame is exact              */
+#define FS_TRAJ_CHANGED 2 /* MBs whose cluster-relevant result changed in the current pass    */
+#define FS_NDIRTY 3       /* MBs whose speculated candidates differ from the replayed ones    */
+#define FS_PASSES 4       /* statistics: passes run                                           */
+#define FS_REENC 5        /* statistics: full re-encodes                                      */
+#define FS_CHECKS 6       /* statistics: candidate-stage re-checks                            */
+#define FS_CL_END 8       /* [8],[9]: cluster state after the last macroblock (raw)           */
+#define FS_WORDS 16
+#define FS_DONE 0x40000000
 
 /* Quantised levels of one macroblock (int16), written by the encode pass and read
  * by the CAVLC pass. Layout in units of int16. */
@@ -153,6 +188,10 @@ struct FrameParams
     MBInfo *mbi;
     int16_t *coef;
     int32_t *clusters;          /* persistent mv_clusters[2] of this encoder (H:766)        */
+    MBSpec *spec;               /* [nmb] speculation records                                */
+    int32_t *cl_true;           /* [nmb][2] rounded cluster candidates from the last replay */
+    int *changed_pass;          /* [nmb] last pass in which the MB's result changed         */
+    int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */
     int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */
     uint32_t *mb_bits;          /* per-MB bit strings, MB_BITS_WORDS words each             */
@@ -161,7 +200,8 @@ struct FrameParams
     uint32_t *out_words;        /* packed slice payload                                     */
     int *out_info;              /* [0] total bits, [1] error flags, [2] trailing skip run   */
     int hdr_bits;               /* bit offset at which the slice data starts                */
-    int serial_rows;            /* 1: a row waits for the whole previous row (exact P mode) */
+    int max_passes;             /* safety bound on verification sweeps                      */
+    int spec_from_prev;         /* 1: speculate with the previous P frame's replayed trajectory */
 };
 
 #define MB_BITS_WORDS 512       /* 2048 bytes per macroblock */
@@ -194,6 +234,9 @@ struct MBWork
     int32_t mvp_save[12];
     int32_t part_mv[4][4], part_mvd[4][4];        /* per mode, per partition                */
     int32_t scal[16];            /* scalars produced by lane 0 for the whole warp          */
+    uint32_t old_mbi[40];        /* previous record / reconstruction of an MB being repaired */
+    uint32_t old_rec[96];
+    int32_t rp_mv0[32], rp_flags[32], rp_used0[32], rp_used1[32], rp_true0[32], rp_true1[32];   /* replay staging */
 };
 
 HD int mb_avail(int mbx, int mby, int nmbx)   /* single slice per frame: H:3605-3622 */

@@ -354,7 +354,7 @@ HD void mc_chroma(const MBState &s, int type, const int32_t *mvs)
  * On return s.type / s.cost / s.pbest are set; w->part_mv / part_mvd of the chosen
  * type are copied to out_mv/out_mvd.  Returns 1 for an early skip decision.
  * ---------------------------------------------------------------------------- */
-HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig)
+HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig, int cand_only)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -447,11 +447,9 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
             if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
         }
     }
-    if (cand_sig)
-    {
-        cand_sig[0] = mv_best; cand_sig[1] = sad_best; cand_sig[2] = cand_cost_best;
-        cand_sig[3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
-    }
+    cand_sig[0] = mv_best; cand_sig[1] = sad_best; cand_sig[2] = cand_cost_best;
+    cand_sig[3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
+    if (cand_only) return 2;
     sad_best += mv_cost(mv_best, mvp16, fp->lambda_mv_q4);
 
     /* partition modes (H:5416-5510) */
@@ -795,7 +793,7 @@ HD int count_nz(const int16_t *q, int i0)
 }
 
 /* mv_clusters_update H:5263 */
-HD void clusters_update(int32_t cl[2], int mv)
+HD void clusters_update(int32_t *cl, int mv)
 {
     int x = mv_x(mv), y = mv_y(mv);
     int norm = x * x + y * y;
@@ -810,7 +808,7 @@ HD void clusters_update(int32_t cl[2], int mv)
  * mb_write H:4378).  cl[] = mv_clusters as seen by this MB; updated in place.
  * Writes the MB's record, quantised levels and unfiltered reconstruction.
  * ---------------------------------------------------------------------------- */
-HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, int32_t cl[2])
+HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
 {
     MBState s;
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
@@ -821,11 +819,11 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, int32_t cl
     int16_t *coef = fp->coef + (size_t)(mby * fp->nmbx + mbx) * COEF_PER_MB;
     int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
     int32_t cand_sig[4] = {0, 0, 0, 0};
-    int32_t cl_in0 = mv_round_fullpel(cl[0]), cl_in1 = mv_round_fullpel(cl[1]);
+    int used_cl = 0;
 
     mb_load(s);
 
-    if (fp->slice_type == SLICE_P) inter_choose(s, pmv, pmvd, cl, cand_sig);
+    if (fp->slice_type == SLICE_P) used_cl = !inter_choose(s, pmv, pmvd, cl, cand_sig, 0);
 
     int nz_mask = 0;
     if (s.type >= 0)
@@ -851,7 +849,10 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, int32_t cl
         }
     }
 
-    if (s.type < 5) clusters_update(cl, pmv[0]);
+    spec_out->mv0 = pmv[0];
+    spec_out->flags = ((fp->slice_type == SLICE_P && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
+    spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
+    for (int k = 0; k < 4; k++) spec_out->cand_sig[k] = cand_sig[k];
 
     if (s.type >= 5)
     {
@@ -933,8 +934,7 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, int32_t cl
             mi->cbp = (uint8_t)(cbpl | (cbpc << 4));
             mi->flags = 0;
             mi->nz_mask = (uint16_t)(type == MBT_SKIP ? 0 : nz_mask);
-            mi->cl_used[0] = cl_in0; mi->cl_used[1] = cl_in1;
-            for (int k = 0; k < 4; k++) mi->cand_sig[k] = cand_sig[k];
+            mi->pad0 = 0;
         }
     }
     if (type != MBT_SKIP)

@@ -1,0 +1,212 @@
+/*
+ * h264_wave.h -- exact wavefront encoding of P frames despite the reference's
+ * raster-order "mv_clusters" chain (SURVEY.md section 0 finding 2, section 7 hard part 1).
+ *
+ * The reference updates two running MV averages after EVERY macroblock in raster order
+ * (mv_clusters_update H:5263, called at H:5776-5779) and offers their rounded values as
+ * the last two motion-search start candidates of the NEXT macroblock (H:5382-5383).  A
+ * wavefront cannot know them.  Scheme used here (all on the GPU):
+ *
+ *   pass 0   every macroblock is decided in x+2y wavefront order with the cluster
+ *            candidates frozen at their frame-start value;
+ *   replay   one warp replays the true cluster trajectory in raster order from the
+ *            macroblocks' final (type, mv[0]) and counts the macroblocks whose speculated
+ *            candidates differ from the true ones ("dirty");
+ *   pass k   another wavefront sweep: a macroblock is revisited only if it is dirty or a
+ *            causal neighbour (L, T, TL, TR) changed in this sweep.  A dirty macroblock
+ *            first re-runs just the candidate stage: if (mv_best, sad_best, cost_best,
+ *            partition hints) are unchanged, so is everything that follows; otherwise the
+ *            macroblock is re-encoded and compared with its previous record to decide
+ *            whether neighbours must follow;
+ *   ...      until a replay finds no dirty macroblock.  Then every macroblock has been
+ *            decided with exactly the candidates the raster-order reference would have
+ *            used, by induction over raster order; each sweep extends the exact prefix,
+ *            so the loop terminates.
+ */
+#pragma once
+#include "h264_common.h"
+#include "h264_mbenc.h"
+
+HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
+{
+    IF_LANE0 { fp->spec[n] = sp; }
+}
+
+/* pass 0 / I frames */
+HD void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
+{
+    const int n = y * fp->nmbx + x;
+    int32_t cl[2] = {0, 0};
+    MBSpec sp;
+    if (fp->slice_type == SLICE_P)
+    {
+        /* speculation: the co-located value of the previous P frame's trajectory when there is
+         * one (motion fields are temporally coherent), else the frame-start value */
+        if (fp->spec_from_prev) { cl[0] = fp->cl_true[2 * n]; cl[1] = fp->cl_true[2 * n + 1]; }
+        else { cl[0] = mv_round_fullpel(fp->clusters[0]); cl[1] = mv_round_fullpel(fp->clusters[1]); }
+    }
+    encode_mb(fp, w, x, y, cl, &sp);
+    if (fp->slice_type == SLICE_P)
+    {
+        spec_store(fp, n, sp);
+        IF_LANE0 { fp->changed_pass[n] = 0; }
+    }
+}
+
+/* candidate stage only: returns 1 when its outcome equals the recorded one */
+HD int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const int32_t cl[2], const MBSpec &old)
+{
+    MBState s;
+    s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
+    s.avail = mb_avail(x, y, fp->nmbx);
+    s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
+    s.pbest = w->store[0]; s.ptest = w->store[1];
+    int32_t pmv[4], pmvd[4], sig[4] = {0, 0, 0, 0};
+    mb_load(s);
+    int r = inter_choose(s, pmv, pmvd, cl, sig, 1);
+    if (r != 2) return 0;
+    return sig[0] == old.cand_sig[0] && sig[1] == old.cand_sig[1] && sig[2] == old.cand_sig[2] && sig[3] == old.cand_sig[3];
+}
+
+/* repair sweep `pass` (>= 1) */
+HD void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+{
+    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    const MBSpec old = fp->spec[n];
+    int32_t ct[2];
+    ct[0] = fp->cl_true[2 * n]; ct[1] = fp->cl_true[2 * n + 1];
+    const int need_cl = (old.flags & SPEC_USED_CL) && (ct[0] != old.cl_used[0] || ct[1] != old.cl_used[1]);
+    int need_nb = 0;
+    if (x > 0 && fp->changed_pass[n - 1] == pass) need_nb = 1;
+    if (y > 0)
+    {
+        if (fp->changed_pass[n - nmbx] == pass) need_nb = 1;
+        if (x > 0 && fp->changed_pass[n - nmbx - 1] == pass) need_nb = 1;
+        if (x < nmbx - 1 && fp->changed_pass[n - nmbx + 1] == pass) need_nb = 1;
+    }
+    if (!need_cl && !need_nb) return;
+    if (!need_nb)
+    {
+        IF_LANE0 { atomic_add_stat(fp->fsync + FS_CHECKS); }
+        if (wave_cand_check(fp, w, x, y, ct, old))
+        {
+            IF_LANE0 { fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1]; }
+            return;
+        }
+    }
+    /* full re-encode; keep the previous record and reconstruction for comparison */
+    MBInfo *mi = fp->mbi + n;
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    const pix_t *dy = fp->dec[0] + (y * 16) * sy + x * 16;
+    const pix_t *du = fp->dec[1] + (y * 8) * sc + x * 8, *dv = fp->dec[2] + (y * 8) * sc + x * 8;
+    FOR_LANES(i, 36) { w->old_mbi[i] = ((const uint32_t *)mi)[i]; }
+    FOR_LANES(i, 96)
+    {
+        uint32_t v;
+        if (i < 64) v = *(const uint32_t *)(dy + (i >> 2) * sy + (i & 3) * 4);
+        else { int k = i - 64, r = k >> 2, q = k & 3; v = *(const uint32_t *)((q < 2 ? du : dv) + r * sc + (q & 1) * 4); }
+        w->old_rec[i] = v;
+    }
+    WSYNC();
+    MBSpec sp;
+    encode_mb(fp, w, x, y, ct, &sp);
+    /* Only what a causal successor consumes can propagate: the MV grid and the I4x4 modes
+     * (MV / mode predictors) and the unfiltered right column / bottom row of the
+     * reconstruction (intra prediction).  mvd, cbp, levels only feed this MB's own bits. */
+    int diff = 0;
+    FOR_LANES(i, 36) { if (i < 16 || (i >= 22 && i < 26)) diff |= w->old_mbi[i] != ((const uint32_t *)mi)[i]; }
+    FOR_LANES(i, 96)
+    {
+        uint32_t v, mask;
+        if (i < 64) { v = *(const uint32_t *)(dy + (i >> 2) * sy + (i & 3) * 4); mask = ((i >> 2) == 15 ? 0xffffffffu : 0u) | ((i & 3) == 3 ? 0xff000000u : 0u); }
+        else
+        {
+            int k = i - 64, r = k >> 2, q = k & 3;
+            v = *(const uint32_t *)((q < 2 ? du : dv) + r * sc + (q & 1) * 4);
+            mask = (r == 7 ? 0xffffffffu : 0u) | ((q & 1) ? 0xff000000u : 0u);
+        }
+        diff |= ((w->old_rec[i] ^ v) & mask) != 0;
+    }
+    diff = wor(diff);
+    spec_store(fp, n, sp);
+    IF_LANE0
+    {
+        atomic_add_stat(fp->fsync + FS_REENC);
+        if (diff) fp->changed_pass[n] = pass;
+        if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES)) atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
+    }
+    WSYNC();
+}
+
+/* Sequential replay of the cluster trajectory by one warp (lane 0 walks, the warp stages
+ * 32 records at a time).  Writes cl_true[], the end state, and returns the dirty count. */
+HD int wave_replay(const FrameParams *fp, MBWork *w)
+{
+    const int nmb = fp->nmbx * fp->nmby;
+    int32_t c[2];
+    c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
+    int ndirty = 0;
+    for (int base = 0; base < nmb; base += 32)
+    {
+        FOR_LANES(i, 32)
+        {
+            int n = base + i;
+            if (n < nmb)
+            {
+                const MBSpec *sp = fp->spec + n;
+                w->rp_mv0[i] = sp->mv0; w->rp_flags[i] = sp->flags;
+                w->rp_used0[i] = sp->cl_used[0]; w->rp_used1[i] = sp->cl_used[1];
+            }
+        }
+        WSYNC();
+        IF_LANE0
+        {
+            int cnt = imin(32, nmb - base);
+            for (int i = 0; i < cnt; i++)
+            {
+                int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+                w->rp_true0[i] = r0; w->rp_true1[i] = r1;
+                int f = w->rp_flags[i];
+                if ((f & SPEC_USED_CL) && (r0 != w->rp_used0[i] || r1 != w->rp_used1[i])) ndirty++;
+                if (f & SPEC_UPDATES) clusters_update(c, w->rp_mv0[i]);
+            }
+        }
+        WSYNC();
+        FOR_LANES(i, 32)
+        {
+            int n = base + i;
+            if (n < nmb) { fp->cl_true[2 * n] = w->rp_true0[i]; fp->cl_true[2 * n + 1] = w->rp_true1[i]; }
+        }
+        WSYNC();
+    }
+    IF_LANE0
+    {
+        fp->fsync[FS_CL_END] = c[0]; fp->fsync[FS_CL_END + 1] = c[1];
+        fp->fsync[FS_NDIRTY] = ndirty;
+        w->scal[0] = ndirty;
+    }
+    WSYNC();
+    return w->scal[0];
+}
+
+/* Executed once per pass by the last row to finish: returns the next pass number or FS_DONE.
+ * On FS_DONE the cluster state is committed for the next frame. */
+HD int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)
+{
+    int next;
+    if (fp->slice_type != SLICE_P) return FS_DONE;
+    int need_replay = pass == 0 || fp->fsync[FS_TRAJ_CHANGED] != 0;
+    WSYNC();
+    if (need_replay)
+    {
+        IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; }
+        int nd = wave_replay(fp, w);
+        next = nd ? pass + 1 : FS_DONE;
+    } else next = FS_DONE;
+    if (next == FS_DONE)
+    {
+        IF_LANE0 { fp->clusters[0] = fp->fsync[FS_CL_END]; fp->clusters[1] = fp->fsync[FS_CL_END + 1]; fp->fsync[FS_PASSES] = pass + 1; }
+    }
+    WSYNC();
+    return next;
+}

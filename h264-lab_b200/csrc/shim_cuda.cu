@@ -28,6 +28,7 @@
 #include "h264_common.h"
 #include "h264_pixel.h"
 #include "h264_mbenc.h"
+#include "h264_wave.h"
 #include "h264_cavlc.h"
 #include "h264_deblock.h"
 #include "../../include/h264b200_shim.h"
@@ -55,8 +56,13 @@ __device__ __forceinline__ void publish_row(int *progress, int done)
     if (LANE_ID == 0) *(volatile int *)progress = done;
 }
 
-/* sync area layout per submission: [0] ticket of k_encode_rows, [1] ticket of k_deblock_rows */
-__global__ void __launch_bounds__(32) k_encode_rows(const FrameParams *fps, int njobs, int max_rows, int *tickets)
+/* sync area layout per submission: [0] ticket of k_encode_rows, [1] ticket of k_deblock_rows.
+ *
+ * k_encode_rows: one warp per macroblock row, persistent over all verification sweeps of the
+ * frame (h264_wave.h).  Row progress counters are monotonic: sweep p of a row counts from
+ * p*nmbx.  Between sweeps the rows of a frame meet at a counter barrier; the last row to
+ * arrive replays the cluster trajectory and publishes the next sweep number (or FS_DONE). */
+__global__ void __launch_bounds__(32) k_encode_rows(const FrameParams *fps, int njobs, int *tickets)
 {
     __shared__ MBWork work;
     __shared__ int s_item;
@@ -64,23 +70,49 @@ __global__ void __launch_bounds__(32) k_encode_rows(const FrameParams *fps, int 
     __syncwarp();
     const int item = s_item;
     const int job = item % njobs, row = item / njobs;
-    (void)max_rows;
     const FrameParams *fp = fps + job;
     if (row >= fp->nmby) return;
-    const int nmbx = fp->nmbx;
+    const int nmbx = fp->nmbx, nmby = fp->nmby;
     int *progress = fp->row_progress;
-    int32_t cl[2] = {0, 0};
-    for (int x = 0; x < nmbx; x++)
+    for (int pass = 0;;)
     {
-        if (row > 0)
+        const int base = pass * nmbx;
+        for (int x = 0; x < nmbx; x++)
         {
-            int need = fp->serial_rows ? nmbx : min(x + 2, nmbx);
-            if (x == 0 || !fp->serial_rows) wait_row(progress + row - 1, need);
+            if (row > 0) wait_row(progress + row - 1, base + min(x + 2, nmbx));
+            if (pass == 0) wave_mb_first(fp, &work, x, row);
+            else wave_mb_repair(fp, &work, x, row, pass);
+            publish_row(progress + row, base + x + 1);
         }
-        if (fp->slice_type == SLICE_P) { cl[0] = ((volatile int32_t *)fp->clusters)[0]; cl[1] = ((volatile int32_t *)fp->clusters)[1]; }
-        encode_mb(fp, &work, x, row, cl);
-        if (fp->slice_type == SLICE_P && threadIdx.x == 0) { fp->clusters[0] = cl[0]; fp->clusters[1] = cl[1]; }
-        publish_row(progress + row, x + 1);
+        if (fp->slice_type != SLICE_P) break;
+        /* frame barrier */
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (threadIdx.x == 0) last = atomicAdd(&fp->fsync[FS_ARRIVE], 1) == (pass + 1) * nmby - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        int next;
+        if (last)
+        {
+            __threadfence();
+            next = wave_end_of_pass(fp, &work, pass);
+            if (next != FS_DONE && next > fp->max_passes) { if (threadIdx.x == 0) atomicOr(&fp->out_info[1], 4); next = FS_DONE; }
+            __threadfence();
+            __syncwarp();
+            if (threadIdx.x == 0) *(volatile int *)&fp->fsync[FS_STATE] = next;
+        } else
+        {
+            if (threadIdx.x == 0)
+            {
+                const volatile int *st = &fp->fsync[FS_STATE];
+                while (*st <= pass) __nanosleep(256);
+                next = *st;
+            }
+            next = __shfl_sync(0xffffffffu, next, 0);
+            __threadfence();
+        }
+        if (next == FS_DONE) break;
+        pass = next;
     }
 }
 
@@ -191,6 +223,8 @@ struct h264b200_ctx
     int out_cap_words;
     int *d_out_info;
     int32_t *d_clusters;
+    MBSpec *d_spec; int32_t *d_cl_true; int *d_changed_pass; int *d_fsync;
+    int have_traj; int stats[4];
     int *d_progress;              /* 2 * nmby */
     uint32_t *h_out_words;        /* pinned */
     int *h_out_info;              /* pinned */
@@ -264,6 +298,12 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_clusters, 16));
     CK(cudaMemset(c->d_clusters, 0, 16));
     CK(cudaMalloc(&c->d_progress, sizeof(int) * 2 * c->nmby));
+    CK(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
+    CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
+    CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
+    CK(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
+    CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
+    CK(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
     CK(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
     CK(cudaMallocHost(&c->h_out_info, 64));
     *out = c;
@@ -279,6 +319,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->d_clip) cudaFree(c->d_clip);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
+    cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_changed_pass); cudaFree(c->d_fsync);
     cudaFreeHost(c->h_out_words); cudaFreeHost(c->h_out_info);
     free(c);
 }
@@ -288,6 +329,7 @@ extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
     if (!c) return;
     cudaMemset(c->d_clusters, 0, 16);
     c->cur = 0;
+    c->have_traj = 0;
 }
 
 static void build_fp(const h264b200_job *job, FrameParams *fp)
@@ -326,7 +368,9 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
-    fp->serial_rows = p.slice_type == SLICE_P;
+    fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->changed_pass = c->d_changed_pass; fp->fsync = c->d_fsync;
+    fp->max_passes = 4096;
+    fp->spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
 }
 
 extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
@@ -377,9 +421,10 @@ static int encode_impl(int n, h264b200_job *jobs)
         h264b200_ctx *c = jobs[i].ctx;
         CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 2 * c->nmby, st));
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
+        CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
     }
     CK(cudaEventRecord(g_ev[1], st));
-    k_encode_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, max_rows, g_d_tickets);
+    k_encode_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, g_d_tickets);
     CK(cudaEventRecord(g_ev[2], st));
     k_deblock_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(g_d_fps, n);
@@ -394,7 +439,10 @@ static int encode_impl(int n, h264b200_job *jobs)
     g_launches += 6;
     CK(cudaEventRecord(g_ev[4], st));
     for (int i = 0; i < n; i++)
+    {
         CK(cudaMemcpyAsync(jobs[i].ctx->h_out_info, jobs[i].ctx->d_out_info, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(jobs[i].ctx->h_out_info + 4, jobs[i].ctx->d_fsync, 32, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     int rc = 0;
@@ -404,6 +452,10 @@ static int encode_impl(int n, h264b200_job *jobs)
         jobs[i].out_bits = c->h_out_info[0];
         jobs[i].trailing_skip_run = c->h_out_info[2];
         jobs[i].out_words = c->h_out_words;
+        c->stats[0] += c->h_out_info[4 + FS_PASSES]; c->stats[1] += c->h_out_info[4 + FS_REENC];
+        c->stats[2] += c->h_out_info[4 + FS_CHECKS]; c->stats[3]++;
+        c->have_traj = jobs[i].p.slice_type == SLICE_P;
+        if (c->h_out_info[1] & 4) { jobs[i].status = -4; if (!rc) rc = -4; continue; }
         if (c->h_out_info[1]) { jobs[i].status = -2; if (!rc) rc = -2; continue; }
         CK(cudaMemcpyAsync(c->h_out_words, c->d_out_words, (size_t)((jobs[i].out_bits + 95) / 32) * 4, cudaMemcpyDeviceToHost, st));
         for (int pl = 0; pl < 3; pl++)
@@ -444,5 +496,6 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
 }
 
 extern "C" void h264b200_last_timing(float out_ms[4]) { for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
+extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "cuda-sm_100a"; }

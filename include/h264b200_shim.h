@@ -83,6 +83,10 @@ int h264b200_preload(h264b200_ctx *ctx, int nframes, const unsigned char *frames
 /* Copy the most recent reconstruction (W16 x H16 luma, W16/2 x H16/2 chroma) to host. */
 int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const int strides[3]);
 
+/* Statistics of the exact-wavefront scheme (csrc/h264_wave.h), accumulated since the ctx was
+ * created: [0] sweeps, [1] macroblocks re-encoded, [2] candidate-stage re-checks, [3] frames. */
+void h264b200_ctx_stats(h264b200_ctx *ctx, int out[4]);
+
 /* Number of kernel launches issued since the library was loaded. */
 long h264b200_launch_count(void);
 const char *h264b200_backend_name(void);

@@ -108,3 +108,34 @@ def chessboard(width, height, nframes):
         out[f, :width * height] = s.reshape(-1)
         out[f, width * height:] = 128
     return out
+
+
+def multi_motion(width, height, nframes, seed=77):
+    """Textured background panning fast (11,-7) px/frame with three textured objects moving
+    with different large velocities: keeps the reference's running MV "clusters" changing
+    inside a frame, which exercises the speculate/verify/repair path (csrc/h264_wave.h)."""
+    pad = 16 * nframes + 64
+    tex = make_texture(seed, height + 2 * pad, width + 2 * pad)
+    objs = []
+    rng = np.random.default_rng(seed + 5)
+    for k in range(3):
+        ow, oh = max(32, width // (3 + k)), max(32, height // (4 + k))
+        objs.append((make_texture(seed + 10 + k, oh, ow), int(rng.integers(0, max(1, width - ow))),
+                     int(rng.integers(0, max(1, height - oh))), int(rng.integers(-14, 15)), int(rng.integers(-9, 10))))
+    out = np.empty((nframes, width * height * 3 // 2), dtype=np.uint8)
+    cw, ch = width // 2, height // 2
+    for f in range(nframes):
+        ox, oy = pad + 11 * f, pad - 7 * f
+        y = tex[oy:oy + height, ox:ox + width].copy()
+        for (ot, x0, y0, vx, vy) in objs:
+            oh, ow = ot.shape
+            px = (x0 + vx * f) % max(1, width - ow)
+            py = (y0 + vy * f) % max(1, height - oh)
+            y[py:py + oh, px:px + ow] = ot
+        y = np.clip(y.astype(np.int16) + rng.integers(-2, 3, size=y.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+        u = (y[0::2, 0::2] // 2 + 64).astype(np.uint8)
+        v = (y[1::2, 1::2] // 2 + 32).astype(np.uint8)
+        out[f, :width * height] = y.reshape(-1)
+        out[f, width * height:width * height + cw * ch] = u.reshape(-1)
+        out[f, width * height + cw * ch:] = v.reshape(-1)
+    return out

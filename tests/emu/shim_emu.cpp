@@ -15,6 +15,7 @@
 #include "../../h264-lab_b200/csrc/h264_common.h"
 #include "../../h264-lab_b200/csrc/h264_pixel.h"
 #include "../../h264-lab_b200/csrc/h264_mbenc.h"
+#include "../../h264-lab_b200/csrc/h264_wave.h"
 #include "../../h264-lab_b200/csrc/h264_cavlc.h"
 #include "../../h264-lab_b200/csrc/h264_deblock.h"
 #include "../../include/h264b200_shim.h"
@@ -32,7 +33,13 @@ struct h264b200_ctx
     std::vector<int> mb_nbits;
     std::vector<uint32_t> out_words;
     std::vector<pix_t> clip;
+    std::vector<MBSpec> spec;
+    std::vector<int32_t> cl_true;
+    std::vector<int> changed_pass;
+    int fsync[FS_WORDS];
+    int stats[4];
     int32_t clusters[2];
+    int have_traj;
 };
 
 static long g_launches = 0;
@@ -55,14 +62,17 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->coef.resize((size_t)nmb * COEF_PER_MB);
     c->mb_bits.resize((size_t)(nmb + 1) * MB_BITS_WORDS);
     c->mb_nbits.resize(nmb + 2);
+    c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->changed_pass.resize(nmb);
     c->out_words.resize((size_t)nmb * 160 + 1024);
     c->cur = 0;
     c->clusters[0] = c->clusters[1] = 0;
+    c->have_traj = 0;
+    memset(c->stats, 0, sizeof(c->stats));
     *out = c;
     return 0;
 }
 extern "C" void h264b200_ctx_destroy(h264b200_ctx *c) { delete c; }
-extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; }
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->have_traj = 0; }
 
 static void run_job(h264b200_job *job)
 {
@@ -97,6 +107,11 @@ static void run_job(h264b200_job *job)
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
+    fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.changed_pass = c->changed_pass.data();
+    memset(c->fsync, 0, sizeof(c->fsync));
+    fp.fsync = c->fsync;
+    fp.max_passes = 1000;
+    fp.spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
     fp.mb_bits = c->mb_bits.data(); fp.mb_nbits = c->mb_nbits.data();
     fp.out_words = c->out_words.data();
     job->out_words = c->out_words.data();
@@ -105,9 +120,22 @@ static void run_job(h264b200_job *job)
     const int nmb = c->nmbx * c->nmby;
 
     MBWork *w = new MBWork();
-    for (int y = 0; y < c->nmby; y++)
-        for (int x = 0; x < c->nmbx; x++) encode_mb(&fp, w, x, y, c->clusters);
+    for (int pass = 0;;)
+    {
+        for (int y = 0; y < c->nmby; y++)
+            for (int x = 0; x < c->nmbx; x++)
+            {
+                if (pass == 0) wave_mb_first(&fp, w, x, y);
+                else wave_mb_repair(&fp, w, x, y, pass);
+            }
+        int next = wave_end_of_pass(&fp, w, pass);
+        if (next == FS_DONE) break;
+        pass = next;
+        if (pass > fp.max_passes) { job->status = -4; delete w; return; }
+    }
     delete w;
+    c->have_traj = (p.slice_type == SLICE_P);
+    c->stats[0] += c->fsync[FS_PASSES]; c->stats[1] += c->fsync[FS_REENC]; c->stats[2] += c->fsync[FS_CHECKS]; c->stats[3]++;
     g_launches++;
 
     memset(c->out_words.data(), 0, c->out_words.size() * 4);
@@ -169,5 +197,6 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
     return 0;
 }
 extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
+extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "host-emulation (test only)"; }
