@@ -214,7 +214,8 @@ struct MBWork
     pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)   */
     pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
     pix_t i4rec[256];            /* I4x4 reconstruction under construction                  */
-    pix_t i4pred[9][16];         /* the nine 4x4 predictions of the current block           */
+    pix_t i4s[40];               /* the 39 source values of the current 4x4 block's predictions */
+    int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
     pix_t top_y[24];             /* unfiltered row above: 16 + 4 of the top-right MB        */
     pix_t left_y[16];
     pix_t top_c[16];             /* U 0..7, V 8..15                                         */
@@ -227,7 +228,6 @@ struct MBWork
     int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
     int16_t dc_c[8], qdc_c[8];
     int16_t hpel[21 * 16];       /* half-pel intermediate rows (H:1992)                     */
-    int32_t i4cost[9];
     int8_t  i4_mode[16], i4_code[16];
     int8_t  zflag1[16], zflag2[16];
     int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */

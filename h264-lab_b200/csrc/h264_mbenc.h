@@ -551,7 +551,44 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
  * (intra_choose_4x4 H:4723, h264e_intra_choose_4x4 H:1810).  Returns the cost;
  * leaves recon in w->i4rec, levels in w->qv_y/dq_y, modes in w->i4_mode/i4_code and
  * the non-zero mask in *nz_mask_out.
+ *
+ * Warp mapping per 4x4 block: every predicted sample of every mode is one of 39 "source"
+ * values derived from the 13 neighbouring samples Z[-4..8] = L3..L0, UL, U0..U7:
+ *   S[0..12]  = Z[k]                                   (V, H, HU tail)
+ *   S[13..23] = F3[k] = (Z[k-1] + 2 Z[k] + Z[k+1] + 2) >> 2,  k = -3..7
+ *   S[24..35] = F2[k] = (Z[k] + Z[k+1] + 1) >> 1,             k = -4..7
+ *   S[36] = (U6 + 3 U7 + 2) >> 2, S[37] = (L2 + 3 L3 + 2) >> 2, S[38] = DC
+ * (ITU-T H.264 8.3.1.2.1-9 rewritten on one edge line).  The lanes build S[], then lane
+ * (g, p) scores sample p for the modes of group g; nine SADs come out of five packed
+ * warp reductions; transform, quantisation and reconstruction of the block run on 16
+ * lanes with the 4-point butterflies exchanged through shared memory.
  * ---------------------------------------------------------------------------- */
+/* source index of every predicted sample, [evaluation slot][y*4+x]; slots in the reference's
+ * evaluation order DC, V, DDL, VL, H, HU, DDR, HD, VR (H:1834-1960) */
+H264_TAB uint8_t i4_src_tab[9][16] = {
+    {38,38,38,38,38,38,38,38,38,38,38,38,38,38,38,38},
+    {5,6,7,8,5,6,7,8,5,6,7,8,5,6,7,8},
+    {18,19,20,21,19,20,21,22,20,21,22,23,21,22,23,36},
+    {29,30,31,32,18,19,20,21,30,31,32,33,19,20,21,22},
+    {3,3,3,3,2,2,2,2,1,1,1,1,0,0,0,0},
+    {26,14,25,13,25,13,24,37,24,37,0,0,0,0,0,0},
+    {16,17,18,19,15,16,17,18,14,15,16,17,13,14,15,16},
+    {27,16,17,18,26,15,27,16,25,14,26,15,24,13,25,14},
+    {28,29,30,31,16,17,18,19,15,28,29,30,14,16,17,18},
+};
+H264_TAB uint8_t i4_slot_mode[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
+
+HD int fwd_row(int k, int a, int b, int c, int d)     /* k-th output of the forward 4-point kernel */
+{
+    int s = a + d, t = a - d, u = b + c, v = b - c;
+    return k == 0 ? s + u : (k == 1 ? 2 * t + v : (k == 2 ? s - u : t - 2 * v));
+}
+HD int inv_row(int k, int a, int b, int c, int d)     /* k-th output of the inverse 4-point kernel */
+{
+    int e0 = a + c, e1 = a - c, e2 = (b >> 1) - d, e3 = b + (d >> 1);
+    return k == 0 ? e0 + e3 : (k == 1 ? e1 + e2 : (k == 2 ? e1 - e2 : e0 - e3));
+}
+
 HD int intra4_choose(MBState &s, int *nz_mask_out)
 {
     const FrameParams *fp = s.fp;
@@ -561,11 +598,11 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
     int nz_mask = 0;
     const int penalty = (3 * fp->lambda_q4) >> 4;
     const MBInfo *mbi = fp->mbi + s.mby * fp->nmbx + s.mbx;
+    const uint16_t *qdat = fp->qdat[0];
 
     for (int n = 0; n < 16; n++)
     {
-        /* which neighbours exist for block n: bits that depend on the MB's own
-         * neighbours / bits that are always there (block2avail H:4750) */
+        /* which neighbours exist for block n (block2avail H:4750) */
         const int r = n >> 2, c = n & 3;
         int a = 0;
         if (c > 0 || (avail & AVAIL_L)) a |= AVAIL_L;
@@ -585,66 +622,148 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
         const pix_t *blockin = w->inp_y + (c + r * 16) * 4;
         pix_t *block = w->i4rec + (c + r * 16) * 4;
 
-        /* evaluation order of the reference: DC, V, DDL, VL, H, HU, DDR, HD, VR */
-        FOR_LANES(k, 9)
+        /* 1. the 13 neighbours Z[-4..8] -> i4s[0..12] */
+        FOR_LANES(i, 13)
         {
-            const int order[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
-            int mode = order[k];
-            int ok = k == 0 ? 1 : (k < 4 ? (a & AVAIL_T) : (k < 6 ? (a & AVAIL_L) : ((a & 7) == 7)));
-            int cst = 0x7FFFFFFF;
-            if (ok)
+            int k = i - 4, v = 0;
+            if (k < 0) { int j = -1 - k; if (a & AVAIL_L) v = c > 0 ? w->i4rec[(r * 4 + j) * 16 + c * 4 - 1] : w->left_y[r * 4 + j]; }
+            else if (k == 0)
             {
-                int e[13];
-                for (int jj = 0; jj < 4; jj++)
-                    e[3 - jj] = c > 0 ? w->i4rec[(r * 4 + jj) * 16 + c * 4 - 1] : w->left_y[r * 4 + jj];
-                if (r > 0 && c > 0) e[4] = w->i4rec[(r * 4 - 1) * 16 + c * 4 - 1];
-                else if (r > 0) e[4] = w->left_y[r * 4 - 1];
-                else if (c > 0) e[4] = w->top_y[c * 4 - 1];
-                else e[4] = w->tl[0];
-                for (int jj = 0; jj < 8; jj++)
+                if (a & AVAIL_TL)
                 {
-                    int x = c * 4 + jj;
-                    e[5 + jj] = r > 0 ? (x < 16 ? w->i4rec[(r * 4 - 1) * 16 + x] : 0) : w->top_y[x < 20 ? x : 19];
+                    if (r > 0 && c > 0) v = w->i4rec[(r * 4 - 1) * 16 + c * 4 - 1];
+                    else if (r > 0) v = w->left_y[r * 4 - 1];
+                    else if (c > 0) v = w->top_y[c * 4 - 1];
+                    else v = w->tl[0];
                 }
-                if (!(a & AVAIL_TR)) e[9] = e[10] = e[11] = e[12] = e[8];
-                pix_t pr[16];
-                intra4_predict(mode, e, a, pr);
-                int sad = 0;
-                for (int y = 0; y < 4; y++)
-                    for (int x = 0; x < 4; x++) sad += iabs((int)blockin[y * 16 + x] - pr[y * 4 + x]);
-                if (mode != mpred) sad += penalty;
-                cst = sad;
-                for (int q = 0; q < 4; q++) *(uint32_t *)(w->i4pred[k] + 4 * q) = (uint32_t)pr[4 * q] | ((uint32_t)pr[4 * q + 1] << 8) | ((uint32_t)pr[4 * q + 2] << 16) | ((uint32_t)pr[4 * q + 3] << 24);
+            } else if (a & AVAIL_T)
+            {
+                int j = k - 1;
+                if (j > 3 && !(a & AVAIL_TR)) j = 3;
+                int x = c * 4 + j;
+                v = r > 0 ? w->i4rec[(r * 4 - 1) * 16 + x] : w->top_y[x];
             }
-            w->i4cost[k] = cst;
+            w->i4s[i] = (pix_t)v;
         }
         WSYNC();
-        int bk = 0, best_sad = w->i4cost[0];
-        for (int k = 1; k < 9; k++) if (w->i4cost[k] < best_sad) { best_sad = w->i4cost[k]; bk = k; }
-        const int order2[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
-        int mode = order2[bk];
-
-        IF_LANE0
+        /* 2. filtered values -> i4s[13..38] */
+        FOR_LANES(i, 26)
         {
-            w->i4_mode[n] = (int8_t)mode;
-            w->i4_code[n] = (int8_t)(mode == mpred ? -1 : (mode > mpred ? mode - 1 : mode));
-            for (int y = 0; y < 4; y++) *(uint32_t *)(block + y * 16) = *(const uint32_t *)(w->i4pred[bk] + 4 * y);
-            int nzb = 0;
-            if (best_sad > fp->skip_thr_i4x4)
+            const pix_t *Z = w->i4s + 4;
+            int v;
+            if (i < 11) { int k = i - 3; v = (Z[k - 1] + 2 * Z[k] + Z[k + 1] + 2) >> 2; }
+            else if (i < 23) { int k = i - 11 - 4; v = (Z[k] + Z[k + 1] + 1) >> 1; }
+            else if (i == 23) v = (Z[7] + 3 * Z[8] + 2) >> 2;
+            else if (i == 24) v = (Z[-3] + 3 * Z[-4] + 2) >> 2;
+            else
             {
-                fwd4x4(blockin, 16, block, w->dq_y[n]);
-                nzb = quant4x4(w->dq_y[n], w->qv_y[n], 0, fp->qdat[0]);
-                if (nzb) inv4x4_add(w->dq_y[n], block, block, 16);
+                int sum = 0, cnt = 0;
+                if (a & AVAIL_L) { sum += Z[-1] + Z[-2] + Z[-3] + Z[-4]; cnt++; }
+                if (a & AVAIL_T) { sum += Z[1] + Z[2] + Z[3] + Z[4]; cnt++; }
+                v = cnt == 0 ? 128 : (cnt == 2 ? (sum + 4) >> 3 : (sum + 2) >> 2);
+            }
+            w->i4s[13 + i] = (pix_t)v;
+        }
+        WSYNC();
+        /* 3. nine SADs: lane (g,p) scores sample p for slots 0..4 (g = 0) or 5..8 (g = 1) */
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0;   /* slots (0,1) (2,3) (4,5) (6,7) (8) packed 16|16 */
+        FOR_LANES(l, 32)
+        {
+            int g = l >> 4, p = l & 15;
+            int in = blockin[(p >> 2) * 16 + (p & 3)];
+            if (g == 0)
+            {
+                acc0 += iabs(in - w->i4s[i4_src_tab[0][p]]) | (iabs(in - w->i4s[i4_src_tab[1][p]]) << 16);
+                acc1 += iabs(in - w->i4s[i4_src_tab[2][p]]) | (iabs(in - w->i4s[i4_src_tab[3][p]]) << 16);
+                acc2 += iabs(in - w->i4s[i4_src_tab[4][p]]);
             } else
             {
-                for (int i = 0; i < 16; i++) { w->qv_y[n][i] = 0; w->dq_y[n][i] = 0; }
+                acc2 += iabs(in - w->i4s[i4_src_tab[5][p]]) << 16;
+                acc3 += iabs(in - w->i4s[i4_src_tab[6][p]]) | (iabs(in - w->i4s[i4_src_tab[7][p]]) << 16);
+                acc4 += iabs(in - w->i4s[i4_src_tab[8][p]]);
             }
-            w->scal[0] = nzb;
+        }
+        acc0 = wsum(acc0); acc1 = wsum(acc1); acc2 = wsum(acc2); acc3 = wsum(acc3); acc4 = wsum(acc4);
+        int sads[9];
+        sads[0] = acc0 & 0xFFFF; sads[1] = (int)((uint32_t)acc0 >> 16);
+        sads[2] = acc1 & 0xFFFF; sads[3] = (int)((uint32_t)acc1 >> 16);
+        sads[4] = acc2 & 0xFFFF; sads[5] = (int)((uint32_t)acc2 >> 16);
+        sads[6] = acc3 & 0xFFFF; sads[7] = (int)((uint32_t)acc3 >> 16);
+        sads[8] = acc4;
+        int bk = 0, best_sad = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+        {
+            int ok = k == 0 ? 1 : (k < 4 ? (a & AVAIL_T) : (k < 6 ? (a & AVAIL_L) : ((a & 7) == 7)));
+            int cst = sads[k] + (i4_slot_mode[k] != mpred ? penalty : 0);
+            if (ok && cst < best_sad) { best_sad = cst; bk = k; }
+        }
+        const int mode = i4_slot_mode[bk];
+        const int do_tq = best_sad > fp->skip_thr_i4x4;
+
+        /* 4. prediction into the reconstruction buffer, residual for the transform */
+        FOR_LANES(p, 16)
+        {
+            int pv = w->i4s[i4_src_tab[bk][p]];
+            int o = (p >> 2) * 16 + (p & 3);
+            block[o] = (pix_t)pv;
+            w->i4t[p] = (int16_t)((int)blockin[o] - pv);
+            if (!do_tq) { w->qv_y[n][p] = 0; w->dq_y[n][p] = 0; }
+            if (p == 0)
+            {
+                w->i4_mode[n] = (int8_t)mode;
+                w->i4_code[n] = (int8_t)(mode == mpred ? -1 : (mode > mpred ? mode - 1 : mode));
+            }
         }
         WSYNC();
-        nz_mask = (nz_mask << 1) | w->scal[0];
+        int nzb = 0;
+        if (do_tq)
+        {
+            /* forward transform: vertical pass (lane = column x, vertical frequency v) ... */
+            FOR_LANES(p, 16)
+            {
+                int x = p & 3, v = p >> 2;
+                w->i4u[v * 4 + x] = (int16_t)fwd_row(v, w->i4t[x], w->i4t[4 + x], w->i4t[8 + x], w->i4t[12 + x]);
+            }
+            WSYNC();
+            /* ... horizontal pass + quantisation (lane = coefficient i = v + 4u) */
+            int nzl = 0;
+            FOR_LANES(i, 16)
+            {
+                int v = i & 3, u = i >> 2;
+                int cf = (int16_t)fwd_row(u, w->i4u[v * 4], w->i4u[v * 4 + 1], w->i4u[v * 4 + 2], w->i4u[v * 4 + 3]);
+                int cl = quant_class(i);
+                int rnd = cf < 0 ? 0xFFFF - qdat[6] : qdat[6];
+                int q = (cf * (int)qdat[cl] + rnd) >> 16;
+                w->qv_y[n][i] = (int16_t)q;
+                w->dq_y[n][i] = (int16_t)(q * (int)qdat[cl + 1]);
+                nzl |= q;
+            }
+            nzb = wor(nzl) != 0;
+            WSYNC();
+            if (nzb)
+            {
+                /* inverse: horizontal pass (lane = vertical frequency v, column x) ... */
+                FOR_LANES(p, 16)
+                {
+                    int x = p & 3, v = p >> 2;
+                    const int16_t *dq = w->dq_y[n];
+                    w->i4u[v * 4 + x] = (int16_t)inv_row(x, dq[v], dq[v + 4], dq[v + 8], dq[v + 12]);
+                }
+                WSYNC();
+                /* ... vertical pass, add prediction, clip */
+                FOR_LANES(p, 16)
+                {
+                    int x = p & 3, y = p >> 2;
+                    int rr = (int16_t)((inv_row(y, w->i4u[x], w->i4u[4 + x], w->i4u[8 + x], w->i4u[12 + x]) + 32) >> 6);
+                    int o = y * 16 + x;
+                    block[o] = (pix_t)clip_u8(rr + block[o]);
+                }
+                WSYNC();
+            }
+        }
+        nz_mask = (nz_mask << 1) | nzb;
         cost += best_sad;
-        WSYNC();
     }
     *nz_mask_out = nz_mask;
     return cost;
