@@ -200,9 +200,14 @@ struct FrameParams
     uint32_t *out_words;        /* packed slice payload                                     */
     int *out_info;              /* [0] total bits, [1] error flags, [2] trailing skip run   */
     int hdr_bits;               /* bit offset at which the slice data starts                */
+    int *prof;                  /* developer builds: per-MB phase cycle counts [nmb][10]    */
     int max_passes;             /* safety bound on verification sweeps                      */
     int spec_from_prev;         /* 1: speculate with the previous P frame's replayed trajectory */
 };
+
+/* shared-memory search window of one macroblock (luma): WIN_W x WIN_H samples */
+#define WIN_W 64
+#define WIN_H 48
 
 #define MB_BITS_WORDS 512       /* 2048 bytes per macroblock */
 
@@ -214,7 +219,9 @@ struct MBWork
     pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)   */
     pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
     pix_t i4rec[256];            /* I4x4 reconstruction under construction                  */
-    pix_t i4s[40];               /* the 39 source values of the current 4x4 block's predictions */
+    pix_t i4r[17 * 24];          /* GPU fast path: padded I4x4 reconstruction (row above, left column) */
+    pix_t i4z[16];               /* the 13 neighbours of the current 4x4 block              */
+    pix_t i4s[32];               /* the 32 source values of its nine predictions            */
     int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
     pix_t top_y[24];             /* unfiltered row above: 16 + 4 of the top-right MB        */
     pix_t left_y[16];
@@ -227,7 +234,8 @@ struct MBWork
     int16_t qv_c[8][16];
     int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
     int16_t dc_c[8], qdc_c[8];
-    int16_t hpel[21 * 16];       /* half-pel intermediate rows (H:1992)                     */
+    pix_t tmpblk[256];           /* second operand of quarter-sample averages               */
+    uint32_t win[(WIN_W * WIN_H + 32) / 4];   /* search window: copy of the reference picture around the MV predictor */
     int8_t  i4_mode[16], i4_code[16];
     int8_t  zflag1[16], zflag2[16];
     int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */

@@ -19,6 +19,8 @@ struct MBState   /* warp-uniform registers of the macroblock being encoded */
     int i16_mode;
     int mv_skip_pred;    /* H:674 */
     pix_t *pbest, *ptest;
+    int win_x0, win_y0;  /* luma coordinates of the search window's first sample; win_x0 % 4 == 0 */
+    int win_ok;
 };
 
 HD int clz32(uint32_t v)
@@ -45,7 +47,7 @@ HD int mv_in_rect(int v, int x0, int y0, int x1, int y1)
 /* ------------------------------------------------------------------------------
  * loading the macroblock's inputs
  * ---------------------------------------------------------------------------- */
-HD void mb_load(MBState &s)
+HDN void mb_load(MBState &s)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -122,7 +124,7 @@ HD void mb_load(MBState &s)
  * (me_mv_medianpredictor_get H:3720).  x,y,wd,ht in units of 4x4 blocks.
  * ---------------------------------------------------------------------------- */
 HD int med3(int a, int b, int c) { return imax(imin(imax(a, b), c), imin(a, b)); }
-HD int mvp_get(const MBWork *w, int flag, int x, int y, int wd, int ht)
+HDN int mvp_get(const MBWork *w, int flag, int x, int y, int wd, int ht)
 {
     int a = w->mvp_left[y], b = w->mvp_top[x], c = w->mvp_top[x + wd], d = w->mvp_tl[y];
     if (!x)
@@ -173,21 +175,61 @@ HD void mvp_put(MBWork *w, int x, int y, int wd, int ht, int mv)
 }
 
 /* ------------------------------------------------------------------------------
+ * Search window: a WIN_W x WIN_H copy of the reference luma around the 16x16 MV predictor,
+ * staged once per macroblock in shared memory.  Every SAD / interpolation asks ref_at() for
+ * its block; inside the window (the common case) the samples come from shared memory,
+ * otherwise straight from the frame in global memory -- identical values either way.
+ * ---------------------------------------------------------------------------- */
+HDN void win_load(MBState &s, int cx, int cy)
+{
+    const FrameParams *fp = s.fp;
+    const int stride = fp->stride[0];
+    const int x0 = (cx - 24) & ~3, y0 = cy - 16;
+    const int xmin = -16, xmax = fp->nmbx * 16 + 12, ymin = -16, ymax = fp->nmby * 16 + 15;
+    const pix_t *plane = fp->ref[0];
+    uint32_t *win = s.w->win;
+    FOR_LANES(i, (WIN_W / 4) * WIN_H)
+    {
+        int r = i / (WIN_W / 4), c4 = i - r * (WIN_W / 4);
+        int y = imin(imax(y0 + r, ymin), ymax), x = imin(imax(x0 + 4 * c4, xmin), xmax);
+        win[i] = *(const uint32_t *)(plane + y * stride + x);
+    }
+    s.win_x0 = x0; s.win_y0 = y0; s.win_ok = 1;
+    WSYNC();
+}
+
+/* pointer to reference sample (bx,by) for a bw x bh block read with up to 3 samples of
+ * filter margin; *stride receives the row pitch to use with it */
+HD const pix_t *ref_at(const MBState &s, int bx, int by, int bw, int bh, int *stride)
+{
+    int lx = bx - s.win_x0, ly = by - s.win_y0;
+    if (s.win_ok && lx >= 3 && ly >= 3 && lx + bw + 8 <= WIN_W && ly + bh + 4 <= WIN_H)
+    {
+        *stride = WIN_W;
+        return (const pix_t *)s.w->win + ly * WIN_W + lx;
+    }
+    *stride = s.fp->stride[0];
+    return s.fp->ref[0] + by * s.fp->stride[0] + bx;
+}
+
+/* ------------------------------------------------------------------------------
  * a4: integer-pel greedy diamond + diagonal step + 7-probe sub-pel refinement
  * (me_search_diamond H:4973-5176).
- *   refp   : reference luma plane + partition offset
+ *   ppx,ppy: partition offset inside the macroblock
  *   inp    : input MB + partition offset (stride 16)
  *   mv     : in/out absolute quarter-pel MV
  *   rng    : search rectangle x0,y0,x1,y1
  *   buf[4] : scratch, hpel, hpel1, hpel2 destinations (stride-16 blocks)
  * Returns the best cost; *pbest receives the buffer holding the best prediction.
  * ---------------------------------------------------------------------------- */
-HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv, const int *rng,
+HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv, const int *rng,
                  int mv_pred, int min_sad, int bw, int bh, pix_t *const buf[4], pix_t **pbest)
 {
     const FrameParams *fp = s.fp;
-    const int stride = fp->stride[0];
     const int lam = fp->lambda_mv_q4;
+    pix_t *tmp = s.w->tmpblk;
+    int rs;
+    const pix_t *rp;
     int mv = *pmv;
     uint32_t cache[8];
     int dir, cloop, dir_prev, cost, v;
@@ -202,7 +244,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
             v = mv_pack(mv_x(mv) + dx, mv_y(mv) + dy);
             if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]) && cache[dir] == 0xffffu)
             {
-                cost = sad_frame_wh(refp + (mv_y(v) >> 2) * stride + (mv_x(v) >> 2), stride, inp, bw, bh);
+                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
+                cost = sad_frame_wh(rp, rs, inp, bw, bh);
                 cost += mv_cost(v, mv_pred, lam);
                 cache[dir] = (uint32_t)cost & 0xffffu;
                 if (cost < min_sad)
@@ -230,7 +273,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
             v = mv_pack(mv_x(mv) + sdx, mv_y(mv) + pdy);
             if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]))
             {
-                cost = sad_frame_wh(refp + (mv_y(v) >> 2) * stride + (mv_x(v) >> 2), stride, inp, bw, bh);
+                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
+                cost = sad_frame_wh(rp, rs, inp, bw, bh);
                 cost += mv_cost(v, mv_pred, lam);
                 if (cost < min_sad) { mv = v; min_sad = cost; continue; }
             }
@@ -238,7 +282,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
         break;
     }
 
-    interp_luma_block(refp, stride, mv_x(mv), mv_y(mv), bw, bh, buf[0]);
+    rp = ref_at(s, (mv_x(mv) >> 2) + ppx, (mv_y(mv) >> 2) + ppy, bw, bh, &rs);
+    copy_block(rp, rs, buf[0], bw, bh);
     WSYNC();
     pix_t *best = buf[0];
 
@@ -252,6 +297,7 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
         if (cache[1] >= cache[0]) { sqx = 1; minsad1 = cache[0]; }
         if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
         int dgx = pqx + sqx, dgy = pqy + sqy;
+#pragma unroll 1
         for (int i = 0; i < 7; i++)
         {
             pix_t *ptest;
@@ -259,7 +305,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
             {
             case 0:
                 v = mv_pack(mv_x(mv) + 2 * pqx, mv_y(mv) + 2 * pqy);
-                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel1);
+                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
+                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel1, tmp);
                 break;
             case 1:
                 v = mv_pack(mv_x(mv) + pqx, mv_y(mv) + pqy);
@@ -267,7 +314,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
                 break;
             case 2:
                 v = mv_pack(mv_x(mv) + 2 * sqx, mv_y(mv) + 2 * sqy);
-                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel2);
+                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
+                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel2, tmp);
                 break;
             case 3:
                 hpel = buf[1]; if (best == hpel) hpel = scratch;
@@ -282,7 +330,8 @@ HD int me_search(const MBState &s, const pix_t *refp, const pix_t *inp, int *pmv
             case 5:
                 if (best == hpel2) { hpel2 = scratch; hpel = buf[1]; }
                 v = mv_pack(mv_x(mv) + 2 * dgx, mv_y(mv) + 2 * dgy);
-                interp_luma_block(refp, stride, mv_x(v), mv_y(v), bw, bh, ptest = hpel2);
+                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
+                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel2, tmp);
                 break;
             default:
                 hpel = buf[1]; if (best == hpel) hpel = scratch;
@@ -328,7 +377,7 @@ HD void inter_partition_hint(const int sad[4], int mode[4])
 
 /* chroma motion compensation for every partition of the current MB type
  * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB. */
-HD void mc_chroma(const MBState &s, int type, const int32_t *mvs)
+HDN void mc_chroma(const MBState &s, int type, const int32_t *mvs)
 {
     const FrameParams *fp = s.fp;
     int bw = (type & 2) ? 4 : 8, bh = (type & 1) ? 4 : 8;
@@ -354,12 +403,10 @@ HD void mc_chroma(const MBState &s, int type, const int32_t *mvs)
  * On return s.type / s.cost / s.pbest are set; w->part_mv / part_mvd of the chosen
  * type are copied to out_mv/out_mvd.  Returns 1 for an early skip decision.
  * ---------------------------------------------------------------------------- */
-HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig, int cand_only)
+HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig, int cand_only)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
-    const int stride = fp->stride[0];
-    const pix_t *refy = fp->ref[0];
     const int mbqx = s.mbx * 64, mbqy = s.mby * 64;
     int pref[4] = {1, 0, 0, 0};
     int cand[12], ncand = 0, j = 0;
@@ -369,6 +416,7 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
 
     /* skip predictor (me_mv_medianpredictor_get_skip H:3877) */
     int mvp16 = mvp_get(w, s.avail, 0, 0, 4, 4);
+    win_load(s, s.mbx * 16 + ((mv_x(mvp16) + 1) >> 2), s.mby * 16 + ((mv_y(mvp16) + 1) >> 2));
     int mv_skip = 0;
     if (!(~s.avail & (AVAIL_L | AVAIL_T)) && w->mvp_left[0] != 0 && w->mvp_top[0] != 0) mv_skip = mvp16;
     s.mv_skip_pred = mv_skip;
@@ -376,9 +424,13 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
 
     if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
-        interp_luma_block(refy, stride, mv_x(mv_skip_a), mv_y(mv_skip_a), 16, 16, s.ptest);
+        {
+            int rs;
+            const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
+            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, s.ptest, w->tmpblk);
+        }
         WSYNC();
-        sad_skip = sad_mb_quad(w->inp_y, 16, 0, s.ptest, sad4v);
+        sad_skip = sad_mb_quad(w->inp_y, 16, s.ptest, sad4v);
         if (imax(imax(sad4v[0], sad4v[1]), imax(sad4v[2], sad4v[3])) < fp->skip_thr_inter)
         {
             int32_t one_mv = mv_skip;
@@ -436,13 +488,16 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
         }
         ncand = k;
     }
+#pragma unroll 1
     for (; j < ncand; j++)
     {
         int mva = mv_pack(mv_x(cand[j]) + mbqx, mv_y(cand[j]) + mbqy);
         if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
         {
             int cc = mv_cost(cand[j], mvp16, fp->lambda_mv_q4);
-            int sad = sad_mb_quad(refy + (mv_y(mva) >> 2) * stride + (mv_x(mva) >> 2), stride, 1, w->inp_y, sad4v);
+            int rs;
+            const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
+            int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
             if (fp->speed < 1) inter_partition_hint(sad4v, pref);
             if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
         }
@@ -459,6 +514,7 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
     IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_save[3 * i] = w->mvp_left[i]; w->mvp_save[3 * i + 1] = w->mvp_tl[i]; w->mvp_save[3 * i + 2] = w->mvp_top[i]; } }
     WSYNC();
     s.cost = 0xffffff;
+#pragma unroll 1
     for (int mb_type = 0; mb_type < 4; mb_type++)
     {
         const int nbits = mb_type == 0 ? 1 : (mb_type == 3 ? 12 : 4);
@@ -478,15 +534,16 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
             {
                 mvabs = mv_round_fullpel(mv_pred_a);
                 me_set_range(fp, &mvabs, rng, mbqy + py * 4);
-                sad_best = sad_frame_wh(refy + ((mv_y(mvabs) >> 2) + py) * stride + (mv_x(mvabs) >> 2) + px, stride,
-                                        w->inp_y + py * 16 + px, bw, bh)
+                int rs;
+                const pix_t *rp = ref_at(s, (mv_x(mvabs) >> 2) + px, (mv_y(mvabs) >> 2) + py, bw, bh, &rs);
+                sad_best = sad_frame_wh(rp, rs, w->inp_y + py * 16 + px, bw, bh)
                          + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
             }
             int sb = mb_type ? (mb_type == 2 ? 8 : 128) : 256;
             pix_t *bufs[4];
             bufs[0] = store; bufs[1] = store + sb; bufs[2] = store + (sb == 8 ? 256 : 2 * sb); bufs[3] = bufs[2] + sb;
             pix_t *dout;
-            part_sad += me_search(s, refy + py * stride + px, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
+            part_sad += me_search(s, px, py, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
                                   bw, bh, bufs, &dout);
             if (!mb_type)
             {
@@ -540,7 +597,11 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
         s.cost = sad_skip + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
         out_mv[0] = mv_skip;
         out_mvd[0] = mv_sub2(mv_skip, mvp16);
-        interp_luma_block(refy, stride, mv_x(mv_skip_a), mv_y(mv_skip_a), 16, 16, s.pbest);
+        {
+            int rs;
+            const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
+            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, s.pbest, w->tmpblk);
+        }
         WSYNC();
     }
     return 0;
@@ -552,12 +613,13 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
  * leaves recon in w->i4rec, levels in w->qv_y/dq_y, modes in w->i4_mode/i4_code and
  * the non-zero mask in *nz_mask_out.
  *
- * Warp mapping per 4x4 block: every predicted sample of every mode is one of 39 "source"
+ * Warp mapping per 4x4 block: every predicted sample of every mode is one of 32 "source"
  * values derived from the 13 neighbouring samples Z[-4..8] = L3..L0, UL, U0..U7:
- *   S[0..12]  = Z[k]                                   (V, H, HU tail)
- *   S[13..23] = F3[k] = (Z[k-1] + 2 Z[k] + Z[k+1] + 2) >> 2,  k = -3..7
- *   S[24..35] = F2[k] = (Z[k] + Z[k+1] + 1) >> 1,             k = -4..7
- *   S[36] = (U6 + 3 U7 + 2) >> 2, S[37] = (L2 + 3 L3 + 2) >> 2, S[38] = DC
+ *   S[0..3]   = Z[-4..-1] (L3..L0),  S[4..7] = Z[1..4] (U0..U3)      (H, V, HU tail)
+ *   S[8..18]  = F3[k] = (Z[k-1] + 2 Z[k] + Z[k+1] + 2) >> 2,  k = -3..7
+ *   S[19..28] = F2[k] = (Z[k] + Z[k+1] + 1) >> 1,             k = -4..5
+ *   S[29] = (U6 + 3 U7 + 2) >> 2, S[30] = (L2 + 3 L3 + 2) >> 2, S[31] = DC
+ * -- exactly 32 distinct values, one per lane
  * (ITU-T H.264 8.3.1.2.1-9 rewritten on one edge line).  The lanes build S[], then lane
  * (g, p) scores sample p for the modes of group g; nine SADs come out of five packed
  * warp reductions; transform, quantisation and reconstruction of the block run on 16
@@ -566,15 +628,15 @@ HD int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, c
 /* source index of every predicted sample, [evaluation slot][y*4+x]; slots in the reference's
  * evaluation order DC, V, DDL, VL, H, HU, DDR, HD, VR (H:1834-1960) */
 H264_TAB uint8_t i4_src_tab[9][16] = {
-    {38,38,38,38,38,38,38,38,38,38,38,38,38,38,38,38},
-    {5,6,7,8,5,6,7,8,5,6,7,8,5,6,7,8},
-    {18,19,20,21,19,20,21,22,20,21,22,23,21,22,23,36},
-    {29,30,31,32,18,19,20,21,30,31,32,33,19,20,21,22},
+    {31,31,31,31,31,31,31,31,31,31,31,31,31,31,31,31},
+    {4,5,6,7,4,5,6,7,4,5,6,7,4,5,6,7},
+    {13,14,15,16,14,15,16,17,15,16,17,18,16,17,18,29},
+    {24,25,26,27,13,14,15,16,25,26,27,28,14,15,16,17},
     {3,3,3,3,2,2,2,2,1,1,1,1,0,0,0,0},
-    {26,14,25,13,25,13,24,37,24,37,0,0,0,0,0,0},
-    {16,17,18,19,15,16,17,18,14,15,16,17,13,14,15,16},
-    {27,16,17,18,26,15,27,16,25,14,26,15,24,13,25,14},
-    {28,29,30,31,16,17,18,19,15,28,29,30,14,16,17,18},
+    {21,9,20,8,20,8,19,30,19,30,0,0,0,0,0,0},
+    {11,12,13,14,10,11,12,13,9,10,11,12,8,9,10,11},
+    {22,11,12,13,21,10,22,11,20,9,21,10,19,8,20,9},
+    {23,24,25,26,11,12,13,14,10,23,24,25,9,11,12,13},
 };
 H264_TAB uint8_t i4_slot_mode[9] = {2, 0, 3, 7, 1, 8, 4, 6, 5};
 
@@ -589,7 +651,211 @@ HD int inv_row(int k, int a, int b, int c, int d)     /* k-th output of the inve
     return k == 0 ? e0 + e3 : (k == 1 ? e1 + e2 : (k == 2 ? e1 - e2 : e0 - e3));
 }
 
-HD int intra4_choose(MBState &s, int *nz_mask_out)
+#if H264_DEVICE
+/* sm_100a fast path of the Intra4x4 decision: same algorithm as the portable version below
+ * (which documents it and is what the host emulation runs), but the whole per-block chain
+ * -- neighbours -> 32 source values -> nine SADs -> mode -> residual -> transform ->
+ * quantisation -> reconstruction -- stays in registers and moves between lanes with warp
+ * shuffles; shared memory is touched once per block (neighbour fetch / recon store). */
+HDN int intra4_choose(MBState &s, int *nz_mask_out)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const int avail = s.avail;
+    const int lane = LANE_ID, p = lane & 15, g = lane >> 4, px = p & 3, py = p >> 2;
+    const unsigned FULL = 0xffffffffu;
+    int cost = fp->lambda_i4_q4;
+    int nz_mask = 0;
+    const int penalty = (3 * fp->lambda_q4) >> 4;
+    const int skip_thr = fp->skip_thr_i4x4;
+    const MBInfo *mbi = fp->mbi + s.mby * fp->nmbx + s.mbx;
+
+    /* ---- per-macroblock constants of this lane ---- */
+    /* padded reconstruction R[17][24]: row 0 = row above (TL at col 3, 16 + 4 samples from col 4),
+     * col 3 = left column; sample (x,y) of the MB at R[(y+1)*24 + x+4] */
+    pix_t *R = w->i4r;
+    for (int i = lane; i < 21 + 16; i += 32)
+    {
+        if (i < 21) R[3 + i] = i == 0 ? w->tl[0] : w->top_y[i - 1];
+        else R[(i - 21 + 1) * 24 + 3] = w->left_y[i - 21];
+    }
+    /* neighbour fetch offset of Z[lane-4] relative to R + (4r)*24 + 4c, with / without top-right */
+    int zoff, zoff_notr;
+    {
+        int k = lane - 4;
+        if (lane > 12) k = 0;
+        zoff = k <= 0 ? (-k) * 24 + 3 : 4 + (k - 1);
+        zoff_notr = k > 4 ? 4 + 3 : zoff;
+    }
+    /* recipe of source value S[lane] from Z: shuffle sources + kind */
+    int sa, sb, sc, kind;
+    if (lane < 4) { sa = sb = sc = lane; kind = 0; }
+    else if (lane < 8) { sa = sb = sc = lane + 1; kind = 0; }
+    else if (lane < 19) { sa = lane - 8; sb = lane - 7; sc = lane - 6; kind = 1; }
+    else if (lane < 29) { sa = lane - 19; sb = sc = lane - 18; kind = 2; }
+    else if (lane == 29) { sa = 11; sb = sc = 12; kind = 3; }
+    else if (lane == 30) { sa = 1; sb = sc = 0; kind = 3; }
+    else { sa = 0; sb = sc = 5; kind = 4; }
+    /* source indices of this lane's sample for the nine slots; slots 0-4 scored by lanes 0-15,
+     * slots 5-8 by lanes 16-31 */
+    unsigned e0 = 0, e1 = 0, e2 = i4_src_tab[8][p];
+    for (int k = 0; k < 4; k++) { e0 |= (unsigned)i4_src_tab[k][p] << (8 * k); e1 |= (unsigned)i4_src_tab[4 + k][p] << (8 * k); }
+    const unsigned my_slots = g ? (e1 >> 8) | (e2 << 24) : e0;     /* four slots: 0-3 or 5-8 */
+    const int my_slot4 = e1 & 0xff;                                 /* slot 4 (group 0 only) */
+    /* quantiser constants of coefficient i = v + 4u held by this lane (v = py, u = px) */
+    const int ci = py + 4 * px;
+    const int qcl = quant_class(ci);
+    const int qmul = fp->qdat[0][qcl], dqmul = fp->qdat[0][qcl + 1], qrnd = fp->qdat[0][6];
+    /* neighbouring MBs' modes */
+    int nb_mode = -1;
+    if (lane < 4) nb_mode = (avail & AVAIL_L) ? mbi[-1].i4_mode[4 * lane + 3] : -1;
+    else if (lane < 8) nb_mode = (avail & AVAIL_T) ? mbi[-fp->nmbx].i4_mode[12 + lane - 4] : -1;
+    unsigned modes_lo = 0, modes_hi = 0;      /* chosen modes of blocks 0-7 / 8-15, 4 bits each */
+    __syncwarp();
+
+#pragma unroll 1
+    for (int n = 0; n < 16; n++)
+    {
+        const int r = n >> 2, c = n & 3;
+        int a = 0;
+        if (c > 0 || (avail & AVAIL_L)) a |= AVAIL_L;
+        if (r > 0 || (avail & AVAIL_T)) a |= AVAIL_T;
+        if (r > 0 && c > 0) a |= AVAIL_TL;
+        else if (r == 0 && c == 0) a |= avail & AVAIL_TL;
+        else if (r == 0) a |= (avail & AVAIL_T) ? AVAIL_TL : 0;
+        else a |= (avail & AVAIL_L) ? AVAIL_TL : 0;
+        if (r == 0) { if (c < 3) a |= (avail & AVAIL_T) ? AVAIL_TR : 0; else a |= avail & AVAIL_TR; }
+        else if (c < 3 && !((r & 1) && (c & 1))) a |= AVAIL_TR;
+
+        /* most probable mode */
+        int ctx_l, ctx_t;
+        {
+            int nl = __shfl_sync(FULL, nb_mode, r), nt = __shfl_sync(FULL, nb_mode, 4 + c);
+            int prevl = n - 1, prevt = n - 4;
+            int ml = (int)(((prevl < 8 ? modes_lo : modes_hi) >> (4 * (prevl & 7))) & 15);
+            int mt = (int)(((prevt < 8 ? modes_lo : modes_hi) >> (4 * (prevt & 7))) & 15);
+            ctx_l = c > 0 ? ml : nl;
+            ctx_t = r > 0 ? mt : nt;
+        }
+        int mpred = imin(ctx_l, ctx_t);
+        if (mpred < 0) mpred = 2;
+
+        /* neighbours and input sample */
+        const pix_t *Rb = R + (4 * r) * 24 + 4 * c;
+        const int z = Rb[(a & AVAIL_TR) ? zoff : zoff_notr];
+        const int in = w->inp_y[(4 * r + py) * 16 + 4 * c + px];
+
+        /* the 32 source values, one per lane */
+        int sv;
+        {
+            int za = __shfl_sync(FULL, z, sa), zb = __shfl_sync(FULL, z, sb), zc = __shfl_sync(FULL, z, sc);
+            int t = z + __shfl_down_sync(FULL, z, 1);
+            int u4 = t + __shfl_down_sync(FULL, t, 2);
+            int sl = __shfl_sync(FULL, u4, 0), su = __shfl_sync(FULL, u4, 5);
+            if (kind == 0) sv = za;
+            else if (kind == 1) sv = (za + 2 * zb + zc + 2) >> 2;
+            else if (kind == 2) sv = (za + zb + 1) >> 1;
+            else if (kind == 3) sv = (za + 3 * zb + 2) >> 2;
+            else
+            {
+                int both = (a & 3) == 3;
+                sv = both ? (sl + su + 4) >> 3 : ((a & AVAIL_L) ? (sl + 2) >> 2 : ((a & AVAIL_T) ? (su + 2) >> 2 : 128));
+            }
+        }
+        /* nine SADs */
+        int d0 = iabs(in - __shfl_sync(FULL, sv, my_slots & 0xff));
+        int d1 = iabs(in - __shfl_sync(FULL, sv, (my_slots >> 8) & 0xff));
+        int d2 = iabs(in - __shfl_sync(FULL, sv, (my_slots >> 16) & 0xff));
+        int d3 = iabs(in - __shfl_sync(FULL, sv, my_slots >> 24));
+        int d4 = iabs(in - __shfl_sync(FULL, sv, my_slot4));
+        int r0 = d0 | (d1 << 16), r1 = d2 | (d3 << 16), r2 = g ? 0 : d4;
+#pragma unroll
+        for (int o = 8; o; o >>= 1)
+        {
+            r0 += __shfl_xor_sync(FULL, r0, o);
+            r1 += __shfl_xor_sync(FULL, r1, o);
+            r2 += __shfl_xor_sync(FULL, r2, o);
+        }
+        int q0 = __shfl_xor_sync(FULL, r0, 16), q1 = __shfl_xor_sync(FULL, r1, 16), q2 = __shfl_xor_sync(FULL, r2, 16);
+        int lo0 = g ? q0 : r0, lo1 = g ? q1 : r1, lo2 = g ? q2 : r2;      /* slots 0-4 */
+        int hi0 = g ? r0 : q0, hi1 = g ? r1 : q1;                          /* slots 5-8 */
+        int sads[9];
+        sads[0] = lo0 & 0xFFFF; sads[1] = (int)((unsigned)lo0 >> 16);
+        sads[2] = lo1 & 0xFFFF; sads[3] = (int)((unsigned)lo1 >> 16);
+        sads[4] = lo2;
+        sads[5] = hi0 & 0xFFFF; sads[6] = (int)((unsigned)hi0 >> 16);
+        sads[7] = hi1 & 0xFFFF; sads[8] = (int)((unsigned)hi1 >> 16);
+        int bk = 0, best_sad = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+        {
+            const int slot_mode = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 3 : (k == 3 ? 7 : (k == 4 ? 1 : (k == 5 ? 8 : (k == 6 ? 4 : (k == 7 ? 6 : 5)))))));
+            int ok = k == 0 ? 1 : (k < 4 ? (a & AVAIL_T) : (k < 6 ? (a & AVAIL_L) : ((a & 7) == 7)));
+            int cst = sads[k] + (slot_mode != mpred ? penalty : 0);
+            if (ok && cst < best_sad) { best_sad = cst; bk = k; }
+        }
+        const int mode = i4_slot_mode[bk];
+        if (n < 8) modes_lo |= (unsigned)mode << (4 * n); else modes_hi |= (unsigned)mode << (4 * (n - 8));
+        const int do_tq = best_sad > skip_thr;
+
+        /* prediction of the chosen mode, residual */
+        unsigned esel = bk < 4 ? e0 : (bk < 8 ? e1 : e2);
+        const int pred = __shfl_sync(FULL, sv, (esel >> (8 * (bk & 3))) & 0xff);
+        int outv = pred;
+        int qv = 0, dqv = 0, nzb = 0;
+        if (do_tq)
+        {
+            const int res = in - pred;
+            const int hb = lane & 16;      /* both half-warps run the same block redundantly */
+            /* forward: vertical pass -> (v = py, column px), horizontal pass -> (v = py, u = px) */
+            int f0 = __shfl_sync(FULL, res, hb + px), f1 = __shfl_sync(FULL, res, hb + 4 + px);
+            int f2 = __shfl_sync(FULL, res, hb + 8 + px), f3 = __shfl_sync(FULL, res, hb + 12 + px);
+            int t1 = fwd_row(py, f0, f1, f2, f3);
+            int g0 = __shfl_sync(FULL, t1, hb + 4 * py), g1 = __shfl_sync(FULL, t1, hb + 4 * py + 1);
+            int g2 = __shfl_sync(FULL, t1, hb + 4 * py + 2), g3 = __shfl_sync(FULL, t1, hb + 4 * py + 3);
+            int cf = (int16_t)fwd_row(px, g0, g1, g2, g3);
+            qv = (cf * qmul + (cf < 0 ? 0xFFFF - qrnd : qrnd)) >> 16;
+            dqv = (int16_t)(qv * dqmul);
+            nzb = (__ballot_sync(FULL, qv != 0) & 0xFFFF) != 0;
+            if (nzb)
+            {
+                /* inverse: horizontal pass over u for this v, then vertical pass over v */
+                int h0 = __shfl_sync(FULL, dqv, hb + 4 * py), h1 = __shfl_sync(FULL, dqv, hb + 4 * py + 1);
+                int h2 = __shfl_sync(FULL, dqv, hb + 4 * py + 2), h3 = __shfl_sync(FULL, dqv, hb + 4 * py + 3);
+                int t2 = (int16_t)inv_row(px, h0, h1, h2, h3);
+                int v0 = __shfl_sync(FULL, t2, hb + px), v1 = __shfl_sync(FULL, t2, hb + 4 + px);
+                int v2 = __shfl_sync(FULL, t2, hb + 8 + px), v3 = __shfl_sync(FULL, t2, hb + 12 + px);
+                int rr = (int16_t)((inv_row(py, v0, v1, v2, v3) + 32) >> 6);
+                outv = clip_u8(rr + pred);
+            }
+        }
+        if (lane < 16)
+        {
+            R[(4 * r + py + 1) * 24 + 4 * c + px + 4] = (pix_t)outv;
+            w->qv_y[n][ci] = (int16_t)qv;
+            w->dq_y[n][ci] = (int16_t)dqv;
+            if (lane == 0)
+            {
+                w->i4_mode[n] = (int8_t)mode;
+                w->i4_code[n] = (int8_t)(mode == mpred ? -1 : (mode > mpred ? mode - 1 : mode));
+            }
+        }
+        nz_mask = (nz_mask << 1) | nzb;
+        cost += best_sad;
+        __syncwarp();
+    }
+    /* hand the reconstruction over in the layout the rest of the MB code expects */
+    for (int i = lane; i < 64; i += 32)
+    {
+        int rr = i >> 2, cc = (i & 3) * 4;
+        *(uint32_t *)(w->i4rec + rr * 16 + cc) = *(const uint32_t *)(R + (rr + 1) * 24 + cc + 4);
+    }
+    __syncwarp();
+    *nz_mask_out = nz_mask;
+    return cost;
+}
+#else
+HDN int intra4_choose(MBState &s, int *nz_mask_out)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -622,7 +888,7 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
         const pix_t *blockin = w->inp_y + (c + r * 16) * 4;
         pix_t *block = w->i4rec + (c + r * 16) * 4;
 
-        /* 1. the 13 neighbours Z[-4..8] -> i4s[0..12] */
+        /* 1. the 13 neighbours Z[-4..8] -> i4z[0..12] */
         FOR_LANES(i, 13)
         {
             int k = i - 4, v = 0;
@@ -643,18 +909,20 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
                 int x = c * 4 + j;
                 v = r > 0 ? w->i4rec[(r * 4 - 1) * 16 + x] : w->top_y[x];
             }
-            w->i4s[i] = (pix_t)v;
+            w->i4z[i] = (pix_t)v;
         }
         WSYNC();
-        /* 2. filtered values -> i4s[13..38] */
-        FOR_LANES(i, 26)
+        /* 2. the 32 source values */
+        FOR_LANES(i, 32)
         {
-            const pix_t *Z = w->i4s + 4;
+            const pix_t *Z = w->i4z + 4;
             int v;
-            if (i < 11) { int k = i - 3; v = (Z[k - 1] + 2 * Z[k] + Z[k + 1] + 2) >> 2; }
-            else if (i < 23) { int k = i - 11 - 4; v = (Z[k] + Z[k + 1] + 1) >> 1; }
-            else if (i == 23) v = (Z[7] + 3 * Z[8] + 2) >> 2;
-            else if (i == 24) v = (Z[-3] + 3 * Z[-4] + 2) >> 2;
+            if (i < 4) v = Z[i - 4];
+            else if (i < 8) v = Z[i - 3];
+            else if (i < 19) { int k = i - 11; v = (Z[k - 1] + 2 * Z[k] + Z[k + 1] + 2) >> 2; }
+            else if (i < 29) { int k = i - 23; v = (Z[k] + Z[k + 1] + 1) >> 1; }
+            else if (i == 29) v = (Z[7] + 3 * Z[8] + 2) >> 2;
+            else if (i == 30) v = (Z[-3] + 3 * Z[-4] + 2) >> 2;
             else
             {
                 int sum = 0, cnt = 0;
@@ -662,7 +930,7 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
                 if (a & AVAIL_T) { sum += Z[1] + Z[2] + Z[3] + Z[4]; cnt++; }
                 v = cnt == 0 ? 128 : (cnt == 2 ? (sum + 4) >> 3 : (sum + 2) >> 2);
             }
-            w->i4s[13 + i] = (pix_t)v;
+            w->i4s[i] = (pix_t)v;
         }
         WSYNC();
         /* 3. nine SADs: lane (g,p) scores sample p for slots 0..4 (g = 0) or 5..8 (g = 1) */
@@ -768,13 +1036,14 @@ HD int intra4_choose(MBState &s, int *nz_mask_out)
     *nz_mask_out = nz_mask;
     return cost;
 }
+#endif
 
 /* ------------------------------------------------------------------------------
  * a9-a11: luma transform / quant / reconstruction of a non-I4x4 macroblock
  * (mb_write H:4423-4434 with h264e_transform_sub_quant_dequant H:2619).
  * Returns the 16-bit block mask (bit 15 = block 0).
  * ---------------------------------------------------------------------------- */
-HD int luma_tq_recon(MBState &s, int intra16)
+HDN int luma_tq_recon(MBState &s, int intra16)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -838,7 +1107,7 @@ HD int luma_tq_recon(MBState &s, int intra16)
 
 /* chroma transform / quant / recon of both planes (mb_write H:4443-4491).
  * Returns cbpc (0..2). */
-HD int chroma_tq_recon(MBState &s)
+HDN int chroma_tq_recon(MBState &s)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -927,13 +1196,27 @@ HD void clusters_update(int32_t *cl, int mv)
  * mb_write H:4378).  cl[] = mv_clusters as seen by this MB; updated in place.
  * Writes the MB's record, quantised levels and unfiltered reconstruction.
  * ---------------------------------------------------------------------------- */
-HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
+/* optional per-macroblock phase timing (developer builds with -DH264_PROFILE) */
+#if defined(H264_PROFILE) && H264_DEVICE
+#  define PROF_DECL long long prof_t0 = clock64(), prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#  define PROF_MARK(k) do { long long t_ = clock64(); prof_t[k] += t_ - prof_t0; prof_t0 = t_; } while (0)
+#  define PROF_STORE(fp, n, type) do { if (LANE_ID == 0 && (fp)->prof) { for (int k_ = 0; k_ < 8; k_++) (fp)->prof[(n) * 10 + k_] = (int)prof_t[k_]; \
+        (fp)->prof[(n) * 10 + 8] = (type); } } while (0)
+#else
+#  define PROF_DECL
+#  define PROF_MARK(k)
+#  define PROF_STORE(fp, n, type)
+#endif
+
+HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
 {
+    PROF_DECL;
     MBState s;
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
     s.avail = mb_avail(mbx, mby, fp->nmbx);
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
     s.pbest = w->store[0]; s.ptest = w->store[1];
+    s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     int16_t *coef = fp->coef + (size_t)(mby * fp->nmbx + mbx) * COEF_PER_MB;
     int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
@@ -941,8 +1224,10 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
     int used_cl = 0;
 
     mb_load(s);
+    PROF_MARK(0);
 
     if (fp->slice_type == SLICE_P) used_cl = !inter_choose(s, pmv, pmvd, cl, cand_sig, 0);
+    PROF_MARK(1);
 
     int nz_mask = 0;
     if (s.type >= 0)
@@ -960,6 +1245,7 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
             s.cost = cost16; s.type = MBT_I16;
             pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
         }
+        PROF_MARK(2);
         if (fp->speed < 2 || fp->slice_type != SLICE_P)
         {
             int nz4;
@@ -968,6 +1254,7 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
         }
     }
 
+    PROF_MARK(3);
     spec_out->mv0 = pmv[0];
     spec_out->flags = ((fp->slice_type == SLICE_P && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
     spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
@@ -982,6 +1269,7 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
         mc_chroma(s, s.type, pmv);
     }
 
+    PROF_MARK(4);
     /* ---- transform, quantisation, reconstruction ---- */
     int cbpl = 0, cbpc = 0;
     const int sy = fp->stride[0], sc = fp->stride[1];
@@ -1015,6 +1303,7 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
     }
     WSYNC();
 
+    PROF_MARK(5);
     /* ---- macroblock record ---- */
     const int type = s.type;
     if (type == MBT_I16 && cbpl) cbpl = 15;
@@ -1070,4 +1359,6 @@ HD void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int3
         }
     }
     WSYNC();
+    PROF_MARK(6);
+    PROF_STORE(fp, mby * fp->nmbx + mbx, type);
 }

@@ -9,29 +9,23 @@
 #include "h264_common.h"
 
 /* ------------------------------------------------------------------------------
- * unaligned 4-byte load from a frame in global memory (read-only this launch)
+ * unaligned 4-byte load through a generic pointer: the reference samples come either
+ * from the shared-memory search window of the macroblock (MBWork.win, the fast case) or
+ * directly from the reference frame in global memory (any position outside the window),
+ * so that both cases run the same code.
  * ---------------------------------------------------------------------------- */
-HD uint32_t ld4_ref(const pix_t *p)
+HD uint32_t ld4u(const pix_t *p)
 {
 #if H264_DEVICE
     uintptr_t a = (uintptr_t)p;
     const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
     unsigned sh = (unsigned)(a & 3) * 8;
-    uint32_t lo = __ldg(q);
-    uint32_t hi = sh ? __ldg(q + 1) : 0;
-    return __funnelshift_r(lo, hi, sh);
+    return __funnelshift_r(q[0], q[1], sh);
 #else
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 #endif
 }
-HD int ldpx(const pix_t *p)
-{
-#if H264_DEVICE
-    return (int)__ldg(p);
-#else
-    return (int)*p;
-#endif
-}
+HD int ldpx(const pix_t *p) { return (int)*p; }
 HD uint32_t ld4_sm(const pix_t *p) { return *(const uint32_t *)p; }   /* 4-aligned shared/local */
 
 HD int sad4(uint32_t a, uint32_t b)      /* sum of |a_i - b_i| over four packed bytes */
@@ -44,25 +38,37 @@ HD int sad4(uint32_t a, uint32_t b)      /* sum of |a_i - b_i| over four packed 
     return s;
 #endif
 }
+HD uint32_t avg4(uint32_t a, uint32_t b)  /* per-byte (a + b + 1) >> 1 */
+{
+#if H264_DEVICE
+    return __vavgu4(a, b);
+#else
+    uint32_t o = 0;
+    for (int k = 0; k < 4; k++) o |= ((((a >> (8 * k)) & 255) + ((b >> (8 * k)) & 255) + 1) >> 1) << (8 * k);
+    return o;
+#endif
+}
+HD void unpack4(uint32_t v, int *o) { o[0] = v & 255; o[1] = (v >> 8) & 255; o[2] = (v >> 16) & 255; o[3] = v >> 24; }
+HD uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 
 /* ------------------------------------------------------------------------------
- * a1: SAD of a w x h block of a frame against the cached input MB (stride 16).
- * (sad_block H:2162, h264e_sad_mb_unlaign_wh H:2189). w, h in {8,16}.
+ * a1: SAD of a w x h block (window or frame, any alignment) against the cached input
+ * MB (stride 16).  (sad_block H:2162, h264e_sad_mb_unlaign_wh H:2189). w, h in {8,16}.
  * Returns the warp-uniform total.
  * ---------------------------------------------------------------------------- */
-HD int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int h)
+HDN int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int h)
 {
     int wq = w >> 2, acc = 0;
     FOR_LANES(i, wq * h)
     {
         int r = i / wq, c = (i - r * wq) * 4;
-        acc += sad4(ld4_ref(a + r * a_stride + c), ld4_sm(b16 + r * 16 + c));
+        acc += sad4(ld4u(a + r * a_stride + c), ld4_sm(b16 + r * 16 + c));
     }
     return wsum(acc);
 }
 
 /* SAD of two stride-16 blocks in the working set */
-HD int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
+HDN int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
 {
     int wq = w >> 2, acc = 0;
     FOR_LANES(i, wq * h)
@@ -74,16 +80,14 @@ HD int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
 }
 
 /* a1: four 8x8 quadrant SADs (TL, TR, BL, BR) of a 16x16 block + their sum
- * (h264e_sad_mb_unlaign_8x8 H:2178).  `a` may be a frame (global) or a stride-16
- * working buffer (a_is_frame = 0). */
-HD int sad_mb_quad(const pix_t *a, int a_stride, int a_is_frame, const pix_t *b16, int sad4out[4])
+ * (h264e_sad_mb_unlaign_8x8 H:2178). */
+HDN int sad_mb_quad(const pix_t *a, int a_stride, const pix_t *b16, int sad4out[4])
 {
     int q01 = 0, q23 = 0;    /* two 16-bit lanes each: an 8x8 SAD is <= 16320 */
     FOR_LANES(i, 64)
     {
         int r = i >> 2, c = (i & 3) * 4;
-        uint32_t av = a_is_frame ? ld4_ref(a + r * a_stride + c) : ld4_sm(a + r * a_stride + c);
-        int s = sad4(av, ld4_sm(b16 + r * 16 + c));
+        int s = sad4(ld4u(a + r * a_stride + c), ld4_sm(b16 + r * 16 + c));
         s <<= (c & 8) ? 16 : 0;
         if (r < 8) q01 += s; else q23 += s;
     }
@@ -95,81 +99,142 @@ HD int sad_mb_quad(const pix_t *a, int a_stride, int a_is_frame, const pix_t *b1
 }
 
 /* ------------------------------------------------------------------------------
- * a2: luma sub-pel sample.  p addresses the integer sample, (dx,dy) the quarter
- * offsets 0..3.  Six-tap (1,-5,20,20,-5,1) half-pel, centre half-pel from 16-bit
- * horizontal intermediates, quarter positions as rounded averages -- the sample
- * definitions of H:1971-2130 restated per output sample.
+ * a2: luma sub-pel interpolation.  Six-tap (1,-5,20,20,-5,1) half-pel, centre half-pel
+ * from 16-bit horizontal intermediates, quarter positions as rounded averages of the two
+ * nearest integer / half samples (H:1971-2130, ITU-T H.264 8.4.2.2.1).  Block functions:
+ * each lane produces 8 output samples from packed words, dst stride 16.
  * ---------------------------------------------------------------------------- */
 HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
-HD int lpf_h(const pix_t *p) { return tap6(ldpx(p - 2), ldpx(p - 1), ldpx(p), ldpx(p + 1), ldpx(p + 2), ldpx(p + 3)); }
-HD int lpf_v(const pix_t *p, int s) { return tap6(ldpx(p - 2 * s), ldpx(p - s), ldpx(p), ldpx(p + s), ldpx(p + 2 * s), ldpx(p + 3 * s)); }
-HD int half_h(const pix_t *p) { return clip_u8((lpf_h(p) + 16) >> 5); }
-HD int half_v(const pix_t *p, int s) { return clip_u8((lpf_v(p, s) + 16) >> 5); }
-HD int half_d(const pix_t *p, int s)
-{
-    int t = tap6((int16_t)lpf_h(p - 2 * s), (int16_t)lpf_h(p - s), (int16_t)lpf_h(p),
-                 (int16_t)lpf_h(p + s), (int16_t)lpf_h(p + 2 * s), (int16_t)lpf_h(p + 3 * s));
-    return clip_u8((t + 512) >> 10);
-}
-HD int qpel_sample(const pix_t *p, int s, int dx, int dy)
-{
-    int a, b;
-    if (!(dx | dy)) return ldpx(p);
-    if (dy == 0) { a = half_h(p); if (dx == 2) return a; b = ldpx(p + (dx >> 1)); return (a + b + 1) >> 1; }
-    if (dx == 0) { a = half_v(p, s); if (dy == 2) return a; b = ldpx(p + (dy >> 1) * s); return (a + b + 1) >> 1; }
-    if (dx == 2 && dy == 2) return half_d(p, s);
-    if (dx == 2) { a = half_d(p, s); b = half_h(p + (dy >> 1) * s); return (a + b + 1) >> 1; }
-    if (dy == 2) { a = half_d(p, s); b = half_v(p + (dx >> 1), s); return (a + b + 1) >> 1; }
-    a = half_h(p + (dy >> 1) * s);
-    b = half_v(p + (dx >> 1), s);
-    return (a + b + 1) >> 1;
-}
 
-/* Interpolate a w x h block at absolute quarter-pel position (qx,qy) of plane `ref`
- * into dst (stride 16).  (interpolate_luma H:4905 + h264e_qpel_interpolate_luma H:2079) */
-HD void interp_luma_block(const pix_t *ref, int stride, int qx, int qy, int w, int h, pix_t *dst)
-{
-    const pix_t *src = ref + (qy >> 2) * stride + (qx >> 2);
-    int dx = qx & 3, dy = qy & 3;
-    if (!(dx | dy))
-    {
-        int wq = w >> 2;
-        FOR_LANES(i, wq * h)
-        {
-            int r = i / wq, c = (i - r * wq) * 4;
-            *(uint32_t *)(dst + r * 16 + c) = ld4_ref(src + r * stride + c);
-        }
-        return;
-    }
-    FOR_LANES(i, w * h)
-    {
-        int r = i / w, c = i - r * w;
-        dst[r * 16 + c] = (pix_t)qpel_sample(src + r * stride + c, stride, dx, dy);
-    }
-}
-
-/* rounded average of two stride-16 blocks (h264e_qpel_average_wh_align H:2065);
- * dst may alias either source (element-wise) */
-HD void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int h)
+HDN void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
     int wq = w >> 2;
     FOR_LANES(i, wq * h)
     {
         int r = i / wq, c = (i - r * wq) * 4;
-        uint32_t a = ld4_sm(s0 + r * 16 + c), b = ld4_sm(s1 + r * 16 + c);
-#if H264_DEVICE
-        *(uint32_t *)(dst + r * 16 + c) = __vavgu4(a, b);
-#else
-        uint32_t o = 0;
-        for (int k = 0; k < 4; k++) o |= ((((a >> (8 * k)) & 255) + ((b >> (8 * k)) & 255) + 1) >> 1) << (8 * k);
-        *(uint32_t *)(dst + r * 16 + c) = o;
-#endif
+        *(uint32_t *)(dst + r * 16 + c) = ld4u(src + r * ss + c);
     }
+}
+
+/* horizontal half samples b: lane = (row, 8-sample segment) */
+HDN void half_h_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+{
+    int segs = w >> 3;
+    FOR_LANES(i, segs * h)
+    {
+        int r = i / segs, x0 = (i - r * segs) * 8;
+        const pix_t *p = src + r * ss + x0 - 2;
+        int b[16];
+        unpack4(ld4u(p), b); unpack4(ld4u(p + 4), b + 4); unpack4(ld4u(p + 8), b + 8); unpack4(ld4u(p + 12), b + 12);
+        int o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = clip_u8((tap6(b[j], b[j + 1], b[j + 2], b[j + 3], b[j + 4], b[j + 5]) + 16) >> 5);
+        *(uint32_t *)(dst + r * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
+        *(uint32_t *)(dst + r * 16 + x0 + 4) = pack4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+/* vertical half samples h: lane = (4-sample column group, row pair) */
+HDN void half_v_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+{
+    int wq = w >> 2;
+    FOR_LANES(i, wq * (h >> 1))
+    {
+        int rp = i / wq, x0 = (i - rp * wq) * 4, y0 = rp * 2;
+        int b[7][4];
+#pragma unroll
+        for (int k = 0; k < 7; k++) unpack4(ld4u(src + (y0 - 2 + k) * ss + x0), b[k]);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++)
+        {
+            int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = clip_u8((tap6(b[rr][j], b[rr + 1][j], b[rr + 2][j], b[rr + 3][j], b[rr + 4][j], b[rr + 5][j]) + 16) >> 5);
+            *(uint32_t *)(dst + (y0 + rr) * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+/* centre half samples j: same lane mapping; 7 rows of 16-bit horizontal intermediates */
+HDN void half_d_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+{
+    int wq = w >> 2;
+    FOR_LANES(i, wq * (h >> 1))
+    {
+        int rp = i / wq, x0 = (i - rp * wq) * 4, y0 = rp * 2;
+        int t[7][4];
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+        {
+            const pix_t *p = src + (y0 - 2 + k) * ss + x0 - 2;
+            int b[12];
+            unpack4(ld4u(p), b); unpack4(ld4u(p + 4), b + 4); unpack4(ld4u(p + 8), b + 8);
+#pragma unroll
+            for (int j = 0; j < 4; j++) t[k][j] = (int16_t)tap6(b[j], b[j + 1], b[j + 2], b[j + 3], b[j + 4], b[j + 5]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++)
+        {
+            int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = clip_u8((tap6(t[rr][j], t[rr + 1][j], t[rr + 2][j], t[rr + 3][j], t[rr + 4][j], t[rr + 5][j]) + 512) >> 10);
+            *(uint32_t *)(dst + (y0 + rr) * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+/* dst = avg(dst, other) where `other` is any-alignment source (window / frame / stride-16 buffer) */
+HDN void average_into(pix_t *dst, const pix_t *other, int os, int w, int h)
+{
+    int wq = w >> 2;
+    FOR_LANES(i, wq * h)
+    {
+        int r = i / wq, c = (i - r * wq) * 4;
+        *(uint32_t *)(dst + r * 16 + c) = avg4(ld4_sm(dst + r * 16 + c), ld4u(other + r * os + c));
+    }
+}
+
+/* rounded average of two stride-16 blocks (h264e_qpel_average_wh_align H:2065);
+ * dst may alias either source (element-wise) */
+HDN void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int h)
+{
+    int wq = w >> 2;
+    FOR_LANES(i, wq * h)
+    {
+        int r = i / wq, c = (i - r * wq) * 4;
+        *(uint32_t *)(dst + r * 16 + c) = avg4(ld4_sm(s0 + r * 16 + c), ld4_sm(s1 + r * 16 + c));
+    }
+}
+
+/* Interpolate a w x h block whose integer sample position is `src` (stride ss) at quarter
+ * offsets (dx,dy) into dst (stride 16); tmp = 256-byte scratch.
+ * (interpolate_luma H:4905 + h264e_qpel_interpolate_luma H:2079) */
+HDN void interp_luma_block(const pix_t *src, int ss, int dx, int dy, int w, int h, pix_t *dst, pix_t *tmp)
+{
+    if (!(dx | dy)) { copy_block(src, ss, dst, w, h); return; }
+    if (dy == 0)
+    {
+        half_h_block(src, ss, dst, w, h);
+        if (dx != 2) { WSYNC(); average_into(dst, src + (dx >> 1), ss, w, h); }
+        return;
+    }
+    if (dx == 0)
+    {
+        half_v_block(src, ss, dst, w, h);
+        if (dy != 2) { WSYNC(); average_into(dst, src + (dy >> 1) * ss, ss, w, h); }
+        return;
+    }
+    if (dx == 2 && dy == 2) { half_d_block(src, ss, dst, w, h); return; }
+    if (dx == 2) { half_d_block(src, ss, dst, w, h); half_h_block(src + (dy >> 1) * ss, ss, tmp, w, h); }
+    else if (dy == 2) { half_d_block(src, ss, dst, w, h); half_v_block(src + (dx >> 1), ss, tmp, w, h); }
+    else { half_h_block(src + (dy >> 1) * ss, ss, dst, w, h); half_v_block(src + (dx >> 1), ss, tmp, w, h); }
+    WSYNC();
+    average_into(dst, tmp, 16, w, h);
 }
 
 /* a3: chroma 1/8-pel bilinear block (h264e_qpel_interpolate_chroma H:2133).
  * src addresses the integer sample of the block's top-left, (dx,dy) in 0..7. */
-HD void interp_chroma_block(const pix_t *src, int stride, int dx, int dy, int w, int h, pix_t *dst)
+HDN void interp_chroma_block(const pix_t *src, int stride, int dx, int dy, int w, int h, pix_t *dst)
 {
     int a = (8 - dx) * (8 - dy), b = dx * (8 - dy), c = (8 - dx) * dy, d = dx * dy;
     FOR_LANES(i, w * h)
@@ -188,7 +253,7 @@ HD void interp_chroma_block(const pix_t *src, int stride, int dx, int dy, int w,
  * out[v + 4u] = coefficient with vertical frequency v and horizontal frequency u
  * (FwdTransformResidual4x42 H:2385, TRANSPOSE_BLOCK 1).
  * ---------------------------------------------------------------------------- */
-HD void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *out)
+HDN void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *out)
 {
     int t[16];
 #pragma unroll
@@ -218,7 +283,7 @@ HD void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *out
 
 /* a11: inverse core transform of dq[] (same transposed layout) added to pred and
  * clipped (TransformResidual4x4 H:2436 + h264e_transform_add H:2638). */
-HD void inv4x4_add(const int16_t *dq, const pix_t *pred, pix_t *out, int out_stride)
+HDN void inv4x4_add(const int16_t *dq, const pix_t *pred, pix_t *out, int out_stride)
 {
     int t[16];
 #pragma unroll
@@ -256,7 +321,7 @@ HD void copy4x4(const pix_t *pred, pix_t *out, int out_stride)
 HD int quant_class(int i) { return ((i & 1) + ((i >> 2) & 1)) * 2; }
 
 /* "all coefficients from i0 on are small" test against 8 thresholds (is_zero H:2491) */
-HD int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
+HDN int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
 {
     for (int i = i0; i < 16; i++)
     {
@@ -268,7 +333,7 @@ HD int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
 
 /* a9: dead-zone quantiser + dequantiser of one 4x4 block, coefficients i0..15
  * (inner loop of quantize(), H:2567-2585).  Returns 1 when any level is non-zero. */
-HD int quant4x4(int16_t *dq, int16_t *qv, int i0, const uint16_t *qdat)
+HDN int quant4x4(int16_t *dq, int16_t *qv, int i0, const uint16_t *qdat)
 {
     int nz = 0;
     int rnd = qdat[6];
@@ -295,7 +360,7 @@ HD void had4(int a, int b, int c, int d, int *o)
 /* a10: luma DC path of an Intra16x16 MB (h264e_quant_luma_dc H:2344):
  * dc[16] = DC transform coefficients of the 16 blocks (raster);
  * out: qdc[16] quantised levels, dq0[16] dequantised DC per block.  Serial (one lane). */
-HD void luma_dc_quant(const int16_t *dc, int16_t *qdc, int16_t *dq0, const uint16_t *qdat)
+HDN void luma_dc_quant(const int16_t *dc, int16_t *qdc, int16_t *dq0, const uint16_t *qdat)
 {
     int t[16], x[16], o[4];
     for (int i = 0; i < 4; i++) { had4(dc[i], dc[i + 4], dc[i + 8], dc[i + 12], o); for (int k = 0; k < 4; k++) t[4 * i + k] = (int16_t)o[k]; }
@@ -317,7 +382,7 @@ HD void luma_dc_quant(const int16_t *dc, int16_t *qdc, int16_t *dq0, const uint1
 
 /* a10: chroma DC path of one plane (h264e_quant_chroma_dc H:2355). Returns 1 when any
  * quantised DC level is non-zero. */
-HD int chroma_dc_quant(const int16_t *dc, int16_t *qdc, int16_t *dq0, const uint16_t *qdat)
+HDN int chroma_dc_quant(const int16_t *dc, int16_t *qdc, int16_t *dq0, const uint16_t *qdat)
 {
     int a = dc[0], b = dc[1], c = dc[2], d = dc[3], x[4], y[4];
     x[0] = (int16_t)(a + b + c + d); x[1] = (int16_t)(a - b + c - d);
@@ -353,7 +418,7 @@ HD int dc_pred(const pix_t *left, const pix_t *top, int n, int log2n)
 
 /* a7: 16x16 luma prediction, mode 0=V 1=H 2=DC (h264e_intra_predict_16x16 H:1677).
  * left/top are NULL when unavailable. */
-HD void intra16_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
+HDN void intra16_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
 {
     int dc = 0;
     if (mode == 2) dc = dc_pred(left, top, 16, 4) * 0x01010101u;
@@ -371,7 +436,7 @@ HD void intra16_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
 /* a7: 8x8 chroma prediction for both planes (h264e_intra_predict_chroma H:1716).
  * dst: U at +0, V at +8, stride 16.  left/top: U 0..7, V 8..15, NULL when unavailable.
  * mode uses the LUMA numbering 0=V 1=H 2=DC, as the reference calls it (H:5784). */
-HD void intra_chroma_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
+HDN void intra_chroma_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
 {
     FOR_LANES(i, 32)
     {

@@ -33,7 +33,7 @@ HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 }
 
 /* pass 0 / I frames */
-HD void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
+HDN void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
 {
     const int n = y * fp->nmbx + x;
     int32_t cl[2] = {0, 0};
@@ -54,13 +54,14 @@ HD void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
 }
 
 /* candidate stage only: returns 1 when its outcome equals the recorded one */
-HD int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const int32_t cl[2], const MBSpec &old)
+HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const int32_t cl[2], const MBSpec &old)
 {
     MBState s;
     s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
     s.avail = mb_avail(x, y, fp->nmbx);
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
     s.pbest = w->store[0]; s.ptest = w->store[1];
+    s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     int32_t pmv[4], pmvd[4], sig[4] = {0, 0, 0, 0};
     mb_load(s);
     int r = inter_choose(s, pmv, pmvd, cl, sig, 1);
@@ -69,7 +70,7 @@ HD int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const int
 }
 
 /* repair sweep `pass` (>= 1) */
-HD void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
     const MBSpec old = fp->spec[n];
@@ -140,7 +141,7 @@ HD void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 
 /* Sequential replay of the cluster trajectory by one warp (lane 0 walks, the warp stages
  * 32 records at a time).  Writes cl_true[], the end state, and returns the dirty count. */
-HD int wave_replay(const FrameParams *fp, MBWork *w)
+HDN int wave_replay(const FrameParams *fp, MBWork *w)
 {
     const int nmb = fp->nmbx * fp->nmby;
     int32_t c[2];
@@ -191,7 +192,7 @@ HD int wave_replay(const FrameParams *fp, MBWork *w)
 
 /* Executed once per pass by the last row to finish: returns the next pass number or FS_DONE.
  * On FS_DONE the cluster state is committed for the next frame. */
-HD int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)
+HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)
 {
     int next;
     if (fp->slice_type != SLICE_P) return FS_DONE;

@@ -225,6 +225,7 @@ struct h264b200_ctx
     int32_t *d_clusters;
     MBSpec *d_spec; int32_t *d_cl_true; int *d_changed_pass; int *d_fsync;
     int have_traj; int stats[4];
+    int *d_prof;
     int *d_progress;              /* 2 * nmby */
     uint32_t *h_out_words;        /* pinned */
     int *h_out_info;              /* pinned */
@@ -304,6 +305,10 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
     CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
     CK(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
+#ifdef H264_PROFILE
+    CK(cudaMalloc(&c->d_prof, sizeof(int) * 10 * c->nmb));
+    CK(cudaMemset(c->d_prof, 0, sizeof(int) * 10 * c->nmb));
+#endif
     CK(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
     CK(cudaMallocHost(&c->h_out_info, 64));
     *out = c;
@@ -370,6 +375,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->hdr_bits = p.hdr_bits;
     fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->changed_pass = c->d_changed_pass; fp->fsync = c->d_fsync;
     fp->max_passes = 4096;
+    fp->prof = c->d_prof;
     fp->spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
 }
 
@@ -496,6 +502,13 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
 }
 
 extern "C" void h264b200_last_timing(float out_ms[4]) { for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
+/* developer builds (-DH264_PROFILE): per-MB phase cycles of the last frame, [nmb][10] ints */
+extern "C" int h264b200_get_profile(h264b200_ctx *c, int *out)
+{
+    if (!c->d_prof) return -1;
+    cudaMemcpy(out, c->d_prof, sizeof(int) * 10 * c->nmb, cudaMemcpyDeviceToHost);
+    return 0;
+}
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "cuda-sm_100a"; }

@@ -1,0 +1,39 @@
+"""Developer tool: per-macroblock phase timing on the GPU (needs libh264lab_b200_prof.so,
+`make -C h264-lab_b200 libh264lab_b200_prof.so`).  Prints, for the last frame encoded, the
+distribution of macroblock latencies by type and the share of each phase."""
+import ctypes as C
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import content  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "h264-lab_b200", "binding.py"))
+B = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(B)
+L = B.Library(os.path.join(ROOT, "h264-lab_b200", "libh264lab_b200_prof.so"))
+L.lib.H264E_b200_ctx.restype = C.c_void_p
+w, h, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+kind = sys.argv[4] if len(sys.argv) > 4 else "panning"
+fr = getattr(content, kind)(w, h, n)
+enc = B.Encoder(L, w, h, 60)
+rp = enc.run_param(qp=28)
+nmb = ((w + 15) // 16) * ((h + 15) // 16)
+names = ["load", "inter", "i16", "i4", "chroma_pred", "tq_recon", "record", "-"]
+for i in range(n):
+    enc.encode(fr[i].copy(), rp)
+    prof = np.zeros((nmb, 10), np.int32)
+    L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
+    tot = prof[:, :7].sum(1)
+    tm = (C.c_float * 4)()
+    L.lib.h264b200_last_timing(tm)
+    print("frame %d: k_encode %.2f ms; MB cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f  (sum/1.9GHz = %.1f ms serial)" % (
+        i, tm[1], tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), np.percentile(tot, 99), tot.max(), tot.sum() / 1.9e6))
+    for t in sorted(set(prof[:, 8].tolist())):
+        m = prof[:, 8] == t
+        ph = prof[m][:, :7].mean(0)
+        print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(7)))
