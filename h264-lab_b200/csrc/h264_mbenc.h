@@ -9,8 +9,24 @@
 #include "h264_common.h"
 #include "h264_pixel.h"
 
+/* optional per-macroblock phase timing (developer builds with -DH264_PROFILE) */
+#if defined(H264_PROFILE) && H264_DEVICE
+#  define PROF_N 16
+#  define PROF_MEMBERS long long prof_t0; int prof[PROF_N];
+#  define PROF_INIT(s) do { (s).prof_t0 = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
+#  define PROF_MARK(s, k) do { long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
+#  define PROF_STORE(s, fp, n, type) do { if (LANE_ID == 0 && (fp)->prof) { for (int k_ = 0; k_ < PROF_N; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
+        (fp)->prof[(n) * 20 + 16] = (type); } } while (0)
+#else
+#  define PROF_MEMBERS
+#  define PROF_INIT(s)
+#  define PROF_MARK(s, k)
+#  define PROF_STORE(s, fp, n, type)
+#endif
+
 struct MBState   /* warp-uniform registers of the macroblock being encoded */
 {
+    PROF_MEMBERS
     const FrameParams *fp;
     MBWork *w;
     int mbx, mby, avail;
@@ -233,6 +249,9 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
     int mv = *pmv;
     uint32_t cache[8];
     int dir, cloop, dir_prev, cost, v;
+    /* costs of the 8 integer neighbours of `nb_center`, evaluated together the first time
+     * the replayed search asks for one of them */
+    int nb[8], nb_center = 0, nb_valid = 0;
 
     for (;;)   /* "restart" loop */
     {
@@ -244,9 +263,13 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
             v = mv_pack(mv_x(mv) + dx, mv_y(mv) + dy);
             if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]) && cache[dir] == 0xffffu)
             {
-                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
-                cost = sad_frame_wh(rp, rs, inp, bw, bh);
-                cost += mv_cost(v, mv_pred, lam);
+                if (!nb_valid || nb_center != mv)
+                {
+                    rp = ref_at(s, (mv_x(mv) >> 2) + ppx - 1, (mv_y(mv) >> 2) + ppy - 1, bw + 2, bh + 2, &rs);
+                    sad_nb8(rp + rs + 1, rs, inp, bw, bh, nb);
+                    nb_center = mv; nb_valid = 1;
+                }
+                cost = nb[dir] + mv_cost(v, mv_pred, lam);
                 cache[dir] = (uint32_t)cost & 0xffffu;
                 if (cost < min_sad)
                 {
@@ -273,78 +296,67 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
             v = mv_pack(mv_x(mv) + sdx, mv_y(mv) + pdy);
             if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]))
             {
-                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
-                cost = sad_frame_wh(rp, rs, inp, bw, bh);
-                cost += mv_cost(v, mv_pred, lam);
+                if (!nb_valid || nb_center != mv)
+                {
+                    rp = ref_at(s, (mv_x(mv) >> 2) + ppx - 1, (mv_y(mv) >> 2) + ppy - 1, bw + 2, bh + 2, &rs);
+                    sad_nb8(rp + rs + 1, rs, inp, bw, bh, nb);
+                    nb_center = mv; nb_valid = 1;
+                }
+                cost = nb[4 + (sdx < 0 ? 1 : 0) + (pdy < 0 ? 2 : 0)] + mv_cost(v, mv_pred, lam);
                 if (cost < min_sad) { mv = v; min_sad = cost; continue; }
             }
         }
         break;
     }
 
-    rp = ref_at(s, (mv_x(mv) >> 2) + ppx, (mv_y(mv) >> 2) + ppy, bw, bh, &rs);
+    rp = ref_at(s, (mv_x(mv) >> 2) + ppx - 1, (mv_y(mv) >> 2) + ppy - 1, bw + 2, bh + 2, &rs);
+    rp += rs + 1;                       /* integer sample position of the block */
     copy_block(rp, rs, buf[0], bw, bh);
-    WSYNC();
     pix_t *best = buf[0];
 
     if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
-        int vbest = mv;
-        pix_t *scratch = buf[0], *hpel = buf[1], *hpel1 = buf[2], *hpel2 = buf[3];
+        /* 7 sub-pel probes around the integer optimum (H:5083-5174): three half-sample blocks,
+         * four quarter-sample averages; costs evaluated together, decision replayed in order */
         uint32_t minsad1 = cache[1], minsad2 = cache[3];
         int sqx = -1, sqy = 0, pqx = 0, pqy = -1;       /* secondary / primary quarter steps */
         if (cache[3] >= cache[2]) { pqy = 1; minsad2 = cache[2]; }
         if (cache[1] >= cache[0]) { sqx = 1; minsad1 = cache[0]; }
         if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
-        int dgx = pqx + sqx, dgy = pqy + sqy;
-#pragma unroll 1
+        const int dgx = pqx + sqx, dgy = pqy + sqy;
+        pix_t *I = buf[0], *C = buf[1], *H1 = buf[2], *H2 = buf[3];
+        int hx, hy;
+        /* half-sample position mv + 2q: integer part floor((2q)/4), fraction (2q) & 3 */
+        hx = 2 * pqx; hy = 2 * pqy;
+        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, H1, tmp);
+        hx = 2 * sqx; hy = 2 * sqy;
+        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, H2, tmp);
+        hx = 2 * dgx; hy = 2 * dgy;
+        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, C, tmp);
+        WSYNC();
+        int sq[7];
+        sad_qpel7(I, H1, H2, C, inp, bw, bh, sq);
+        int vbest = mv, ibest = -1;
+#pragma unroll
         for (int i = 0; i < 7; i++)
         {
-            pix_t *ptest;
-            switch (i)
-            {
-            case 0:
-                v = mv_pack(mv_x(mv) + 2 * pqx, mv_y(mv) + 2 * pqy);
-                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
-                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel1, tmp);
-                break;
-            case 1:
-                v = mv_pack(mv_x(mv) + pqx, mv_y(mv) + pqy);
-                average_block(scratch, hpel1, ptest = hpel, bw, bh);
-                break;
-            case 2:
-                v = mv_pack(mv_x(mv) + 2 * sqx, mv_y(mv) + 2 * sqy);
-                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
-                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel2, tmp);
-                break;
-            case 3:
-                hpel = buf[1]; if (best == hpel) hpel = scratch;
-                v = mv_pack(mv_x(mv) + sqx, mv_y(mv) + sqy);
-                average_block(scratch, hpel2, ptest = hpel, bw, bh);
-                break;
-            case 4:
-                hpel = buf[1]; if (best == hpel) hpel = scratch;
-                v = mv_pack(mv_x(mv) + dgx, mv_y(mv) + dgy);
-                average_block(hpel1, hpel2, ptest = hpel, bw, bh);
-                break;
-            case 5:
-                if (best == hpel2) { hpel2 = scratch; hpel = buf[1]; }
-                v = mv_pack(mv_x(mv) + 2 * dgx, mv_y(mv) + 2 * dgy);
-                rp = ref_at(s, (mv_x(v) >> 2) + ppx, (mv_y(v) >> 2) + ppy, bw, bh, &rs);
-                interp_luma_block(rp, rs, mv_x(v) & 3, mv_y(v) & 3, bw, bh, ptest = hpel2, tmp);
-                break;
-            default:
-                hpel = buf[1]; if (best == hpel) hpel = scratch;
-                v = mv_pack(mv_x(mv) + pqx + dgx, mv_y(mv) + pqy + dgy);
-                average_block(hpel2, hpel1, ptest = hpel, bw, bh);
-                break;
-            }
-            WSYNC();
-            int sad_test = sad_sm_wh(ptest, inp, bw, bh) + mv_cost(v, mv_pred, lam);
-            if (sad_test < min_sad) { min_sad = sad_test; vbest = v; best = ptest; }
+            int ox = i == 0 ? 2 * pqx : (i == 1 ? pqx : (i == 2 ? 2 * sqx : (i == 3 ? sqx : (i == 4 ? dgx : (i == 5 ? 2 * dgx : pqx + dgx)))));
+            int oy = i == 0 ? 2 * pqy : (i == 1 ? pqy : (i == 2 ? 2 * sqy : (i == 3 ? sqy : (i == 4 ? dgy : (i == 5 ? 2 * dgy : pqy + dgy)))));
+            v = mv_pack(mv_x(mv) + ox, mv_y(mv) + oy);
+            int sad_test = sq[i] + mv_cost(v, mv_pred, lam);
+            if (sad_test < min_sad) { min_sad = sad_test; vbest = v; ibest = i; }
         }
         mv = vbest;
+        /* materialise the winning prediction (averages in place over an operand no longer needed) */
+        if (ibest == 0) best = H1;
+        else if (ibest == 2) best = H2;
+        else if (ibest == 5) best = C;
+        else if (ibest == 1) { average_block(I, H1, I, bw, bh); best = I; }
+        else if (ibest == 3) { average_block(I, H2, I, bw, bh); best = I; }
+        else if (ibest == 4) { average_block(H1, H2, H1, bw, bh); best = H1; }
+        else if (ibest == 6) { average_block(C, H1, C, bw, bh); best = C; }
     }
+    WSYNC();
     *pmv = mv;
     *pbest = best;
     return min_sad;
@@ -417,6 +429,7 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
     /* skip predictor (me_mv_medianpredictor_get_skip H:3877) */
     int mvp16 = mvp_get(w, s.avail, 0, 0, 4, 4);
     win_load(s, s.mbx * 16 + ((mv_x(mvp16) + 1) >> 2), s.mby * 16 + ((mv_y(mvp16) + 1) >> 2));
+    PROF_MARK(s, 1);
     int mv_skip = 0;
     if (!(~s.avail & (AVAIL_L | AVAIL_T)) && w->mvp_left[0] != 0 && w->mvp_top[0] != 0) mv_skip = mvp16;
     s.mv_skip_pred = mv_skip;
@@ -467,6 +480,7 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
         }
     }
 
+    PROF_MARK(s, 2);
     /* candidate start points (H:5370-5386) */
     cand[ncand++] = mvp16;
     cand[ncand++] = 0;
@@ -506,6 +520,7 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
     cand_sig[3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
     if (cand_only) return 2;
     sad_best += mv_cost(mv_best, mvp16, fp->lambda_mv_q4);
+    PROF_MARK(s, 3);
 
     /* partition modes (H:5416-5510) */
     pix_t *store = w->store[0];
@@ -579,6 +594,7 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
         }
         IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_left[i] = w->mvp_save[3 * i]; w->mvp_tl[i] = w->mvp_save[3 * i + 1]; w->mvp_top[i] = w->mvp_save[3 * i + 2]; } }
         WSYNC();
+        PROF_MARK(s, mb_type ? 5 : 4);
         if (part_sad < s.cost)
         {
             pix_t *t = pred_best; pred_best = pred_test; pred_test = t;
@@ -1196,21 +1212,8 @@ HD void clusters_update(int32_t *cl, int mv)
  * mb_write H:4378).  cl[] = mv_clusters as seen by this MB; updated in place.
  * Writes the MB's record, quantised levels and unfiltered reconstruction.
  * ---------------------------------------------------------------------------- */
-/* optional per-macroblock phase timing (developer builds with -DH264_PROFILE) */
-#if defined(H264_PROFILE) && H264_DEVICE
-#  define PROF_DECL long long prof_t0 = clock64(), prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#  define PROF_MARK(k) do { long long t_ = clock64(); prof_t[k] += t_ - prof_t0; prof_t0 = t_; } while (0)
-#  define PROF_STORE(fp, n, type) do { if (LANE_ID == 0 && (fp)->prof) { for (int k_ = 0; k_ < 8; k_++) (fp)->prof[(n) * 10 + k_] = (int)prof_t[k_]; \
-        (fp)->prof[(n) * 10 + 8] = (type); } } while (0)
-#else
-#  define PROF_DECL
-#  define PROF_MARK(k)
-#  define PROF_STORE(fp, n, type)
-#endif
-
 HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
 {
-    PROF_DECL;
     MBState s;
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
     s.avail = mb_avail(mbx, mby, fp->nmbx);
@@ -1223,11 +1226,12 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     int32_t cand_sig[4] = {0, 0, 0, 0};
     int used_cl = 0;
 
+    PROF_INIT(s);
     mb_load(s);
-    PROF_MARK(0);
+    PROF_MARK(s, 0);
 
     if (fp->slice_type == SLICE_P) used_cl = !inter_choose(s, pmv, pmvd, cl, cand_sig, 0);
-    PROF_MARK(1);
+    PROF_MARK(s, 6);
 
     int nz_mask = 0;
     if (s.type >= 0)
@@ -1245,7 +1249,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             s.cost = cost16; s.type = MBT_I16;
             pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
         }
-        PROF_MARK(2);
+        PROF_MARK(s, 7);
         if (fp->speed < 2 || fp->slice_type != SLICE_P)
         {
             int nz4;
@@ -1254,7 +1258,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         }
     }
 
-    PROF_MARK(3);
+    PROF_MARK(s, 8);
     spec_out->mv0 = pmv[0];
     spec_out->flags = ((fp->slice_type == SLICE_P && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
     spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
@@ -1269,7 +1273,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         mc_chroma(s, s.type, pmv);
     }
 
-    PROF_MARK(4);
+    PROF_MARK(s, 9);
     /* ---- transform, quantisation, reconstruction ---- */
     int cbpl = 0, cbpc = 0;
     const int sy = fp->stride[0], sc = fp->stride[1];
@@ -1303,7 +1307,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     }
     WSYNC();
 
-    PROF_MARK(5);
+    PROF_MARK(s, 10);
     /* ---- macroblock record ---- */
     const int type = s.type;
     if (type == MBT_I16 && cbpl) cbpl = 15;
@@ -1359,6 +1363,6 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         }
     }
     WSYNC();
-    PROF_MARK(6);
-    PROF_STORE(fp, mby * fp->nmbx + mbx, type);
+    PROF_MARK(s, 11);
+    PROF_STORE(s, fp, mby * fp->nmbx + mbx, type);
 }

@@ -58,10 +58,11 @@ HD uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)
  * ---------------------------------------------------------------------------- */
 HDN int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int h)
 {
-    int wq = w >> 2, acc = 0;
-    FOR_LANES(i, wq * h)
+    const int sh = w == 16 ? 2 : 1;      /* words per row: 4 or 2 */
+    int acc = 0;
+    FOR_LANES(i, h << sh)
     {
-        int r = i / wq, c = (i - r * wq) * 4;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
         acc += sad4(ld4u(a + r * a_stride + c), ld4_sm(b16 + r * 16 + c));
     }
     return wsum(acc);
@@ -70,10 +71,11 @@ HDN int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int 
 /* SAD of two stride-16 blocks in the working set */
 HDN int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
 {
-    int wq = w >> 2, acc = 0;
-    FOR_LANES(i, wq * h)
+    const int sh = w == 16 ? 2 : 1;
+    int acc = 0;
+    FOR_LANES(i, h << sh)
     {
-        int r = i / wq, c = (i - r * wq) * 4;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
         acc += sad4(ld4_sm(a16 + r * 16 + c), ld4_sm(b16 + r * 16 + c));
     }
     return wsum(acc);
@@ -98,6 +100,56 @@ HDN int sad_mb_quad(const pix_t *a, int a_stride, const pix_t *b16, int sad4out[
     return sad4out[0] + sad4out[1] + sad4out[2] + sad4out[3];
 }
 
+/* SADs of the eight integer neighbours of block position p in ONE pass (speculative
+ * evaluation for the greedy diamond of me_search: the search consumes them in the
+ * reference's order, so evaluating more positions than the reference changes nothing).
+ * out[0..3] = (+1,0) (-1,0) (0,+1) (0,-1); out[4..7] = (+1,+1) (-1,+1) (+1,-1) (-1,-1).
+ * A 16x16 SAD is <= 65280, so two fit one 32-bit accumulator. */
+HDN void sad_nb8(const pix_t *p, int ps, const pix_t *b16, int w, int h, int out[8])
+{
+    const int sh = w == 16 ? 2 : 1;
+    uint32_t a01 = 0, a23 = 0, a45 = 0, a67 = 0;
+    FOR_LANES(i, h << sh)
+    {
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
+        const pix_t *q = p + r * ps + c;
+        uint32_t in = ld4_sm(b16 + r * 16 + c);
+        uint32_t up_l = ld4u(q - ps - 1), up_c = ld4u(q - ps), up_r = ld4u(q - ps + 1);
+        uint32_t mi_l = ld4u(q - 1), mi_r = ld4u(q + 1);
+        uint32_t dn_l = ld4u(q + ps - 1), dn_c = ld4u(q + ps), dn_r = ld4u(q + ps + 1);
+        a01 += (uint32_t)sad4(mi_r, in) | ((uint32_t)sad4(mi_l, in) << 16);
+        a23 += (uint32_t)sad4(dn_c, in) | ((uint32_t)sad4(up_c, in) << 16);
+        a45 += (uint32_t)sad4(dn_r, in) | ((uint32_t)sad4(dn_l, in) << 16);
+        a67 += (uint32_t)sad4(up_r, in) | ((uint32_t)sad4(up_l, in) << 16);
+    }
+    a01 = (uint32_t)wsum((int)a01); a23 = (uint32_t)wsum((int)a23);
+    a45 = (uint32_t)wsum((int)a45); a67 = (uint32_t)wsum((int)a67);
+    out[0] = a01 & 0xFFFF; out[1] = a01 >> 16; out[2] = a23 & 0xFFFF; out[3] = a23 >> 16;
+    out[4] = a45 & 0xFFFF; out[5] = a45 >> 16; out[6] = a67 & 0xFFFF; out[7] = a67 >> 16;
+}
+
+/* SADs of the seven sub-pel probes of me_search in one pass, from the integer prediction I
+ * and the three half-sample blocks H1 (primary), H2 (secondary), C (diagonal):
+ * out = { H1, avg(I,H1), H2, avg(I,H2), avg(H1,H2), C, avg(C,H1) }  (H:5119-5161) */
+HDN void sad_qpel7(const pix_t *I, const pix_t *H1, const pix_t *H2, const pix_t *C, const pix_t *b16, int w, int h, int out[7])
+{
+    const int sh = w == 16 ? 2 : 1;
+    uint32_t a01 = 0, a23 = 0, a45 = 0, a6 = 0;
+    FOR_LANES(i, h << sh)
+    {
+        int r = i >> sh, o = r * 16 + (i & ((1 << sh) - 1)) * 4;
+        uint32_t in = ld4_sm(b16 + o), vi = ld4_sm(I + o), v1 = ld4_sm(H1 + o), v2 = ld4_sm(H2 + o), vc = ld4_sm(C + o);
+        a01 += (uint32_t)sad4(v1, in) | ((uint32_t)sad4(avg4(vi, v1), in) << 16);
+        a23 += (uint32_t)sad4(v2, in) | ((uint32_t)sad4(avg4(vi, v2), in) << 16);
+        a45 += (uint32_t)sad4(avg4(v1, v2), in) | ((uint32_t)sad4(vc, in) << 16);
+        a6 += (uint32_t)sad4(avg4(vc, v1), in);
+    }
+    a01 = (uint32_t)wsum((int)a01); a23 = (uint32_t)wsum((int)a23);
+    a45 = (uint32_t)wsum((int)a45); a6 = (uint32_t)wsum((int)a6);
+    out[0] = a01 & 0xFFFF; out[1] = a01 >> 16; out[2] = a23 & 0xFFFF; out[3] = a23 >> 16;
+    out[4] = a45 & 0xFFFF; out[5] = a45 >> 16; out[6] = a6;
+}
+
 /* ------------------------------------------------------------------------------
  * a2: luma sub-pel interpolation.  Six-tap (1,-5,20,20,-5,1) half-pel, centre half-pel
  * from 16-bit horizontal intermediates, quarter positions as rounded averages of the two
@@ -108,10 +160,10 @@ HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * 
 
 HDN void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
-    int wq = w >> 2;
-    FOR_LANES(i, wq * h)
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, h << sh)
     {
-        int r = i / wq, c = (i - r * wq) * 4;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
         *(uint32_t *)(dst + r * 16 + c) = ld4u(src + r * ss + c);
     }
 }
@@ -119,10 +171,10 @@ HDN void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 /* horizontal half samples b: lane = (row, 8-sample segment) */
 HDN void half_h_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
-    int segs = w >> 3;
-    FOR_LANES(i, segs * h)
+    const int sh = w == 16 ? 1 : 0;      /* 8-sample segments per row: 2 or 1 */
+    FOR_LANES(i, h << sh)
     {
-        int r = i / segs, x0 = (i - r * segs) * 8;
+        int r = i >> sh, x0 = (i & ((1 << sh) - 1)) * 8;
         const pix_t *p = src + r * ss + x0 - 2;
         int b[16];
         unpack4(ld4u(p), b); unpack4(ld4u(p + 4), b + 4); unpack4(ld4u(p + 8), b + 8); unpack4(ld4u(p + 12), b + 12);
@@ -137,10 +189,10 @@ HDN void half_h_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 /* vertical half samples h: lane = (4-sample column group, row pair) */
 HDN void half_v_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
-    int wq = w >> 2;
-    FOR_LANES(i, wq * (h >> 1))
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, (h >> 1) << sh)
     {
-        int rp = i / wq, x0 = (i - rp * wq) * 4, y0 = rp * 2;
+        int rp = i >> sh, x0 = (i & ((1 << sh) - 1)) * 4, y0 = rp * 2;
         int b[7][4];
 #pragma unroll
         for (int k = 0; k < 7; k++) unpack4(ld4u(src + (y0 - 2 + k) * ss + x0), b[k]);
@@ -158,10 +210,10 @@ HDN void half_v_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 /* centre half samples j: same lane mapping; 7 rows of 16-bit horizontal intermediates */
 HDN void half_d_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
-    int wq = w >> 2;
-    FOR_LANES(i, wq * (h >> 1))
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, (h >> 1) << sh)
     {
-        int rp = i / wq, x0 = (i - rp * wq) * 4, y0 = rp * 2;
+        int rp = i >> sh, x0 = (i & ((1 << sh) - 1)) * 4, y0 = rp * 2;
         int t[7][4];
 #pragma unroll
         for (int k = 0; k < 7; k++)
@@ -186,10 +238,10 @@ HDN void half_d_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 /* dst = avg(dst, other) where `other` is any-alignment source (window / frame / stride-16 buffer) */
 HDN void average_into(pix_t *dst, const pix_t *other, int os, int w, int h)
 {
-    int wq = w >> 2;
-    FOR_LANES(i, wq * h)
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, h << sh)
     {
-        int r = i / wq, c = (i - r * wq) * 4;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
         *(uint32_t *)(dst + r * 16 + c) = avg4(ld4_sm(dst + r * 16 + c), ld4u(other + r * os + c));
     }
 }
@@ -198,10 +250,10 @@ HDN void average_into(pix_t *dst, const pix_t *other, int os, int w, int h)
  * dst may alias either source (element-wise) */
 HDN void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int h)
 {
-    int wq = w >> 2;
-    FOR_LANES(i, wq * h)
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, h << sh)
     {
-        int r = i / wq, c = (i - r * wq) * 4;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
         *(uint32_t *)(dst + r * 16 + c) = avg4(ld4_sm(s0 + r * 16 + c), ld4_sm(s1 + r * 16 + c));
     }
 }

@@ -306,8 +306,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
     CK(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
 #ifdef H264_PROFILE
-    CK(cudaMalloc(&c->d_prof, sizeof(int) * 10 * c->nmb));
-    CK(cudaMemset(c->d_prof, 0, sizeof(int) * 10 * c->nmb));
+    CK(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
+    CK(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
 #endif
     CK(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
     CK(cudaMallocHost(&c->h_out_info, 64));
@@ -506,7 +506,7 @@ extern "C" void h264b200_last_timing(float out_ms[4]) { for (int i = 0; i < 4; i
 extern "C" int h264b200_get_profile(h264b200_ctx *c, int *out)
 {
     if (!c->d_prof) return -1;
-    cudaMemcpy(out, c->d_prof, sizeof(int) * 10 * c->nmb, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, c->d_prof, sizeof(int) * 20 * c->nmb, cudaMemcpyDeviceToHost);
     return 0;
 }
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }

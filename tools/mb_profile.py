@@ -23,17 +23,17 @@ fr = getattr(content, kind)(w, h, n)
 enc = B.Encoder(L, w, h, 60)
 rp = enc.run_param(qp=28)
 nmb = ((w + 15) // 16) * ((h + 15) // 16)
-names = ["load", "inter", "i16", "i4", "chroma_pred", "tq_recon", "record", "-"]
+names = ["load", "win", "skiptest", "cands", "search16", "parts", "inter_rest", "i16", "i4", "chroma_pred", "tq_recon", "record"]
 for i in range(n):
     enc.encode(fr[i].copy(), rp)
-    prof = np.zeros((nmb, 10), np.int32)
+    prof = np.zeros((nmb, 20), np.int32)
     L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
-    tot = prof[:, :7].sum(1)
+    tot = prof[:, :12].sum(1)
     tm = (C.c_float * 4)()
     L.lib.h264b200_last_timing(tm)
     print("frame %d: k_encode %.2f ms; MB cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f  (sum/1.9GHz = %.1f ms serial)" % (
         i, tm[1], tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), np.percentile(tot, 99), tot.max(), tot.sum() / 1.9e6))
-    for t in sorted(set(prof[:, 8].tolist())):
-        m = prof[:, 8] == t
-        ph = prof[m][:, :7].mean(0)
-        print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(7)))
+    for t in sorted(set(prof[:, 16].tolist())):
+        m = prof[:, 16] == t
+        ph = prof[m][:, :12].mean(0)
+        print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(12)))
