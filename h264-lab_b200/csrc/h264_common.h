@@ -65,6 +65,27 @@ HD int wmax(int v) { return v; }
 HD int wor(int v) { return v; }
 #endif
 
+/* One macroblock is encoded by a CTA of MB_WARPS warps: the warps split it by TASK
+ * (16x16 search | 16x8 + 8x16 searches | 8x8 search | intra decision, then luma halves |
+ * chroma planes).  ON_WARP(k) guards a task; the host emulation runs the tasks one after
+ * the other in program order, which satisfies every producer -> consumer dependency. */
+#define MB_WARPS 4
+#if H264_DEVICE
+#  define WARP_ID ((int)(threadIdx.x >> 5))
+#  define ON_WARP(k) if (WARP_ID == (k))
+#  define CTA_SYNC() __syncthreads()
+#  define FOR_THREADS(i, n) for (int i = (int)threadIdx.x; i < (n); i += MB_WARPS * 32)
+#  define IF_THREAD0 if (threadIdx.x == 0)
+HD void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#else
+#  define WARP_ID 0
+#  define ON_WARP(k)
+#  define CTA_SYNC() ((void)0)
+#  define FOR_THREADS(i, n) for (int i = 0; i < (n); i++)
+#  define IF_THREAD0
+HD void bar_sync(int, int) {}
+#endif
+
 typedef uint8_t pix_t;
 
 HD void atomic_add_stat(int *p)
@@ -212,36 +233,53 @@ struct FrameParams
 #define MB_BITS_WORDS 512       /* 2048 bytes per macroblock */
 
 /* ---- per-macroblock working set (shared memory on the GPU) --------------------- */
+/* private scratch of one motion-search warp */
+struct SearchScratch
+{
+    pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)    */
+    pix_t tmpblk[256];           /* second operand of quarter-sample averages               */
+    int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */
+};
+
 struct MBWork
 {
+    /* inputs, read-only after mb_load */
     pix_t inp_y[256];            /* input MB, stride 16 (mb_pix_inp, H:566)                 */
     pix_t inp_c[128];            /* U at +0, V at +8, stride 16                             */
-    pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)   */
-    pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
-    pix_t i4rec[256];            /* I4x4 reconstruction under construction                  */
-    pix_t i4r[17 * 24];          /* GPU fast path: padded I4x4 reconstruction (row above, left column) */
-    pix_t i4z[16];               /* the 13 neighbours of the current 4x4 block              */
-    pix_t i4s[32];               /* the 32 source values of its nine predictions            */
-    int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
     pix_t top_y[24];             /* unfiltered row above: 16 + 4 of the top-right MB        */
     pix_t left_y[16];
     pix_t top_c[16];             /* U 0..7, V 8..15                                         */
     pix_t left_c[16];
     pix_t tl[4];                 /* top-left Y, U, V                                        */
+    int32_t mvp0_left[4], mvp0_tl[4], mvp0_top[5];   /* MV predictor context at MB start    */
+    int32_t nb_i4mode[8];        /* I4x4 modes of the left MB's right column / top MB's bottom row */
+    uint32_t win[(WIN_W * WIN_H + 32) / 4];   /* search window: copy of the reference picture around the MV predictor */
+    /* motion search */
+    SearchScratch ss[3];
+    int32_t ic[16];              /* result of the candidate stage, see IC_* in h264_mbenc.h  */
+    int32_t mode_cost[4], mode_pred[4];      /* per partition mode: cost, byte offset of its prediction in MBWork */
+    int32_t part_mv[4][4], part_mvd[4][4];   /* per mode, per partition                     */
+    /* intra */
+    pix_t i16pred[256];
+    pix_t i4rec[256];            /* I4x4 reconstruction                                     */
+    pix_t i4r[17 * 24];          /* GPU fast path: padded I4x4 reconstruction (row above, left column) */
+    pix_t i4z[16];               /* the 13 neighbours of the current 4x4 block              */
+    pix_t i4s[32];               /* the 32 source values of its nine predictions            */
+    int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
+    int8_t  i4_mode[16], i4_code[16];
+    int32_t intra_res[8];        /* cost16, i16 mode, cost4, nz mask of I4x4                */
+    /* chroma prediction, transform / quantisation */
+    pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
+    pix_t skip_pred[256];        /* luma prediction at the skip vector                      */
     int16_t dq_y[16][16];        /* transform coefficients / dequantised (quant_t.dq)       */
     int16_t qv_y[16][16];        /* quantised levels (quant_t.qv)                           */
     int16_t dq_c[8][16];
     int16_t qv_c[8][16];
     int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
     int16_t dc_c[8], qdc_c[8];
-    pix_t tmpblk[256];           /* second operand of quarter-sample averages               */
-    uint32_t win[(WIN_W * WIN_H + 32) / 4];   /* search window: copy of the reference picture around the MV predictor */
-    int8_t  i4_mode[16], i4_code[16];
-    int8_t  zflag1[16], zflag2[16];
-    int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */
-    int32_t mvp_save[12];
-    int32_t part_mv[4][4], part_mvd[4][4];        /* per mode, per partition                */
-    int32_t scal[16];            /* scalars produced by lane 0 for the whole warp          */
+    int8_t  zflag1[16], zflag2[16], zflagc[8];
+    int32_t tq_res[8];           /* luma nz bits of the two halves, chroma nz bits / dc flags */
+    int32_t scal[16];            /* scalars produced by one lane for everybody              */
     uint32_t old_mbi[40];        /* previous record / reconstruction of an MB being repaired */
     uint32_t old_rec[96];
     int32_t rp_mv0[32], rp_flags[32], rp_used0[32], rp_used1[32], rp_true0[32], rp_true1[32];   /* replay staging */

@@ -15,7 +15,7 @@
 #  define PROF_MEMBERS long long prof_t0; int prof[PROF_N];
 #  define PROF_INIT(s) do { (s).prof_t0 = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
 #  define PROF_MARK(s, k) do { long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
-#  define PROF_STORE(s, fp, n, type) do { if (LANE_ID == 0 && (fp)->prof) { for (int k_ = 0; k_ < PROF_N; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
+#  define PROF_STORE(s, fp, n, type) do { if (threadIdx.x == 0 && (fp)->prof) { for (int k_ = 0; k_ < PROF_N; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
         (fp)->prof[(n) * 20 + 16] = (type); } } while (0)
 #else
 #  define PROF_MEMBERS
@@ -34,10 +34,21 @@ struct MBState   /* warp-uniform registers of the macroblock being encoded */
     int cost;
     int i16_mode;
     int mv_skip_pred;    /* H:674 */
-    pix_t *pbest, *ptest;
+    pix_t *pbest;        /* luma prediction of the chosen mode */
+    SearchScratch *ss;   /* private scratch of the search warp running this code */
     int win_x0, win_y0;  /* luma coordinates of the search window's first sample; win_x0 % 4 == 0 */
     int win_ok;
 };
+
+/* slots of MBWork::ic, the outcome of the candidate stage (inter_stage_a) */
+#define IC_STATE 0        /* 0 not known yet, 1 early skip, 2 continue with the searches */
+#define IC_PREF 1         /* bit t: partition mode t is worth a search (H:5224)           */
+#define IC_MV_BEST 2
+#define IC_SAD_BEST 3     /* incl. MV cost: the min_sad seed of the 16x16 search (H:5414) */
+#define IC_MVP16 4
+#define IC_MV_SKIP 5
+#define IC_SAD_SKIP 6
+#define IC_SIG 7          /* [7..10] candidate-stage signature for the speculation check  */
 
 HD int clz32(uint32_t v)
 {
@@ -67,72 +78,73 @@ HDN void mb_load(MBState &s)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
-    int mbx = s.mbx, mby = s.mby;
-    /* input pixels; samples beyond the visible picture replicate the last column / row
-     * (pix_copy_cropped_mb H:3536) */
-    int wv = fp->width, hv = fp->height;
-    FOR_LANES(i, 64)
+    const int mbx = s.mbx, mby = s.mby;
+    const int wv = fp->width, hv = fp->height;
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    const pix_t *dy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+    const pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8;
+    const pix_t *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
+    const MBInfo *mbi = fp->mbi + mby * fp->nmbx + mbx;
+    const int nmbx = fp->nmbx, av = s.avail;
+    const int inside = (mbx + 1) * 16 <= wv && (mby + 1) * 16 <= hv;
+    /* one flat list of independent loads so that all of them are in flight together:
+     * [0,64) luma words, [64,96) chroma words, [96,169) neighbour samples / MVs / modes */
+    FOR_THREADS(i, 169)
     {
-        int r = i >> 2, c = (i & 3) * 4;
-        int y = imin(mby * 16 + r, hv - 1);
-        const pix_t *row = fp->inp[0] + y * fp->inp_stride[0];
-        uint32_t v = 0;
-        for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 16 + c + k, wv - 1)] << (8 * k);
-        *(uint32_t *)(w->inp_y + r * 16 + c) = v;
-    }
-    FOR_LANES(i, 32)
-    {
-        int r = i >> 2, q = i & 3, pl = q >> 1, c = (q & 1) * 4;
-        int y = imin(mby * 8 + r, hv / 2 - 1);
-        const pix_t *row = fp->inp[1 + pl] + y * fp->inp_stride[1 + pl];
-        uint32_t v = 0;
-        for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 8 + c + k, wv / 2 - 1)] << (8 * k);
-        *(uint32_t *)(w->inp_c + r * 16 + pl * 8 + c) = v;
-    }
-    /* unfiltered neighbour samples of the picture under construction (the reference's
-     * top_line context, H:4693-4714): row above incl. 4 samples of the top-right MB,
-     * left column, top-left corners */
-    {
-        int sy = fp->stride[0], sc = fp->stride[1];
-        const pix_t *dy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
-        const pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8;
-        const pix_t *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
-        int av = s.avail;
-        FOR_LANES(i, 32)
+        if (i < 64)
+        {   /* input luma; samples beyond the visible picture replicate the last column / row
+             * (pix_copy_cropped_mb H:3536) */
+            int r = i >> 2, c = (i & 3) * 4;
+            uint32_t v;
+            if (inside) v = ld4u(fp->inp[0] + (mby * 16 + r) * fp->inp_stride[0] + mbx * 16 + c);
+            else
+            {
+                const pix_t *row = fp->inp[0] + imin(mby * 16 + r, hv - 1) * fp->inp_stride[0];
+                v = 0;
+                for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 16 + c + k, wv - 1)] << (8 * k);
+            }
+            *(uint32_t *)(w->inp_y + r * 16 + c) = v;
+        } else if (i < 96)
         {
-            if (i < 20) { if ((av & AVAIL_T) && (i < 16 || (av & AVAIL_TR))) w->top_y[i] = dy[-sy + i]; else w->top_y[i] = 0; }
-            if (i < 16) w->left_y[i] = (av & AVAIL_L) ? dy[i * sy - 1] : 0;
-            if (i < 8)
+            int k2 = i - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
+            uint32_t v;
+            if (inside) v = ld4u(fp->inp[1 + pl] + (mby * 8 + r) * fp->inp_stride[1 + pl] + mbx * 8 + c);
+            else
             {
-                w->top_c[i] = (av & AVAIL_T) ? du[-sc + i] : 0;
-                w->top_c[8 + i] = (av & AVAIL_T) ? dv[-sc + i] : 0;
-                w->left_c[i] = (av & AVAIL_L) ? du[i * sc - 1] : 0;
-                w->left_c[8 + i] = (av & AVAIL_L) ? dv[i * sc - 1] : 0;
+                const pix_t *row = fp->inp[1 + pl] + imin(mby * 8 + r, hv / 2 - 1) * fp->inp_stride[1 + pl];
+                v = 0;
+                for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 8 + c + k, wv / 2 - 1)] << (8 * k);
             }
-            if (i == 31)
-            {
-                w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
-                w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
-                w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            }
+            *(uint32_t *)(w->inp_c + r * 16 + pl * 8 + c) = v;
+        } else
+        {
+            /* unfiltered neighbour samples of the picture under construction (the reference's
+             * top_line context, H:4693-4714), neighbours' MVs (enc->mv_pred, H:742) and I4x4 modes */
+            int j = i - 96;
+            if (j < 20) w->top_y[j] = ((av & AVAIL_T) && (j < 16 || (av & AVAIL_TR))) ? dy[-sy + j] : 0;
+            else if (j < 36) w->left_y[j - 20] = (av & AVAIL_L) ? dy[(j - 20) * sy - 1] : 0;
+            else if (j < 44) w->top_c[j - 36] = (av & AVAIL_T) ? du[-sc + (j - 36)] : 0;
+            else if (j < 52) w->top_c[8 + j - 44] = (av & AVAIL_T) ? dv[-sc + (j - 44)] : 0;
+            else if (j < 60) w->left_c[j - 52] = (av & AVAIL_L) ? du[(j - 52) * sc - 1] : 0;
+            else if (j < 68) w->left_c[8 + j - 60] = (av & AVAIL_L) ? dv[(j - 60) * sc - 1] : 0;
+            else if (j == 68) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
+            else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
+            else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
+            else if (j == 71) w->ic[IC_STATE] = 0;
+            else if (j == 72) { /* spare */ }
         }
     }
-    /* MV predictor context from the neighbours' final MVs (replaces the rolling
-     * enc->mv_pred row, H:742, H:3696-3715) */
-    if (fp->slice_type == SLICE_P)
+    FOR_THREADS(i, 21)
     {
-        const MBInfo *mbi = fp->mbi + mby * fp->nmbx + mbx;
-        int nmbx = fp->nmbx, av = s.avail;
-        FOR_LANES(i, 13)
-        {
-            if (i < 4) w->mvp_left[i] = (av & AVAIL_L) ? mbi[-1].mv[4 * i + 3] : MV_NA;
-            else if (i == 4) w->mvp_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
-            else if (i < 8) w->mvp_tl[i - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (i - 5) + 3] : MV_NA;
-            else if (i < 12) w->mvp_top[i - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (i - 8)] : MV_NA;
-            else w->mvp_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
-        }
+        if (i < 4) w->mvp0_left[i] = (av & AVAIL_L) ? mbi[-1].mv[4 * i + 3] : MV_NA;
+        else if (i == 4) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
+        else if (i < 8) w->mvp0_tl[i - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (i - 5) + 3] : MV_NA;
+        else if (i < 12) w->mvp0_top[i - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (i - 8)] : MV_NA;
+        else if (i == 12) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
+        else if (i < 17) w->nb_i4mode[i - 13] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (i - 13) + 3] : -1;
+        else w->nb_i4mode[4 + i - 17] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (i - 17)] : -1;
     }
-    WSYNC();
+    CTA_SYNC();
 }
 
 /* ------------------------------------------------------------------------------
@@ -140,9 +152,9 @@ HDN void mb_load(MBState &s)
  * (me_mv_medianpredictor_get H:3720).  x,y,wd,ht in units of 4x4 blocks.
  * ---------------------------------------------------------------------------- */
 HD int med3(int a, int b, int c) { return imax(imin(imax(a, b), c), imin(a, b)); }
-HDN int mvp_get(const MBWork *w, int flag, int x, int y, int wd, int ht)
+HDN int mvp_get(const int32_t *left, const int32_t *tlv, const int32_t *top, int flag, int x, int y, int wd, int ht)
 {
-    int a = w->mvp_left[y], b = w->mvp_top[x], c = w->mvp_top[x + wd], d = w->mvp_tl[y];
+    int a = left[y], b = top[x], c = top[x + wd], d = tlv[y];
     if (!x)
     {
         if (!(flag & AVAIL_L)) a = MV_NA;
@@ -182,7 +194,7 @@ HDN int mvp_get(const MBWork *w, int flag, int x, int y, int wd, int ht)
 }
 
 /* me_mv_medianpredictor_put H:3696 -- must be called by one lane, followed by WSYNC */
-HD void mvp_put(MBWork *w, int x, int y, int wd, int ht, int mv)
+HD void mvp_put(SearchScratch *w, int x, int y, int wd, int ht, int mv)
 {
     w->mvp_tl[y] = w->mvp_top[x + wd - 1];
     for (int i = 1; i < ht; i++) w->mvp_tl[y + i] = mv;
@@ -204,14 +216,14 @@ HDN void win_load(MBState &s, int cx, int cy)
     const int xmin = -16, xmax = fp->nmbx * 16 + 12, ymin = -16, ymax = fp->nmby * 16 + 15;
     const pix_t *plane = fp->ref[0];
     uint32_t *win = s.w->win;
-    FOR_LANES(i, (WIN_W / 4) * WIN_H)
+    FOR_THREADS(i, (WIN_W / 4) * WIN_H)
     {
-        int r = i / (WIN_W / 4), c4 = i - r * (WIN_W / 4);
+        int r = i >> 4, c4 = i & 15;      /* WIN_W / 4 == 16 words per row */
         int y = imin(imax(y0 + r, ymin), ymax), x = imin(imax(x0 + 4 * c4, xmin), xmax);
         win[i] = *(const uint32_t *)(plane + y * stride + x);
     }
     s.win_x0 = x0; s.win_y0 = y0; s.win_ok = 1;
-    WSYNC();
+    CTA_SYNC();
 }
 
 /* pointer to reference sample (bx,by) for a bw x bh block read with up to 3 samples of
@@ -243,7 +255,7 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
 {
     const FrameParams *fp = s.fp;
     const int lam = fp->lambda_mv_q4;
-    pix_t *tmp = s.w->tmpblk;
+    pix_t *tmp = s.ss->tmpblk;
     int rs;
     const pix_t *rp;
     int mv = *pmv;
@@ -387,35 +399,32 @@ HD void inter_partition_hint(const int sad[4], int mode[4])
     if (iabs(skew) > (sum >> 4) && iabs(slope) <= (sum >> 4)) mode[3] = 1;
 }
 
-/* chroma motion compensation for every partition of the current MB type
- * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB. */
-HDN void mc_chroma(const MBState &s, int type, const int32_t *mvs)
+/* chroma motion compensation of plane pl for every partition of the current MB type
+ * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB.  Warp-level. */
+HDN void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
 {
     const FrameParams *fp = s.fp;
     int bw = (type & 2) ? 4 : 8, bh = (type & 1) ? 4 : 8;
     if (type == MBT_SKIP) bw = bh = 8;
     int sc = fp->stride[1];
-    for (int pl = 0; pl < 2; pl++)
+    int part = 0, x = 0, y = 0;
+    for (;; part++)
     {
-        int part = 0, x = 0, y = 0;
-        for (;; part++)
-        {
-            int ax = mv_x(mvs[part]) + s.mbx * 64, ay = mv_y(mvs[part]) + s.mby * 64;
-            const pix_t *ref = fp->ref[1 + pl] + ((ay >> 3) + y) * sc + (ax >> 3) + x;
-            interp_chroma_block(ref, sc, ax & 7, ay & 7, bw, bh, s.w->predc + pl * 8 + 16 * y + x);
-            x = (x + bw) & 7;
-            if (!x) { y = (y + bh) & 7; if (!y) break; }
-        }
+        int ax = mv_x(mvs[part]) + s.mbx * 64, ay = mv_y(mvs[part]) + s.mby * 64;
+        const pix_t *ref = fp->ref[1 + pl] + ((ay >> 3) + y) * sc + (ax >> 3) + x;
+        interp_chroma_block(ref, sc, ax & 7, ay & 7, bw, bh, s.w->predc + pl * 8 + 16 * y + x);
+        x = (x + bw) & 7;
+        if (!x) { y = (y + bh) & 7; if (!y) break; }
     }
     WSYNC();
 }
 
 /* ------------------------------------------------------------------------------
- * a5: inter mode decision (inter_choose_mode H:5283-5524).
- * On return s.type / s.cost / s.pbest are set; w->part_mv / part_mvd of the chosen
- * type are copied to out_mv/out_mvd.  Returns 1 for an early skip decision.
+ * a5: inter mode decision (inter_choose_mode H:5283-5524), split into the candidate stage
+ * (skip test + start candidates, one warp) and one search task per partition mode.
  * ---------------------------------------------------------------------------- */
-HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, const int32_t cl[2], int32_t *cand_sig, int cand_only)
+/* Candidate stage.  Needs the window loaded around mvp16.  Publishes w->ic[] (lane 0). */
+HDN void inter_stage_a(MBState &s, const int32_t cl[2])
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -425,32 +434,30 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
     int sad4v[4];
     int sad_skip = 0x7FFFFFFF, sad_best = 0x7FFFFFFF, cand_cost_best = 0;
     int mv_best = mv_pack(MV_NA, 0);
+    int state = 2;
 
     /* skip predictor (me_mv_medianpredictor_get_skip H:3877) */
-    int mvp16 = mvp_get(w, s.avail, 0, 0, 4, 4);
-    win_load(s, s.mbx * 16 + ((mv_x(mvp16) + 1) >> 2), s.mby * 16 + ((mv_y(mvp16) + 1) >> 2));
-    PROF_MARK(s, 1);
+    const int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
     int mv_skip = 0;
-    if (!(~s.avail & (AVAIL_L | AVAIL_T)) && w->mvp_left[0] != 0 && w->mvp_top[0] != 0) mv_skip = mvp16;
-    s.mv_skip_pred = mv_skip;
-    int mv_skip_a = mv_pack(mv_x(mv_skip) + mbqx, mv_y(mv_skip) + mbqy);
+    if (!(~s.avail & (AVAIL_L | AVAIL_T)) && w->mvp0_left[0] != 0 && w->mvp0_top[0] != 0) mv_skip = mvp16;
+    const int mv_skip_a = mv_pack(mv_x(mv_skip) + mbqx, mv_y(mv_skip) + mbqy);
 
     if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
         {
             int rs;
             const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
-            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, s.ptest, w->tmpblk);
+            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, w->skip_pred, s.ss->tmpblk);
         }
         WSYNC();
-        sad_skip = sad_mb_quad(w->inp_y, 16, s.ptest, sad4v);
+        sad_skip = sad_mb_quad(w->inp_y, 16, w->skip_pred, sad4v);
         if (imax(imax(sad4v[0], sad4v[1]), imax(sad4v[2], sad4v[3])) < fp->skip_thr_inter)
         {
             int32_t one_mv = mv_skip;
-            mc_chroma(s, MBT_SKIP, &one_mv);
             int ok = 1;
             for (int pl = 0; pl < 2 && ok; pl++)
             {
+                mc_chroma_plane(s, pl, MBT_SKIP, &one_mv);
                 int acc = 0;
                 FOR_LANES(i, 16)
                 {
@@ -460,167 +467,155 @@ HDN int inter_choose(MBState &s, int32_t *out_mv /*4*/, int32_t *out_mvd /*4*/, 
                 acc = wsum(acc);
                 if (acc >= fp->skip_thr_inter) ok = 0;
             }
-            if (ok)
-            {
-                pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
-                s.type = MBT_SKIP;
-                s.cost = 0;
-                out_mv[0] = mv_skip;
-                out_mvd[0] = 0;
-                return 1;
-            }
+            if (ok) state = 1;
         }
-        if (fp->speed < 1) inter_partition_hint(sad4v, pref);
-        mv_best = cand[ncand++] = mv_round_fullpel(mv_skip);
-        if (!((mv_x(mv_skip) | mv_y(mv_skip)) & 3))
+        if (state != 1)
         {
-            sad_best = sad_skip;
-            cand_cost_best = mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
-            j = 1;
-        }
-    }
-
-    PROF_MARK(s, 2);
-    /* candidate start points (H:5370-5386) */
-    cand[ncand++] = mvp16;
-    cand[ncand++] = 0;
-    if ((s.avail & AVAIL_L) && w->mvp_left[0] != MV_NA) cand[ncand++] = w->mvp_left[0];
-    if ((s.avail & AVAIL_T) && w->mvp_top[0] != MV_NA) cand[ncand++] = w->mvp_top[0];
-    if ((s.avail & AVAIL_TR) && w->mvp_top[4] != MV_NA) cand[ncand++] = w->mvp_top[4];
-    if (s.mbx <= 0) cand[ncand++] = mv_pack(8 * 4, 0);
-    if (s.mby <= 0) cand[ncand++] = mv_pack(0, 8 * 4);
-    cand[ncand++] = cl[0];
-    cand[ncand++] = cl[1];
-    {   /* round to full-pel and drop duplicates, keeping first occurrences (H:5198) */
-        int k = 1;
-        cand[0] = mv_round_fullpel(cand[0]);
-        for (int a = 1; a < ncand; a++)
-        {
-            int m = mv_round_fullpel(cand[a]), i;
-            for (i = 0; i < k; i++) if (m == cand[i]) break;
-            if (i == k) cand[k++] = m;
-        }
-        ncand = k;
-    }
-#pragma unroll 1
-    for (; j < ncand; j++)
-    {
-        int mva = mv_pack(mv_x(cand[j]) + mbqx, mv_y(cand[j]) + mbqy);
-        if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
-        {
-            int cc = mv_cost(cand[j], mvp16, fp->lambda_mv_q4);
-            int rs;
-            const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
-            int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
             if (fp->speed < 1) inter_partition_hint(sad4v, pref);
-            if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
+            mv_best = cand[ncand++] = mv_round_fullpel(mv_skip);
+            if (!((mv_x(mv_skip) | mv_y(mv_skip)) & 3))
+            {
+                sad_best = sad_skip;
+                cand_cost_best = mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+                j = 1;
+            }
         }
     }
-    cand_sig[0] = mv_best; cand_sig[1] = sad_best; cand_sig[2] = cand_cost_best;
-    cand_sig[3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
-    if (cand_only) return 2;
-    sad_best += mv_cost(mv_best, mvp16, fp->lambda_mv_q4);
-    PROF_MARK(s, 3);
 
-    /* partition modes (H:5416-5510) */
-    pix_t *store = w->store[0];
-    pix_t *pred_best = store, *pred_test = store + 256;
-    int best_type = 0;
-    IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_save[3 * i] = w->mvp_left[i]; w->mvp_save[3 * i + 1] = w->mvp_tl[i]; w->mvp_save[3 * i + 2] = w->mvp_top[i]; } }
-    WSYNC();
-    s.cost = 0xffffff;
+    if (state != 1)
+    {
+        /* candidate start points (H:5370-5386) */
+        cand[ncand++] = mvp16;
+        cand[ncand++] = 0;
+        if ((s.avail & AVAIL_L) && w->mvp0_left[0] != MV_NA) cand[ncand++] = w->mvp0_left[0];
+        if ((s.avail & AVAIL_T) && w->mvp0_top[0] != MV_NA) cand[ncand++] = w->mvp0_top[0];
+        if ((s.avail & AVAIL_TR) && w->mvp0_top[4] != MV_NA) cand[ncand++] = w->mvp0_top[4];
+        if (s.mbx <= 0) cand[ncand++] = mv_pack(8 * 4, 0);
+        if (s.mby <= 0) cand[ncand++] = mv_pack(0, 8 * 4);
+        cand[ncand++] = cl[0];
+        cand[ncand++] = cl[1];
+        {   /* round to full-pel and drop duplicates, keeping first occurrences (H:5198) */
+            int k = 1;
+            cand[0] = mv_round_fullpel(cand[0]);
+            for (int a = 1; a < ncand; a++)
+            {
+                int m = mv_round_fullpel(cand[a]), i;
+                for (i = 0; i < k; i++) if (m == cand[i]) break;
+                if (i == k) cand[k++] = m;
+            }
+            ncand = k;
+        }
 #pragma unroll 1
-    for (int mb_type = 0; mb_type < 4; mb_type++)
-    {
-        const int nbits = mb_type == 0 ? 1 : (mb_type == 3 ? 12 : 4);
-        int imv = 0;
-        int part_sad = (nbits * fp->lambda_q4) >> 4;
-        if (!pref[mb_type]) continue;
-        int bw = (mb_type & 2) ? 8 : 16, bh = (mb_type & 1) ? 8 : 16;
-        int px = 0, py = 0;
-        for (;;)
+        for (; j < ncand; j++)
         {
-            int rng[4];
-            int mvabs = mv_pack(mv_x(mv_best) + mbqx, mv_y(mv_best) + mbqy);
-            me_set_range(fp, &mvabs, rng, mbqy + py * 4);
-            int mv_pred = mvp_get(w, s.avail, px >> 2, py >> 2, bw >> 2, bh >> 2);
-            int mv_pred_a = mv_pack(mv_x(mv_pred) + mbqx, mv_y(mv_pred) + mbqy);
-            if (mb_type)
+            int mva = mv_pack(mv_x(cand[j]) + mbqx, mv_y(cand[j]) + mbqy);
+            if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
             {
-                mvabs = mv_round_fullpel(mv_pred_a);
-                me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+                int cc = mv_cost(cand[j], mvp16, fp->lambda_mv_q4);
                 int rs;
-                const pix_t *rp = ref_at(s, (mv_x(mvabs) >> 2) + px, (mv_y(mvabs) >> 2) + py, bw, bh, &rs);
-                sad_best = sad_frame_wh(rp, rs, w->inp_y + py * 16 + px, bw, bh)
-                         + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
+                const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
+                int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                if (fp->speed < 1) inter_partition_hint(sad4v, pref);
+                if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
             }
-            int sb = mb_type ? (mb_type == 2 ? 8 : 128) : 256;
-            pix_t *bufs[4];
-            bufs[0] = store; bufs[1] = store + sb; bufs[2] = store + (sb == 8 ? 256 : 2 * sb); bufs[3] = bufs[2] + sb;
-            pix_t *dout;
-            part_sad += me_search(s, px, py, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
-                                  bw, bh, bufs, &dout);
-            if (!mb_type)
-            {
-                pred_test = dout;
-                if (pred_test < store + 2 * 256)
-                {
-                    pred_best = (pred_test == store ? store + 256 : store);
-                    store += 2 * 256;
-                } else
-                {
-                    pred_best = (pred_test == (store + 512) ? store + 512 + 256 : store + 512);
-                }
-            } else
-            {
-                int wq = bw >> 2;
-                FOR_LANES(i, wq * bh)
-                {
-                    int r = i / wq, c = (i - r * wq) * 4;
-                    *(uint32_t *)(pred_test + (py + r) * 16 + px + c) = ld4_sm(dout + r * 16 + c);
-                }
-            }
-            int mv = mv_pack(mv_x(mvabs) - mbqx, mv_y(mvabs) - mbqy);
-            IF_LANE0
-            {
-                w->part_mvd[mb_type][imv] = mv_sub2(mv, mv_pred);
-                w->part_mv[mb_type][imv] = mv;
-                mvp_put(w, px >> 2, py >> 2, bw >> 2, bh >> 2, mv);
-            }
-            imv++;
-            WSYNC();
-            px = (px + bw) & 15;
-            if (!px) { py = (py + bh) & 15; if (!py) break; }
-        }
-        IF_LANE0 { for (int i = 0; i < 4; i++) { w->mvp_left[i] = w->mvp_save[3 * i]; w->mvp_tl[i] = w->mvp_save[3 * i + 1]; w->mvp_top[i] = w->mvp_save[3 * i + 2]; } }
-        WSYNC();
-        PROF_MARK(s, mb_type ? 5 : 4);
-        if (part_sad < s.cost)
-        {
-            pix_t *t = pred_best; pred_best = pred_test; pred_test = t;
-            s.cost = part_sad;
-            best_type = mb_type;
         }
     }
-    s.type = best_type;
-    s.pbest = pred_best;
-    s.ptest = pred_test;
-    for (int i = 0; i < 4; i++) { out_mv[i] = w->part_mv[best_type][i]; out_mvd[i] = w->part_mvd[best_type][i]; }
-
-    if (s.cost > sad_skip)     /* P16x16 at the skip vector is cheaper (H:5512) */
+    IF_LANE0
     {
-        s.type = 0;
-        s.cost = sad_skip + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
-        out_mv[0] = mv_skip;
-        out_mvd[0] = mv_sub2(mv_skip, mvp16);
-        {
-            int rs;
-            const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
-            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, s.pbest, w->tmpblk);
-        }
-        WSYNC();
+        w->ic[IC_PREF] = pref[0] | (pref[1] << 1) | (pref[2] << 2) | (pref[3] << 3);
+        w->ic[IC_MV_BEST] = mv_best;
+        w->ic[IC_SIG] = mv_best; w->ic[IC_SIG + 1] = sad_best; w->ic[IC_SIG + 2] = cand_cost_best;
+        w->ic[IC_SIG + 3] = pref[1] | (pref[2] << 1) | (pref[3] << 2);
+        w->ic[IC_SAD_BEST] = state == 1 ? 0 : sad_best + mv_cost(mv_best, mvp16, fp->lambda_mv_q4);
+        w->ic[IC_MVP16] = mvp16;
+        w->ic[IC_MV_SKIP] = mv_skip;
+        w->ic[IC_SAD_SKIP] = sad_skip;
+#if H264_DEVICE
+        __threadfence_block();
+        *(volatile int32_t *)&w->ic[IC_STATE] = state;
+#else
+        w->ic[IC_STATE] = state;
+#endif
     }
-    return 0;
+    WSYNC();
+}
+
+/* Search of one partition mode (one warp, private scratch s.ss).  The prediction of the
+ * whole macroblock for this mode ends up at w->mode_pred[mb_type]. */
+HDN void inter_mode_search(MBState &s, int mb_type)
+{
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    SearchScratch *ss = s.ss;
+    const int mbqx = s.mbx * 64, mbqy = s.mby * 64;
+    const int mv_best = w->ic[IC_MV_BEST];
+    int sad_best = w->ic[IC_SAD_BEST];
+    const int nbits = mb_type == 0 ? 1 : (mb_type == 3 ? 12 : 4);
+    int imv = 0;
+    int part_sad = (nbits * fp->lambda_q4) >> 4;
+    const int bw = (mb_type & 2) ? 8 : 16, bh = (mb_type & 1) ? 8 : 16;
+    /* scratch tiles of the diamond / sub-pel search, and where this mode's MB prediction is assembled */
+    pix_t *store = ss->store[0];
+    pix_t *assembled = mb_type == 2 ? ss->store[3] : ss->store[2];
+    pix_t *result = assembled;
+    FOR_LANES(i, 13)
+    {
+        if (i < 4) ss->mvp_left[i] = w->mvp0_left[i];
+        else if (i < 8) ss->mvp_tl[i - 4] = w->mvp0_tl[i - 4];
+        else ss->mvp_top[i - 8] = w->mvp0_top[i - 8];
+    }
+    WSYNC();
+    int px = 0, py = 0;
+    for (;;)
+    {
+        int rng[4];
+        int mvabs = mv_pack(mv_x(mv_best) + mbqx, mv_y(mv_best) + mbqy);
+        me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+        int mv_pred = mvp_get(ss->mvp_left, ss->mvp_tl, ss->mvp_top, s.avail, px >> 2, py >> 2, bw >> 2, bh >> 2);
+        int mv_pred_a = mv_pack(mv_x(mv_pred) + mbqx, mv_y(mv_pred) + mbqy);
+        if (mb_type)
+        {
+            mvabs = mv_round_fullpel(mv_pred_a);
+            me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+            int rs;
+            const pix_t *rp = ref_at(s, (mv_x(mvabs) >> 2) + px, (mv_y(mvabs) >> 2) + py, bw, bh, &rs);
+            sad_best = sad_frame_wh(rp, rs, w->inp_y + py * 16 + px, bw, bh)
+                     + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
+        }
+        int sb = mb_type ? (mb_type == 2 ? 8 : 128) : 256;
+        pix_t *bufs[4];
+        bufs[0] = store; bufs[1] = store + sb; bufs[2] = store + (sb == 8 ? 256 : 2 * sb); bufs[3] = bufs[2] + sb;
+        pix_t *dout;
+        part_sad += me_search(s, px, py, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
+                              bw, bh, bufs, &dout);
+        if (!mb_type) result = dout;
+        else
+        {
+            const int sh = bw == 16 ? 2 : 1;
+            FOR_LANES(i, bh << sh)
+            {
+                int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
+                *(uint32_t *)(assembled + (py + r) * 16 + px + c) = ld4_sm(dout + r * 16 + c);
+            }
+        }
+        int mv = mv_pack(mv_x(mvabs) - mbqx, mv_y(mvabs) - mbqy);
+        IF_LANE0
+        {
+            w->part_mvd[mb_type][imv] = mv_sub2(mv, mv_pred);
+            w->part_mv[mb_type][imv] = mv;
+            mvp_put(ss, px >> 2, py >> 2, bw >> 2, bh >> 2, mv);
+        }
+        imv++;
+        WSYNC();
+        px = (px + bw) & 15;
+        if (!px) { py = (py + bh) & 15; if (!py) break; }
+    }
+    IF_LANE0
+    {
+        w->mode_cost[mb_type] = part_sad;
+        w->mode_pred[mb_type] = (int32_t)(result - (pix_t *)w);
+    }
+    WSYNC();
 }
 
 /* ------------------------------------------------------------------------------
@@ -684,7 +679,7 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     int nz_mask = 0;
     const int penalty = (3 * fp->lambda_q4) >> 4;
     const int skip_thr = fp->skip_thr_i4x4;
-    const MBInfo *mbi = fp->mbi + s.mby * fp->nmbx + s.mbx;
+    const int poll_skip = fp->slice_type == SLICE_P;
 
     /* ---- per-macroblock constants of this lane ---- */
     /* padded reconstruction R[17][24]: row 0 = row above (TL at col 3, 16 + 4 samples from col 4),
@@ -723,15 +718,16 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     const int qcl = quant_class(ci);
     const int qmul = fp->qdat[0][qcl], dqmul = fp->qdat[0][qcl + 1], qrnd = fp->qdat[0][6];
     /* neighbouring MBs' modes */
-    int nb_mode = -1;
-    if (lane < 4) nb_mode = (avail & AVAIL_L) ? mbi[-1].i4_mode[4 * lane + 3] : -1;
-    else if (lane < 8) nb_mode = (avail & AVAIL_T) ? mbi[-fp->nmbx].i4_mode[12 + lane - 4] : -1;
+    int nb_mode = lane < 8 ? w->nb_i4mode[lane] : -1;
     unsigned modes_lo = 0, modes_hi = 0;      /* chosen modes of blocks 0-7 / 8-15, 4 bits each */
     __syncwarp();
 
 #pragma unroll 1
     for (int n = 0; n < 16; n++)
     {
+        /* the candidate stage runs concurrently on another warp: stop as soon as it has
+         * decided for an early skip (the intra result would be discarded, H:5767) */
+        if (poll_skip && *(volatile int32_t *)&w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         const int r = n >> 2, c = n & 3;
         int a = 0;
         if (c > 0 || (avail & AVAIL_L)) a |= AVAIL_L;
@@ -879,11 +875,11 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     int cost = fp->lambda_i4_q4;
     int nz_mask = 0;
     const int penalty = (3 * fp->lambda_q4) >> 4;
-    const MBInfo *mbi = fp->mbi + s.mby * fp->nmbx + s.mbx;
     const uint16_t *qdat = fp->qdat[0];
 
     for (int n = 0; n < 16; n++)
     {
+        if (fp->slice_type == SLICE_P && w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         /* which neighbours exist for block n (block2avail H:4750) */
         const int r = n >> 2, c = n & 3;
         int a = 0;
@@ -896,8 +892,8 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
         if (r == 0) { if (c < 3) a |= (avail & AVAIL_T) ? AVAIL_TR : 0; else a |= avail & AVAIL_TR; }
         else if (c < 3 && !((r & 1) && (c & 1))) a |= AVAIL_TR;     /* raster blocks 4,6,8,9,10,12,14 */
 
-        int ctx_l = c > 0 ? w->i4_mode[n - 1] : ((avail & AVAIL_L) ? mbi[-1].i4_mode[4 * r + 3] : -1);
-        int ctx_t = r > 0 ? w->i4_mode[n - 4] : ((avail & AVAIL_T) ? mbi[-fp->nmbx].i4_mode[12 + c] : -1);
+        int ctx_l = c > 0 ? w->i4_mode[n - 1] : w->nb_i4mode[r];
+        int ctx_t = r > 0 ? w->i4_mode[n - 4] : w->nb_i4mode[4 + c];
         int mpred = imin(ctx_l, ctx_t);
         if (mpred < 0) mpred = 2;
 
@@ -1056,52 +1052,57 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
 
 /* ------------------------------------------------------------------------------
  * a9-a11: luma transform / quant / reconstruction of a non-I4x4 macroblock
- * (mb_write H:4423-4434 with h264e_transform_sub_quant_dequant H:2619).
- * Returns the 16-bit block mask (bit 15 = block 0).
+ * (mb_write H:4423-4434 with h264e_transform_sub_quant_dequant H:2619), one warp per half
+ * of the macroblock (blocks 8*half .. 8*half+7; the 8x8 zeroing groups never straddle the
+ * halves).  For Intra16x16 the two warps meet at named barrier 2 around the DC transform.
+ * Publishes the half's block mask in w->tq_res[half] (bit 15 = block 0).
  * ---------------------------------------------------------------------------- */
-HDN int luma_tq_recon(MBState &s, int intra16)
+HDN void luma_tq_half(MBState &s, int half, int intra16, int stage)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
     const uint16_t *qdat = fp->qdat[0];
     pix_t *dec = fp->dec[0] + (s.mby * 16) * fp->stride[0] + s.mbx * 16;
-    FOR_LANES(b, 16)
+    const int b0 = half * 8;
+    if (stage == 0)
     {
-        int off = (b & 3) * 4 + (b >> 2) * 64;
-        fwd4x4(w->inp_y + off, 16, s.pbest + off, w->dq_y[b]);
-        if (intra16) w->dc_y[b] = w->dq_y[b][0];
-        else
+        FOR_LANES(k, 8)
         {
-            w->zflag1[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 10);
-            w->zflag2[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 18);
+            int b = b0 + k, off = (b & 3) * 4 + (b >> 2) * 64;
+            fwd4x4(w->inp_y + off, 16, s.pbest + off, w->dq_y[b]);
+            if (intra16) w->dc_y[b] = w->dq_y[b][0];
+            else
+            {
+                w->zflag1[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 10);
+                w->zflag2[b] = (int8_t)coefs_small(w->dq_y[b], 0, qdat + 18);
+            }
         }
-    }
-    WSYNC();
-    int zmask = 0;
-    if (!intra16)       /* zero_smallq H:2512: drop isolated small blocks / 8x8 groups */
-    {
-        for (int b = 0; b < 16; b++) if (w->zflag1[b]) zmask |= 1 << b;
-        const int g0[4] = {0, 2, 8, 10};
-        for (int g = 0; g < 4; g++)
+        WSYNC();
+        int zmask = 0;
+        if (!intra16)       /* zero_smallq H:2512: drop isolated small blocks / 8x8 groups */
         {
-            int m = 0x33 << g0[g];
-            int b0 = g0[g];
-            if ((~zmask & m) && w->zflag2[b0] && w->zflag2[b0 + 1] && w->zflag2[b0 + 4] && w->zflag2[b0 + 5]) zmask |= m;
+            for (int k = 0; k < 8; k++) if (w->zflag1[b0 + k]) zmask |= 1 << (b0 + k);
+            for (int g = 0; g < 2; g++)
+            {
+                int f = b0 + 2 * g, m = 0x33 << f;
+                if ((~zmask & m) && w->zflag2[f] && w->zflag2[f + 1] && w->zflag2[f + 4] && w->zflag2[f + 5]) zmask |= m;
+            }
         }
+        int nzbits = 0;
+        FOR_LANES(k, 8)
+        {
+            int b = b0 + k, nz = 0;
+            if (zmask & (1 << b)) { for (int i = 0; i < 16; i++) w->qv_y[b][i] = 0; }
+            else nz = quant4x4(w->dq_y[b], w->qv_y[b], intra16, qdat);
+            if (nz) nzbits |= 0x8000 >> b;
+        }
+        nzbits = wor(nzbits);
+        IF_LANE0 { w->tq_res[half] = nzbits; }
+        WSYNC();
+        return;
     }
-    int nzbits = 0;
-    FOR_LANES(b, 16)
-    {
-        int nz = 0;
-        if (zmask & (1 << b)) { for (int i = 0; i < 16; i++) w->qv_y[b][i] = 0; }
-        else nz = quant4x4(w->dq_y[b], w->qv_y[b], intra16, qdat);
-        if (nz) nzbits |= 0x8000 >> b;
-    }
-    nzbits = wor(nzbits);
-    WSYNC();
-    int recon_mask = nzbits;
-    if (intra16)
-    {
+    if (stage == 1)
+    {   /* Intra16x16 DC path, once for the macroblock */
         IF_LANE0
         {
             int16_t dq0[16];
@@ -1109,84 +1110,95 @@ HDN int luma_tq_recon(MBState &s, int intra16)
             for (int b = 0; b < 16; b++) w->dq_y[b][0] = dq0[b];
         }
         WSYNC();
-        recon_mask = 0xFFFF;
+        return;
     }
-    FOR_LANES(b, 16)
+    const int recon_mask = intra16 ? 0xFFFF : w->tq_res[half];
+    FOR_LANES(k, 8)
     {
-        int off = (b & 3) * 4 + (b >> 2) * 64;
+        int b = b0 + k, off = (b & 3) * 4 + (b >> 2) * 64;
         pix_t *o = dec + (b & 3) * 4 + (b >> 2) * 4 * fp->stride[0];
         if (recon_mask & (0x8000 >> b)) inv4x4_add(w->dq_y[b], s.pbest + off, o, fp->stride[0]);
         else copy4x4(s.pbest + off, o, fp->stride[0]);
     }
-    return nzbits;
+    WSYNC();
 }
 
-/* chroma transform / quant / recon of both planes (mb_write H:4443-4491).
- * Returns cbpc (0..2). */
-HDN int chroma_tq_recon(MBState &s)
+/* chroma transform / quant / recon of plane pl (mb_write H:4443-4491), one warp.
+ * Publishes w->tq_res[2 + pl] = nz mask (bit 3 = block 0) | dc_flag << 8. */
+HDN void chroma_tq_plane(MBState &s, int pl)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
     const uint16_t *qdat = fp->qdat[1];
-    int sc = fp->stride[1];
-    /* forward transform + DC extraction + small-coefficient flags, 8 blocks */
-    FOR_LANES(b, 8)
+    const int sc = fp->stride[1];
+    FOR_LANES(k, 4)
     {
-        int pl = b >> 2, k = b & 3;
+        int b = pl * 4 + k;
         int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64;
         fwd4x4(w->inp_c + off, 16, w->predc + off, w->dq_c[b]);
         w->dc_c[b] = w->dq_c[b][0];
-        w->zflag1[b] = (int8_t)coefs_small(w->dq_c[b], 1, qdat + 10);
-    }
-    WSYNC();
-    int nzbits = 0;     /* bit (7 - b) */
-    FOR_LANES(b, 8)
-    {
         int nz = 0;
-        if (w->zflag1[b]) { for (int i = 0; i < 16; i++) w->qv_c[b][i] = 0; }
+        if (coefs_small(w->dq_c[b], 1, qdat + 10)) { for (int i = 0; i < 16; i++) w->qv_c[b][i] = 0; }
         else nz = quant4x4(w->dq_c[b], w->qv_c[b], 1, qdat);
-        if (nz) nzbits |= 0x80 >> b;
+        w->zflagc[b] = (int8_t)nz;
     }
-    nzbits = wor(nzbits);
     WSYNC();
+    int nzm = 0;
+    for (int k = 0; k < 4; k++) if (w->zflagc[pl * 4 + k]) nzm |= 8 >> k;
     IF_LANE0
     {
-        for (int pl = 0; pl < 2; pl++)
-        {
-            int16_t dq0[4];
-            int dcf = chroma_dc_quant(w->dc_c + 4 * pl, w->qdc_c + 4 * pl, dq0, qdat);
-            for (int k = 0; k < 4; k++) w->dq_c[pl * 4 + k][0] = dq0[k];
-            w->scal[1 + pl] = dcf;
-        }
+        int16_t dq0[4];
+        int dcf = chroma_dc_quant(w->dc_c + 4 * pl, w->qdc_c + 4 * pl, dq0, qdat);
+        for (int k = 0; k < 4; k++) w->dq_c[pl * 4 + k][0] = dq0[k];
+        w->tq_res[2 + pl] = nzm | (dcf << 8);
     }
     WSYNC();
-    int cbpc = 0;
-    for (int pl = 0; pl < 2; pl++)
+    const int dcf = w->tq_res[2 + pl] >> 8;
+    pix_t *dec = fp->dec[1 + pl] + (s.mby * 8) * sc + s.mbx * 8;
+    FOR_LANES(k, 4)
     {
-        int nzm = (nzbits >> (4 * (1 - pl))) & 15;
-        int dcf = w->scal[1 + pl];
-        if (nzm) cbpc = 2;
-        cbpc |= dcf;
-        pix_t *dec = fp->dec[1 + pl] + (s.mby * 8) * sc + s.mbx * 8;
-        FOR_LANES(k, 4)
+        int b = pl * 4 + k;
+        int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64;
+        pix_t *o = dec + (k & 1) * 4 + (k >> 1) * 4 * sc;
+        if (!(dcf | nzm)) copy4x4(w->predc + off, o, sc);
+        else if (dcf)
         {
-            int b = pl * 4 + k;
-            int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64;
-            pix_t *o = dec + (k & 1) * 4 + (k >> 1) * 4 * sc;
-            if (!(dcf | nzm)) copy4x4(w->predc + off, o, sc);
-            else if (dcf)
-            {
-                if (!(nzm & (8 >> k))) for (int i = 1; i < 16; i++) w->dq_c[b][i] = 0;
-                inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
-            } else
-            {
-                if (nzm & (8 >> k)) inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
-                else copy4x4(w->predc + off, o, sc);
-            }
+            if (!(nzm & (8 >> k))) for (int i = 1; i < 16; i++) w->dq_c[b][i] = 0;
+            inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
+        } else
+        {
+            if (nzm & (8 >> k)) inv4x4_add(w->dq_c[b], w->predc + off, o, sc);
+            else copy4x4(w->predc + off, o, sc);
         }
     }
     WSYNC();
-    return imin(cbpc, 2);
+}
+
+/* chroma intra prediction of plane pl (warp-level) */
+HDN void intra_chroma_plane(MBState &s, int pl)
+{
+    MBWork *w = s.w;
+    const pix_t *left = (s.avail & AVAIL_L) ? w->left_c : 0, *top = (s.avail & AVAIL_T) ? w->top_c : 0;
+    const int mode = s.i16_mode;
+    FOR_LANES(i, 16)
+    {
+        int r = i >> 1, xh = i & 1, yh = r >> 2;
+        uint32_t v;
+        if (mode == 0) v = ld4_sm(top + pl * 8 + xh * 4);
+        else if (mode == 1) v = left[pl * 8 + r] * 0x01010101u;
+        else
+        {
+            const pix_t *l = left ? left + pl * 8 + yh * 4 : 0;
+            const pix_t *t = top ? top + pl * 8 + xh * 4 : 0;
+            int dc;
+            if (xh == yh) dc = dc_pred(l, t, 4, 2);
+            else if (xh) dc = t ? dc_pred(0, t, 4, 2) : dc_pred(l, 0, 4, 2);
+            else dc = l ? dc_pred(l, 0, 4, 2) : dc_pred(0, t, 4, 2);
+            v = (uint32_t)dc * 0x01010101u;
+        }
+        *(uint32_t *)(w->predc + r * 16 + pl * 8 + xh * 4) = v;
+    }
+    WSYNC();
 }
 
 HD int count_nz(const int16_t *q, int i0)
@@ -1209,8 +1221,18 @@ HD void clusters_update(int32_t *cl, int mv)
 
 /* ------------------------------------------------------------------------------
  * a17: encode one macroblock (mb_encode H:5724 + the pixel/coefficient half of
- * mb_write H:4378).  cl[] = mv_clusters as seen by this MB; updated in place.
- * Writes the MB's record, quantised levels and unfiltered reconstruction.
+ * mb_write H:4378) with the whole CTA.  cl[] = rounded mv_clusters candidates.
+ * Writes the MB's record, quantised levels, unfiltered reconstruction and *spec_out
+ * (identical in every thread).
+ *
+ *   all      : load inputs, neighbours, MV context; load the search window
+ *   warp 0   : skip test + start candidates, then the 16x16 search
+ *   warp 1   : 16x8 and 8x16 searches      } start when warp 0 has published the
+ *   warp 2   : 8x8 search                  } candidate stage (named barrier 1)
+ *   warp 3   : Intra16x16 + Intra4x4 (stops early when warp 0 decides "skip")
+ *   all      : mode decision (same strict comparisons and order as the reference)
+ *   warps 0,1: luma halves;  warps 2,3: chroma planes (prediction + transform)
+ *   all      : coded block pattern, skip rollback, record
  * ---------------------------------------------------------------------------- */
 HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
 {
@@ -1218,100 +1240,188 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
     s.avail = mb_avail(mbx, mby, fp->nmbx);
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
-    s.pbest = w->store[0]; s.ptest = w->store[1];
+    s.pbest = w->skip_pred; s.ss = &w->ss[WARP_ID < 3 ? WARP_ID : 0];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
+    const int is_p = fp->slice_type == SLICE_P;
     MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     int16_t *coef = fp->coef + (size_t)(mby * fp->nmbx + mbx) * COEF_PER_MB;
     int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
-    int32_t cand_sig[4] = {0, 0, 0, 0};
-    int used_cl = 0;
-
     PROF_INIT(s);
+
     mb_load(s);
     PROF_MARK(s, 0);
-
-    if (fp->slice_type == SLICE_P) used_cl = !inter_choose(s, pmv, pmvd, cl, cand_sig, 0);
-    PROF_MARK(s, 6);
-
-    int nz_mask = 0;
-    if (s.type >= 0)
+    if (is_p)
     {
-        const pix_t *left = (s.avail & AVAIL_L) ? w->left_y : 0;
-        const pix_t *top = (s.avail & AVAIL_T) ? w->top_y : 0;
-        /* Intra16x16: heuristic mode, one prediction, SAD cost (intra_choose_16x16 H:4876) */
-        s.i16_mode = intra16_estimate(w->inp_y, s.avail, fp->qp);
-        intra16_pred(s.ptest, left, top, s.i16_mode);
-        WSYNC();
-        int cost16 = sad_sm_wh(w->inp_y, s.ptest, 16, 16)
-                   + ((bitsize_ue(s.i16_mode + 1) * fp->lambda_q4) >> 4) + fp->lambda_i16_q4;
-        if (cost16 < s.cost)
+        int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
+        win_load(s, mbx * 16 + ((mv_x(mvp16) + 1) >> 2), mby * 16 + ((mv_y(mvp16) + 1) >> 2));
+    }
+    PROF_MARK(s, 1);
+
+    /* ---- concurrent tasks ---- */
+    if (is_p)
+    {
+        ON_WARP(0)
         {
-            s.cost = cost16; s.type = MBT_I16;
-            pix_t *t = s.pbest; s.pbest = s.ptest; s.ptest = t;
+            s.ss = &w->ss[0];
+            inter_stage_a(s, cl);
+            PROF_MARK(s, 2);
+            bar_sync(1, 96);
+            if (w->ic[IC_STATE] != 1) inter_mode_search(s, 0);
+            PROF_MARK(s, 4);
         }
-        PROF_MARK(s, 7);
-        if (fp->speed < 2 || fp->slice_type != SLICE_P)
+        ON_WARP(1)
         {
-            int nz4;
-            int cost4 = intra4_choose(s, &nz4);
-            if (cost4 < s.cost) { s.cost = cost4; s.type = MBT_I4; nz_mask = nz4; }
+            s.ss = &w->ss[1];
+            bar_sync(1, 96);
+            if (w->ic[IC_STATE] != 1)
+            {
+                if (w->ic[IC_PREF] & 2) inter_mode_search(s, 1);
+                if (w->ic[IC_PREF] & 4) inter_mode_search(s, 2);
+            }
+        }
+        ON_WARP(2)
+        {
+            s.ss = &w->ss[2];
+            bar_sync(1, 96);
+            if (w->ic[IC_STATE] != 1 && (w->ic[IC_PREF] & 8)) inter_mode_search(s, 3);
         }
     }
+    ON_WARP(3)
+    {
+        /* Intra16x16: heuristic mode, one prediction, SAD cost (intra_choose_16x16 H:4876) */
+        const pix_t *left = (s.avail & AVAIL_L) ? w->left_y : 0;
+        const pix_t *top = (s.avail & AVAIL_T) ? w->top_y : 0;
+        int m16 = intra16_estimate(w->inp_y, s.avail, fp->qp);
+        intra16_pred(w->i16pred, left, top, m16);
+        WSYNC();
+        int cost16 = sad_sm_wh(w->inp_y, w->i16pred, 16, 16)
+                   + ((bitsize_ue(m16 + 1) * fp->lambda_q4) >> 4) + fp->lambda_i16_q4;
+        int cost4 = 0x7FFFFFFF, nz4 = 0;
+        if (fp->speed < 2 || !is_p) cost4 = intra4_choose(s, &nz4);
+        IF_LANE0 { w->intra_res[0] = cost16; w->intra_res[1] = m16; w->intra_res[2] = cost4; w->intra_res[3] = nz4; }
+    }
+    CTA_SYNC();
+    PROF_MARK(s, 5);
 
-    PROF_MARK(s, 8);
+    /* ---- mode decision (every thread, same values) ---- */
+    int nz_mask = 0, used_cl = 0;
+    int32_t cand_sig[4] = {0, 0, 0, 0};
+    if (is_p)
+    {
+        const int mvp16 = w->ic[IC_MVP16], mv_skip = w->ic[IC_MV_SKIP];
+        s.mv_skip_pred = mv_skip;
+        if (w->ic[IC_STATE] == 1)
+        {
+            s.type = MBT_SKIP; s.cost = 0;
+            pmv[0] = mv_skip;
+            s.pbest = w->skip_pred;
+        } else
+        {
+            used_cl = 1;
+            for (int k = 0; k < 4; k++) cand_sig[k] = w->ic[IC_SIG + k];
+            s.cost = 0xffffff;
+            int best_type = 0;
+            for (int t = 0; t < 4; t++)
+                if ((w->ic[IC_PREF] >> t) & 1)
+                    if (w->mode_cost[t] < s.cost) { s.cost = w->mode_cost[t]; best_type = t; }
+            s.type = best_type;
+            s.pbest = (pix_t *)w + w->mode_pred[best_type];
+            for (int i = 0; i < 4; i++) { pmv[i] = w->part_mv[best_type][i]; pmvd[i] = w->part_mvd[best_type][i]; }
+            if (s.cost > w->ic[IC_SAD_SKIP])     /* P16x16 at the skip vector is cheaper (H:5512) */
+            {
+                s.type = 0;
+                s.cost = w->ic[IC_SAD_SKIP] + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+                pmv[0] = mv_skip;
+                pmvd[0] = mv_sub2(mv_skip, mvp16);
+                s.pbest = w->skip_pred;      /* same samples the reference re-interpolates (H:5520) */
+            }
+        }
+    }
+    if (s.type >= 0)
+    {
+        s.i16_mode = w->intra_res[1];
+        if (w->intra_res[0] < s.cost) { s.cost = w->intra_res[0]; s.type = MBT_I16; s.pbest = w->i16pred; }
+        if (w->intra_res[2] < s.cost) { s.cost = w->intra_res[2]; s.type = MBT_I4; nz_mask = w->intra_res[3]; }
+    }
+
     spec_out->mv0 = pmv[0];
-    spec_out->flags = ((fp->slice_type == SLICE_P && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
+    spec_out->flags = ((is_p && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
     spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
     for (int k = 0; k < 4; k++) spec_out->cand_sig[k] = cand_sig[k];
 
-    if (s.type >= 5)
-    {
-        intra_chroma_pred(w->predc, (s.avail & AVAIL_L) ? w->left_c : 0, (s.avail & AVAIL_T) ? w->top_c : 0, s.i16_mode);
-        WSYNC();
-    } else
-    {
-        mc_chroma(s, s.type, pmv);
-    }
-
-    PROF_MARK(s, 9);
-    /* ---- transform, quantisation, reconstruction ---- */
+    /* ---- prediction of chroma, transform, quantisation, reconstruction ---- */
     int cbpl = 0, cbpc = 0;
     const int sy = fp->stride[0], sc = fp->stride[1];
     pix_t *decy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+    pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8, *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
     if (s.type != MBT_SKIP)
     {
-        if (s.type != MBT_I4) nz_mask = luma_tq_recon(s, s.type == MBT_I16);
-        else
+        const int i16 = s.type == MBT_I16;
+        if (s.type != MBT_I4)
         {
-            FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(w->i4rec + r * 16 + c); }
+            ON_WARP(0) { luma_tq_half(s, 0, i16, 0); }
+            ON_WARP(1) { luma_tq_half(s, 1, i16, 0); }
+            if (i16)
+            {   /* the DC transform needs all 16 blocks: warps 0 and 1 meet at named barriers */
+                if (WARP_ID < 2) bar_sync(2, 64);
+                ON_WARP(0) { luma_tq_half(s, 0, 1, 1); }
+                if (WARP_ID < 2) bar_sync(3, 64);
+            }
+            ON_WARP(0) { luma_tq_half(s, 0, i16, 2); }
+            ON_WARP(1) { luma_tq_half(s, 1, i16, 2); }
+        } else
+        {
+            ON_WARP(0)
+            {
+                FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(w->i4rec + r * 16 + c); }
+            }
         }
+        ON_WARP(2)
+        {
+            if (s.type >= 5) intra_chroma_plane(s, 0); else mc_chroma_plane(s, 0, s.type, pmv);
+            chroma_tq_plane(s, 0);
+        }
+        ON_WARP(3)
+        {
+            if (s.type >= 5) intra_chroma_plane(s, 1); else mc_chroma_plane(s, 1, s.type, pmv);
+            chroma_tq_plane(s, 1);
+        }
+        CTA_SYNC();
+        if (s.type != MBT_I4) nz_mask = w->tq_res[0] | w->tq_res[1];
         if (nz_mask & 0xCC00) cbpl |= 1;
         if (nz_mask & 0x3300) cbpl |= 2;
         if (nz_mask & 0x00CC) cbpl |= 4;
         if (nz_mask & 0x0033) cbpl |= 8;
-        cbpc = chroma_tq_recon(s);
+        for (int pl = 0; pl < 2; pl++)
+        {
+            if (w->tq_res[2 + pl] & 0xFF) cbpc = 2;
+            cbpc |= w->tq_res[2 + pl] >> 8;
+        }
+        cbpc = imin(cbpc, 2);
         if (!(s.type | cbpl | cbpc) && pmv[0] == s.mv_skip_pred) s.type = MBT_SKIP;   /* rollback H:4494 */
     }
+    PROF_MARK(s, 10);
     if (s.type == MBT_SKIP)
     {
-        /* reconstruction = prediction (H:4417-4420) */
-        pix_t *du = fp->dec[1] + (mby * 8) * sc + mbx * 8, *dv = fp->dec[2] + (mby * 8) * sc + mbx * 8;
-        FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(s.pbest + r * 16 + c); }
-        FOR_LANES(i, 32)
+        /* reconstruction = prediction (H:4417-4420); for the early skip predc holds the chroma
+         * prediction of the skip test, for a rollback the chroma prediction just computed */
+        FOR_THREADS(i, 96)
         {
-            int r = i >> 2, q = i & 3;
-            pix_t *d = (q < 2 ? du : dv) + r * sc + (q & 1) * 4;
-            *(uint32_t *)d = ld4_sm(w->predc + r * 16 + q * 4);
+            if (i < 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(s.pbest + r * 16 + c); }
+            else
+            {
+                int k = i - 64, r = k >> 2, q = k & 3;
+                pix_t *d = (q < 2 ? du : dv) + r * sc + (q & 1) * 4;
+                *(uint32_t *)d = ld4_sm(w->predc + r * 16 + q * 4);
+            }
         }
         nz_mask = 0; cbpl = cbpc = 0;
     }
-    WSYNC();
 
-    PROF_MARK(s, 10);
     /* ---- macroblock record ---- */
     const int type = s.type;
     if (type == MBT_I16 && cbpl) cbpl = 15;
-    FOR_LANES(i, 32)
+    FOR_THREADS(i, 32)
     {
         if (i < 16)
         {
@@ -1351,7 +1461,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     }
     if (type != MBT_SKIP)
     {
-        FOR_LANES(i, COEF_PER_MB / 2)      /* two int16 per item */
+        FOR_THREADS(i, COEF_PER_MB / 2)      /* two int16 per item */
         {
             int k = i * 2;
             uint32_t v;
@@ -1362,7 +1472,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             *(uint32_t *)(coef + k) = v;
         }
     }
-    WSYNC();
+    CTA_SYNC();
     PROF_MARK(s, 11);
     PROF_STORE(s, fp, mby * fp->nmbx + mbx, type);
 }

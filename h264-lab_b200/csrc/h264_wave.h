@@ -29,7 +29,7 @@
 
 HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 {
-    IF_LANE0 { fp->spec[n] = sp; }
+    IF_THREAD0 { fp->spec[n] = sp; }
 }
 
 /* pass 0 / I frames */
@@ -49,7 +49,7 @@ HDN void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
     if (fp->slice_type == SLICE_P)
     {
         spec_store(fp, n, sp);
-        IF_LANE0 { fp->changed_pass[n] = 0; }
+        IF_THREAD0 { fp->changed_pass[n] = 0; }
     }
 }
 
@@ -60,13 +60,17 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
     s.avail = mb_avail(x, y, fp->nmbx);
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
-    s.pbest = w->store[0]; s.ptest = w->store[1];
+    s.pbest = w->skip_pred; s.ss = &w->ss[0];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
-    int32_t pmv[4], pmvd[4], sig[4] = {0, 0, 0, 0};
     mb_load(s);
-    int r = inter_choose(s, pmv, pmvd, cl, sig, 1);
-    if (r != 2) return 0;
-    return sig[0] == old.cand_sig[0] && sig[1] == old.cand_sig[1] && sig[2] == old.cand_sig[2] && sig[3] == old.cand_sig[3];
+    int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
+    win_load(s, x * 16 + ((mv_x(mvp16) + 1) >> 2), y * 16 + ((mv_y(mvp16) + 1) >> 2));
+    ON_WARP(0) { inter_stage_a(s, cl); }
+    CTA_SYNC();
+    int same = w->ic[IC_STATE] == 2 && w->ic[IC_SIG] == old.cand_sig[0] && w->ic[IC_SIG + 1] == old.cand_sig[1] &&
+               w->ic[IC_SIG + 2] == old.cand_sig[2] && w->ic[IC_SIG + 3] == old.cand_sig[3];
+    CTA_SYNC();
+    return same;
 }
 
 /* repair sweep `pass` (>= 1) */
@@ -88,10 +92,10 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
     if (!need_cl && !need_nb) return;
     if (!need_nb)
     {
-        IF_LANE0 { atomic_add_stat(fp->fsync + FS_CHECKS); }
+        IF_THREAD0 { atomic_add_stat(fp->fsync + FS_CHECKS); }
         if (wave_cand_check(fp, w, x, y, ct, old))
         {
-            IF_LANE0 { fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1]; }
+            IF_THREAD0 { fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1]; }
             return;
         }
     }
@@ -100,43 +104,49 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
     const int sy = fp->stride[0], sc = fp->stride[1];
     const pix_t *dy = fp->dec[0] + (y * 16) * sy + x * 16;
     const pix_t *du = fp->dec[1] + (y * 8) * sc + x * 8, *dv = fp->dec[2] + (y * 8) * sc + x * 8;
-    FOR_LANES(i, 36) { w->old_mbi[i] = ((const uint32_t *)mi)[i]; }
-    FOR_LANES(i, 96)
+    FOR_THREADS(i, 36) { w->old_mbi[i] = ((const uint32_t *)mi)[i]; }
+    FOR_THREADS(i, 96)
     {
         uint32_t v;
         if (i < 64) v = *(const uint32_t *)(dy + (i >> 2) * sy + (i & 3) * 4);
         else { int k = i - 64, r = k >> 2, q = k & 3; v = *(const uint32_t *)((q < 2 ? du : dv) + r * sc + (q & 1) * 4); }
         w->old_rec[i] = v;
     }
-    WSYNC();
+    CTA_SYNC();
     MBSpec sp;
     encode_mb(fp, w, x, y, ct, &sp);
     /* Only what a causal successor consumes can propagate: the MV grid and the I4x4 modes
      * (MV / mode predictors) and the unfiltered right column / bottom row of the
      * reconstruction (intra prediction).  mvd, cbp, levels only feed this MB's own bits. */
-    int diff = 0;
-    FOR_LANES(i, 36) { if (i < 16 || (i >= 22 && i < 26)) diff |= w->old_mbi[i] != ((const uint32_t *)mi)[i]; }
-    FOR_LANES(i, 96)
+    ON_WARP(0)
     {
-        uint32_t v, mask;
-        if (i < 64) { v = *(const uint32_t *)(dy + (i >> 2) * sy + (i & 3) * 4); mask = ((i >> 2) == 15 ? 0xffffffffu : 0u) | ((i & 3) == 3 ? 0xff000000u : 0u); }
-        else
+        int diff = 0;
+        FOR_LANES(i, 36) { if (i < 16 || (i >= 22 && i < 26)) diff |= w->old_mbi[i] != ((const uint32_t *)mi)[i]; }
+        FOR_LANES(i, 96)
         {
-            int k = i - 64, r = k >> 2, q = k & 3;
-            v = *(const uint32_t *)((q < 2 ? du : dv) + r * sc + (q & 1) * 4);
-            mask = (r == 7 ? 0xffffffffu : 0u) | ((q & 1) ? 0xff000000u : 0u);
+            uint32_t v, mask;
+            if (i < 64) { v = *(const uint32_t *)(dy + (i >> 2) * sy + (i & 3) * 4); mask = ((i >> 2) == 15 ? 0xffffffffu : 0u) | ((i & 3) == 3 ? 0xff000000u : 0u); }
+            else
+            {
+                int k = i - 64, r = k >> 2, q = k & 3;
+                v = *(const uint32_t *)((q < 2 ? du : dv) + r * sc + (q & 1) * 4);
+                mask = (r == 7 ? 0xffffffffu : 0u) | ((q & 1) ? 0xff000000u : 0u);
+            }
+            diff |= ((w->old_rec[i] ^ v) & mask) != 0;
         }
-        diff |= ((w->old_rec[i] ^ v) & mask) != 0;
+        diff = wor(diff);
+        IF_LANE0 { w->scal[3] = diff; }
     }
-    diff = wor(diff);
+    CTA_SYNC();
+    const int diff = w->scal[3];
     spec_store(fp, n, sp);
-    IF_LANE0
+    IF_THREAD0
     {
         atomic_add_stat(fp->fsync + FS_REENC);
         if (diff) fp->changed_pass[n] = pass;
         if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES)) atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
     }
-    WSYNC();
+    CTA_SYNC();
 }
 
 /* Sequential replay of the cluster trajectory by one warp (lane 0 walks, the warp stages
@@ -192,7 +202,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w)
 
 /* Executed once per pass by the last row to finish: returns the next pass number or FS_DONE.
  * On FS_DONE the cluster state is committed for the next frame. */
-HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)
+HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one warp */
 {
     int next;
     if (fp->slice_type != SLICE_P) return FS_DONE;

@@ -39,7 +39,7 @@
 /* ------------------------------------------------------------------------------ */
 /* wavefront helpers                                                                */
 /* ------------------------------------------------------------------------------ */
-__device__ __forceinline__ void wait_row(const int *progress_above, int need)
+__device__ __forceinline__ void wait_row(const int *progress_above, int need)      /* one warp */
 {
     if (LANE_ID == 0)
     {
@@ -49,71 +49,71 @@ __device__ __forceinline__ void wait_row(const int *progress_above, int need)
     __syncwarp();
     __threadfence();
 }
-__device__ __forceinline__ void publish_row(int *progress, int done)
+__device__ __forceinline__ void publish_row(int *progress, int done)               /* one warp */
 {
     __threadfence();
     __syncwarp();
     if (LANE_ID == 0) *(volatile int *)progress = done;
 }
+__device__ __forceinline__ void wait_row_cta(const int *progress_above, int need)  /* whole CTA */
+{
+    if (threadIdx.x == 0)
+    {
+        const volatile int *p = progress_above;
+        while (*p < need) { __nanosleep(32); }
+    }
+    __syncthreads();
+    __threadfence();
+}
+__device__ __forceinline__ void publish_row_cta(int *progress, int done)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile int *)progress = done;
+}
 
 /* sync area layout per submission: [0] ticket of k_encode_rows, [1] ticket of k_deblock_rows.
  *
- * k_encode_rows: one warp per macroblock row, persistent over all verification sweeps of the
- * frame (h264_wave.h).  Row progress counters are monotonic: sweep p of a row counts from
- * p*nmbx.  Between sweeps the rows of a frame meet at a counter barrier; the last row to
- * arrive replays the cluster trajectory and publishes the next sweep number (or FS_DONE). */
-__global__ void __launch_bounds__(32) k_encode_rows(const FrameParams *fps, int njobs, int *tickets)
+ * k_encode_rows: one sweep (h264_wave.h) over the frames of the submission; one CTA of
+ * MB_WARPS warps per macroblock row.  Rows are claimed from an atomic ticket, so the row a
+ * CTA waits for (same frame, row - 1, an earlier ticket) is always running or finished:
+ * no co-residency assumption, no deadlock.  Row progress counters are monotonic: sweep p of
+ * a row counts from p*nmbx.  k_replay then replays the cluster trajectory of every frame and
+ * publishes FS_DONE or the number of the repair sweep the host has to launch. */
+__global__ void __launch_bounds__(MB_WARPS * 32) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
+    __shared__ FrameParams sfp;
     __shared__ int s_item;
     if (threadIdx.x == 0) s_item = atomicAdd(&tickets[0], 1);
-    __syncwarp();
+    __syncthreads();
     const int item = s_item;
     const int job = item % njobs, row = item / njobs;
-    const FrameParams *fp = fps + job;
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
+        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + job))[i];
+    __syncthreads();
+    const FrameParams *fp = &sfp;
     if (row >= fp->nmby) return;
-    const int nmbx = fp->nmbx, nmby = fp->nmby;
+    const int nmbx = fp->nmbx;
     int *progress = fp->row_progress;
-    for (int pass = 0;;)
+    const int base = pass * nmbx;
+    for (int x = 0; x < nmbx; x++)
     {
-        const int base = pass * nmbx;
-        for (int x = 0; x < nmbx; x++)
-        {
-            if (row > 0) wait_row(progress + row - 1, base + min(x + 2, nmbx));
-            if (pass == 0) wave_mb_first(fp, &work, x, row);
-            else wave_mb_repair(fp, &work, x, row, pass);
-            publish_row(progress + row, base + x + 1);
-        }
-        if (fp->slice_type != SLICE_P) break;
-        /* frame barrier */
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (threadIdx.x == 0) last = atomicAdd(&fp->fsync[FS_ARRIVE], 1) == (pass + 1) * nmby - 1;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        int next;
-        if (last)
-        {
-            __threadfence();
-            next = wave_end_of_pass(fp, &work, pass);
-            if (next != FS_DONE && next > fp->max_passes) { if (threadIdx.x == 0) atomicOr(&fp->out_info[1], 4); next = FS_DONE; }
-            __threadfence();
-            __syncwarp();
-            if (threadIdx.x == 0) *(volatile int *)&fp->fsync[FS_STATE] = next;
-        } else
-        {
-            if (threadIdx.x == 0)
-            {
-                const volatile int *st = &fp->fsync[FS_STATE];
-                while (*st <= pass) __nanosleep(256);
-                next = *st;
-            }
-            next = __shfl_sync(0xffffffffu, next, 0);
-            __threadfence();
-        }
-        if (next == FS_DONE) break;
-        pass = next;
+        if (row > 0) wait_row_cta(progress + row - 1, base + min(x + 2, nmbx));
+        if (pass == 0) wave_mb_first(fp, &work, x, row);
+        else wave_mb_repair(fp, &work, x, row, pass);
+        publish_row_cta(progress + row, base + x + 1);
     }
+}
+
+/* one warp per frame: end-of-sweep bookkeeping (trajectory replay, convergence test) */
+__global__ void __launch_bounds__(32) k_replay(const FrameParams *fps, int njobs, int pass)
+{
+    __shared__ MBWork work;
+    const FrameParams *fp = fps + blockIdx.x;
+    int next = wave_end_of_pass(fp, &work, pass);
+    if (next != FS_DONE && next > fp->max_passes) { if (threadIdx.x == 0) atomicOr(&fp->out_info[1], 4); next = FS_DONE; }
+    if (threadIdx.x == 0) fp->fsync[FS_STATE] = next;
 }
 
 __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int njobs, int *tickets)
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     const int item = s_item;
     const int job = item % njobs, row = item / njobs;
     const FrameParams *fp = fps + job;
-    if (row >= fp->nmby || fp->disable_deblock) return;
+    if (row >= fp->nmby || fp->disable_deblock || fp->fsync[FS_STATE] != FS_DONE) return;
     const int nmbx = fp->nmbx;
     int *progress = fp->row_progress_df;
     for (int x = 0; x < nmbx; x++)
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
 __global__ void k_borders(const FrameParams *fps, int njobs)
 {
     const FrameParams *fp = fps + blockIdx.y;
+    if (fp->fsync[FS_STATE] != FS_DONE) return;
     for (int pl = 0; pl < 3; pl++)
     {
         long n = border_samples(fp, pl);
@@ -151,7 +152,7 @@ __global__ void k_cavlc(const FrameParams *fps, int njobs)
     const FrameParams *fp = fps + blockIdx.y;
     const int nmb = fp->nmbx * fp->nmby;
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n > nmb) return;
+    if (n > nmb || fp->fsync[FS_STATE] != FS_DONE) return;
     fp->mb_nbits[n] = cavlc_mb(fp, n);
 }
 
@@ -159,6 +160,7 @@ __global__ void k_cavlc(const FrameParams *fps, int njobs)
 __global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs, int out_cap_words)
 {
     const FrameParams *fp = fps + blockIdx.x;
+    if (fp->fsync[FS_STATE] != FS_DONE) return;
     const int cnt = fp->nmbx * fp->nmby + 1;
     __shared__ int part[1024];
     const int tid = threadIdx.x;
@@ -196,7 +198,7 @@ __global__ void k_pack(const FrameParams *fps, int njobs)
     const FrameParams *fp = fps + blockIdx.y;
     const int nmb = fp->nmbx * fp->nmby;
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n > nmb || fp->out_info[1]) return;
+    if (n > nmb || fp->out_info[1] || fp->fsync[FS_STATE] != FS_DONE) return;
     int nb = fp->mb_nbits[n];
     if (nb) pack_mb(fp, n, nb, fp->mb_bitoff[n]);
 }
@@ -390,12 +392,40 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
     return 0;
 }
 
+/* kernels that follow the macroblock sweeps; frames that are not FS_DONE are skipped inside */
+static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nmb, int cap_words, cudaStream_t st,
+                       cudaEvent_t ev_mid)
+{
+    CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
+    k_deblock_rows<<<n * max_rows, 32, 0, st>>>(d_fps, n, g_d_tickets);
+    k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
+    if (ev_mid) CK(cudaEventRecord(ev_mid, st));
+    k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, st>>>(d_fps, n);
+    k_scan<<<n, 1024, 0, st>>>(d_fps, n, cap_words);
+    k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, st>>>(d_fps, n);
+    g_launches += 5;
+    return 0;
+}
+
+static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st)
+{
+    for (int k = 0; k < n; k++)
+    {
+        h264b200_ctx *c = jobs[idx ? idx[k] : k].ctx;
+        CK(cudaMemcpyAsync(c->h_out_info, c->d_out_info, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_out_info + 4, c->d_fsync, 32, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int encode_impl(int n, h264b200_job *jobs)
 {
     if (n <= 0) return 0;
-    if (ensure_globals(n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
+    if (ensure_globals(2 * n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
     cudaStream_t st = g_stream;
-    int max_rows = 0, max_nmb = 0;
+    int max_rows = 0, max_nmb = 0, cap = 0x7fffffff;
     for (int i = 0; i < n; i++)
     {
         h264b200_ctx *c = jobs[i].ctx;
@@ -403,23 +433,24 @@ static int encode_impl(int n, h264b200_job *jobs)
         build_fp(&jobs[i], &g_h_fps[i]);
         max_rows = c->nmby > max_rows ? c->nmby : max_rows;
         max_nmb = c->nmb > max_nmb ? c->nmb : max_nmb;
+        cap = c->out_cap_words < cap ? c->out_cap_words : cap;
     }
     CK(cudaEventRecord(g_ev[0], st));
     for (int i = 0; i < n; i++)
+    {
+        h264b200_ctx *c = jobs[i].ctx;
+        if (jobs[i].preloaded_index >= 0)
         {
-            h264b200_ctx *c = jobs[i].ctx;
-            if (jobs[i].preloaded_index >= 0)
-            {
-                if (jobs[i].preloaded_index >= c->clip_frames) { jobs[i].status = -3; return -3; }
-                continue;
-            }
-            for (int pl = 0; pl < 3; pl++)
-            {
-                int w = pl ? c->width / 2 : c->width, h = pl ? c->height / 2 : c->height;
-                CK(cudaMemcpy2DAsync(c->d_inp[pl], c->inp_stride[pl], jobs[i].yuv[pl], jobs[i].stride[pl], w, h,
-                                     cudaMemcpyHostToDevice, st));
-            }
+            if (jobs[i].preloaded_index >= c->clip_frames) { jobs[i].status = -3; return -3; }
+            continue;
         }
+        for (int pl = 0; pl < 3; pl++)
+        {
+            int w = pl ? c->width / 2 : c->width, h = pl ? c->height / 2 : c->height;
+            CK(cudaMemcpy2DAsync(c->d_inp[pl], c->inp_stride[pl], jobs[i].yuv[pl], jobs[i].stride[pl], w, h,
+                                 cudaMemcpyHostToDevice, st));
+        }
+    }
     CK(cudaMemcpyAsync(g_d_fps, g_h_fps, sizeof(FrameParams) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(g_d_tickets, 0, 64, st));
     for (int i = 0; i < n; i++)
@@ -429,28 +460,53 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
     }
+    /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
-    k_encode_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, g_d_tickets);
+    k_encode_rows<<<n * max_rows, MB_WARPS * 32, 0, st>>>(g_d_fps, n, g_d_tickets, 0);
+    k_replay<<<n, 32, 0, st>>>(g_d_fps, n, 0);
+    g_launches += 2;
     CK(cudaEventRecord(g_ev[2], st));
-    k_deblock_rows<<<n * max_rows, 32, 0, st>>>(g_d_fps, n, g_d_tickets);
-    k_borders<<<dim3(64, n), 256, 0, st>>>(g_d_fps, n);
-    CK(cudaEventRecord(g_ev[3], st));
-    k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, st>>>(g_d_fps, n);
-    {
-        int cap = jobs[0].ctx->out_cap_words;
-        for (int i = 1; i < n; i++) cap = jobs[i].ctx->out_cap_words < cap ? jobs[i].ctx->out_cap_words : cap;
-        k_scan<<<n, 1024, 0, st>>>(g_d_fps, n, cap);
-    }
-    k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, st>>>(g_d_fps, n);
-    g_launches += 6;
+    if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;
     CK(cudaEventRecord(g_ev[4], st));
+    if (fetch_info(n, jobs, NULL, st)) return -3;
+
+    /* frames whose speculated mv_clusters candidates did not verify: repair sweeps (h264_wave.h) */
+    std::vector<int> dirty;
     for (int i = 0; i < n; i++)
+        if (jobs[i].ctx->h_out_info[4 + FS_STATE] != FS_DONE && !(jobs[i].ctx->h_out_info[1] & 4)) dirty.push_back(i);
+    FrameParams *h2 = g_h_fps + n, *d2 = g_d_fps + n;
+    while (!dirty.empty())
     {
-        CK(cudaMemcpyAsync(jobs[i].ctx->h_out_info, jobs[i].ctx->d_out_info, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(jobs[i].ctx->h_out_info + 4, jobs[i].ctx->d_fsync, 32, cudaMemcpyDeviceToHost, st));
+        int m = (int)dirty.size(), rows2 = 0, nmb2 = 0, pass = 0;
+        for (int k = 0; k < m; k++)
+        {
+            h264b200_ctx *c = jobs[dirty[k]].ctx;
+            h2[k] = g_h_fps[dirty[k]];
+            rows2 = c->nmby > rows2 ? c->nmby : rows2;
+            nmb2 = c->nmb > nmb2 ? c->nmb : nmb2;
+            pass = c->h_out_info[4 + FS_STATE];       /* sweeps advance in lock step for all dirty frames */
+        }
+        CK(cudaMemcpyAsync(d2, h2, sizeof(FrameParams) * m, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
+        k_encode_rows<<<m * rows2, MB_WARPS * 32, 0, st>>>(d2, m, g_d_tickets, pass);
+        k_replay<<<m, 32, 0, st>>>(d2, m, pass);
+        g_launches += 2;
+        if (launch_post(d2, m, rows2, nmb2, cap, st, NULL)) return -3;
+        if (fetch_info(m, jobs, dirty.data(), st)) return -3;
+        std::vector<int> still;
+        for (int k = 0; k < m; k++)
+        {
+            h264b200_ctx *c = jobs[dirty[k]].ctx;
+            int stt = c->h_out_info[4 + FS_STATE];
+            if (stt != FS_DONE && !(c->h_out_info[1] & 4))
+            {
+                if (stt != pass + 1) { jobs[dirty[k]].status = -4; continue; }
+                still.push_back(dirty[k]);
+            }
+        }
+        dirty.swap(still);
     }
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
+
     int rc = 0;
     for (int i = 0; i < n; i++)
     {
@@ -461,16 +517,15 @@ static int encode_impl(int n, h264b200_job *jobs)
         c->stats[0] += c->h_out_info[4 + FS_PASSES]; c->stats[1] += c->h_out_info[4 + FS_REENC];
         c->stats[2] += c->h_out_info[4 + FS_CHECKS]; c->stats[3]++;
         c->have_traj = jobs[i].p.slice_type == SLICE_P;
+        if (jobs[i].status) { if (!rc) rc = jobs[i].status; continue; }
         if (c->h_out_info[1] & 4) { jobs[i].status = -4; if (!rc) rc = -4; continue; }
         if (c->h_out_info[1]) { jobs[i].status = -2; if (!rc) rc = -2; continue; }
         CK(cudaMemcpyAsync(c->h_out_words, c->d_out_words, (size_t)((jobs[i].out_bits + 95) / 32) * 4, cudaMemcpyDeviceToHost, st));
         for (int pl = 0; pl < 3; pl++)
             if (jobs[i].recon[pl])
             {
-                int w = c->nmbx * (pl ? 8 : 16), h = c->nmby * (pl ? 8 : 16);
                 /* in-place mode hands us the caller's planes: copy only the visible area */
                 int cw = pl ? c->width / 2 : c->width, chh = pl ? c->height / 2 : c->height;
-                (void)w; (void)h;
                 CK(cudaMemcpy2DAsync(jobs[i].recon[pl], jobs[i].recon_stride[pl],
                                      c->d_frames[c->cur] + c->plane_off[pl], c->stride[pl != 0], cw, chh,
                                      cudaMemcpyDeviceToHost, st));
