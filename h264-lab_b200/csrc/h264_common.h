@@ -161,6 +161,9 @@ struct MBSpec
                             SPEC_USED_CL: the decision consumed the cluster candidates       */
     int32_t cl_used[2];  /* rounded cluster candidates the decision was made with           */
     int32_t cand_sig[4]; /* candidate-stage outcome: mv_best, sad_best, cost_best, partition hints */
+    int32_t mode_cost[4];/* cost of every partition mode that was searched                   */
+    int32_t inter_best;  /* partition mode that won the inter decision                      */
+    int32_t pad[3];
 };
 #define SPEC_UPDATES 1
 #define SPEC_USED_CL 2
@@ -174,6 +177,8 @@ struct MBSpec
 #define FS_REENC 5        /* statistics: full re-encodes                                      */
 #define FS_CHECKS 6       /* statistics: candidate-stage re-checks                            */
 #define FS_CL_END 8       /* [8],[9]: cluster state after the last macroblock (raw)           */
+#define FS_LIVE 10        /* [10],[11]: cluster state after the raster-contiguous prefix of finished
+                             macroblocks of sweep 0, published while the sweep runs; [12] prefix length */
 #define FS_WORDS 16
 #define FS_DONE 0x40000000
 

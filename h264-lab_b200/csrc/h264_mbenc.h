@@ -1306,6 +1306,8 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     /* ---- mode decision (every thread, same values) ---- */
     int nz_mask = 0, used_cl = 0;
     int32_t cand_sig[4] = {0, 0, 0, 0};
+    spec_out->inter_best = 0;
+    for (int k = 0; k < 4; k++) spec_out->mode_cost[k] = 0x7FFFFFFF;
     if (is_p)
     {
         const int mvp16 = w->ic[IC_MVP16], mv_skip = w->ic[IC_MV_SKIP];
@@ -1323,7 +1325,11 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             int best_type = 0;
             for (int t = 0; t < 4; t++)
                 if ((w->ic[IC_PREF] >> t) & 1)
+                {
+                    spec_out->mode_cost[t] = w->mode_cost[t];
                     if (w->mode_cost[t] < s.cost) { s.cost = w->mode_cost[t]; best_type = t; }
+                }
+            spec_out->inter_best = best_type;
             s.type = best_type;
             s.pbest = (pix_t *)w + w->mode_pred[best_type];
             for (int i = 0; i < 4; i++) { pmv[i] = w->part_mv[best_type][i]; pmvd[i] = w->part_mvd[best_type][i]; }

@@ -7,11 +7,14 @@
  * the last two motion-search start candidates of the NEXT macroblock (H:5382-5383).  A
  * wavefront cannot know them.  Scheme used here (all on the GPU):
  *
- *   pass 0   every macroblock is decided in x+2y wavefront order with the cluster
- *            candidates frozen at their frame-start value;
- *   replay   one warp replays the true cluster trajectory in raster order from the
- *            macroblocks' final (type, mv[0]) and counts the macroblocks whose speculated
- *            candidates differ from the true ones ("dirty");
+ *   predict  before the sweep, one warp replays the cluster update over the PREVIOUS frame's
+ *            motion field starting from this frame's true start state: the predicted
+ *            trajectory (motion fields are temporally coherent);
+ *   pass 0   every macroblock is decided in x+2y wavefront order with the predicted cluster
+ *            candidates (frame-start value after an intra frame);
+ *   replay   the follower (sweep 0) / one warp (later sweeps) replays the true cluster
+ *            trajectory in raster order from the macroblocks' final (type, mv[0]) and counts
+ *            the macroblocks whose speculated candidates differ from the true ones ("dirty");
  *   pass k   another wavefront sweep: a macroblock is revisited only if it is dirty or a
  *            causal neighbour (L, T, TL, TR) changed in this sweep.  A dirty macroblock
  *            first re-runs just the candidate stage: if (mv_best, sad_best, cost_best,
@@ -42,6 +45,10 @@ HDN void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
     {
         /* speculation: the co-located value of the previous P frame's trajectory when there is
          * one (motion fields are temporally coherent), else the frame-start value */
+        /* speculation: when the previous frame was a P frame, the trajectory PREDICTED for this
+         * frame by replaying the cluster update over the previous frame's motion field from
+         * this frame's true start state (wave_replay(predict), motion is temporally coherent);
+         * otherwise the frame-start value */
         if (fp->spec_from_prev) { cl[0] = fp->cl_true[2 * n]; cl[1] = fp->cl_true[2 * n + 1]; }
         else { cl[0] = mv_round_fullpel(fp->clusters[0]); cl[1] = mv_round_fullpel(fp->clusters[1]); }
     }
@@ -67,8 +74,34 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     win_load(s, x * 16 + ((mv_x(mvp16) + 1) >> 2), y * 16 + ((mv_y(mvp16) + 1) >> 2));
     ON_WARP(0) { inter_stage_a(s, cl); }
     CTA_SYNC();
-    int same = w->ic[IC_STATE] == 2 && w->ic[IC_SIG] == old.cand_sig[0] && w->ic[IC_SIG + 1] == old.cand_sig[1] &&
-               w->ic[IC_SIG + 2] == old.cand_sig[2] && w->ic[IC_SIG + 3] == old.cand_sig[3];
+    int same = 0;
+    if (w->ic[IC_STATE] == 2 && w->ic[IC_SIG] == old.cand_sig[0] && w->ic[IC_SIG + 1] == old.cand_sig[1] &&
+        w->ic[IC_SIG + 2] == old.cand_sig[2])
+    {
+        const int newp = w->ic[IC_SIG + 3], oldp = old.cand_sig[3];
+        if (newp == oldp) same = 1;
+        else if (!(newp & ~oldp))
+        {
+            /* only partition hints were withdrawn: the searches that remain are the ones already
+             * done (they do not depend on the candidates), so re-run just the decision (H:5500) */
+            int cost = 0xffffff, best = 0;
+            for (int t = 0; t < 4; t++)
+                if (t == 0 || ((newp >> (t - 1)) & 1))
+                    if (old.mode_cost[t] < cost) { cost = old.mode_cost[t]; best = t; }
+            if (best == old.inter_best) same = 2;
+        }
+    }
+#if !H264_DEVICE
+    {
+        extern int g_emu_dbg[8];
+        if (!same)
+        {
+            if (w->ic[IC_STATE] != 2) g_emu_dbg[0]++;
+            else if (w->ic[IC_SIG] != old.cand_sig[0] || w->ic[IC_SIG + 1] != old.cand_sig[1] || w->ic[IC_SIG + 2] != old.cand_sig[2]) g_emu_dbg[1]++;
+            else { g_emu_dbg[2]++; if ((w->ic[IC_SIG + 3] & old.cand_sig[3]) == old.cand_sig[3]) g_emu_dbg[3]++; }
+        } else g_emu_dbg[4]++;
+    }
+#endif
     CTA_SYNC();
     return same;
 }
@@ -93,9 +126,15 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
     if (!need_nb)
     {
         IF_THREAD0 { atomic_add_stat(fp->fsync + FS_CHECKS); }
-        if (wave_cand_check(fp, w, x, y, ct, old))
+        int chk = wave_cand_check(fp, w, x, y, ct, old);
+        if (chk)
         {
-            IF_THREAD0 { fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1]; }
+            IF_THREAD0
+            {
+                fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1];
+                if (chk == 2) fp->spec[n].cand_sig[3] = w->ic[IC_SIG + 3];
+            }
+            CTA_SYNC();
             return;
         }
     }
@@ -151,7 +190,7 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
 
 /* Sequential replay of the cluster trajectory by one warp (lane 0 walks, the warp stages
  * 32 records at a time).  Writes cl_true[], the end state, and returns the dirty count. */
-HDN int wave_replay(const FrameParams *fp, MBWork *w)
+HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
 {
     const int nmb = fp->nmbx * fp->nmby;
     int32_t c[2];
@@ -190,6 +229,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w)
         }
         WSYNC();
     }
+    if (predict) return 0;
     IF_LANE0
     {
         fp->fsync[FS_CL_END] = c[0]; fp->fsync[FS_CL_END + 1] = c[1];
@@ -211,7 +251,7 @@ HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one wa
     if (need_replay)
     {
         IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; }
-        int nd = wave_replay(fp, w);
+        int nd = wave_replay(fp, w, 0);
         next = nd ? pass + 1 : FS_DONE;
     } else next = FS_DONE;
     if (next == FS_DONE)

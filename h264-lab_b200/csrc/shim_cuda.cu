@@ -80,6 +80,67 @@ __device__ __forceinline__ void publish_row_cta(int *progress, int done)
  * no co-residency assumption, no deadlock.  Row progress counters are monotonic: sweep p of
  * a row counts from p*nmbx.  k_replay then replays the cluster trajectory of every frame and
  * publishes FS_DONE or the number of the repair sweep the host has to launch. */
+/* Trajectory follower of sweep 0 (one warp per frame): consumes the macroblocks of the frame in
+ * raster order as they finish, replays mv_clusters_update, publishes the running state for
+ * the macroblocks still to start (their speculation) and, at the end, does what
+ * wave_end_of_pass(pass 0) does: true candidates per macroblock, dirty count, FS_DONE or 1. */
+__device__ void trajectory_follower(const FrameParams *fp)
+{
+    const int lane = threadIdx.x;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
+    volatile int32_t *fs = (volatile int32_t *)fp->fsync;
+    if (fp->slice_type != SLICE_P)
+    {
+        if (lane == 0) { fs[FS_PASSES] = 1; __threadfence(); fs[FS_STATE] = FS_DONE; }
+        return;
+    }
+    int32_t c[2];
+    c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
+    int ndirty = 0, n = 0;
+    while (n < nmb)
+    {
+        /* how many macroblocks of the raster order are finished from n on (at most 32) */
+        int row = n / nmbx, x = n - row * nmbx, avail = 0;
+        if (lane == 0)
+        {
+            const volatile int *pr = fp->row_progress + row;
+            int p;
+            while ((p = *pr) <= x) __nanosleep(200);
+            avail = min(p - x, 32);
+        }
+        avail = __shfl_sync(0xffffffffu, avail, 0);
+        __threadfence();
+        int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
+        if (lane < avail)
+        {
+            const MBSpec *sp = fp->spec + n + lane;
+            mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
+        }
+        int t0 = 0, t1 = 0;
+        for (int i = 0; i < avail; i++)
+        {
+            int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+            int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
+            int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
+            if (lane == i) { t0 = r0; t1 = r1; }
+            if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+            if (f & SPEC_UPDATES) clusters_update(c, m);
+        }
+        if (lane < avail) { fp->cl_true[2 * (n + lane)] = t0; fp->cl_true[2 * (n + lane) + 1] = t1; }
+        n += avail;
+        if (lane == 0) { fs[FS_LIVE] = c[0]; fs[FS_LIVE + 1] = c[1]; fs[FS_LIVE + 2] = n; }
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        fs[FS_CL_END] = c[0]; fs[FS_CL_END + 1] = c[1];
+        fs[FS_NDIRTY] = ndirty;
+        if (!ndirty) { fp->clusters[0] = c[0]; fp->clusters[1] = c[1]; fs[FS_PASSES] = 1; }
+        __threadfence();
+        fs[FS_STATE] = ndirty ? 1 : FS_DONE;
+    }
+}
+
 __global__ void __launch_bounds__(MB_WARPS * 32) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
@@ -87,7 +148,16 @@ __global__ void __launch_bounds__(MB_WARPS * 32) k_encode_rows(const FrameParams
     __shared__ int s_item;
     if (threadIdx.x == 0) s_item = atomicAdd(&tickets[0], 1);
     __syncthreads();
-    const int item = s_item;
+    int item = s_item;
+    if (pass == 0)
+    {   /* the first njobs tickets of sweep 0 are the trajectory followers */
+        if (item < njobs)
+        {
+            if (threadIdx.x < 32) trajectory_follower(fps + item);
+            return;
+        }
+        item -= njobs;
+    }
     const int job = item % njobs, row = item / njobs;
     for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
         ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + job))[i];
@@ -104,6 +174,14 @@ __global__ void __launch_bounds__(MB_WARPS * 32) k_encode_rows(const FrameParams
         else wave_mb_repair(fp, &work, x, row, pass);
         publish_row_cta(progress + row, base + x + 1);
     }
+}
+
+/* one warp per frame, before sweep 0: predicted cluster trajectory (h264_wave.h) */
+__global__ void __launch_bounds__(32) k_predict(const FrameParams *fps, int njobs)
+{
+    __shared__ MBWork work;
+    const FrameParams *fp = fps + blockIdx.x;
+    if (fp->spec_from_prev) wave_replay(fp, &work, 1);
 }
 
 /* one warp per frame: end-of-sweep bookkeeping (trajectory replay, convergence test) */
@@ -459,11 +537,12 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 2 * c->nmby, st));
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
+        CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
     }
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
-    k_encode_rows<<<n * max_rows, MB_WARPS * 32, 0, st>>>(g_d_fps, n, g_d_tickets, 0);
-    k_replay<<<n, 32, 0, st>>>(g_d_fps, n, 0);
+    k_predict<<<n, 32, 0, st>>>(g_d_fps, n);
+    k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, 0, st>>>(g_d_fps, n, g_d_tickets, 0);
     g_launches += 2;
     CK(cudaEventRecord(g_ev[2], st));
     if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+int g_emu_dbg[8];
+extern "C" int *emu_dbg(void) { return g_emu_dbg; }
 #include "../../h264-lab_b200/csrc/h264_common.h"
 #include "../../h264-lab_b200/csrc/h264_pixel.h"
 #include "../../h264-lab_b200/csrc/h264_mbenc.h"
@@ -120,6 +122,7 @@ static void run_job(h264b200_job *job)
     const int nmb = c->nmbx * c->nmby;
 
     MBWork *w = new MBWork();
+    if (fp.spec_from_prev) wave_replay(&fp, w, 1);
     for (int pass = 0;;)
     {
         for (int y = 0; y < c->nmby; y++)
@@ -200,3 +203,4 @@ extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = 
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "host-emulation (test only)"; }
+extern "C" void emu_get_cl_true(h264b200_ctx *c, int32_t *out) { memcpy(out, c->cl_true.data(), c->cl_true.size() * 4); }
