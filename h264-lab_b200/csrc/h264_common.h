@@ -179,6 +179,7 @@ struct MBSpec
 #define FS_CL_END 8       /* [8],[9]: cluster state after the last macroblock (raw)           */
 #define FS_LIVE 10        /* [10],[11]: cluster state after the raster-contiguous prefix of finished
                              macroblocks of sweep 0, published while the sweep runs; [12] prefix length */
+#define FS_NFAIL 13       /* dirty macroblocks whose candidate-stage re-check failed (need a re-encode)  */
 #define FS_WORDS 16
 #define FS_DONE 0x40000000
 
@@ -217,6 +218,7 @@ struct FrameParams
     MBSpec *spec;               /* [nmb] speculation records                                */
     int32_t *cl_true;           /* [nmb][2] rounded cluster candidates from the last replay */
     int *changed_pass;          /* [nmb] last pass in which the MB's result changed         */
+    int *need_reenc;            /* [nmb] pass for which the parallel re-check asked for a re-encode */
     int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */
     int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */

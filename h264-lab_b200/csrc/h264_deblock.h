@@ -80,83 +80,103 @@ HD int bs_inter(const MBInfo *mp, int ip, const MBInfo *mq, int iq)
     return mv_far(mp->mv[ip], mq->mv[iq]) ? 1 : 0;
 }
 
-HD void deblock_mb(const FrameParams *fp, int mbx, int mby)
+/* working tile of one macroblock being deblocked (shared memory) */
+struct DeblockTile
+{
+    uint32_t y[20 * 6];      /* luma: rows -4..15, cols -4..19 (6 words per row, sample x at col x + 4) */
+    uint32_t c[2][12 * 3];   /* chroma: rows -4..7, cols -4..7                                          */
+    uint8_t bs[32];          /* [4*e + seg] vertical edges, [16 + 4*e + seg] horizontal edges          */
+};
+
+/* One macroblock, one warp.  The samples the filters can touch (the macroblock, 4 columns of
+ * the left and 4 rows of the upper neighbour) are staged as aligned words in shared memory,
+ * filtered there (lanes 0-15: the 16 luma lines, 16-23 / 24-31: the 8 U / V lines crossing the
+ * edges; vertical edges left to right, then horizontal edges top to bottom -- the reference's
+ * per-macroblock order) and written back as words. */
+HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
 {
     const MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     const MBInfo *ml = mi - 1, *mt = mi - fp->nmbx;
-    const int intra = mi->type >= 5;
-    const int lane = LANE_ID;
-    (void)lane;
-    FOR_LANES(ln, 32)
-    {
-        const int pl = ln < 16 ? 0 : (ln < 24 ? 1 : 2);
-        const int line = ln < 16 ? ln : ((ln - 16) & 7);
-        const int cr = pl != 0;
-        const int n = cr ? 8 : 16;
-        const int stride = fp->stride[cr];
-        pix_t *base = fp->dec[pl] + (mby * n) * stride + mbx * n;
-        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
-        const int seg = cr ? (line >> 1) : (line >> 2);      /* 4x4 luma block row/col this line crosses */
-        int v[20];
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    pix_t *py = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+    pix_t *pc[2];
+    pc[0] = fp->dec[1] + (mby * 8) * sc + mbx * 8;
+    pc[1] = fp->dec[2] + (mby * 8) * sc + mbx * 8;
 
-        /* ---- vertical edges: this lane owns row `line` ---- */
+    /* 1. stage samples (the guard band makes the reads safe at picture edges) */
+    FOR_LANES(i, 100 + 72)
+    {
+        if (i < 100) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
+        else { int k = i - 100, pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3; t->c[pl][r * 3 + c] = *(const uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4); }
+    }
+    /* 2. boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg */
+    FOR_LANES(j, 32)
+    {
+        const int horiz = j >> 4, e = (j >> 2) & 3, seg = j & 3;
+        const int intra = mi->type >= 5;
+        int bs;
+        if (e == 0)
         {
-            pix_t *row = base + line * stride;
-            int lo = mbx > 0 ? -4 : 0;
-            for (int i = lo; i < n; i++) v[4 + i] = row[i];
-            for (int e = 0; e < 4; e++)
-            {
-                int bs;
-                if (e == 0)
-                {
-                    if (mbx == 0) bs = 0;
-                    else if (intra || ml->type >= 5) bs = 4;
-                    else bs = bs_inter(ml, seg * 4 + 3, mi, seg * 4);
-                } else
-                {
-                    if (intra) bs = 3;
-                    else bs = bs_inter(mi, seg * 4 + e - 1, mi, seg * 4 + e);
-                }
-                if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
-                else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
-            }
-            for (int i = lo; i < n; i++) row[i] = (pix_t)v[4 + i];
-        }
+            const MBInfo *mn = horiz ? mt : ml;
+            if ((horiz ? mby : mbx) == 0) bs = 0;
+            else if (intra || mn->type >= 5) bs = 4;
+            else bs = horiz ? bs_inter(mn, 12 + seg, mi, seg) : bs_inter(mn, seg * 4 + 3, mi, seg * 4);
+        } else if (intra) bs = 3;
+        else bs = horiz ? bs_inter(mi, (e - 1) * 4 + seg, mi, e * 4 + seg) : bs_inter(mi, seg * 4 + e - 1, mi, seg * 4 + e);
+        t->bs[j] = (uint8_t)bs;
     }
     WSYNC();
+    /* 3. vertical edges: lane owns one line (row) */
     FOR_LANES(ln, 32)
     {
-        const int pl = ln < 16 ? 0 : (ln < 24 ? 1 : 2);
-        const int line = ln < 16 ? ln : ((ln - 16) & 7);
-        const int cr = pl != 0;
-        const int n = cr ? 8 : 16;
-        const int stride = fp->stride[cr];
-        pix_t *base = fp->dec[pl] + (mby * n) * stride + mbx * n;
+        const int cr = ln >= 16, pl = ln < 24 ? 0 : 1, line = cr ? (ln & 7) : ln;
         const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
         const int seg = cr ? (line >> 1) : (line >> 2);
+        pix_t *row = cr ? (pix_t *)(t->c[pl] + (line + 4) * 3) : (pix_t *)(t->y + (line + 4) * 6);
+        const int n = cr ? 8 : 16;
         int v[20];
-        /* ---- horizontal edges: this lane owns column `line` ---- */
+        for (int i = 0; i < n + 4; i++) v[i] = row[i];
+        for (int e = 0; e < 4; e++)
         {
-            pix_t *col = base + line;
-            int lo = mby > 0 ? -4 : 0;
-            for (int i = lo; i < n; i++) v[4 + i] = col[i * stride];
-            for (int e = 0; e < 4; e++)
-            {
-                int bs;
-                if (e == 0)
-                {
-                    if (mby == 0) bs = 0;
-                    else if (intra || mt->type >= 5) bs = 4;
-                    else bs = bs_inter(mt, 12 + seg, mi, seg);
-                } else
-                {
-                    if (intra) bs = 3;
-                    else bs = bs_inter(mi, (e - 1) * 4 + seg, mi, e * 4 + seg);
-                }
-                if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
-                else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
-            }
-            for (int i = lo; i < n; i++) col[i * stride] = (pix_t)v[4 + i];
+            int bs = t->bs[4 * e + seg];
+            if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
+            else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+        }
+        for (int i = 0; i < n + 4; i++) row[i] = (pix_t)v[i];
+    }
+    WSYNC();
+    /* 4. horizontal edges: lane owns one column */
+    FOR_LANES(ln, 32)
+    {
+        const int cr = ln >= 16, pl = ln < 24 ? 0 : 1, line = cr ? (ln & 7) : ln;
+        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
+        const int seg = cr ? (line >> 1) : (line >> 2);
+        pix_t *col = cr ? (pix_t *)t->c[pl] + line + 4 : (pix_t *)t->y + line + 4;
+        const int n = cr ? 8 : 16, rs = cr ? 12 : 24;
+        int v[20];
+        for (int i = 0; i < n + 4; i++) v[i] = col[i * rs];
+        for (int e = 0; e < 4; e++)
+        {
+            int bs = t->bs[16 + 4 * e + seg];
+            if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
+            else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+        }
+        for (int i = 0; i < n + 4; i++) col[i * rs] = (pix_t)v[i];
+    }
+    WSYNC();
+    /* 5. write back: the macroblock, the 4 columns to its left, the 4 rows above it */
+    FOR_LANES(i, 100 + 72)
+    {
+        if (i < 100)
+        {
+            int r = i / 5, c = i - r * 5;
+            if ((r >= 4 || (mby > 0 && c > 0)) && (c > 0 || (mbx > 0 && r >= 4)))
+                *(uint32_t *)(py + (r - 4) * sy + c * 4 - 4) = t->y[r * 6 + c];
+        } else
+        {
+            int k = i - 100, pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3;
+            if ((r >= 4 || (mby > 0 && c > 0)) && (c > 0 || (mbx > 0 && r >= 4)))
+                *(uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4) = t->c[pl][r * 3 + c];
         }
     }
     WSYNC();

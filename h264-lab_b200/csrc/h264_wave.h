@@ -56,7 +56,7 @@ HDN void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
     if (fp->slice_type == SLICE_P)
     {
         spec_store(fp, n, sp);
-        IF_THREAD0 { fp->changed_pass[n] = 0; }
+        IF_THREAD0 { fp->changed_pass[n] = 0; fp->need_reenc[n] = 0; }
     }
 }
 
@@ -106,38 +106,53 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     return same;
 }
 
-/* repair sweep `pass` (>= 1) */
-HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+/* Parallel re-check of one macroblock before repair sweep `pass`: independent of every other
+ * macroblock (it only reads sweep results), so all dirty macroblocks of all frames are checked
+ * at once.  A dirty macroblock re-runs just the candidate stage with its true candidates; if
+ * the outcome is the recorded one nothing downstream can change and the record simply adopts
+ * the true candidates, else the macroblock is queued for a re-encode in the sweep. */
+HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 {
-    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    const int n = y * fp->nmbx + x;
     const MBSpec old = fp->spec[n];
     int32_t ct[2];
     ct[0] = fp->cl_true[2 * n]; ct[1] = fp->cl_true[2 * n + 1];
     const int need_cl = (old.flags & SPEC_USED_CL) && (ct[0] != old.cl_used[0] || ct[1] != old.cl_used[1]);
-    int need_nb = 0;
-    if (x > 0 && fp->changed_pass[n - 1] == pass) need_nb = 1;
-    if (y > 0)
+    if (!need_cl) return;
+    int chk = wave_cand_check(fp, w, x, y, ct, old);
+    IF_THREAD0
     {
-        if (fp->changed_pass[n - nmbx] == pass) need_nb = 1;
-        if (x > 0 && fp->changed_pass[n - nmbx - 1] == pass) need_nb = 1;
-        if (x < nmbx - 1 && fp->changed_pass[n - nmbx + 1] == pass) need_nb = 1;
-    }
-    if (!need_cl && !need_nb) return;
-    if (!need_nb)
-    {
-        IF_THREAD0 { atomic_add_stat(fp->fsync + FS_CHECKS); }
-        int chk = wave_cand_check(fp, w, x, y, ct, old);
+        atomic_add_stat(fp->fsync + FS_CHECKS);
         if (chk)
         {
-            IF_THREAD0
-            {
-                fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1];
-                if (chk == 2) fp->spec[n].cand_sig[3] = w->ic[IC_SIG + 3];
-            }
-            CTA_SYNC();
-            return;
+            fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1];
+            if (chk == 2) fp->spec[n].cand_sig[3] = w->ic[IC_SIG + 3];
+        } else
+        {
+            fp->need_reenc[n] = pass;
+            atomic_add_stat(fp->fsync + FS_NFAIL);
         }
     }
+    CTA_SYNC();
+}
+
+/* repair sweep `pass` (>= 1): re-encode what the re-check queued and whatever depends on a
+ * macroblock that changed in this sweep */
+HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+{
+    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    int need = fp->need_reenc[n] == pass;
+    if (x > 0 && fp->changed_pass[n - 1] == pass) need = 1;
+    if (y > 0)
+    {
+        if (fp->changed_pass[n - nmbx] == pass) need = 1;
+        if (x > 0 && fp->changed_pass[n - nmbx - 1] == pass) need = 1;
+        if (x < nmbx - 1 && fp->changed_pass[n - nmbx + 1] == pass) need = 1;
+    }
+    if (!need) return;
+    const MBSpec old = fp->spec[n];
+    int32_t ct[2];
+    ct[0] = fp->cl_true[2 * n]; ct[1] = fp->cl_true[2 * n + 1];
     /* full re-encode; keep the previous record and reconstruction for comparison */
     MBInfo *mi = fp->mbi + n;
     const int sy = fp->stride[0], sc = fp->stride[1];
@@ -238,6 +253,22 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
     }
     WSYNC();
     return w->scal[0];
+}
+
+/* After the parallel re-check for sweep `pass`: when no macroblock needs a re-encode, every
+ * record is consistent with the replayed trajectory and the frame is exact. Returns the state. */
+HD int wave_after_check(const FrameParams *fp, int pass)
+{
+    if (fp->fsync[FS_STATE] != pass) return fp->fsync[FS_STATE];
+    if (fp->fsync[FS_NFAIL] == 0)
+    {
+        fp->clusters[0] = fp->fsync[FS_CL_END]; fp->clusters[1] = fp->fsync[FS_CL_END + 1];
+        fp->fsync[FS_PASSES] = pass;
+        fp->fsync[FS_STATE] = FS_DONE;
+        return FS_DONE;
+    }
+    fp->fsync[FS_NFAIL] = 0;
+    return pass;
 }
 
 /* Executed once per pass by the last row to finish: returns the next pass number or FS_DONE.

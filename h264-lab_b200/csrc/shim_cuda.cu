@@ -33,6 +33,9 @@
 #include "h264_deblock.h"
 #include "../../include/h264b200_shim.h"
 
+#ifndef ENC_MIN_BLOCKS
+#define ENC_MIN_BLOCKS 5
+#endif
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf(stderr, "h264b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -3; } } while (0)
 
@@ -141,7 +144,7 @@ __device__ void trajectory_follower(const FrameParams *fp)
     }
 }
 
-__global__ void __launch_bounds__(MB_WARPS * 32) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
+__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
@@ -184,6 +187,29 @@ __global__ void __launch_bounds__(32) k_predict(const FrameParams *fps, int njob
     if (fp->spec_from_prev) wave_replay(fp, &work, 1);
 }
 
+/* parallel re-check of the dirty macroblocks of every frame that waits for repair sweep `pass` */
+__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_check(const FrameParams *fps, int njobs, int pass)
+{
+    __shared__ MBWork work;
+    __shared__ FrameParams sfp;
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
+        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
+    __syncthreads();
+    const FrameParams *fp = &sfp;
+    if (fp->fsync[FS_STATE] != pass) return;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
+    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+    {
+        int y = n / nmbx;
+        wave_mb_check(fp, &work, n - y * nmbx, y, pass);
+    }
+}
+__global__ void k_after_check(const FrameParams *fps, int njobs, int pass)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < njobs) wave_after_check(fps + j, pass);
+}
+
 /* one warp per frame: end-of-sweep bookkeeping (trajectory replay, convergence test) */
 __global__ void __launch_bounds__(32) k_replay(const FrameParams *fps, int njobs, int pass)
 {
@@ -197,6 +223,7 @@ __global__ void __launch_bounds__(32) k_replay(const FrameParams *fps, int njobs
 __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int njobs, int *tickets)
 {
     __shared__ int s_item;
+    __shared__ DeblockTile tile;
     if (threadIdx.x == 0) s_item = atomicAdd(&tickets[1], 1);
     __syncwarp();
     const int item = s_item;
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     for (int x = 0; x < nmbx; x++)
     {
         if (row > 0) wait_row(progress + row - 1, min(x + 2, nmbx));
-        deblock_mb(fp, x, row);
+        deblock_mb(fp, &tile, x, row);
         publish_row(progress + row, x + 1);
     }
 }
@@ -303,7 +330,7 @@ struct h264b200_ctx
     int out_cap_words;
     int *d_out_info;
     int32_t *d_clusters;
-    MBSpec *d_spec; int32_t *d_cl_true; int *d_changed_pass; int *d_fsync;
+    MBSpec *d_spec; int32_t *d_cl_true; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
     int have_traj; int stats[4];
     int *d_prof;
     int *d_progress;              /* 2 * nmby */
@@ -384,6 +411,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
     CK(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
     CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
+    CK(cudaMalloc(&c->d_need_reenc, sizeof(int) * c->nmb));
+    CK(cudaMemset(c->d_need_reenc, 0, sizeof(int) * c->nmb));
     CK(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
 #ifdef H264_PROFILE
     CK(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
@@ -404,7 +433,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->d_clip) cudaFree(c->d_clip);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
-    cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_changed_pass); cudaFree(c->d_fsync);
+    cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
     cudaFreeHost(c->h_out_words); cudaFreeHost(c->h_out_info);
     free(c);
 }
@@ -453,7 +482,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
-    fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->changed_pass = c->d_changed_pass; fp->fsync = c->d_fsync;
+    fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->changed_pass = c->d_changed_pass; fp->need_reenc = c->d_need_reenc; fp->fsync = c->d_fsync;
     fp->max_passes = 4096;
     fp->prof = c->d_prof;
     fp->spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
@@ -543,7 +572,9 @@ static int encode_impl(int n, h264b200_job *jobs)
     CK(cudaEventRecord(g_ev[1], st));
     k_predict<<<n, 32, 0, st>>>(g_d_fps, n);
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, 0, st>>>(g_d_fps, n, g_d_tickets, 0);
-    g_launches += 2;
+    k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, 1);
+    k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
+    g_launches += 4;
     CK(cudaEventRecord(g_ev[2], st));
     if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;
     CK(cudaEventRecord(g_ev[4], st));
@@ -569,7 +600,9 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
         k_encode_rows<<<m * rows2, MB_WARPS * 32, 0, st>>>(d2, m, g_d_tickets, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
-        g_launches += 2;
+        k_check<<<dim3(148, m), MB_WARPS * 32, 0, st>>>(d2, m, pass + 1);
+        k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);
+        g_launches += 4;
         if (launch_post(d2, m, rows2, nmb2, cap, st, NULL)) return -3;
         if (fetch_info(m, jobs, dirty.data(), st)) return -3;
         std::vector<int> still;

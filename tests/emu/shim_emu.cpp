@@ -37,7 +37,7 @@ struct h264b200_ctx
     std::vector<pix_t> clip;
     std::vector<MBSpec> spec;
     std::vector<int32_t> cl_true;
-    std::vector<int> changed_pass;
+    std::vector<int> changed_pass, need_reenc;
     int fsync[FS_WORDS];
     int stats[4];
     int32_t clusters[2];
@@ -64,7 +64,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->coef.resize((size_t)nmb * COEF_PER_MB);
     c->mb_bits.resize((size_t)(nmb + 1) * MB_BITS_WORDS);
     c->mb_nbits.resize(nmb + 2);
-    c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->changed_pass.resize(nmb);
+    c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->changed_pass.resize(nmb); c->need_reenc.resize(nmb);
     c->out_words.resize((size_t)nmb * 160 + 1024);
     c->cur = 0;
     c->clusters[0] = c->clusters[1] = 0;
@@ -109,7 +109,7 @@ static void run_job(h264b200_job *job)
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
-    fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.changed_pass = c->changed_pass.data();
+    fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
     memset(c->fsync, 0, sizeof(c->fsync));
     fp.fsync = c->fsync;
     fp.max_passes = 1000;
@@ -133,6 +133,11 @@ static void run_job(h264b200_job *job)
             }
         int next = wave_end_of_pass(&fp, w, pass);
         if (next == FS_DONE) break;
+        /* parallel re-check of the dirty macroblocks before the repair sweep */
+        c->fsync[FS_STATE] = next;
+        for (int y = 0; y < c->nmby; y++)
+            for (int x = 0; x < c->nmbx; x++) wave_mb_check(&fp, w, x, y, next);
+        if (wave_after_check(&fp, next) == FS_DONE) break;
         pass = next;
         if (pass > fp.max_passes) { job->status = -4; delete w; return; }
     }
@@ -159,8 +164,11 @@ static void run_job(h264b200_job *job)
     g_launches++;
 
     if (!p.disable_deblock)
+    {
+        DeblockTile tile;
         for (int y = 0; y < c->nmby; y++)
-            for (int x = 0; x < c->nmbx; x++) deblock_mb(&fp, x, y);
+            for (int x = 0; x < c->nmbx; x++) deblock_mb(&fp, &tile, x, y);
+    }
     for (int pl = 0; pl < 3; pl++)
     {
         long ns = border_samples(&fp, pl);
