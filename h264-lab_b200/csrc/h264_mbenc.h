@@ -12,16 +12,19 @@
 /* optional per-macroblock phase timing (developer builds with -DH264_PROFILE) */
 #if defined(H264_PROFILE) && H264_DEVICE
 #  define PROF_N 16
-#  define PROF_MEMBERS long long prof_t0; int prof[PROF_N];
-#  define PROF_INIT(s) do { (s).prof_t0 = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
+#  define PROF_MEMBERS long long prof_t0, prof_start; int prof[PROF_N];
+#  define PROF_INIT(s) do { (s).prof_t0 = (s).prof_start = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
 #  define PROF_MARK(s, k) do { long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
-#  define PROF_STORE(s, fp, n, type) do { if (threadIdx.x == 0 && (fp)->prof) { for (int k_ = 0; k_ < PROF_N; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
+#  define PROF_STORE(s, fp, n, type) do { if (threadIdx.x == 0 && (fp)->prof) { for (int k_ = 0; k_ < 12; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
         (fp)->prof[(n) * 20 + 16] = (type); } } while (0)
+/* cycles since the start of the macroblock at which warp `wid` reaches this point (slot 12 + wid / 17 + wid) */
+#  define PROF_WARP(s, fp, n, slot) do { if ((threadIdx.x & 31) == 0 && (fp)->prof) (fp)->prof[(n) * 20 + (slot)] = (int)(clock64() - (s).prof_start); } while (0)
 #else
 #  define PROF_MEMBERS
 #  define PROF_INIT(s)
 #  define PROF_MARK(s, k)
 #  define PROF_STORE(s, fp, n, type)
+#  define PROF_WARP(s, fp, n, slot)
 #endif
 
 struct MBState   /* warp-uniform registers of the macroblock being encoded */
@@ -1174,6 +1177,217 @@ HDN void chroma_tq_plane(MBState &s, int pl)
     WSYNC();
 }
 
+#if H264_DEVICE
+/* ------------------------------------------------------------------------------
+ * sm_100a fast path of a9-a11 (same arithmetic as luma_tq_half / chroma_tq_plane above, which
+ * document it and are what the host emulation runs): lane l owns sample row r = l & 3 of 4x4
+ * block l >> 2; the horizontal 4-point kernels run inside the lane, the vertical ones across
+ * the four lanes of a block with two xor-shuffles per value.  After the forward transform lane
+ * r holds the coefficients of vertical frequency v = {0,2,3,1}[r], horizontal u = 0..3, i.e.
+ * indices v + 4u of the reference's transposed layout (H:2391).
+ * ---------------------------------------------------------------------------- */
+struct TQLane { int c[4]; int v; };
+
+HD void tq_fwd_lane(uint32_t in4, uint32_t pr4, int r, TQLane &t)
+{
+    const unsigned FULL = 0xffffffffu;
+    int d0 = (int)(in4 & 255) - (int)(pr4 & 255), d1 = (int)((in4 >> 8) & 255) - (int)((pr4 >> 8) & 255);
+    int d2 = (int)((in4 >> 16) & 255) - (int)((pr4 >> 16) & 255), d3 = (int)(in4 >> 24) - (int)(pr4 >> 24);
+    int s03 = d0 + d3, e03 = d0 - d3, s12 = d1 + d2, e12 = d1 - d2;
+    int h[4];
+    h[0] = s03 + s12; h[1] = 2 * e03 + e12; h[2] = s03 - s12; h[3] = e03 - 2 * e12;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+        int p = __shfl_xor_sync(FULL, h[u], 3);
+        int a = r < 2 ? h[u] + p : p - h[u];             /* r: 0 s03, 1 s12, 2 d12, 3 d03 */
+        int q = __shfl_xor_sync(FULL, a, 1);
+        t.c[u] = (int16_t)(r == 0 ? a + q : (r == 1 ? q - a : (r == 2 ? q - 2 * a : 2 * a + q)));
+    }
+    t.v = r == 0 ? 0 : (r == 1 ? 2 : (r == 2 ? 3 : 1));
+}
+
+/* inverse transform of the lane-distributed dequantised block + prediction -> 4 packed samples of row r */
+HD uint32_t tq_inv_lane(const int d[4], uint32_t pr4, int r)
+{
+    const unsigned FULL = 0xffffffffu;
+    int e0 = d[0] + d[2], e1 = d[0] - d[2], e2 = (d[1] >> 1) - d[3], e3 = d[1] + (d[3] >> 1);
+    int t[4];
+    t[0] = (int16_t)(e0 + e3); t[1] = (int16_t)(e1 + e2); t[2] = (int16_t)(e1 - e2); t[3] = (int16_t)(e0 - e3);
+    uint32_t out = 0;
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+    {
+        int p = __shfl_xor_sync(FULL, t[x], 1);          /* r: 0 f0|f2, 1 f2|f0, 2 f3|f1, 3 f1|f3 */
+        int g = r == 0 ? t[x] + p : (r == 1 ? p - t[x] : (r == 2 ? (p >> 1) - t[x] : t[x] + (p >> 1)));
+        int q = __shfl_xor_sync(FULL, g, 3);             /* r: 0 g0|g3, 1 g1|g2, 2 g2|g1, 3 g3|g0 */
+        int val = (r == 0 || r == 1) ? g + q : q - g;
+        int rr = (int16_t)((val + 32) >> 6);
+        out |= (uint32_t)clip_u8(rr + (int)((pr4 >> (8 * x)) & 255)) << (8 * x);
+    }
+    return out;
+}
+
+/* 1 where every nibble of m is 0xF, at the nibble's lowest bit */
+HD uint32_t nibble_all(uint32_t m) { m &= m >> 1; m &= m >> 2; return m & 0x11111111u; }
+HD uint32_t nibble_any(uint32_t m) { m |= m >> 1; m |= m >> 2; return m & 0x11111111u; }
+
+/* luma of a non-I4x4 macroblock; called by warps 0 and 1 (half = warp) */
+HDN void luma_tq_fast(MBState &s, int half, int intra16)
+{
+    const unsigned FULL = 0xffffffffu;
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const uint16_t *qdat = fp->qdat[0];
+    const int lane = LANE_ID, r = lane & 3, k = lane >> 2, b = half * 8 + k;
+    const int off = (b & 3) * 4 + (b >> 2) * 64 + r * 16;
+    const uint32_t in4 = ld4_sm(w->inp_y + off), pr4 = ld4_sm(s.pbest + off);
+    TQLane t;
+    tq_fwd_lane(in4, pr4, r, t);
+    const int v = t.v;
+    int zero_blk = 0;
+    if (intra16) { if (r == 0) w->dc_y[b] = (int16_t)t.c[0]; }
+    else
+    {   /* zero_smallq H:2512: blocks / 8x8 groups whose coefficients are all below the thresholds */
+        const int t1a = qdat[10 + v], t1b = qdat[10 + v + 4], t2a = qdat[18 + v], t2b = qdat[18 + v + 4];
+        int s1 = 1, s2 = 1;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+        {
+            int ta = (u & 1) ? t1b : t1a, tb = (u & 1) ? t2b : t2a;
+            if ((unsigned)(t.c[u] + ta) > 2u * ta) s1 = 0;
+            if ((unsigned)(t.c[u] + tb) > 2u * tb) s2 = 0;
+        }
+        const uint32_t x1 = nibble_all(__ballot_sync(FULL, s1)), x2 = nibble_all(__ballot_sync(FULL, s2));
+        const uint32_t mg = 0x00110011u << (8 * ((k & 3) >> 1));
+        zero_blk = (int)((x1 >> (4 * k)) & 1) | (((x1 & mg) != mg && (x2 & mg) == mg) ? 1 : 0);
+    }
+    /* quantisation / dequantisation (quantize H:2567-2585) */
+    const int rnd = qdat[6];
+    const int cl0 = (v & 1) * 2;
+    const int qm0 = qdat[cl0], dq0m = qdat[cl0 + 1], qm1 = qdat[cl0 + 2], dq1m = qdat[cl0 + 3];
+    int q[4], d[4], any = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+        int c = t.c[u];
+        int qq = (c * ((u & 1) ? qm1 : qm0) + (c < 0 ? 0xFFFF - rnd : rnd)) >> 16;
+        if (zero_blk || (intra16 && u == 0 && v == 0)) qq = 0;
+        q[u] = qq; any |= qq;
+        d[u] = (int16_t)(qq * ((u & 1) ? dq1m : dq0m));
+        w->qv_y[b][v + 4 * u] = (int16_t)qq;
+    }
+    const uint32_t nzn = nibble_any(__ballot_sync(FULL, any != 0));
+    int nzbits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) if ((nzn >> (4 * j)) & 1) nzbits |= 0x8000 >> (half * 8 + j);
+    if (lane == 0) w->tq_res[half] = nzbits;
+    if (intra16)
+    {   /* DC path (h264e_quant_luma_dc H:2344) on 16 lanes of warp 0; the halves meet at named barriers */
+        bar_sync(2, 64);
+        if (half == 0)
+        {
+            const int j = lane & 15, ji = j >> 2, jk = j & 3;
+            int x = w->dc_y[j];
+#pragma unroll
+            for (int rep = 0; rep < 2; rep++)
+            {
+                int a, bb, c, dd, ss, tt, uu, ww;
+                a = __shfl_sync(FULL, x, ji); bb = __shfl_sync(FULL, x, ji + 4); c = __shfl_sync(FULL, x, ji + 8); dd = __shfl_sync(FULL, x, ji + 12);
+                ss = a + c; tt = a - c; uu = bb + dd; ww = bb - dd;
+                int t1 = (int16_t)(jk == 0 ? ss + uu : (jk == 1 ? tt + ww : (jk == 2 ? tt - ww : ss - uu)));      /* t[4i + k] */
+                a = __shfl_sync(FULL, t1, jk); bb = __shfl_sync(FULL, t1, jk + 4); c = __shfl_sync(FULL, t1, jk + 8); dd = __shfl_sync(FULL, t1, jk + 12);
+                ss = a + c; tt = a - c; uu = bb + dd; ww = bb - dd;
+                x = (int16_t)(ji == 0 ? ss + uu : (ji == 1 ? tt + ww : (ji == 2 ? tt - ww : ss - uu)));          /* x[k + 4m] */
+                if (rep == 0)
+                {
+                    int qd = (int16_t)qdat[0];
+                    int vq = (x * qd + (x < 0 ? (1 << 18) - 0x20000 : 0x20000)) >> 18;
+                    if (lane < 16) w->qdc_y[j] = (int16_t)vq;
+                    x = (int16_t)vq;
+                }
+            }
+            if (lane < 16) w->dq_y[j][0] = (int16_t)(x * (int)(int16_t)(qdat[1] >> 2));
+        }
+        bar_sync(3, 64);
+        if (v == 0) d[0] = w->dq_y[b][0];
+    } else if (!((nzn >> (4 * k)) & 1)) { d[0] = d[1] = d[2] = d[3] = 0; }
+    const uint32_t o4 = tq_inv_lane(d, pr4, r);
+    pix_t *dec = fp->dec[0] + (s.mby * 16 + (b >> 2) * 4 + r) * fp->stride[0] + s.mbx * 16 + (b & 3) * 4;
+    *(uint32_t *)dec = o4;
+    WSYNC();
+}
+
+/* chroma plane pl; one warp, lanes 16-31 mirror lanes 0-15 */
+HDN void chroma_tq_fast(MBState &s, int pl)
+{
+    const unsigned FULL = 0xffffffffu;
+    const FrameParams *fp = s.fp;
+    MBWork *w = s.w;
+    const uint16_t *qdat = fp->qdat[1];
+    const int lane = LANE_ID, l16 = lane & 15, r = l16 & 3, k = l16 >> 2, b = pl * 4 + k;
+    const int off = pl * 8 + (k & 1) * 4 + (k >> 1) * 64 + r * 16;
+    const uint32_t in4 = ld4_sm(w->inp_c + off), pr4 = ld4_sm(w->predc + off);
+    TQLane t;
+    tq_fwd_lane(in4, pr4, r, t);
+    const int v = t.v;
+    const int t1a = qdat[10 + v], t1b = qdat[10 + v + 4];
+    int s1 = 1;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+        int ta = (u & 1) ? t1b : t1a;
+        if (!(u == 0 && v == 0) && (unsigned)(t.c[u] + ta) > 2u * ta) s1 = 0;
+    }
+    const uint32_t x1 = nibble_all(__ballot_sync(FULL, s1));
+    const int zero_blk = (int)((x1 >> (4 * k)) & 1);
+    const int rnd = qdat[6];
+    const int cl0 = (v & 1) * 2;
+    const int qm0 = qdat[cl0], dq0m = qdat[cl0 + 1], qm1 = qdat[cl0 + 2], dq1m = qdat[cl0 + 3];
+    int d[4], any = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+        int c = t.c[u];
+        int qq = (c * ((u & 1) ? qm1 : qm0) + (c < 0 ? 0xFFFF - rnd : rnd)) >> 16;
+        if (zero_blk || (u == 0 && v == 0)) qq = 0;
+        any |= qq;
+        d[u] = (int16_t)(qq * ((u & 1) ? dq1m : dq0m));
+        if (lane < 16) w->qv_c[b][v + 4 * u] = (int16_t)qq;
+    }
+    const uint32_t nzn = nibble_any(__ballot_sync(FULL, any != 0)) & 0x1111u;
+    const int nzm = ((nzn & 1) ? 8 : 0) | ((nzn & 0x10) ? 4 : 0) | ((nzn & 0x100) ? 2 : 0) | ((nzn & 0x1000) ? 1 : 0);
+    /* DC path (h264e_quant_chroma_dc H:2355), computed redundantly by every lane */
+    int dcf, dq0k;
+    {
+        const int a = __shfl_sync(FULL, t.c[0], 0), bb = __shfl_sync(FULL, t.c[0], 4);
+        const int c = __shfl_sync(FULL, t.c[0], 8), dd = __shfl_sync(FULL, t.c[0], 12);
+        int x0 = (int16_t)(a + bb + c + dd), x1d = (int16_t)(a - bb + c - dd), x2 = (int16_t)(a + bb - c - dd), x3 = (int16_t)(a - bb - c + dd);
+        const int qd = (int16_t)(qdat[0] << 1);
+        x0 = (int16_t)((x0 * qd + (x0 < 0 ? (1 << 18) - 0xAAAA : 0xAAAA)) >> 18);
+        x1d = (int16_t)((x1d * qd + (x1d < 0 ? (1 << 18) - 0xAAAA : 0xAAAA)) >> 18);
+        x2 = (int16_t)((x2 * qd + (x2 < 0 ? (1 << 18) - 0xAAAA : 0xAAAA)) >> 18);
+        x3 = (int16_t)((x3 * qd + (x3 < 0 ? (1 << 18) - 0xAAAA : 0xAAAA)) >> 18);
+        if (lane < 4) w->qdc_c[4 * pl + lane] = (int16_t)(lane == 0 ? x0 : (lane == 1 ? x1d : (lane == 2 ? x2 : x3)));
+        const int y0 = (int16_t)(x0 + x1d + x2 + x3), y1 = (int16_t)(x0 - x1d + x2 - x3);
+        const int y2 = (int16_t)(x0 + x1d - x2 - x3), y3 = (int16_t)(x0 - x1d - x2 + x3);
+        const int dqm = (int16_t)(qdat[1] >> 1);
+        dcf = (y0 | y1 | y2 | y3) != 0;
+        dq0k = (int16_t)((k == 0 ? y0 : (k == 1 ? y1 : (k == 2 ? y2 : y3))) * dqm);
+    }
+    if (lane == 0) w->tq_res[2 + pl] = nzm | (dcf << 8);
+    if (!((nzn >> (4 * k)) & 1)) { d[0] = d[1] = d[2] = d[3] = 0; }
+    if (v == 0) d[0] = dq0k;
+    const uint32_t o4 = tq_inv_lane(d, pr4, r);
+    if (lane < 16)
+    {
+        pix_t *dec = fp->dec[1 + pl] + (s.mby * 8 + (k >> 1) * 4 + r) * fp->stride[1] + s.mbx * 8 + (k & 1) * 4;
+        *(uint32_t *)dec = o4;
+    }
+    WSYNC();
+}
+#endif
+
 /* chroma intra prediction of plane pl (warp-level) */
 HDN void intra_chroma_plane(MBState &s, int pl)
 {
@@ -1300,6 +1514,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         if (fp->speed < 2 || !is_p) cost4 = intra4_choose(s, &nz4);
         IF_LANE0 { w->intra_res[0] = cost16; w->intra_res[1] = m16; w->intra_res[2] = cost4; w->intra_res[3] = nz4; }
     }
+    PROF_WARP(s, fp, mby * fp->nmbx + mbx, 12 + WARP_ID);
     CTA_SYNC();
     PROF_MARK(s, 5);
 
@@ -1356,6 +1571,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     for (int k = 0; k < 4; k++) spec_out->cand_sig[k] = cand_sig[k];
 
     /* ---- prediction of chroma, transform, quantisation, reconstruction ---- */
+    PROF_MARK(s, 6);
     int cbpl = 0, cbpc = 0;
     const int sy = fp->stride[0], sc = fp->stride[1];
     pix_t *decy = fp->dec[0] + (mby * 16) * sy + mbx * 16;
@@ -1363,6 +1579,28 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     if (s.type != MBT_SKIP)
     {
         const int i16 = s.type == MBT_I16;
+#if H264_DEVICE
+        if (s.type != MBT_I4)
+        {
+            if (WARP_ID < 2) luma_tq_fast(s, WARP_ID, i16);
+        } else
+        {
+            ON_WARP(0)
+            {
+                FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(w->i4rec + r * 16 + c); }
+            }
+        }
+        ON_WARP(2)
+        {
+            if (s.type >= 5) intra_chroma_plane(s, 0); else mc_chroma_plane(s, 0, s.type, pmv);
+            chroma_tq_fast(s, 0);
+        }
+        ON_WARP(3)
+        {
+            if (s.type >= 5) intra_chroma_plane(s, 1); else mc_chroma_plane(s, 1, s.type, pmv);
+            chroma_tq_fast(s, 1);
+        }
+#else
         if (s.type != MBT_I4)
         {
             ON_WARP(0) { luma_tq_half(s, 0, i16, 0); }
@@ -1392,6 +1630,8 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             if (s.type >= 5) intra_chroma_plane(s, 1); else mc_chroma_plane(s, 1, s.type, pmv);
             chroma_tq_plane(s, 1);
         }
+#endif
+        if (WARP_ID >= 2) PROF_WARP(s, fp, mby * fp->nmbx + mbx, 15 + WARP_ID);
         CTA_SYNC();
         if (s.type != MBT_I4) nz_mask = w->tq_res[0] | w->tq_res[1];
         if (nz_mask & 0xCC00) cbpl |= 1;

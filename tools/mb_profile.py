@@ -23,7 +23,7 @@ fr = getattr(content, kind)(w, h, n)
 enc = B.Encoder(L, w, h, 60)
 rp = enc.run_param(qp=28)
 nmb = ((w + 15) // 16) * ((h + 15) // 16)
-names = ["load", "win", "skiptest", "cands", "search16", "parts", "inter_rest", "i16", "i4", "chroma_pred", "tq_recon", "record"]
+names = ["load", "win", "stage_a", "-", "search16", "wait_tasks", "decide", "-", "-", "-", "tq_recon", "record"]
 for i in range(n):
     enc.encode(fr[i].copy(), rp)
     prof = np.zeros((nmb, 20), np.int32)
@@ -36,4 +36,5 @@ for i in range(n):
     for t in sorted(set(prof[:, 16].tolist())):
         m = prof[:, 16] == t
         ph = prof[m][:, :12].mean(0)
-        print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(12)))
+        print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(12) if names[k] != "-")
+              + " | arrive w0..3 %s chroma w2,w3 %s" % (prof[m][:, 12:16].mean(0).astype(int).tolist(), prof[m][:, 17:19].mean(0).astype(int).tolist()))
