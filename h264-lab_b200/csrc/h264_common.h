@@ -211,6 +211,11 @@ struct FrameParams
     const pix_t *inp[3]; int inp_stride[3];
     pix_t *dec[3];              /* reconstruction being built (padded planes, pixel (0,0))  */
     const pix_t *ref[3];        /* previous reconstruction (deblocked, borders extended)    */
+    const pix_t *hp[3];         /* half-sample planes b, h, j of ref[0] (same geometry, pixel (0,0)), see hpel_word() */
+    pix_t *hp_out;              /* 3 planes of luma_bytes each, filled from dec[0] once the frame is finished */
+    pix_t *dec_base;            /* first byte of the padded luma plane of dec                */
+    int luma_bytes;             /* size of one padded luma plane                              */
+    int update_ref;             /* the frame becomes the next reference picture              */
     int stride[2];              /* luma / chroma stride of dec and ref                      */
     MBInfo *mbi;
     int16_t *coef;
@@ -271,7 +276,7 @@ struct MBWork
     pix_t i4rec[256];            /* I4x4 reconstruction                                     */
     pix_t i4r[17 * 24];          /* GPU fast path: padded I4x4 reconstruction (row above, left column) */
     pix_t i4z[16];               /* the 13 neighbours of the current 4x4 block              */
-    pix_t i4s[32];               /* the 32 source values of its nine predictions            */
+    pix_t i4s[64];               /* the 32 source values of its nine predictions (GPU: one table per half-warp) */
     int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
     int8_t  i4_mode[16], i4_code[16];
     int32_t intra_res[8];        /* cost16, i16 mode, cost4, nz mask of I4x4                */

@@ -216,3 +216,14 @@ HD long border_samples(const FrameParams *fp, int pl)
     const int w = fp->nmbx * (cr ? 8 : 16), h = fp->nmby * (cr ? 8 : 16);
     return (long)2 * g * h + (long)2 * g * (w + 2 * g);
 }
+
+
+/* half-sample planes of the finished picture (h264_pixel.h hpel_word): word wi of the padded luma plane */
+HD void hpel_plane_word(const FrameParams *fp, long wi)
+{
+    uint32_t h, v, d;
+    const long nwords = fp->luma_bytes >> 2;
+    hpel_word(fp->dec_base, nwords, fp->stride[0], wi, &h, &v, &d);
+    uint32_t *o = (uint32_t *)fp->hp_out;
+    o[wi] = h; o[nwords + wi] = v; o[2 * nwords + wi] = d;
+}

@@ -14,11 +14,11 @@
 #  define PROF_N 16
 #  define PROF_MEMBERS long long prof_t0, prof_start; int prof[PROF_N];
 #  define PROF_INIT(s) do { (s).prof_t0 = (s).prof_start = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
-#  define PROF_MARK(s, k) do { long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
+#  define PROF_MARK(s, k) do { (void)*(volatile int32_t *)&(s).w->scal[15]; long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
 #  define PROF_STORE(s, fp, n, type) do { if (threadIdx.x == 0 && (fp)->prof) { for (int k_ = 0; k_ < 12; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
         (fp)->prof[(n) * 20 + 16] = (type); } } while (0)
 /* cycles since the start of the macroblock at which warp `wid` reaches this point (slot 12 + wid / 17 + wid) */
-#  define PROF_WARP(s, fp, n, slot) do { if ((threadIdx.x & 31) == 0 && (fp)->prof) (fp)->prof[(n) * 20 + (slot)] = (int)(clock64() - (s).prof_start); } while (0)
+#  define PROF_WARP(s, fp, n, slot) do { (void)*(volatile int32_t *)&(s).w->scal[15]; if ((threadIdx.x & 31) == 0 && (fp)->prof) (fp)->prof[(n) * 20 + (slot)] = (int)(clock64() - (s).prof_start); } while (0)
 #else
 #  define PROF_MEMBERS
 #  define PROF_INIT(s)
@@ -258,7 +258,6 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
 {
     const FrameParams *fp = s.fp;
     const int lam = fp->lambda_mv_q4;
-    pix_t *tmp = s.ss->tmpblk;
     int rs;
     const pix_t *rp;
     int mv = *pmv;
@@ -340,14 +339,24 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
         if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
         const int dgx = pqx + sqx, dgy = pqy + sqy;
         pix_t *I = buf[0], *C = buf[1], *H1 = buf[2], *H2 = buf[3];
-        int hx, hy;
-        /* half-sample position mv + 2q: integer part floor((2q)/4), fraction (2q) & 3 */
-        hx = 2 * pqx; hy = 2 * pqy;
-        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, H1, tmp);
-        hx = 2 * sqx; hy = 2 * sqy;
-        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, H2, tmp);
-        hx = 2 * dgx; hy = 2 * dgy;
-        interp_luma_block(rp + (hy >> 2) * rs + (hx >> 2), rs, hx & 3, hy & 3, bw, bh, C, tmp);
+        /* the three half-sample blocks mv + 2q come straight from the half-sample planes */
+        const int st = fp->stride[0];
+        const long go = (long)((mv_y(mv) >> 2) + ppy) * st + (mv_x(mv) >> 2) + ppx;
+        {
+            const int hx = 2 * pqx, hy = 2 * pqy;
+            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
+            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, H1);
+        }
+        {
+            const int hx = 2 * sqx, hy = 2 * sqy;
+            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
+            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, H2);
+        }
+        {
+            const int hx = 2 * dgx, hy = 2 * dgy;
+            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
+            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, C);
+        }
         WSYNC();
         int sq[7];
         sad_qpel7(I, H1, H2, C, inp, bw, bh, sq);
@@ -448,9 +457,10 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
     if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
         {
-            int rs;
-            const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
-            interp_luma_block(rp, rs, mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, w->skip_pred, s.ss->tmpblk);
+            const int st = fp->stride[0];
+            const long o = (long)(mv_y(mv_skip_a) >> 2) * st + (mv_x(mv_skip_a) >> 2);
+            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st,
+                               mv_x(mv_skip_a) & 3, mv_y(mv_skip_a) & 3, 16, 16, w->skip_pred);
         }
         WSYNC();
         sad_skip = sad_mb_quad(w->inp_y, 16, w->skip_pred, sad4v);
@@ -666,25 +676,37 @@ HD int inv_row(int k, int a, int b, int c, int d)     /* k-th output of the inve
 }
 
 #if H264_DEVICE
+HD int lds_u8(unsigned addr)
+{
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 /* sm_100a fast path of the Intra4x4 decision: same algorithm as the portable version below
- * (which documents it and is what the host emulation runs), but the whole per-block chain
- * -- neighbours -> 32 source values -> nine SADs -> mode -> residual -> transform ->
- * quantisation -> reconstruction -- stays in registers and moves between lanes with warp
- * shuffles; shared memory is touched once per block (neighbour fetch / recon store). */
+ * (which documents it and is what the host emulation runs).  Differences in execution only:
+ *  - a 4x4 block needs the reconstruction of its left, top, top-left and top-right blocks, so
+ *    the 16 blocks are walked in anti-diagonal order t = c + 2r (10 steps instead of 16) with
+ *    the two blocks of a step on the two half-warps (lane = sample y*4+x of its block);
+ *  - lane j < 13 of a half-warp fetches neighbour Z[j-4] and derives F3[j-4], F2[j-4] and the
+ *    two corner cases from its lane neighbours; the 31 source values go through a 32-byte
+ *    shared table from which every lane picks its nine predicted samples;
+ *  - the nine SADs are reduced with a halving exchange (each level a lane keeps half of its
+ *    partial sums), the mode costs are formed where the sums end up and the strict-'<'-in-
+ *    evaluation-order decision is a min-reduction of (cost << 4 | slot);
+ *  - residual -> transform -> quantisation -> inverse -> reconstruction stay in registers. */
 HDN int intra4_choose(MBState &s, int *nz_mask_out)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
     const int avail = s.avail;
-    const int lane = LANE_ID, p = lane & 15, g = lane >> 4, px = p & 3, py = p >> 2;
+    const int lane = LANE_ID, g = lane >> 4, l16 = lane & 15, px = l16 & 3, py = l16 >> 2;
     const unsigned FULL = 0xffffffffu;
-    int cost = fp->lambda_i4_q4;
+    int cost = 0;
     int nz_mask = 0;
     const int penalty = (3 * fp->lambda_q4) >> 4;
     const int skip_thr = fp->skip_thr_i4x4;
     const int poll_skip = fp->slice_type == SLICE_P;
 
-    /* ---- per-macroblock constants of this lane ---- */
     /* padded reconstruction R[17][24]: row 0 = row above (TL at col 3, 16 + 4 samples from col 4),
      * col 3 = left column; sample (x,y) of the MB at R[(y+1)*24 + x+4] */
     pix_t *R = w->i4r;
@@ -693,44 +715,28 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
         if (i < 21) R[3 + i] = i == 0 ? w->tl[0] : w->top_y[i - 1];
         else R[(i - 21 + 1) * 24 + 3] = w->left_y[i - 21];
     }
-    /* neighbour fetch offset of Z[lane-4] relative to R + (4r)*24 + 4c, with / without top-right */
+    /* neighbour fetch offset of Z[l16-4] relative to R + (4r)*24 + 4c, with / without top-right */
     int zoff, zoff_notr;
     {
-        int k = lane - 4;
-        if (lane > 12) k = 0;
+        int k = l16 - 4;
+        if (l16 > 12) k = 0;
         zoff = k <= 0 ? (-k) * 24 + 3 : 4 + (k - 1);
         zoff_notr = k > 4 ? 4 + 3 : zoff;
     }
-    /* recipe of source value S[lane] from Z: shuffle sources + kind */
-    int sa, sb, sc, kind;
-    if (lane < 4) { sa = sb = sc = lane; kind = 0; }
-    else if (lane < 8) { sa = sb = sc = lane + 1; kind = 0; }
-    else if (lane < 19) { sa = lane - 8; sb = lane - 7; sc = lane - 6; kind = 1; }
-    else if (lane < 29) { sa = lane - 19; sb = sc = lane - 18; kind = 2; }
-    else if (lane == 29) { sa = 11; sb = sc = 12; kind = 3; }
-    else if (lane == 30) { sa = 1; sb = sc = 0; kind = 3; }
-    else { sa = 0; sb = sc = 5; kind = 4; }
-    /* source indices of this lane's sample for the nine slots; slots 0-4 scored by lanes 0-15,
-     * slots 5-8 by lanes 16-31 */
-    unsigned e0 = 0, e1 = 0, e2 = i4_src_tab[8][p];
-    for (int k = 0; k < 4; k++) { e0 |= (unsigned)i4_src_tab[k][p] << (8 * k); e1 |= (unsigned)i4_src_tab[4 + k][p] << (8 * k); }
-    const unsigned my_slots = g ? (e1 >> 8) | (e2 << 24) : e0;     /* four slots: 0-3 or 5-8 */
-    const int my_slot4 = e1 & 0xff;                                 /* slot 4 (group 0 only) */
-    /* quantiser constants of coefficient i = v + 4u held by this lane (v = py, u = px) */
-    const int ci = py + 4 * px;
-    const int qcl = quant_class(ci);
-    const int qmul = fp->qdat[0][qcl], dqmul = fp->qdat[0][qcl + 1], qrnd = fp->qdat[0][6];
-    /* neighbouring MBs' modes */
-    int nb_mode = lane < 8 ? w->nb_i4mode[lane] : -1;
-    unsigned modes_lo = 0, modes_hi = 0;      /* chosen modes of blocks 0-7 / 8-15, 4 bits each */
-    __syncwarp();
-
-#pragma unroll 1
+    /* source-value table of this half-warp: where this lane's values go, where its samples come from */
+    pix_t *Sb = w->i4s + 32 * g;
+    const int zi = l16 < 4 ? l16 : ((l16 >= 5 && l16 <= 8) ? l16 - 1 : -1);
+    const int f3i = (l16 >= 1 && l16 <= 11) ? l16 + 7 : -1;
+    const int f2i = l16 <= 9 ? 19 + l16 : -1;
+    const int spi = l16 == 11 ? 29 : (l16 == 1 ? 30 : -1);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(Sb);
+    unsigned ap[9];
+#pragma unroll
+    for (int k = 1; k < 9; k++) ap[k] = sbase + i4_src_tab[k][l16];
+    /* block availability (block2avail H:4750), 4 bits per block */
+    unsigned long long av64 = 0;
     for (int n = 0; n < 16; n++)
     {
-        /* the candidate stage runs concurrently on another warp: stop as soon as it has
-         * decided for an early skip (the intra result would be discarded, H:5767) */
-        if (poll_skip && *(volatile int32_t *)&w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         const int r = n >> 2, c = n & 3;
         int a = 0;
         if (c > 0 || (avail & AVAIL_L)) a |= AVAIL_L;
@@ -741,17 +747,37 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
         else a |= (avail & AVAIL_L) ? AVAIL_TL : 0;
         if (r == 0) { if (c < 3) a |= (avail & AVAIL_T) ? AVAIL_TR : 0; else a |= avail & AVAIL_TR; }
         else if (c < 3 && !((r & 1) && (c & 1))) a |= AVAIL_TR;
+        av64 |= (unsigned long long)a << (4 * n);
+    }
+    /* the evaluation slots whose SADs end up in this lane after the halving reduction */
+    const int b3 = (l16 >> 3) & 1, b2 = (l16 >> 2) & 1, b1 = (l16 >> 1) & 1;
+    const int kA = b3 ? 8 : 4 * b2 + 2 * b1, kB = kA + 1;
+#define I4_SLOT_MODE(k) ((k) == 0 ? 2 : ((k) == 1 ? 0 : ((k) == 2 ? 3 : ((k) == 3 ? 7 : ((k) == 4 ? 1 : ((k) == 5 ? 8 : ((k) == 6 ? 4 : ((k) == 7 ? 6 : 5))))))))
+#define I4_SLOT_NEED(k) ((k) == 0 ? 0 : ((k) < 4 ? AVAIL_T : ((k) < 6 ? AVAIL_L : 7)))
+    const int modeA = I4_SLOT_MODE(kA), modeB = I4_SLOT_MODE(kB);
+    const int needA = I4_SLOT_NEED(kA), needB = b3 ? 16 : I4_SLOT_NEED(kB);      /* 16: unsatisfiable, there is no slot B */
+    /* quantiser constants of coefficient i = v + 4u held by this lane (v = py, u = px) */
+    const int ci = py + 4 * px;
+    const int qcl = quant_class(ci);
+    const int qmul = fp->qdat[0][qcl], dqmul = fp->qdat[0][qcl + 1], qrnd = fp->qdat[0][6];
+    unsigned long long modes = 0, codes = 0;  /* chosen modes / coded values + 1 of blocks 0..15, 4 bits each */
+    __syncwarp();
+
+#pragma unroll 1
+    for (int t = 0; t < 10; t++)
+    {
+        /* the candidate stage runs concurrently on another warp: stop as soon as it has
+         * decided for an early skip (the intra result would be discarded, H:5767) */
+        if (poll_skip && *(volatile int32_t *)&w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        const int nA = t < 2 ? t : 4 * (t >> 1) + (t & 1) - 2;
+        const int active = !g || (t >= 2 && t <= 7);
+        const int n = (g && active) ? nA + 2 : nA;
+        const int r = n >> 2, c = n & 3;
+        const int a = (int)(av64 >> (4 * n)) & 15;
 
         /* most probable mode */
-        int ctx_l, ctx_t;
-        {
-            int nl = __shfl_sync(FULL, nb_mode, r), nt = __shfl_sync(FULL, nb_mode, 4 + c);
-            int prevl = n - 1, prevt = n - 4;
-            int ml = (int)(((prevl < 8 ? modes_lo : modes_hi) >> (4 * (prevl & 7))) & 15);
-            int mt = (int)(((prevt < 8 ? modes_lo : modes_hi) >> (4 * (prevt & 7))) & 15);
-            ctx_l = c > 0 ? ml : nl;
-            ctx_t = r > 0 ? mt : nt;
-        }
+        const int ctx_l = c > 0 ? (int)((modes >> (4 * (n - 1))) & 15) : w->nb_i4mode[r];
+        const int ctx_t = r > 0 ? (int)((modes >> (4 * (n - 4))) & 15) : w->nb_i4mode[4 + c];
         int mpred = imin(ctx_l, ctx_t);
         if (mpred < 0) mpred = 2;
 
@@ -760,114 +786,111 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
         const int z = Rb[(a & AVAIL_TR) ? zoff : zoff_notr];
         const int in = w->inp_y[(4 * r + py) * 16 + 4 * c + px];
 
-        /* the 32 source values, one per lane */
-        int sv;
+        /* source values -> table */
+        int dc;
         {
-            int za = __shfl_sync(FULL, z, sa), zb = __shfl_sync(FULL, z, sb), zc = __shfl_sync(FULL, z, sc);
-            int t = z + __shfl_down_sync(FULL, z, 1);
-            int u4 = t + __shfl_down_sync(FULL, t, 2);
-            int sl = __shfl_sync(FULL, u4, 0), su = __shfl_sync(FULL, u4, 5);
-            if (kind == 0) sv = za;
-            else if (kind == 1) sv = (za + 2 * zb + zc + 2) >> 2;
-            else if (kind == 2) sv = (za + zb + 1) >> 1;
-            else if (kind == 3) sv = (za + 3 * zb + 2) >> 2;
-            else
-            {
-                int both = (a & 3) == 3;
-                sv = both ? (sl + su + 4) >> 3 : ((a & AVAIL_L) ? (sl + 2) >> 2 : ((a & AVAIL_T) ? (su + 2) >> 2 : 128));
-            }
+            const int up = __shfl_up_sync(FULL, z, 1, 16), dn = __shfl_down_sync(FULL, z, 1, 16);
+            const int t2 = z + dn;
+            const int u4 = t2 + __shfl_down_sync(FULL, t2, 2, 16);
+            if (zi >= 0) Sb[zi] = (pix_t)z;
+            if (f3i >= 0) Sb[f3i] = (pix_t)((up + 2 * z + dn + 2) >> 2);
+            if (f2i >= 0) Sb[f2i] = (pix_t)((z + dn + 1) >> 1);
+            if (spi >= 0) Sb[spi] = (pix_t)(l16 == 11 ? (z + 3 * dn + 2) >> 2 : (z + 3 * up + 2) >> 2);
+            const int sl = __shfl_sync(FULL, u4, 0, 16), su = __shfl_sync(FULL, u4, 5, 16);
+            dc = (a & 3) == 3 ? (sl + su + 4) >> 3 : ((a & AVAIL_L) ? (sl + 2) >> 2 : ((a & AVAIL_T) ? (su + 2) >> 2 : 128));
         }
-        /* nine SADs */
-        int d0 = iabs(in - __shfl_sync(FULL, sv, my_slots & 0xff));
-        int d1 = iabs(in - __shfl_sync(FULL, sv, (my_slots >> 8) & 0xff));
-        int d2 = iabs(in - __shfl_sync(FULL, sv, (my_slots >> 16) & 0xff));
-        int d3 = iabs(in - __shfl_sync(FULL, sv, my_slots >> 24));
-        int d4 = iabs(in - __shfl_sync(FULL, sv, my_slot4));
-        int r0 = d0 | (d1 << 16), r1 = d2 | (d3 << 16), r2 = g ? 0 : d4;
+        __syncwarp();
+        /* the nine predictions of this lane's sample and their absolute errors */
+        int pv[9], dv[9];
+        pv[0] = dc;
 #pragma unroll
-        for (int o = 8; o; o >>= 1)
-        {
-            r0 += __shfl_xor_sync(FULL, r0, o);
-            r1 += __shfl_xor_sync(FULL, r1, o);
-            r2 += __shfl_xor_sync(FULL, r2, o);
-        }
-        int q0 = __shfl_xor_sync(FULL, r0, 16), q1 = __shfl_xor_sync(FULL, r1, 16), q2 = __shfl_xor_sync(FULL, r2, 16);
-        int lo0 = g ? q0 : r0, lo1 = g ? q1 : r1, lo2 = g ? q2 : r2;      /* slots 0-4 */
-        int hi0 = g ? r0 : q0, hi1 = g ? r1 : q1;                          /* slots 5-8 */
-        int sads[9];
-        sads[0] = lo0 & 0xFFFF; sads[1] = (int)((unsigned)lo0 >> 16);
-        sads[2] = lo1 & 0xFFFF; sads[3] = (int)((unsigned)lo1 >> 16);
-        sads[4] = lo2;
-        sads[5] = hi0 & 0xFFFF; sads[6] = (int)((unsigned)hi0 >> 16);
-        sads[7] = hi1 & 0xFFFF; sads[8] = (int)((unsigned)hi1 >> 16);
-        int bk = 0, best_sad = 0x7FFFFFFF;
+        for (int k = 1; k < 9; k++) pv[k] = lds_u8(ap[k]);
 #pragma unroll
-        for (int k = 0; k < 9; k++)
-        {
-            const int slot_mode = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 3 : (k == 3 ? 7 : (k == 4 ? 1 : (k == 5 ? 8 : (k == 6 ? 4 : (k == 7 ? 6 : 5)))))));
-            int ok = k == 0 ? 1 : (k < 4 ? (a & AVAIL_T) : (k < 6 ? (a & AVAIL_L) : ((a & 7) == 7)));
-            int cst = sads[k] + (slot_mode != mpred ? penalty : 0);
-            if (ok && cst < best_sad) { best_sad = cst; bk = k; }
+        for (int k = 0; k < 9; k++) dv[k] = iabs(in - pv[k]);
+        int T;
+        {   /* halving reduction over the 16 lanes; slots (kA, kB) end up in this lane */
+            int P0 = dv[0] | (dv[1] << 16), P1 = dv[2] | (dv[3] << 16), P2 = dv[4] | (dv[5] << 16), P3 = dv[6] | (dv[7] << 16), P4 = dv[8];
+            const int s0 = __shfl_xor_sync(FULL, b3 ? P0 : P4, 8);
+            P1 += __shfl_xor_sync(FULL, P1, 8); P2 += __shfl_xor_sync(FULL, P2, 8); P3 += __shfl_xor_sync(FULL, P3, 8);
+            if (b3) P4 += s0; else P0 += s0;
+            const int a4 = __shfl_xor_sync(FULL, b3 ? P4 : (b2 ? P0 : P2), 4);
+            const int b4 = __shfl_xor_sync(FULL, b2 ? P1 : P3, 4);
+            const int Q0 = (b3 ? P4 : (b2 ? P2 : P0)) + a4, Q1 = (b2 ? P3 : P1) + b4;
+            const int c2 = __shfl_xor_sync(FULL, b3 ? Q0 : (b1 ? Q0 : Q1), 2);
+            T = (b3 ? Q0 : (b1 ? Q1 : Q0)) + c2;
+            T += __shfl_xor_sync(FULL, T, 1);
         }
-        const int mode = i4_slot_mode[bk];
-        if (n < 8) modes_lo |= (unsigned)mode << (4 * n); else modes_hi |= (unsigned)mode << (4 * (n - 8));
+        /* strict '<' in evaluation order == minimum of (cost << 4 | slot) */
+        int best;
+        {
+            const int cA = ((a & needA) == needA) ? ((((T & 0xFFFF) + (modeA != mpred ? penalty : 0)) << 4) | kA) : 0x7FFFFFFF;
+            const int cB = ((a & needB) == needB) ? ((((int)((unsigned)T >> 16) + (modeB != mpred ? penalty : 0)) << 4) | kB) : 0x7FFFFFFF;
+            best = imin(cA, cB);
+#pragma unroll
+            for (int o = 8; o; o >>= 1) best = imin(best, __shfl_xor_sync(FULL, best, o));
+        }
+        const int bk = best & 15, best_sad = best >> 4;
+        const int mode = I4_SLOT_MODE(bk);
+        const int code = mode == mpred ? 0 : (mode > mpred ? mode : mode + 1);      /* coded value + 1 */
+        {   /* both halves record both blocks' modes */
+            const int mo = __shfl_xor_sync(FULL, mode | (code << 4) | (n << 8), 16);
+            const int no = mo >> 8;
+            modes |= (unsigned long long)mode << (4 * n);
+            codes |= (unsigned long long)code << (4 * n);
+            if (no != n) { modes |= (unsigned long long)(mo & 15) << (4 * no); codes |= (unsigned long long)((mo >> 4) & 15) << (4 * no); }
+        }
         const int do_tq = best_sad > skip_thr;
 
-        /* prediction of the chosen mode, residual */
-        unsigned esel = bk < 4 ? e0 : (bk < 8 ? e1 : e2);
-        const int pred = __shfl_sync(FULL, sv, (esel >> (8 * (bk & 3))) & 0xff);
-        int outv = pred;
-        int qv = 0, dqv = 0, nzb = 0;
-        if (do_tq)
-        {
-            const int res = in - pred;
-            const int hb = lane & 16;      /* both half-warps run the same block redundantly */
-            /* forward: vertical pass -> (v = py, column px), horizontal pass -> (v = py, u = px) */
-            int f0 = __shfl_sync(FULL, res, hb + px), f1 = __shfl_sync(FULL, res, hb + 4 + px);
-            int f2 = __shfl_sync(FULL, res, hb + 8 + px), f3 = __shfl_sync(FULL, res, hb + 12 + px);
-            int t1 = fwd_row(py, f0, f1, f2, f3);
-            int g0 = __shfl_sync(FULL, t1, hb + 4 * py), g1 = __shfl_sync(FULL, t1, hb + 4 * py + 1);
-            int g2 = __shfl_sync(FULL, t1, hb + 4 * py + 2), g3 = __shfl_sync(FULL, t1, hb + 4 * py + 3);
-            int cf = (int16_t)fwd_row(px, g0, g1, g2, g3);
-            qv = (cf * qmul + (cf < 0 ? 0xFFFF - qrnd : qrnd)) >> 16;
-            dqv = (int16_t)(qv * dqmul);
-            nzb = (__ballot_sync(FULL, qv != 0) & 0xFFFF) != 0;
-            if (nzb)
-            {
-                /* inverse: horizontal pass over u for this v, then vertical pass over v */
-                int h0 = __shfl_sync(FULL, dqv, hb + 4 * py), h1 = __shfl_sync(FULL, dqv, hb + 4 * py + 1);
-                int h2 = __shfl_sync(FULL, dqv, hb + 4 * py + 2), h3 = __shfl_sync(FULL, dqv, hb + 4 * py + 3);
-                int t2 = (int16_t)inv_row(px, h0, h1, h2, h3);
-                int v0 = __shfl_sync(FULL, t2, hb + px), v1 = __shfl_sync(FULL, t2, hb + 4 + px);
-                int v2 = __shfl_sync(FULL, t2, hb + 8 + px), v3 = __shfl_sync(FULL, t2, hb + 12 + px);
-                int rr = (int16_t)((inv_row(py, v0, v1, v2, v3) + 32) >> 6);
-                outv = clip_u8(rr + pred);
-            }
-        }
-        if (lane < 16)
+        /* prediction of the chosen mode, residual, transform, quantisation, reconstruction */
+        int pred = pv[0];
+#pragma unroll
+        for (int k = 1; k < 9; k++) if (bk == k) pred = pv[k];
+        const int res = do_tq ? in - pred : 0;
+        /* forward: vertical pass -> (v = py, column px), horizontal pass -> (v = py, u = px) */
+        const int f0 = __shfl_sync(FULL, res, px, 16), f1 = __shfl_sync(FULL, res, 4 + px, 16);
+        const int f2_ = __shfl_sync(FULL, res, 8 + px, 16), f3_ = __shfl_sync(FULL, res, 12 + px, 16);
+        const int t1 = fwd_row(py, f0, f1, f2_, f3_);
+        const int g0 = __shfl_sync(FULL, t1, 4 * py, 16), g1 = __shfl_sync(FULL, t1, 4 * py + 1, 16);
+        const int g2 = __shfl_sync(FULL, t1, 4 * py + 2, 16), g3 = __shfl_sync(FULL, t1, 4 * py + 3, 16);
+        const int cf = (int16_t)fwd_row(px, g0, g1, g2, g3);
+        const int qv = (cf * qmul + (cf < 0 ? 0xFFFF - qrnd : qrnd)) >> 16;
+        const int dqv = (int16_t)(qv * dqmul);
+        const int nzb = ((__ballot_sync(FULL, qv != 0) >> (16 * g)) & 0xFFFF) != 0;
+        /* inverse: horizontal pass over u for this v, then vertical pass over v (all zero -> prediction) */
+        const int h0 = __shfl_sync(FULL, dqv, 4 * py, 16), h1 = __shfl_sync(FULL, dqv, 4 * py + 1, 16);
+        const int h2 = __shfl_sync(FULL, dqv, 4 * py + 2, 16), h3 = __shfl_sync(FULL, dqv, 4 * py + 3, 16);
+        const int t2i = (int16_t)inv_row(px, h0, h1, h2, h3);
+        const int v0 = __shfl_sync(FULL, t2i, px, 16), v1 = __shfl_sync(FULL, t2i, 4 + px, 16);
+        const int v2 = __shfl_sync(FULL, t2i, 8 + px, 16), v3 = __shfl_sync(FULL, t2i, 12 + px, 16);
+        const int rr = (int16_t)((inv_row(py, v0, v1, v2, v3) + 32) >> 6);
+        const int outv = clip_u8(rr + pred);
+        if (active)
         {
             R[(4 * r + py + 1) * 24 + 4 * c + px + 4] = (pix_t)outv;
             w->qv_y[n][ci] = (int16_t)qv;
-            w->dq_y[n][ci] = (int16_t)dqv;
-            if (lane == 0)
-            {
-                w->i4_mode[n] = (int8_t)mode;
-                w->i4_code[n] = (int8_t)(mode == mpred ? -1 : (mode > mpred ? mode - 1 : mode));
-            }
+            nz_mask |= nzb << (15 - n);
+            cost += best_sad;
         }
-        nz_mask = (nz_mask << 1) | nzb;
-        cost += best_sad;
         __syncwarp();
     }
-    /* hand the reconstruction over in the layout the rest of the MB code expects */
+#undef I4_SLOT_MODE
+#undef I4_SLOT_NEED
+    /* modes / coded values, and the reconstruction in the layout the rest of the MB code expects */
+    if (lane < 16)
+    {
+        w->i4_mode[lane] = (int8_t)((modes >> (4 * lane)) & 15);
+        w->i4_code[lane] = (int8_t)((int)((codes >> (4 * lane)) & 15) - 1);
+    }
     for (int i = lane; i < 64; i += 32)
     {
         int rr = i >> 2, cc = (i & 3) * 4;
         *(uint32_t *)(w->i4rec + rr * 16 + cc) = *(const uint32_t *)(R + (rr + 1) * 24 + cc + 4);
     }
     __syncwarp();
+    cost += __shfl_xor_sync(FULL, cost, 16);
+    nz_mask |= __shfl_xor_sync(FULL, nz_mask, 16);
     *nz_mask_out = nz_mask;
-    return cost;
+    return cost + fp->lambda_i4_q4;
 }
 #else
 HDN int intra4_choose(MBState &s, int *nz_mask_out)
@@ -1632,6 +1655,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         }
 #endif
         if (WARP_ID >= 2) PROF_WARP(s, fp, mby * fp->nmbx + mbx, 15 + WARP_ID);
+        PROF_MARK(s, 7);
         CTA_SYNC();
         if (s.type != MBT_I4) nz_mask = w->tq_res[0] | w->tq_res[1];
         if (nz_mask & 0xCC00) cbpl |= 1;
@@ -1705,6 +1729,23 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             mi->pad0 = 0;
         }
     }
+    /* the quantised levels are only read by the CAVLC pass: mb_store_coefs() writes them out after
+     * the macroblock has been published to the wavefront */
+    IF_THREAD0 { w->scal[8] = type; w->scal[9] = 1 + mby * fp->nmbx + mbx; }
+    CTA_SYNC();
+    PROF_MARK(s, 11);
+    PROF_STORE(s, fp, mby * fp->nmbx + mbx, type);
+}
+
+/* Second half of the macroblock record: quantised levels -> HBM (for the CAVLC pass).  Called by
+ * the whole CTA after encode_mb(), once the wavefront counters have been advanced; a no-op when
+ * no macroblock has been encoded since the last call. */
+HDN void mb_store_coefs(const FrameParams *fp, MBWork *w)
+{
+    const int tag = w->scal[9];
+    if (!tag) return;
+    const int type = w->scal[8];
+    int16_t *coef = fp->coef + (size_t)(tag - 1) * COEF_PER_MB;
     if (type != MBT_SKIP)
     {
         FOR_THREADS(i, COEF_PER_MB / 2)      /* two int16 per item */
@@ -1719,6 +1760,6 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         }
     }
     CTA_SYNC();
-    PROF_MARK(s, 11);
-    PROF_STORE(s, fp, mby * fp->nmbx + mbx, type);
+    IF_THREAD0 { w->scal[9] = 0; }
+    CTA_SYNC();
 }

@@ -168,82 +168,49 @@ HDN void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
     }
 }
 
-/* horizontal half samples b: lane = (row, 8-sample segment) */
-HDN void half_h_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+/* ------------------------------------------------------------------------------
+ * Half-sample planes.  The reference filters every probed block on the fly (hpel_lpf_hor /
+ * _ver / _diag, H:1971-2051); the filters depend on nothing but the reference picture, so
+ * here they are applied ONCE per finished picture, to the whole padded luma plane, by a
+ * trivially parallel pass (k_hpel): planes b (horizontal), h (vertical), j (centre, from the
+ * 16-bit horizontal intermediates), stored with the luma plane's own linear indexing so that a
+ * probe is a copy.  One call produces the four samples of word `wi` of each plane; taps
+ * address the padded buffer linearly, exactly like a filter run at that position would
+ * (indices clamped to the buffer, which no position the search may use ever needs).
+ * ---------------------------------------------------------------------------- */
+HD uint32_t hp_ldw(const pix_t *buf, long nwords, long wi)
 {
-    const int sh = w == 16 ? 1 : 0;      /* 8-sample segments per row: 2 or 1 */
-    FOR_LANES(i, h << sh)
-    {
-        int r = i >> sh, x0 = (i & ((1 << sh) - 1)) * 8;
-        const pix_t *p = src + r * ss + x0 - 2;
-        int b[16];
-        unpack4(ld4u(p), b); unpack4(ld4u(p + 4), b + 4); unpack4(ld4u(p + 8), b + 8); unpack4(ld4u(p + 12), b + 12);
-        int o[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = clip_u8((tap6(b[j], b[j + 1], b[j + 2], b[j + 3], b[j + 4], b[j + 5]) + 16) >> 5);
-        *(uint32_t *)(dst + r * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
-        *(uint32_t *)(dst + r * 16 + x0 + 4) = pack4(o[4], o[5], o[6], o[7]);
-    }
+    wi = wi < 0 ? 0 : (wi >= nwords ? nwords - 1 : wi);
+    return *(const uint32_t *)(buf + 4 * wi);
 }
-
-/* vertical half samples h: lane = (4-sample column group, row pair) */
-HDN void half_v_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+HD void hpel_word(const pix_t *buf, long nwords, int stride, long wi, uint32_t *ph, uint32_t *pv, uint32_t *pd)
 {
-    const int sh = w == 16 ? 2 : 1;
-    FOR_LANES(i, (h >> 1) << sh)
+    const int sw = stride >> 2;
+    int t[6][4], c[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
     {
-        int rp = i >> sh, x0 = (i & ((1 << sh) - 1)) * 4, y0 = rp * 2;
-        int b[7][4];
+        const long wr = wi + (long)(k - 2) * sw;
+        int b[12];
+        unpack4(hp_ldw(buf, nwords, wr - 1), b); unpack4(hp_ldw(buf, nwords, wr), b + 4); unpack4(hp_ldw(buf, nwords, wr + 1), b + 8);
 #pragma unroll
-        for (int k = 0; k < 7; k++) unpack4(ld4u(src + (y0 - 2 + k) * ss + x0), b[k]);
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++)
+        for (int j = 0; j < 4; j++)
         {
-            int o[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) o[j] = clip_u8((tap6(b[rr][j], b[rr + 1][j], b[rr + 2][j], b[rr + 3][j], b[rr + 4][j], b[rr + 5][j]) + 16) >> 5);
-            *(uint32_t *)(dst + (y0 + rr) * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
+            t[k][j] = (int16_t)tap6(b[j + 2], b[j + 3], b[j + 4], b[j + 5], b[j + 6], b[j + 7]);
+            c[k][j] = b[j + 4];
         }
     }
-}
-
-/* centre half samples j: same lane mapping; 7 rows of 16-bit horizontal intermediates */
-HDN void half_d_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
-{
-    const int sh = w == 16 ? 2 : 1;
-    FOR_LANES(i, (h >> 1) << sh)
+    int oh[4], ov[4], od[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
     {
-        int rp = i >> sh, x0 = (i & ((1 << sh) - 1)) * 4, y0 = rp * 2;
-        int t[7][4];
-#pragma unroll
-        for (int k = 0; k < 7; k++)
-        {
-            const pix_t *p = src + (y0 - 2 + k) * ss + x0 - 2;
-            int b[12];
-            unpack4(ld4u(p), b); unpack4(ld4u(p + 4), b + 4); unpack4(ld4u(p + 8), b + 8);
-#pragma unroll
-            for (int j = 0; j < 4; j++) t[k][j] = (int16_t)tap6(b[j], b[j + 1], b[j + 2], b[j + 3], b[j + 4], b[j + 5]);
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++)
-        {
-            int o[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) o[j] = clip_u8((tap6(t[rr][j], t[rr + 1][j], t[rr + 2][j], t[rr + 3][j], t[rr + 4][j], t[rr + 5][j]) + 512) >> 10);
-            *(uint32_t *)(dst + (y0 + rr) * 16 + x0) = pack4(o[0], o[1], o[2], o[3]);
-        }
+        oh[j] = clip_u8((t[2][j] + 16) >> 5);
+        ov[j] = clip_u8((tap6(c[0][j], c[1][j], c[2][j], c[3][j], c[4][j], c[5][j]) + 16) >> 5);
+        od[j] = clip_u8((tap6(t[0][j], t[1][j], t[2][j], t[3][j], t[4][j], t[5][j]) + 512) >> 10);
     }
-}
-
-/* dst = avg(dst, other) where `other` is any-alignment source (window / frame / stride-16 buffer) */
-HDN void average_into(pix_t *dst, const pix_t *other, int os, int w, int h)
-{
-    const int sh = w == 16 ? 2 : 1;
-    FOR_LANES(i, h << sh)
-    {
-        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
-        *(uint32_t *)(dst + r * 16 + c) = avg4(ld4_sm(dst + r * 16 + c), ld4u(other + r * os + c));
-    }
+    *ph = pack4(oh[0], oh[1], oh[2], oh[3]);
+    *pv = pack4(ov[0], ov[1], ov[2], ov[3]);
+    *pd = pack4(od[0], od[1], od[2], od[3]);
 }
 
 /* rounded average of two stride-16 blocks (h264e_qpel_average_wh_align H:2065);
@@ -258,30 +225,31 @@ HDN void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int 
     }
 }
 
-/* Interpolate a w x h block whose integer sample position is `src` (stride ss) at quarter
- * offsets (dx,dy) into dst (stride 16); tmp = 256-byte scratch.
- * (interpolate_luma H:4905 + h264e_qpel_interpolate_luma H:2079) */
-HDN void interp_luma_block(const pix_t *src, int ss, int dx, int dy, int w, int h, pix_t *dst, pix_t *tmp)
+/* Prediction block at quarter-sample offset (dx,dy) from integer position `g` (a pointer into
+ * the integer plane, any alignment) -> dst (stride 16): the position table of
+ * h264e_qpel_interpolate_luma (H:2079-2130) with the filters replaced by the half-sample
+ * planes.  hb/hv/hd address the same sample as g in planes b/h/j; all four share `stride`. */
+HDN void interp_luma_planes(const pix_t *g, const pix_t *hb, const pix_t *hv, const pix_t *hd, int stride,
+                            int dx, int dy, int w, int h, pix_t *dst)
 {
-    if (!(dx | dy)) { copy_block(src, ss, dst, w, h); return; }
-    if (dy == 0)
+    const int pos = 1 << (dx + 4 * dy);
+    const pix_t *a = g, *b = 0;
+    if (pos != 1)
     {
-        half_h_block(src, ss, dst, w, h);
-        if (dx != 2) { WSYNC(); average_into(dst, src + (dx >> 1), ss, w, h); }
-        return;
+        a = 0;
+        if (pos & 0xe0ee) a = hb + ((pos & 0xe000) ? stride : 0);
+        if (pos & 0xbbb0) { const pix_t *q = hv + ((pos & 0x8880) ? 1 : 0); if (a) b = q; else a = q; }
+        if (pos & 0x4e40) { if (a) b = hd; else a = hd; }
+        if ((pos & 0xfafa) && !b) b = g + ((dx + 1) >> 2) + ((dy + 1) >> 2) * stride;
     }
-    if (dx == 0)
+    const int sh = w == 16 ? 2 : 1;
+    FOR_LANES(i, h << sh)
     {
-        half_v_block(src, ss, dst, w, h);
-        if (dy != 2) { WSYNC(); average_into(dst, src + (dy >> 1) * ss, ss, w, h); }
-        return;
+        int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
+        uint32_t v = ld4u(a + r * stride + c);
+        if (b) v = avg4(v, ld4u(b + r * stride + c));
+        *(uint32_t *)(dst + r * 16 + c) = v;
     }
-    if (dx == 2 && dy == 2) { half_d_block(src, ss, dst, w, h); return; }
-    if (dx == 2) { half_d_block(src, ss, dst, w, h); half_h_block(src + (dy >> 1) * ss, ss, tmp, w, h); }
-    else if (dy == 2) { half_d_block(src, ss, dst, w, h); half_v_block(src + (dx >> 1), ss, tmp, w, h); }
-    else { half_h_block(src + (dy >> 1) * ss, ss, dst, w, h); half_v_block(src + (dx >> 1), ss, tmp, w, h); }
-    WSYNC();
-    average_into(dst, tmp, 16, w, h);
 }
 
 /* a3: chroma 1/8-pel bilinear block (h264e_qpel_interpolate_chroma H:2133).

@@ -42,37 +42,39 @@
 /* ------------------------------------------------------------------------------ */
 /* wavefront helpers                                                                */
 /* ------------------------------------------------------------------------------ */
+/* Row progress counters: the producer's samples / records are ordinary stores by all threads of
+ * its CTA, made visible by ONE release (bar.sync orders them before thread 0's st.release.gpu,
+ * cumulativity does the rest); the consumer's thread 0 polls with ld.acquire.gpu and the CTA
+ * barrier extends the acquire to the other threads (they share the SM's L1). */
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void wait_row(const int *progress_above, int need)      /* one warp */
 {
-    if (LANE_ID == 0)
-    {
-        const volatile int *p = progress_above;
-        while (*p < need) { __nanosleep(64); }
-    }
+    if (LANE_ID == 0) { while (ld_acquire(progress_above) < need) __nanosleep(32); }
     __syncwarp();
-    __threadfence();
 }
 __device__ __forceinline__ void publish_row(int *progress, int done)               /* one warp */
 {
-    __threadfence();
     __syncwarp();
-    if (LANE_ID == 0) *(volatile int *)progress = done;
+    if (LANE_ID == 0) st_release(progress, done);
 }
 __device__ __forceinline__ void wait_row_cta(const int *progress_above, int need)  /* whole CTA */
 {
-    if (threadIdx.x == 0)
-    {
-        const volatile int *p = progress_above;
-        while (*p < need) { __nanosleep(32); }
-    }
+    if (threadIdx.x == 0) { while (ld_acquire(progress_above) < need) __nanosleep(20); }
     __syncthreads();
-    __threadfence();
 }
 __device__ __forceinline__ void publish_row_cta(int *progress, int done)
 {
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) *(volatile int *)progress = done;
+    if (threadIdx.x == 0) st_release(progress, done);
 }
 
 /* sync area layout per submission: [0] ticket of k_encode_rows, [1] ticket of k_deblock_rows.
@@ -106,13 +108,11 @@ __device__ void trajectory_follower(const FrameParams *fp)
         int row = n / nmbx, x = n - row * nmbx, avail = 0;
         if (lane == 0)
         {
-            const volatile int *pr = fp->row_progress + row;
             int p;
-            while ((p = *pr) <= x) __nanosleep(200);
+            while ((p = ld_acquire(fp->row_progress + row)) <= x) __nanosleep(200);
             avail = min(p - x, 32);
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
-        __threadfence();
         int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
         if (lane < avail)
         {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
     __shared__ int s_item;
-    if (threadIdx.x == 0) s_item = atomicAdd(&tickets[0], 1);
+    if (threadIdx.x == 0) { s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; }
     __syncthreads();
     int item = s_item;
     if (pass == 0)
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
         if (pass == 0) wave_mb_first(fp, &work, x, row);
         else wave_mb_repair(fp, &work, x, row, pass);
         publish_row_cta(progress + row, base + x + 1);
+        mb_store_coefs(fp, &work);
     }
 }
 
@@ -252,6 +253,16 @@ __global__ void k_borders(const FrameParams *fps, int njobs)
     }
 }
 
+/* half-sample planes of the new reference picture (after deblocking and border extension) */
+__global__ void __launch_bounds__(256) k_hpel(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    if (fp->fsync[FS_STATE] != FS_DONE || !fp->update_ref) return;
+    const long nwords = fp->luma_bytes >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long)gridDim.x * blockDim.x)
+        hpel_plane_word(fp, i);
+}
+
 __global__ void k_cavlc(const FrameParams *fps, int njobs)
 {
     const FrameParams *fp = fps + blockIdx.y;
@@ -318,6 +329,8 @@ struct h264b200_ctx
     int stride[2];
     int inp_stride[3];
     pix_t *d_frames[2];
+    pix_t *d_hpel;                /* half-sample planes b, h, j of the current reference picture */
+    size_t luma_bytes;
     size_t plane_off[3];
     pix_t *d_inp[3];
     pix_t *d_clip; int clip_frames;
@@ -388,6 +401,9 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
         CK(cudaMalloc(&c->d_frames[i], ysz + 2 * csz + 256));
         CK(cudaMemset(c->d_frames[i], 0, ysz + 2 * csz + 256));
     }
+    c->luma_bytes = ysz;
+    CK(cudaMalloc(&c->d_hpel, 3 * ysz + 256));
+    CK(cudaMemset(c->d_hpel, 0, 3 * ysz + 256));
     c->inp_stride[0] = (width + 63) & ~63;
     c->inp_stride[1] = c->inp_stride[2] = (width / 2 + 63) & ~63;
     CK(cudaMalloc(&c->d_inp[0], (size_t)c->inp_stride[0] * height + 256));
@@ -429,6 +445,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < 2; i++) cudaFree(c->d_frames[i]);
+    cudaFree(c->d_hpel);
     for (int i = 0; i < 3; i++) cudaFree(c->d_inp[i]);
     if (c->d_clip) cudaFree(c->d_clip);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
@@ -475,6 +492,9 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
         fp->dec[i] = c->d_frames[c->cur] + c->plane_off[i];
         fp->ref[i] = c->d_frames[c->cur ^ 1] + c->plane_off[i];
     }
+    for (int i = 0; i < 3; i++) fp->hp[i] = c->d_hpel + i * c->luma_bytes + c->plane_off[0];
+    fp->hp_out = c->d_hpel; fp->dec_base = c->d_frames[c->cur]; fp->luma_bytes = (int)c->luma_bytes;
+    fp->update_ref = job->update_ref;
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
@@ -506,11 +526,12 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
     CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
     k_deblock_rows<<<n * max_rows, 32, 0, st>>>(d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
+    k_hpel<<<dim3(148, n), 256, 0, st>>>(d_fps, n);
     if (ev_mid) CK(cudaEventRecord(ev_mid, st));
     k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, st>>>(d_fps, n);
     k_scan<<<n, 1024, 0, st>>>(d_fps, n, cap_words);
     k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, st>>>(d_fps, n);
-    g_launches += 5;
+    g_launches += 6;
     return 0;
 }
 

@@ -27,6 +27,8 @@ struct h264b200_ctx
     int width, height, nmbx, nmby;
     int stride[2];
     std::vector<pix_t> frame[2];     /* two padded frames: [cur] = dec, [cur^1] = ref */
+    std::vector<pix_t> hpel;         /* half-sample planes b, h, j of the reference picture */
+    size_t luma_bytes;
     size_t plane_off[3];
     int cur;
     std::vector<MBInfo> mbi;
@@ -59,6 +61,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->plane_off[1] = ysz + (size_t)c->stride[1] * 8 + 8;
     c->plane_off[2] = ysz + csz + (size_t)c->stride[1] * 8 + 8;
     for (int i = 0; i < 2; i++) c->frame[i].assign(ysz + 2 * csz + 64, 0);
+    c->luma_bytes = ysz;
+    c->hpel.assign(3 * ysz + 64, 0);
     int nmb = c->nmbx * c->nmby;
     c->mbi.resize(nmb);
     c->coef.resize((size_t)nmb * COEF_PER_MB);
@@ -106,6 +110,9 @@ static void run_job(h264b200_job *job)
         fp.dec[i] = c->frame[c->cur].data() + c->plane_off[i];
         fp.ref[i] = c->frame[c->cur ^ 1].data() + c->plane_off[i];
     }
+    for (int i = 0; i < 3; i++) fp.hp[i] = c->hpel.data() + i * c->luma_bytes + c->plane_off[0];
+    fp.hp_out = c->hpel.data(); fp.dec_base = c->frame[c->cur].data(); fp.luma_bytes = (int)c->luma_bytes;
+    fp.update_ref = job->update_ref;
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
@@ -130,6 +137,7 @@ static void run_job(h264b200_job *job)
             {
                 if (pass == 0) wave_mb_first(&fp, w, x, y);
                 else wave_mb_repair(&fp, w, x, y, pass);
+                mb_store_coefs(&fp, w);
             }
         int next = wave_end_of_pass(&fp, w, pass);
         if (next == FS_DONE) break;
@@ -174,6 +182,8 @@ static void run_job(h264b200_job *job)
         long ns = border_samples(&fp, pl);
         for (long i = 0; i < ns; i++) extend_border_sample(&fp, pl, i);
     }
+    if (job->update_ref)
+        for (long i = 0; i < (long)(c->luma_bytes >> 2); i++) hpel_plane_word(&fp, i);
     g_launches++;
     for (int pl = 0; pl < 3; pl++)
         if (job->recon[pl])

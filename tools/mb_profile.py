@@ -20,12 +20,15 @@ L.lib.H264E_b200_ctx.restype = C.c_void_p
 w, h, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 kind = sys.argv[4] if len(sys.argv) > 4 else "panning"
 fr = getattr(content, kind)(w, h, n)
-enc = B.Encoder(L, w, h, 60)
-rp = enc.run_param(qp=28)
+nsess = int(sys.argv[5]) if len(sys.argv) > 5 else 1      # concurrent sessions (profile shows session 0)
+encs = [B.Encoder(L, w, h, 60) for _ in range(nsess)]
+enc = encs[0]
+rps = [e.run_param(qp=28) for e in encs]
+rp = rps[0]
 nmb = ((w + 15) // 16) * ((h + 15) // 16)
-names = ["load", "win", "stage_a", "-", "search16", "wait_tasks", "decide", "-", "-", "-", "tq_recon", "record"]
+names = ["load", "win", "stage_a", "-", "search16", "wait_tasks", "decide", "tq_w0", "-", "-", "tq_join", "record"]
 for i in range(n):
-    enc.encode(fr[i].copy(), rp)
+    B.encode_batch(L, encs, [fr[i].copy() for _ in encs], rps)
     prof = np.zeros((nmb, 20), np.int32)
     L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
     tot = prof[:, :12].sum(1)
