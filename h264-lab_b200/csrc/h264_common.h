@@ -71,7 +71,14 @@ HD int wor(int v) { return v; }
  * the other in program order, which satisfies every producer -> consumer dependency. */
 #define MB_WARPS 4
 #if H264_DEVICE
-#  define WARP_ID ((int)(threadIdx.x >> 5))
+/* WARP_ID is the warp's ROLE.  A CTA's warp k always runs on SM sub-partition k, so with the
+ * plain numbering every CTA on an SM would put its heaviest task on the same sub-partition
+ * (one issue port, one L0 instruction cache); co-resident CTAs therefore rotate the roles. */
+#  if defined(H264_PROFILE) || defined(H264_NO_ROLE_SPREAD)
+#    define WARP_ID ((int)(threadIdx.x >> 5))
+#  else
+#    define WARP_ID ((int)(((threadIdx.x >> 5) + blockIdx.x / 148u + blockIdx.y) & 3))
+#  endif
 #  define ON_WARP(k) if (WARP_ID == (k))
 #  define CTA_SYNC() __syncthreads()
 #  define FOR_THREADS(i, n) for (int i = (int)threadIdx.x; i < (n); i += MB_WARPS * 32)

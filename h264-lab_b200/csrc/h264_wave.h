@@ -80,15 +80,37 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     {
         const int newp = w->ic[IC_SIG + 3], oldp = old.cand_sig[3];
         if (newp == oldp) same = 1;
-        else if (!(newp & ~oldp))
+        else
         {
-            /* only partition hints were withdrawn: the searches that remain are the ones already
-             * done (they do not depend on the candidates), so re-run just the decision (H:5500) */
+            /* Same start point, different partition hints.  Searches of a mode do not depend on the
+             * candidates, so the modes searched before keep their recorded cost; hinted modes that
+             * were not searched yet are searched now (same tasks / warps as in encode_mb), and the
+             * inter decision (H:5500) is re-run over the hinted set.  Unchanged winner == unchanged
+             * macroblock. */
+            const int extra = newp & ~oldp;
+            if (extra)
+            {
+                ON_WARP(1)
+                {
+                    s.ss = &w->ss[1];
+                    if (extra & 1) inter_mode_search(s, 1);
+                    if (extra & 2) inter_mode_search(s, 2);
+                }
+                ON_WARP(2)
+                {
+                    s.ss = &w->ss[2];
+                    if (extra & 4) inter_mode_search(s, 3);
+                }
+                CTA_SYNC();
+            }
             int cost = 0xffffff, best = 0;
             for (int t = 0; t < 4; t++)
                 if (t == 0 || ((newp >> (t - 1)) & 1))
-                    if (old.mode_cost[t] < cost) { cost = old.mode_cost[t]; best = t; }
-            if (best == old.inter_best) same = 2;
+                {
+                    const int ct = (t > 0 && ((extra >> (t - 1)) & 1)) ? w->mode_cost[t] : old.mode_cost[t];
+                    if (ct < cost) { cost = ct; best = t; }
+                }
+            if (best == old.inter_best) same = extra ? 3 : 2;
         }
     }
 #if !H264_DEVICE
@@ -126,11 +148,19 @@ HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
         if (chk)
         {
             fp->spec[n].cl_used[0] = ct[0]; fp->spec[n].cl_used[1] = ct[1];
-            if (chk == 2) fp->spec[n].cand_sig[3] = w->ic[IC_SIG + 3];
+            if (chk >= 2)
+            {
+                const int newp = w->ic[IC_SIG + 3], extra = newp & ~old.cand_sig[3];
+                for (int t = 1; t < 4; t++) if ((extra >> (t - 1)) & 1) fp->spec[n].mode_cost[t] = w->mode_cost[t];
+                fp->spec[n].cand_sig[3] = newp;
+            }
         } else
         {
             fp->need_reenc[n] = pass;
             atomic_add_stat(fp->fsync + FS_NFAIL);
+#if !H264_DEVICE
+            { extern int g_emu_dbg[8]; g_emu_dbg[5]++; }
+#endif
         }
     }
     CTA_SYNC();
@@ -198,6 +228,9 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
     {
         atomic_add_stat(fp->fsync + FS_REENC);
         if (diff) fp->changed_pass[n] = pass;
+#if !H264_DEVICE
+        { extern int g_emu_dbg[8]; g_emu_dbg[6]++; if (diff) g_emu_dbg[7]++; }
+#endif
         if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES)) atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
     }
     CTA_SYNC();
