@@ -234,6 +234,7 @@ struct FrameParams
     int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */
     int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */
+    int *row_clean;             /* [nmby] last repair sweep the row went through without anything to do */
     uint32_t *mb_bits;          /* per-MB bit strings, MB_BITS_WORDS words each             */
     int *mb_nbits;              /* [nmb + 1]                                                */
     int *mb_bitoff;             /* [nmb + 1] exclusive prefix sum of mb_nbits + hdr_bits    */
@@ -273,6 +274,11 @@ struct MBWork
     int32_t mvp0_left[4], mvp0_tl[4], mvp0_top[5];   /* MV predictor context at MB start    */
     int32_t nb_i4mode[8];        /* I4x4 modes of the left MB's right column / top MB's bottom row */
     uint32_t win[(WIN_W * WIN_H + 32) / 4];   /* search window: copy of the reference picture around the MV predictor */
+    /* GPU: asynchronous prefetch for the NEXT macroblock of the row (cp.async): its input samples,
+     * and -- once this macroblock's searches are over -- its search window, placed where this
+     * macroblock's motion vector points.  Tags = 1 + macroblock index the data belongs to. */
+    uint32_t pf_inp[96];         /* 64 luma words (stride 16) + 32 chroma words (U | V, stride 16) */
+    int32_t pf_inp_tag, pf_win_tag, pf_win_x0, pf_win_y0;
     /* motion search */
     SearchScratch ss[3];
     int32_t ic[16];              /* result of the candidate stage, see IC_* in h264_mbenc.h  */

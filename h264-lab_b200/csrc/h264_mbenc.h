@@ -77,6 +77,54 @@ HD int mv_in_rect(int v, int x0, int y0, int x1, int y1)
 /* ------------------------------------------------------------------------------
  * loading the macroblock's inputs
  * ---------------------------------------------------------------------------- */
+#if H264_DEVICE
+HD void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+HD void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+/* input samples of macroblock (mbx, mby) -> w->pf_inp, asynchronously; only for macroblocks entirely
+ * inside the picture whose rows are word-aligned (else mb_load fetches synchronously) */
+HD void mb_prefetch_input(const FrameParams *fp, MBWork *w, int mbx, int mby)
+{
+    const int ok = mbx < fp->nmbx && (mbx + 1) * 16 <= fp->width && (mby + 1) * 16 <= fp->height &&
+                   !(((fp->inp_stride[0] | fp->inp_stride[1] | fp->inp_stride[2]) & 3) |
+                     (((uintptr_t)fp->inp[0] | (uintptr_t)fp->inp[1] | (uintptr_t)fp->inp[2]) & 3));
+    if (ok)
+    {
+        FOR_THREADS(i, 96)
+        {
+            if (i < 64) { int r = i >> 2, c = (i & 3) * 4; cp_async4(&w->pf_inp[i], fp->inp[0] + (mby * 16 + r) * fp->inp_stride[0] + mbx * 16 + c); }
+            else
+            {
+                int k2 = i - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
+                cp_async4(&w->pf_inp[i], fp->inp[1 + pl] + (mby * 8 + r) * fp->inp_stride[1 + pl] + mbx * 8 + c);
+            }
+        }
+    }
+    IF_THREAD0 { w->pf_inp_tag = ok ? 1 + mby * fp->nmbx + mbx : 0; }
+}
+/* search window for macroblock (mbx, mby) around luma position (cx, cy) -> w->win, asynchronously */
+HD void win_prefetch(const FrameParams *fp, MBWork *w, int mbx, int mby, int cx, int cy)
+{
+    const int stride = fp->stride[0];
+    const int x0 = (cx - 24) & ~3, y0 = cy - 16;
+    const int xmin = -16, xmax = fp->nmbx * 16 + 12, ymin = -16, ymax = fp->nmby * 16 + 15;
+    const pix_t *plane = fp->ref[0];
+    FOR_THREADS(i, (WIN_W / 4) * WIN_H)
+    {
+        int r = i >> 4, c4 = i & 15;
+        int y = imin(imax(y0 + r, ymin), ymax), x = imin(imax(x0 + 4 * c4, xmin), xmax);
+        cp_async4(&w->win[i], plane + y * stride + x);
+    }
+    IF_THREAD0 { w->pf_win_tag = 1 + mby * fp->nmbx + mbx; w->pf_win_x0 = x0; w->pf_win_y0 = y0; }
+}
+#endif
+
 HDN void mb_load(MBState &s)
 {
     const FrameParams *fp = s.fp;
@@ -90,40 +138,51 @@ HDN void mb_load(MBState &s)
     const MBInfo *mbi = fp->mbi + mby * fp->nmbx + mbx;
     const int nmbx = fp->nmbx, av = s.avail;
     const int inside = (mbx + 1) * 16 <= wv && (mby + 1) * 16 <= hv;
+    int have_inp = 0;
+#if H264_DEVICE
+    /* whatever was prefetched (input of this macroblock, its search window) has to have landed */
+    cp_async_commit_wait_all();
+    CTA_SYNC();
+    have_inp = w->pf_inp_tag == 1 + mby * nmbx + mbx;
+#endif
     /* one flat list of independent loads so that all of them are in flight together:
-     * [0,64) luma words, [64,96) chroma words, [96,169) neighbour samples / MVs / modes */
-    FOR_THREADS(i, 169)
+     * [0,96) neighbour samples / MVs / modes, [96,192) input words (unless prefetched) */
+    FOR_THREADS(i, 192)
     {
-        if (i < 64)
-        {   /* input luma; samples beyond the visible picture replicate the last column / row
-             * (pix_copy_cropped_mb H:3536) */
-            int r = i >> 2, c = (i & 3) * 4;
-            uint32_t v;
-            if (inside) v = ld4u(fp->inp[0] + (mby * 16 + r) * fp->inp_stride[0] + mbx * 16 + c);
-            else
-            {
-                const pix_t *row = fp->inp[0] + imin(mby * 16 + r, hv - 1) * fp->inp_stride[0];
-                v = 0;
-                for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 16 + c + k, wv - 1)] << (8 * k);
-            }
-            *(uint32_t *)(w->inp_y + r * 16 + c) = v;
-        } else if (i < 96)
+        if (i >= 96)
         {
-            int k2 = i - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
+            const int k = i - 96;
             uint32_t v;
-            if (inside) v = ld4u(fp->inp[1 + pl] + (mby * 8 + r) * fp->inp_stride[1 + pl] + mbx * 8 + c);
-            else
+            if (have_inp) v = w->pf_inp[k];
+            else if (k < 64)
+            {   /* input luma; samples beyond the visible picture replicate the last column / row
+                 * (pix_copy_cropped_mb H:3536) */
+                int r = k >> 2, c = (k & 3) * 4;
+                if (inside) v = ld4u(fp->inp[0] + (mby * 16 + r) * fp->inp_stride[0] + mbx * 16 + c);
+                else
+                {
+                    const pix_t *row = fp->inp[0] + imin(mby * 16 + r, hv - 1) * fp->inp_stride[0];
+                    v = 0;
+                    for (int q = 0; q < 4; q++) v |= (uint32_t)row[imin(mbx * 16 + c + q, wv - 1)] << (8 * q);
+                }
+            } else
             {
-                const pix_t *row = fp->inp[1 + pl] + imin(mby * 8 + r, hv / 2 - 1) * fp->inp_stride[1 + pl];
-                v = 0;
-                for (int k = 0; k < 4; k++) v |= (uint32_t)row[imin(mbx * 8 + c + k, wv / 2 - 1)] << (8 * k);
+                int k2 = k - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
+                if (inside) v = ld4u(fp->inp[1 + pl] + (mby * 8 + r) * fp->inp_stride[1 + pl] + mbx * 8 + c);
+                else
+                {
+                    const pix_t *row = fp->inp[1 + pl] + imin(mby * 8 + r, hv / 2 - 1) * fp->inp_stride[1 + pl];
+                    v = 0;
+                    for (int q2 = 0; q2 < 4; q2++) v |= (uint32_t)row[imin(mbx * 8 + c + q2, wv / 2 - 1)] << (8 * q2);
+                }
             }
-            *(uint32_t *)(w->inp_c + r * 16 + pl * 8 + c) = v;
+            if (k < 64) *(uint32_t *)(w->inp_y + (k >> 2) * 16 + (k & 3) * 4) = v;
+            else { int k2 = k - 64; *(uint32_t *)(w->inp_c + (k2 >> 2) * 16 + (k2 & 3) * 4) = v; }
         } else
         {
             /* unfiltered neighbour samples of the picture under construction (the reference's
              * top_line context, H:4693-4714), neighbours' MVs (enc->mv_pred, H:742) and I4x4 modes */
-            int j = i - 96;
+            const int j = i;
             if (j < 20) w->top_y[j] = ((av & AVAIL_T) && (j < 16 || (av & AVAIL_TR))) ? dy[-sy + j] : 0;
             else if (j < 36) w->left_y[j - 20] = (av & AVAIL_L) ? dy[(j - 20) * sy - 1] : 0;
             else if (j < 44) w->top_c[j - 36] = (av & AVAIL_T) ? du[-sc + (j - 36)] : 0;
@@ -134,20 +193,19 @@ HDN void mb_load(MBState &s)
             else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
             else if (j == 71) w->ic[IC_STATE] = 0;
-            else if (j == 72) { /* spare */ }
+            else if (j < 76) w->mvp0_left[j - 72] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 72) + 3] : MV_NA;
+            else if (j == 76) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
+            else if (j < 80) w->mvp0_tl[j - 76] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 77) + 3] : MV_NA;
+            else if (j < 84) w->mvp0_top[j - 80] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (j - 80)] : MV_NA;
+            else if (j == 84) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
+            else if (j < 89) w->nb_i4mode[j - 85] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (j - 85) + 3] : -1;
+            else if (j < 93) w->nb_i4mode[4 + j - 89] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (j - 89)] : -1;
         }
     }
-    FOR_THREADS(i, 21)
-    {
-        if (i < 4) w->mvp0_left[i] = (av & AVAIL_L) ? mbi[-1].mv[4 * i + 3] : MV_NA;
-        else if (i == 4) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
-        else if (i < 8) w->mvp0_tl[i - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (i - 5) + 3] : MV_NA;
-        else if (i < 12) w->mvp0_top[i - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (i - 8)] : MV_NA;
-        else if (i == 12) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
-        else if (i < 17) w->nb_i4mode[i - 13] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (i - 13) + 3] : -1;
-        else w->nb_i4mode[4 + i - 17] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (i - 17)] : -1;
-    }
     CTA_SYNC();
+#if H264_DEVICE
+    mb_prefetch_input(fp, w, mbx + 1, mby);      /* for the next macroblock of the row */
+#endif
 }
 
 /* ------------------------------------------------------------------------------
@@ -216,6 +274,15 @@ HDN void win_load(MBState &s, int cx, int cy)
     const FrameParams *fp = s.fp;
     const int stride = fp->stride[0];
     const int x0 = (cx - 24) & ~3, y0 = cy - 16;
+#if H264_DEVICE
+    /* a window prefetched for this macroblock is used as it is when it sits close enough to the
+     * wanted one (any window is exact: ref_at() goes to the frame for what the window lacks) */
+    if (s.w->pf_win_tag == 1 + s.mby * fp->nmbx + s.mbx && iabs(s.w->pf_win_x0 - x0) <= 8 && iabs(s.w->pf_win_y0 - y0) <= 6)
+    {
+        s.win_x0 = s.w->pf_win_x0; s.win_y0 = s.w->pf_win_y0; s.win_ok = 1;
+        return;
+    }
+#endif
     const int xmin = -16, xmax = fp->nmbx * 16 + 12, ymin = -16, ymax = fp->nmby * 16 + 15;
     const pix_t *plane = fp->ref[0];
     uint32_t *win = s.w->win;
@@ -226,6 +293,9 @@ HDN void win_load(MBState &s, int cx, int cy)
         win[i] = *(const uint32_t *)(plane + y * stride + x);
     }
     s.win_x0 = x0; s.win_y0 = y0; s.win_ok = 1;
+#if H264_DEVICE
+    IF_THREAD0 { s.w->pf_win_tag = 0; }
+#endif
     CTA_SYNC();
 }
 
@@ -1593,6 +1663,15 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
     spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
     for (int k = 0; k < 4; k++) spec_out->cand_sig[k] = cand_sig[k];
 
+#if H264_DEVICE
+    /* the searches are over: the window buffer is free for the next macroblock of the row, whose
+     * MV predictor will most likely be this macroblock's vector */
+    if (is_p && mbx + 1 < fp->nmbx)
+    {
+        const int mvn = s.type >= 5 ? 0 : (s.type <= 1 ? pmv[0] : pmv[1]);
+        win_prefetch(fp, w, mbx + 1, mby, (mbx + 1) * 16 + ((mv_x(mvn) + 1) >> 2), mby * 16 + ((mv_y(mvn) + 1) >> 2));
+    }
+#endif
     /* ---- prediction of chroma, transform, quantisation, reconstruction ---- */
     PROF_MARK(s, 6);
     int cbpl = 0, cbpc = 0;

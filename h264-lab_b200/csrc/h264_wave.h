@@ -171,14 +171,14 @@ HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
-    int need = fp->need_reenc[n] == pass;
-    if (x > 0 && fp->changed_pass[n - 1] == pass) need = 1;
-    if (y > 0)
-    {
-        if (fp->changed_pass[n - nmbx] == pass) need = 1;
-        if (x > 0 && fp->changed_pass[n - nmbx - 1] == pass) need = 1;
-        if (x < nmbx - 1 && fp->changed_pass[n - nmbx + 1] == pass) need = 1;
-    }
+    /* all flags with independent loads: one memory round trip on the common "nothing to do" path */
+    const int has_l = x > 0, has_t = y > 0, has_tl = y > 0 && x > 0, has_tr = y > 0 && x < nmbx - 1;
+    const int f0 = fp->need_reenc[n];
+    const int f1 = fp->changed_pass[has_l ? n - 1 : n];
+    const int f2 = fp->changed_pass[has_t ? n - nmbx : n];
+    const int f3 = fp->changed_pass[has_tl ? n - nmbx - 1 : n];
+    const int f4 = fp->changed_pass[has_tr ? n - nmbx + 1 : n];
+    const int need = (f0 == pass) | (has_l & (f1 == pass)) | (has_t & (f2 == pass)) | (has_tl & (f3 == pass)) | (has_tr & (f4 == pass));
     if (!need) return;
     const MBSpec old = fp->spec[n];
     int32_t ct[2];
@@ -244,6 +244,39 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
     int32_t c[2];
     c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
     int ndirty = 0;
+#if H264_DEVICE
+    /* every lane replays the (cheap, strictly sequential) recurrence redundantly; the records of
+     * 32 macroblocks at a time sit in registers and are broadcast with shuffles, the next 32
+     * are prefetched meanwhile */
+    {
+        const int lane = LANE_ID;
+        int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
+        if (lane < nmb) { const MBSpec *sp = fp->spec + lane; mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1]; }
+        for (int base = 0; base < nmb; base += 32)
+        {
+            int nmv0 = 0, nflags = 0, nu0 = 0, nu1 = 0;
+            if (base + 32 + lane < nmb)
+            {
+                const MBSpec *sp = fp->spec + base + 32 + lane;
+                nmv0 = sp->mv0; nflags = sp->flags; nu0 = sp->cl_used[0]; nu1 = sp->cl_used[1];
+            }
+            const int cnt = imin(32, nmb - base);
+            int t0 = 0, t1 = 0;
+#pragma unroll 4
+            for (int i = 0; i < cnt; i++)
+            {
+                const int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
+                const int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
+                const int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+                if (lane == i) { t0 = r0; t1 = r1; }
+                if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+                if (f & SPEC_UPDATES) clusters_update(c, m);
+            }
+            if (lane < cnt) { fp->cl_true[2 * (base + lane)] = t0; fp->cl_true[2 * (base + lane) + 1] = t1; }
+            mv0 = nmv0; flags = nflags; u0 = nu0; u1 = nu1;
+        }
+    }
+#else
     for (int base = 0; base < nmb; base += 32)
     {
         FOR_LANES(i, 32)
@@ -277,6 +310,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
         }
         WSYNC();
     }
+#endif
     if (predict) return 0;
     IF_LANE0
     {

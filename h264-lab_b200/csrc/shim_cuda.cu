@@ -52,13 +52,23 @@ __device__ __forceinline__ int ld_acquire(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+/* Polling uses RELAXED loads (served by L2, they leave the SM's L1 alone); one acquire fence
+ * follows when the awaited value has been seen.  Polling with ld.acquire would invalidate the
+ * L1 of every co-resident CTA at each iteration. */
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void wait_row(const int *progress_above, int need)      /* one warp */
 {
-    if (LANE_ID == 0) { while (ld_acquire(progress_above) < need) __nanosleep(32); }
+    if (LANE_ID == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(32); fence_acquire(); }
     __syncwarp();
 }
 __device__ __forceinline__ void publish_row(int *progress, int done)               /* one warp */
@@ -68,7 +78,7 @@ __device__ __forceinline__ void publish_row(int *progress, int done)            
 }
 __device__ __forceinline__ void wait_row_cta(const int *progress_above, int need)  /* whole CTA */
 {
-    if (threadIdx.x == 0) { while (ld_acquire(progress_above) < need) __nanosleep(20); }
+    if (threadIdx.x == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(20); fence_acquire(); }
     __syncthreads();
 }
 __device__ __forceinline__ void publish_row_cta(int *progress, int done)
@@ -109,7 +119,8 @@ __device__ void trajectory_follower(const FrameParams *fp)
         if (lane == 0)
         {
             int p;
-            while ((p = ld_acquire(fp->row_progress + row)) <= x) __nanosleep(200);
+            while ((p = ld_relaxed(fp->row_progress + row)) <= x) __nanosleep(200);
+            fence_acquire();
             avail = min(p - x, 32);
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
     __shared__ int s_item;
-    if (threadIdx.x == 0) { s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; }
+    if (threadIdx.x == 0) { s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; }
     __syncthreads();
     int item = s_item;
     if (pass == 0)
@@ -167,9 +178,40 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     __syncthreads();
     const FrameParams *fp = &sfp;
     if (row >= fp->nmby) return;
+    if (pass > 0 && fp->fsync[FS_STATE] != pass) return;      /* frame already exact (or failed) */
     const int nmbx = fp->nmbx;
     int *progress = fp->row_progress;
     const int base = pass * nmbx;
+    if (pass > 0)
+    {
+        /* Repair sweeps touch few macroblocks.  A row in which nothing is queued, below a row that
+         * went through the sweep without anything to do, has nothing to do either: it says so
+         * and leaves, so that "nothing to do" travels down the frame at one global round trip
+         * per row instead of one per macroblock. */
+        int has_need = 0;
+        for (int i = threadIdx.x; i < nmbx; i += blockDim.x) has_need |= fp->need_reenc[row * nmbx + i] == pass;
+        has_need = __syncthreads_or(has_need);
+        if (!has_need)
+        {
+            __shared__ int s_clean;
+            if (threadIdx.x == 0)
+            {
+                int clean = 1;
+                if (row > 0)
+                    for (;;)
+                    {
+                        if (ld_relaxed(fp->row_clean + row - 1) == pass) break;
+                        if (ld_relaxed(progress + row - 1) >= base + 1) { clean = ld_relaxed(fp->row_clean + row - 1) == pass; break; }
+                        __nanosleep(20);
+                    }
+                fence_acquire();
+                s_clean = clean;
+                if (clean) { st_release(fp->row_clean + row, pass); st_release(progress + row, base + nmbx); }
+            }
+            __syncthreads();
+            if (s_clean) return;
+        }
+    }
     for (int x = 0; x < nmbx; x++)
     {
         if (row > 0) wait_row_cta(progress + row - 1, base + min(x + 2, nmbx));
@@ -180,14 +222,6 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     }
 }
 
-/* one warp per frame, before sweep 0: predicted cluster trajectory (h264_wave.h) */
-__global__ void __launch_bounds__(32) k_predict(const FrameParams *fps, int njobs)
-{
-    __shared__ MBWork work;
-    const FrameParams *fp = fps + blockIdx.x;
-    if (fp->spec_from_prev) wave_replay(fp, &work, 1);
-}
-
 /* parallel re-check of the dirty macroblocks of every frame that waits for repair sweep `pass` */
 __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_check(const FrameParams *fps, int njobs, int pass)
 {
@@ -195,6 +229,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_check(const F
     __shared__ FrameParams sfp;
     for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
         ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
+    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; }
     __syncthreads();
     const FrameParams *fp = &sfp;
     if (fp->fsync[FS_STATE] != pass) return;
@@ -216,18 +251,30 @@ __global__ void __launch_bounds__(32) k_replay(const FrameParams *fps, int njobs
 {
     __shared__ MBWork work;
     const FrameParams *fp = fps + blockIdx.x;
+    if (fp->fsync[FS_STATE] != pass) return;
     int next = wave_end_of_pass(fp, &work, pass);
     if (next != FS_DONE && next > fp->max_passes) { if (threadIdx.x == 0) atomicOr(&fp->out_info[1], 4); next = FS_DONE; }
     if (threadIdx.x == 0) fp->fsync[FS_STATE] = next;
 }
 
+/* In-loop filter, x+2y wavefront, one warp per macroblock row.  The first njobs tickets do
+ * something unrelated that only has to happen once the frame is exact: they replay the cluster
+ * update over this frame's final motion field from its END state, i.e. the trajectory
+ * speculated for the NEXT frame (h264_wave.h "predict"). */
 __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int njobs, int *tickets)
 {
     __shared__ int s_item;
     __shared__ DeblockTile tile;
     if (threadIdx.x == 0) s_item = atomicAdd(&tickets[1], 1);
     __syncwarp();
-    const int item = s_item;
+    int item = s_item;
+    if (item < njobs)
+    {
+        const FrameParams *fp = fps + item;
+        if (fp->fsync[FS_STATE] == FS_DONE && fp->slice_type == SLICE_P) wave_replay(fp, (MBWork *)0, 1);
+        return;
+    }
+    item -= njobs;
     const int job = item % njobs, row = item / njobs;
     const FrameParams *fp = fps + job;
     if (row >= fp->nmby || fp->disable_deblock || fp->fsync[FS_STATE] != FS_DONE) return;
@@ -360,8 +407,17 @@ static cudaEvent_t g_ev[6];
 static int g_ev_ok = 0;
 static float g_last_ms[4];
 
+static int g_enc_dyn_smem = 0;     /* developer knob H264B200_ENC_SMEM: extra dynamic shared memory per CTA of k_encode_rows
+                                       (limits the CTAs resident per SM, to study cache contention) */
 static int ensure_globals(int njobs)
 {
+    static int once = 0;
+    if (!once)
+    {
+        once = 1;
+        const char *e = getenv("H264B200_ENC_SMEM");
+        if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
+    }
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
     if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ok = 1; }
@@ -421,7 +477,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_out_info, 64));
     CK(cudaMalloc(&c->d_clusters, 16));
     CK(cudaMemset(c->d_clusters, 0, 16));
-    CK(cudaMalloc(&c->d_progress, sizeof(int) * 2 * c->nmby));
+    CK(cudaMalloc(&c->d_progress, sizeof(int) * 3 * c->nmby));
     CK(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
     CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
     CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
@@ -498,7 +554,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
-    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby;
+    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby; fp->row_clean = c->d_progress + 2 * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
@@ -524,7 +580,7 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
                        cudaEvent_t ev_mid)
 {
     CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
-    k_deblock_rows<<<n * max_rows, 32, 0, st>>>(d_fps, n, g_d_tickets);
+    k_deblock_rows<<<n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
     k_hpel<<<dim3(148, n), 256, 0, st>>>(d_fps, n);
     if (ev_mid) CK(cudaEventRecord(ev_mid, st));
@@ -584,18 +640,28 @@ static int encode_impl(int n, h264b200_job *jobs)
     for (int i = 0; i < n; i++)
     {
         h264b200_ctx *c = jobs[i].ctx;
-        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 2 * c->nmby, st));
+        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 3 * c->nmby, st));
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
         CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
     }
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
-    k_predict<<<n, 32, 0, st>>>(g_d_fps, n);
-    k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, 0, st>>>(g_d_fps, n, g_d_tickets, 0);
+    k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
     k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, 1);
     k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
-    g_launches += 4;
+    g_launches += 3;
+    /* two repair rounds are queued unconditionally (frames that are already exact skip them on
+     * the device), so that the common case needs no host round trip before the post-processing */
+    for (int pass = 1; pass <= 2; pass++)
+    {
+        CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
+        k_encode_rows<<<n * max_rows, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
+        k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
+        k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass + 1);
+        k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
+        g_launches += 4;
+    }
     CK(cudaEventRecord(g_ev[2], st));
     if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;
     CK(cudaEventRecord(g_ev[4], st));
@@ -619,7 +685,7 @@ static int encode_impl(int n, h264b200_job *jobs)
         }
         CK(cudaMemcpyAsync(d2, h2, sizeof(FrameParams) * m, cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
-        k_encode_rows<<<m * rows2, MB_WARPS * 32, 0, st>>>(d2, m, g_d_tickets, pass);
+        k_encode_rows<<<m * rows2, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
         k_check<<<dim3(148, m), MB_WARPS * 32, 0, st>>>(d2, m, pass + 1);
         k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);
