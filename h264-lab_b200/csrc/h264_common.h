@@ -82,6 +82,8 @@ HD int wor(int v) { return v; }
 #  define ON_WARP(k) if (WARP_ID == (k))
 #  define CTA_SYNC() __syncthreads()
 #  define FOR_THREADS(i, n) for (int i = (int)threadIdx.x; i < (n); i += MB_WARPS * 32)
+/* the 96 threads of the three motion-search warps (roles 0-2) */
+#  define FOR_SEARCH_THREADS(i, n) for (int i = WARP_ID * 32 + LANE_ID; i < (n); i += 96)
 #  define IF_THREAD0 if (threadIdx.x == 0)
 HD void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #else
@@ -89,6 +91,7 @@ HD void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(i
 #  define ON_WARP(k)
 #  define CTA_SYNC() ((void)0)
 #  define FOR_THREADS(i, n) for (int i = 0; i < (n); i++)
+#  define FOR_SEARCH_THREADS(i, n) for (int i = 0; i < (n); i++)
 #  define IF_THREAD0
 HD void bar_sync(int, int) {}
 #endif

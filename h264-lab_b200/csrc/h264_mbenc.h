@@ -52,6 +52,7 @@ struct MBState   /* warp-uniform registers of the macroblock being encoded */
 #define IC_MV_SKIP 5
 #define IC_SAD_SKIP 6
 #define IC_SIG 7          /* [7..10] candidate-stage signature for the speculation check  */
+#define IC_COST0 11       /* cost of the 16x16 mode once its search has finished, -1 before */
 
 HD int clz32(uint32_t v)
 {
@@ -73,6 +74,35 @@ HD int mv_in_rect(int v, int x0, int y0, int x1, int y1)
     int x = mv_x(v), y = mv_y(v);
     return y >= y0 && y <= y1 && x >= x0 && x <= x1;
 }
+
+/* Exact pruning.  Every partition mode competes with the 16x16 mode, which is always searched,
+ * and wins only with a strictly smaller cost (ascending order, strict '<', H:5500); Intra4x4 wins
+ * only with a cost strictly below Intra16x16's and below the final inter cost (H:4827).  The 16x16
+ * cost is at most lambda(1 bit) + the seed of its search (the search only lowers it), and costs
+ * accumulate non-negative terms, so a partial sum that has reached that bound decides the
+ * comparison: the remaining partitions / 4x4 blocks need not be evaluated.  Their side
+ * effects (MVs, modes, levels) are only kept for the winning mode.  Returns the bound. */
+HD int inter_cost_bound(const FrameParams *fp, const MBWork *w)
+{
+    int bound = ((1 * fp->lambda_q4) >> 4) + *(volatile const int32_t *)&w->ic[IC_SAD_BEST];
+    const int c0 = *(volatile const int32_t *)&w->ic[IC_COST0];
+    if (c0 >= 0 && c0 < bound) bound = c0;
+    return bound;
+}
+/* upper bound of the cost the inter decision will end with: the best mode's cost, or -- when the raw
+ * skip SAD is smaller -- the cost of P16x16 at the skip vector, which may be larger (H:5512-5522) */
+HD int inter_final_bound(const FrameParams *fp, const MBWork *w)
+{
+    int bound = inter_cost_bound(fp, w);
+    const int sad_skip = *(volatile const int32_t *)&w->ic[IC_SAD_SKIP];
+    if (sad_skip != 0x7FFFFFFF)
+    {
+        const int alt = sad_skip + mv_cost(*(volatile const int32_t *)&w->ic[IC_MV_SKIP], *(volatile const int32_t *)&w->ic[IC_MVP16], fp->lambda_mv_q4);
+        if (alt > bound) bound = alt;
+    }
+    return bound;
+}
+
 
 /* ------------------------------------------------------------------------------
  * loading the macroblock's inputs
@@ -145,6 +175,47 @@ HDN void mb_load(MBState &s)
     CTA_SYNC();
     have_inp = w->pf_inp_tag == 1 + mby * nmbx + mbx;
 #endif
+#if H264_DEVICE
+    if (have_inp && inside)
+    {
+        /* Fast path: the input is already in shared memory (prefetched); every physical warp
+         * fetches one kind of neighbour data with lane-indexed addresses -- a few instructions
+         * per warp, all loads of the macroblock in flight together. */
+        const int pw = (int)(threadIdx.x >> 5) & 3, lane = LANE_ID;
+        if (lane < 24)
+        {
+            const uint32_t v = w->pf_inp[pw * 24 + lane];
+            const int k = pw * 24 + lane;
+            if (k < 64) *(uint32_t *)(w->inp_y + (k >> 2) * 16 + (k & 3) * 4) = v;
+            else { const int k2 = k - 64; *(uint32_t *)(w->inp_c + (k2 >> 2) * 16 + (k2 & 3) * 4) = v; }
+        }
+        if (pw == 0)
+        {   /* row above: 16 + 4 luma samples, top-left samples */
+            if (lane < 20) w->top_y[lane] = ((av & AVAIL_T) && (lane < 16 || (av & AVAIL_TR))) ? dy[-sy + lane] : 0;
+            else if (lane == 20) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
+            else if (lane == 21) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
+            else if (lane == 22) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
+            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; }
+        } else if (pw == 1)
+        {   /* left column: 16 luma + 8 + 8 chroma samples */
+            if (lane < 16) w->left_y[lane] = (av & AVAIL_L) ? dy[lane * sy - 1] : 0;
+            else { const int k = lane - 16; w->left_c[k] = (av & AVAIL_L) ? ((k < 8 ? du : dv)[(k & 7) * sc - 1]) : 0; }
+        } else if (pw == 2)
+        {   /* chroma row above, I4x4 modes of the neighbours */
+            if (lane < 16) w->top_c[lane] = (av & AVAIL_T) ? ((lane < 8 ? du : dv)[-sc + (lane & 7)]) : 0;
+            else if (lane < 20) w->nb_i4mode[lane - 16] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (lane - 16) + 3] : -1;
+            else if (lane < 24) w->nb_i4mode[4 + lane - 20] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (lane - 20)] : -1;
+        } else
+        {   /* motion vectors of the neighbours */
+            if (lane < 4) w->mvp0_left[lane] = (av & AVAIL_L) ? mbi[-1].mv[4 * lane + 3] : MV_NA;
+            else if (lane == 4) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
+            else if (lane < 8) w->mvp0_tl[lane - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (lane - 5) + 3] : MV_NA;
+            else if (lane < 12) w->mvp0_top[lane - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (lane - 8)] : MV_NA;
+            else if (lane == 12) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
+        }
+    } else
+#endif
+    {
     /* one flat list of independent loads so that all of them are in flight together:
      * [0,96) neighbour samples / MVs / modes, [96,192) input words (unless prefetched) */
     FOR_THREADS(i, 192)
@@ -192,7 +263,7 @@ HDN void mb_load(MBState &s)
             else if (j == 68) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
             else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (j == 71) w->ic[IC_STATE] = 0;
+            else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; }
             else if (j < 76) w->mvp0_left[j - 72] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 72) + 3] : MV_NA;
             else if (j == 76) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
             else if (j < 80) w->mvp0_tl[j - 76] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 77) + 3] : MV_NA;
@@ -201,6 +272,7 @@ HDN void mb_load(MBState &s)
             else if (j < 89) w->nb_i4mode[j - 85] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (j - 85) + 3] : -1;
             else if (j < 93) w->nb_i4mode[4 + j - 89] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (j - 89)] : -1;
         }
+    }
     }
     CTA_SYNC();
 #if H264_DEVICE
@@ -409,23 +481,29 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
         if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
         const int dgx = pqx + sqx, dgy = pqy + sqy;
         pix_t *I = buf[0], *C = buf[1], *H1 = buf[2], *H2 = buf[3];
-        /* the three half-sample blocks mv + 2q come straight from the half-sample planes */
+        /* the three half-sample blocks mv + 2q come straight from the half-sample planes: pure half
+         * positions, i.e. plane h (0,2), b (2,0) or j (2,2) at an integer offset; the three copies
+         * are issued together (one memory round trip) */
         const int st = fp->stride[0];
         const long go = (long)((mv_y(mv) >> 2) + ppy) * st + (mv_x(mv) >> 2) + ppx;
+        const pix_t *src3[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
         {
-            const int hx = 2 * pqx, hy = 2 * pqy;
-            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
-            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, H1);
+            const int hx = 2 * (k == 0 ? pqx : (k == 1 ? sqx : dgx)), hy = 2 * (k == 0 ? pqy : (k == 1 ? sqy : dgy));
+            const pix_t *pl = (hx & 3) ? ((hy & 3) ? fp->hp[2] : fp->hp[0]) : fp->hp[1];
+            src3[k] = pl + go + (long)(hy >> 2) * st + (hx >> 2);
         }
         {
-            const int hx = 2 * sqx, hy = 2 * sqy;
-            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
-            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, H2);
-        }
-        {
-            const int hx = 2 * dgx, hy = 2 * dgy;
-            const long o = go + (long)(hy >> 2) * st + (hx >> 2);
-            interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, hx & 3, hy & 3, bw, bh, C);
+            const int sh = bw == 16 ? 2 : 1;
+            FOR_LANES(i, bh << sh)
+            {
+                const int r = i >> sh, c = (i & ((1 << sh) - 1)) * 4;
+                const uint32_t v1 = ld4u(src3[0] + r * st + c), v2 = ld4u(src3[1] + r * st + c), v3 = ld4u(src3[2] + r * st + c);
+                *(uint32_t *)(H1 + r * 16 + c) = v1;
+                *(uint32_t *)(H2 + r * 16 + c) = v2;
+                *(uint32_t *)(C + r * 16 + c) = v3;
+            }
         }
         WSYNC();
         int sq[7];
@@ -692,9 +770,11 @@ HDN void inter_mode_search(MBState &s, int mb_type)
         WSYNC();
         px = (px + bw) & 15;
         if (!px) { py = (py + bh) & 15; if (!py) break; }
+        if (mb_type && part_sad >= inter_cost_bound(fp, w)) break;      /* this mode has lost (exact pruning, see above) */
     }
     IF_LANE0
     {
+        if (!mb_type) *(volatile int32_t *)&w->ic[IC_COST0] = part_sad;
         w->mode_cost[mb_type] = part_sad;
         w->mode_pred[mb_type] = (int32_t)(result - (pix_t *)w);
     }
@@ -764,7 +844,7 @@ HD int lds_u8(unsigned addr)
  *    partial sums), the mode costs are formed where the sums end up and the strict-'<'-in-
  *    evaluation-order decision is a min-reduction of (cost << 4 | slot);
  *  - residual -> transform -> quantisation -> inverse -> reconstruction stay in registers. */
-HDN int intra4_choose(MBState &s, int *nz_mask_out)
+HDN int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -838,7 +918,14 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     {
         /* the candidate stage runs concurrently on another warp: stop as soon as it has
          * decided for an early skip (the intra result would be discarded, H:5767) */
-        if (poll_skip && *(volatile int32_t *)&w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        {
+            const int st = poll_skip ? *(volatile int32_t *)&w->ic[IC_STATE] : 0;
+            if (st == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+            /* exact pruning: the blocks decided so far already cost as much as a competitor */
+            int bound = cost16;
+            if (st == 2) bound = imin(bound, inter_final_bound(fp, w));
+            if (cost + __shfl_xor_sync(FULL, cost, 16) + fp->lambda_i4_q4 >= bound) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        }
         const int nA = t < 2 ? t : 4 * (t >> 1) + (t & 1) - 2;
         const int active = !g || (t >= 2 && t <= 7);
         const int n = (g && active) ? nA + 2 : nA;
@@ -963,7 +1050,7 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     return cost + fp->lambda_i4_q4;
 }
 #else
-HDN int intra4_choose(MBState &s, int *nz_mask_out)
+HDN int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -976,6 +1063,11 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out)
     for (int n = 0; n < 16; n++)
     {
         if (fp->slice_type == SLICE_P && w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        {   /* exact pruning (see inter_cost_bound) */
+            int bound = cost16;
+            if (fp->slice_type == SLICE_P && w->ic[IC_STATE] == 2) bound = imin(bound, inter_final_bound(fp, w));
+            if (cost >= bound) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        }
         /* which neighbours exist for block n (block2avail H:4750) */
         const int r = n >> 2, c = n & 3;
         int a = 0;
@@ -1604,7 +1696,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         int cost16 = sad_sm_wh(w->inp_y, w->i16pred, 16, 16)
                    + ((bitsize_ue(m16 + 1) * fp->lambda_q4) >> 4) + fp->lambda_i16_q4;
         int cost4 = 0x7FFFFFFF, nz4 = 0;
-        if (fp->speed < 2 || !is_p) cost4 = intra4_choose(s, &nz4);
+        if (fp->speed < 2 || !is_p) cost4 = intra4_choose(s, &nz4, cost16);
         IF_LANE0 { w->intra_res[0] = cost16; w->intra_res[1] = m16; w->intra_res[2] = cost4; w->intra_res[3] = nz4; }
     }
     PROF_WARP(s, fp, mby * fp->nmbx + mbx, 12 + WARP_ID);

@@ -36,6 +36,14 @@ for i in range(n):
     L.lib.h264b200_last_timing(tm)
     print("frame %d: k_encode %.2f ms; MB cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f  (sum/1.9GHz = %.1f ms serial)" % (
         i, tm[1], tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), np.percentile(tot, 99), tot.max(), tot.sum() / 1.9e6))
+    # who decides the join time of the slow macroblocks (critical path of the wavefront)?
+    arr = prof[:, 12:16]
+    late = arr.argmax(1)
+    join = arr.max(1)
+    thr = np.percentile(tot, 90)
+    slow = tot >= thr
+    print("   join time mean %.0f; last warp to arrive: %s ; among slowest 10%% (>= %.0f cyc): %s, their mean arrive %s" % (
+        join.mean(), np.bincount(late, minlength=4).tolist(), thr, np.bincount(late[slow], minlength=4).tolist(), arr[slow].mean(0).astype(int).tolist()))
     for t in sorted(set(prof[:, 16].tolist())):
         m = prof[:, 16] == t
         ph = prof[m][:, :12].mean(0)
