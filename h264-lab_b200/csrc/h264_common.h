@@ -237,6 +237,7 @@ struct FrameParams
     int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */
     int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */
+    int *row_progress_dfc;      /* [nmby] deblock pass, chroma wavefront                     */
     int *row_clean;             /* [nmby] last repair sweep the row went through without anything to do */
     uint32_t *mb_bits;          /* per-MB bit strings, MB_BITS_WORDS words each             */
     int *mb_nbits;              /* [nmb + 1]                                                */
@@ -283,7 +284,9 @@ struct MBWork
     uint32_t pf_inp[96];         /* 64 luma words (stride 16) + 32 chroma words (U | V, stride 16) */
     int32_t pf_inp_tag, pf_win_tag, pf_win_x0, pf_win_y0;
     /* motion search */
-    SearchScratch ss[3];
+    SearchScratch ss[4];         /* one per warp that may run a partition-mode search */
+    int32_t task_next;           /* partition-mode search tasks handed out so far (encode_mb) */
+    pix_t mode_store[3][256];    /* assembled prediction of partition modes 1..3 (whichever warp searched them) */
     int32_t ic[16];              /* result of the candidate stage, see IC_* in h264_mbenc.h  */
     int32_t mode_cost[4], mode_pred[4];      /* per partition mode: cost, byte offset of its prediction in MBWork */
     int32_t part_mv[4][4], part_mvd[4][4];   /* per mode, per partition                     */

@@ -88,28 +88,17 @@ struct DeblockTile
     uint8_t bs[32];          /* [4*e + seg] vertical edges, [16 + 4*e + seg] horizontal edges          */
 };
 
-/* One macroblock, one warp.  The samples the filters can touch (the macroblock, 4 columns of
- * the left and 4 rows of the upper neighbour) are staged as aligned words in shared memory,
- * filtered there (lanes 0-15: the 16 luma lines, 16-23 / 24-31: the 8 U / V lines crossing the
- * edges; vertical edges left to right, then horizontal edges top to bottom -- the reference's
- * per-macroblock order) and written back as words. */
-HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
+/* One macroblock, one warp, luma (part 0) or both chroma planes (part 1) -- the two are
+ * independent and run as separate wavefronts.  The samples the filters can touch (the macroblock,
+ * 4 columns of the left and 4 rows of the upper neighbour) are staged as aligned words in shared
+ * memory, filtered there (one lane per line crossing the edges, held in registers; vertical
+ * edges left to right, then horizontal edges top to bottom -- the reference's per-macroblock
+ * order) and written back as words. */
+HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
 {
     const MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     const MBInfo *ml = mi - 1, *mt = mi - fp->nmbx;
-    const int sy = fp->stride[0], sc = fp->stride[1];
-    pix_t *py = fp->dec[0] + (mby * 16) * sy + mbx * 16;
-    pix_t *pc[2];
-    pc[0] = fp->dec[1] + (mby * 8) * sc + mbx * 8;
-    pc[1] = fp->dec[2] + (mby * 8) * sc + mbx * 8;
-
-    /* 1. stage samples (the guard band makes the reads safe at picture edges) */
-    FOR_LANES(i, 100 + 72)
-    {
-        if (i < 100) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
-        else { int k = i - 100, pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3; t->c[pl][r * 3 + c] = *(const uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4); }
-    }
-    /* 2. boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg */
+    /* boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg */
     FOR_LANES(j, 32)
     {
         const int horiz = j >> 4, e = (j >> 2) & 3, seg = j & 3;
@@ -125,62 +114,94 @@ HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
         else bs = horiz ? bs_inter(mi, (e - 1) * 4 + seg, mi, e * 4 + seg) : bs_inter(mi, seg * 4 + e - 1, mi, seg * 4 + e);
         t->bs[j] = (uint8_t)bs;
     }
-    WSYNC();
-    /* 3. vertical edges: lane owns one line (row) */
-    FOR_LANES(ln, 32)
+}
+
+HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part)
+{
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    const int alpha = fp->df_alpha[part], beta = fp->df_beta[part];
+    int tc0[4];
+    for (int k = 0; k < 4; k++) tc0[k] = fp->df_tc0[part][k];
+    if (part == 0)
     {
-        const int cr = ln >= 16, pl = ln < 24 ? 0 : 1, line = cr ? (ln & 7) : ln;
-        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
-        const int seg = cr ? (line >> 1) : (line >> 2);
-        pix_t *row = cr ? (pix_t *)(t->c[pl] + (line + 4) * 3) : (pix_t *)(t->y + (line + 4) * 6);
-        const int n = cr ? 8 : 16;
-        int v[20];
-        for (int i = 0; i < n + 4; i++) v[i] = row[i];
-        for (int e = 0; e < 4; e++)
+        pix_t *py = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+        FOR_LANES(i, 100) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
+        deblock_bs(fp, t, mbx, mby);
+        WSYNC();
+        FOR_LANES(ln, 16)      /* vertical edges: lane owns one row */
         {
-            int bs = t->bs[4 * e + seg];
-            if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
-            else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+            uint32_t *row = t->y + (ln + 4) * 6;
+            int v[20];
+#pragma unroll
+            for (int k = 0; k < 5; k++) unpack4(row[k], v + 4 * k);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const int bs = t->bs[4 * e + (ln >> 2)]; df_luma_line(v, 4 + 4 * e, bs, alpha, beta, tc0[bs & 3]); }
+#pragma unroll
+            for (int k = 0; k < 5; k++) row[k] = pack4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
-        for (int i = 0; i < n + 4; i++) row[i] = (pix_t)v[i];
-    }
-    WSYNC();
-    /* 4. horizontal edges: lane owns one column */
-    FOR_LANES(ln, 32)
-    {
-        const int cr = ln >= 16, pl = ln < 24 ? 0 : 1, line = cr ? (ln & 7) : ln;
-        const int alpha = fp->df_alpha[cr], beta = fp->df_beta[cr];
-        const int seg = cr ? (line >> 1) : (line >> 2);
-        pix_t *col = cr ? (pix_t *)t->c[pl] + line + 4 : (pix_t *)t->y + line + 4;
-        const int n = cr ? 8 : 16, rs = cr ? 12 : 24;
-        int v[20];
-        for (int i = 0; i < n + 4; i++) v[i] = col[i * rs];
-        for (int e = 0; e < 4; e++)
+        WSYNC();
+        FOR_LANES(ln, 16)      /* horizontal edges: lane owns one column */
         {
-            int bs = t->bs[16 + 4 * e + seg];
-            if (!cr) df_luma_line(v, 4 + 4 * e, bs, alpha, beta, fp->df_tc0[0][bs & 3]);
-            else if (!(e & 1)) df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, fp->df_tc0[1][bs & 3]);
+            pix_t *col = (pix_t *)t->y + ln + 4;
+            int v[20];
+#pragma unroll
+            for (int i = 0; i < 20; i++) v[i] = col[i * 24];
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const int bs = t->bs[16 + 4 * e + (ln >> 2)]; df_luma_line(v, 4 + 4 * e, bs, alpha, beta, tc0[bs & 3]); }
+#pragma unroll
+            for (int i = 1; i < 19; i++) col[i * 24] = (pix_t)v[i];
         }
-        for (int i = 0; i < n + 4; i++) col[i * rs] = (pix_t)v[i];
-    }
-    WSYNC();
-    /* 5. write back: the macroblock, the 4 columns to its left, the 4 rows above it */
-    FOR_LANES(i, 100 + 72)
-    {
-        if (i < 100)
+        WSYNC();
+        FOR_LANES(i, 100)
         {
             int r = i / 5, c = i - r * 5;
             if ((r >= 4 || (mby > 0 && c > 0)) && (c > 0 || (mbx > 0 && r >= 4)))
                 *(uint32_t *)(py + (r - 4) * sy + c * 4 - 4) = t->y[r * 6 + c];
-        } else
+        }
+    } else
+    {
+        pix_t *pc[2];
+        pc[0] = fp->dec[1] + (mby * 8) * sc + mbx * 8;
+        pc[1] = fp->dec[2] + (mby * 8) * sc + mbx * 8;
+        FOR_LANES(k, 72) { int pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3; t->c[pl][r * 3 + c] = *(const uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4); }
+        deblock_bs(fp, t, mbx, mby);
+        WSYNC();
+        FOR_LANES(ln, 16)      /* lanes 0-7: U lines, 8-15: V lines */
         {
-            int k = i - 100, pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3;
+            const int pl = ln >> 3, line = ln & 7;
+            uint32_t *row = t->c[pl] + (line + 4) * 3;
+            int v[12];
+#pragma unroll
+            for (int k = 0; k < 3; k++) unpack4(row[k], v + 4 * k);
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) { const int bs = t->bs[4 * e + (line >> 1)]; df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, tc0[bs & 3]); }
+#pragma unroll
+            for (int k = 0; k < 3; k++) row[k] = pack4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+        WSYNC();
+        FOR_LANES(ln, 16)
+        {
+            const int pl = ln >> 3, line = ln & 7;
+            pix_t *col = (pix_t *)t->c[pl] + line + 4;
+            int v[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) v[i] = col[i * 12];
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) { const int bs = t->bs[16 + 4 * e + (line >> 1)]; df_chroma_line(v, 4 + 2 * e, bs, alpha, beta, tc0[bs & 3]); }
+#pragma unroll
+            for (int i = 2; i < 10; i++) col[i * 12] = (pix_t)v[i];
+        }
+        WSYNC();
+        FOR_LANES(k, 72)
+        {
+            int pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3;
             if ((r >= 4 || (mby > 0 && c > 0)) && (c > 0 || (mbx > 0 && r >= 4)))
                 *(uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4) = t->c[pl][r * 3 + c];
         }
     }
     WSYNC();
 }
+
 
 /* a16: replicate the picture edges into the 16 (luma) / 8 (chroma) sample guard band.
  * One work item per guard sample; idx enumerates the guard samples of plane pl. */

@@ -195,7 +195,7 @@ HDN void mb_load(MBState &s)
             else if (lane == 20) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
             else if (lane == 21) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (lane == 22) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; }
+            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; }
         } else if (pw == 1)
         {   /* left column: 16 luma + 8 + 8 chroma samples */
             if (lane < 16) w->left_y[lane] = (av & AVAIL_L) ? dy[lane * sy - 1] : 0;
@@ -263,7 +263,7 @@ HDN void mb_load(MBState &s)
             else if (j == 68) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
             else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; }
+            else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; }
             else if (j < 76) w->mvp0_left[j - 72] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 72) + 3] : MV_NA;
             else if (j == 76) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
             else if (j < 80) w->mvp0_tl[j - 76] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 77) + 3] : MV_NA;
@@ -717,7 +717,7 @@ HDN void inter_mode_search(MBState &s, int mb_type)
     const int bw = (mb_type & 2) ? 8 : 16, bh = (mb_type & 1) ? 8 : 16;
     /* scratch tiles of the diamond / sub-pel search, and where this mode's MB prediction is assembled */
     pix_t *store = ss->store[0];
-    pix_t *assembled = mb_type == 2 ? ss->store[3] : ss->store[2];
+    pix_t *assembled = mb_type ? w->mode_store[mb_type - 1] : ss->store[2];
     pix_t *result = assembled;
     FOR_LANES(i, 13)
     {
@@ -1618,6 +1618,32 @@ HD void clusters_update(int32_t *cl, int mv)
     if (norm >= n0) cl[1] = mv_pack((63 * c1x + x + 32) >> 6, (63 * c1y + y + 32) >> 6);
 }
 
+/* The hinted partition modes (16x8, 8x16, 8x8) are independent search tasks; the warps that are
+ * free (roles 1, 2, and 3 once the intra decision is over) take them from a shared counter, the
+ * longest (8x8, four partitions) first.  `slot` selects the warp's private scratch. */
+HDN void partition_tasks(MBState &s, int slot)
+{
+    MBWork *w = s.w;
+    const int pref = w->ic[IC_PREF];
+    s.ss = &w->ss[slot];
+    for (;;)
+    {
+        int k = 0;
+#if H264_DEVICE
+        if (LANE_ID == 0) k = atomicAdd(&w->task_next, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+#else
+        k = w->task_next++;
+#endif
+        int t = -1;
+        if ((pref & 8) && k-- == 0) t = 3;
+        else if ((pref & 2) && k-- == 0) t = 1;
+        else if ((pref & 4) && k-- == 0) t = 2;
+        if (t < 0) break;
+        inter_mode_search(s, t);
+    }
+}
+
 /* ------------------------------------------------------------------------------
  * a17: encode one macroblock (mb_encode H:5724 + the pixel/coefficient half of
  * mb_write H:4378) with the whole CTA.  cl[] = rounded mv_clusters candidates.
@@ -1668,22 +1694,8 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             if (w->ic[IC_STATE] != 1) inter_mode_search(s, 0);
             PROF_MARK(s, 4);
         }
-        ON_WARP(1)
-        {
-            s.ss = &w->ss[1];
-            bar_sync(1, 96);
-            if (w->ic[IC_STATE] != 1)
-            {
-                if (w->ic[IC_PREF] & 2) inter_mode_search(s, 1);
-                if (w->ic[IC_PREF] & 4) inter_mode_search(s, 2);
-            }
-        }
-        ON_WARP(2)
-        {
-            s.ss = &w->ss[2];
-            bar_sync(1, 96);
-            if (w->ic[IC_STATE] != 1 && (w->ic[IC_PREF] & 8)) inter_mode_search(s, 3);
-        }
+        ON_WARP(1) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 1); }
+        ON_WARP(2) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 2); }
     }
     ON_WARP(3)
     {
@@ -1698,6 +1710,16 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
         int cost4 = 0x7FFFFFFF, nz4 = 0;
         if (fp->speed < 2 || !is_p) cost4 = intra4_choose(s, &nz4, cost16);
         IF_LANE0 { w->intra_res[0] = cost16; w->intra_res[1] = m16; w->intra_res[2] = cost4; w->intra_res[3] = nz4; }
+#if H264_DEVICE
+        /* the intra decision is usually over early (pruning): help with the partition-mode searches */
+        if (is_p)
+        {
+            int st;
+            while ((st = *(volatile int32_t *)&w->ic[IC_STATE]) == 0) { }
+            __threadfence_block();
+            if (st == 2) partition_tasks(s, 3);
+        }
+#endif
     }
     PROF_WARP(s, fp, mby * fp->nmbx + mbx, 12 + WARP_ID);
     CTA_SYNC();

@@ -30,6 +30,15 @@
 #include "h264_common.h"
 #include "h264_mbenc.h"
 
+/* Repair of pass p: macroblocks whose re-check failed are re-encoded in REPAIR_ROUNDS fully
+ * parallel rounds (round r re-encodes everything tagged REPAIR_TAG(p, r), with whatever
+ * neighbour data is current, and tags the causal successors of every macroblock whose
+ * neighbour-visible result changed for round r + 1 -- a fixpoint iteration that ends when a round
+ * changes nothing); what is still tagged after the last round goes through one wavefront
+ * sweep, which follows cascades of any length. */
+#define REPAIR_ROUNDS 6
+#define REPAIR_TAG(pass, r) ((pass) * 8 + (r))
+
 HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 {
     IF_THREAD0 { fp->spec[n] = sp; }
@@ -156,7 +165,7 @@ HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
             }
         } else
         {
-            fp->need_reenc[n] = pass;
+            fp->need_reenc[n] = REPAIR_TAG(pass, 0);
             atomic_add_stat(fp->fsync + FS_NFAIL);
 #if !H264_DEVICE
             { extern int g_emu_dbg[8]; g_emu_dbg[5]++; }
@@ -168,18 +177,11 @@ HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
 
 /* repair sweep `pass` (>= 1): re-encode what the re-check queued and whatever depends on a
  * macroblock that changed in this sweep */
-HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+/* full re-encode of one macroblock with its true candidates; returns 1 when what its causal
+ * successors consume has changed */
+HDN int wave_mb_reencode(const FrameParams *fp, MBWork *w, int x, int y)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
-    /* all flags with independent loads: one memory round trip on the common "nothing to do" path */
-    const int has_l = x > 0, has_t = y > 0, has_tl = y > 0 && x > 0, has_tr = y > 0 && x < nmbx - 1;
-    const int f0 = fp->need_reenc[n];
-    const int f1 = fp->changed_pass[has_l ? n - 1 : n];
-    const int f2 = fp->changed_pass[has_t ? n - nmbx : n];
-    const int f3 = fp->changed_pass[has_tl ? n - nmbx - 1 : n];
-    const int f4 = fp->changed_pass[has_tr ? n - nmbx + 1 : n];
-    const int need = (f0 == pass) | (has_l & (f1 == pass)) | (has_t & (f2 == pass)) | (has_tl & (f3 == pass)) | (has_tr & (f4 == pass));
-    if (!need) return;
     const MBSpec old = fp->spec[n];
     int32_t ct[2];
     ct[0] = fp->cl_true[2 * n]; ct[1] = fp->cl_true[2 * n + 1];
@@ -227,12 +229,51 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
     IF_THREAD0
     {
         atomic_add_stat(fp->fsync + FS_REENC);
-        if (diff) fp->changed_pass[n] = pass;
 #if !H264_DEVICE
         { extern int g_emu_dbg[8]; g_emu_dbg[6]++; if (diff) g_emu_dbg[7]++; }
 #endif
         if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES)) atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
     }
+    CTA_SYNC();
+    return diff;
+}
+
+/* parallel repair round r of pass `pass`: the macroblock is tagged for this round */
+HDN void wave_mb_round(const FrameParams *fp, MBWork *w, int x, int y, int pass, int r)
+{
+    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    if (wave_mb_reencode(fp, w, x, y))
+    {
+        IF_THREAD0
+        {
+            const int tag = REPAIR_TAG(pass, r + 1);
+            if (x < nmbx - 1) fp->need_reenc[n + 1] = tag;
+            if (y < fp->nmby - 1)
+            {
+                if (x > 0) fp->need_reenc[n + nmbx - 1] = tag;
+                fp->need_reenc[n + nmbx] = tag;
+                if (x < nmbx - 1) fp->need_reenc[n + nmbx + 1] = tag;
+            }
+        }
+    }
+    CTA_SYNC();
+}
+
+/* wavefront repair sweep of pass `pass` (after the parallel rounds): re-encode what is still
+ * tagged and whatever depends on a macroblock that changed in this sweep */
+HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass)
+{
+    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    /* all flags with independent loads: one memory round trip on the common "nothing to do" path */
+    const int has_l = x > 0, has_t = y > 0, has_tl = y > 0 && x > 0, has_tr = y > 0 && x < nmbx - 1;
+    const int f0 = fp->need_reenc[n];
+    const int f1 = fp->changed_pass[has_l ? n - 1 : n];
+    const int f2 = fp->changed_pass[has_t ? n - nmbx : n];
+    const int f3 = fp->changed_pass[has_tl ? n - nmbx - 1 : n];
+    const int f4 = fp->changed_pass[has_tr ? n - nmbx + 1 : n];
+    const int need = (f0 == REPAIR_TAG(pass, REPAIR_ROUNDS)) | (has_l & (f1 == pass)) | (has_t & (f2 == pass)) | (has_tl & (f3 == pass)) | (has_tr & (f4 == pass));
+    if (!need) return;
+    if (wave_mb_reencode(fp, w, x, y)) { IF_THREAD0 { fp->changed_pass[n] = pass; } }
     CTA_SYNC();
 }
 

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
          * and leaves, so that "nothing to do" travels down the frame at one global round trip
          * per row instead of one per macroblock. */
         int has_need = 0;
-        for (int i = threadIdx.x; i < nmbx; i += blockDim.x) has_need |= fp->need_reenc[row * nmbx + i] == pass;
+        for (int i = threadIdx.x; i < nmbx; i += blockDim.x) has_need |= fp->need_reenc[row * nmbx + i] == REPAIR_TAG(pass, REPAIR_ROUNDS);
         has_need = __syncthreads_or(has_need);
         if (!has_need)
         {
@@ -212,13 +212,98 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
             if (s_clean) return;
         }
     }
-    for (int x = 0; x < nmbx; x++)
+    if (pass == 0)
     {
-        if (row > 0) wait_row_cta(progress + row - 1, base + min(x + 2, nmbx));
-        if (pass == 0) wave_mb_first(fp, &work, x, row);
-        else wave_mb_repair(fp, &work, x, row, pass);
-        publish_row_cta(progress + row, base + x + 1);
+        for (int x = 0; x < nmbx; x++)
+        {
+            if (row > 0) wait_row_cta(progress + row - 1, base + min(x + 2, nmbx));
+            wave_mb_first(fp, &work, x, row);
+            publish_row_cta(progress + row, base + x + 1);
+            mb_store_coefs(fp, &work);
+        }
+        return;
+    }
+    /* Repair sweep: as far as the row above has got, the macroblocks of this row are examined
+     * 128 at a time (one thread each: queued for a re-encode, or a causal neighbour changed in
+     * this sweep?); a stretch with nothing to do costs one step, the sweep only serialises at
+     * the macroblocks that are actually re-encoded. */
+    __shared__ int s_above, s_first;
+    int x = 0;
+    while (x < nmbx)
+    {
+        if (threadIdx.x == 0)
+        {
+            int p = nmbx;
+            if (row > 0)
+            {
+                const int need = base + min(x + 2, nmbx);
+                while ((p = ld_relaxed(progress + row - 1)) < need) __nanosleep(20);
+                fence_acquire();
+                p -= base;
+            }
+            s_above = p;
+            s_first = 0x7fffffff;
+        }
+        __syncthreads();
+        const int xe = s_above >= nmbx ? nmbx - 1 : s_above - 2;       /* last macroblock whose top-right neighbour is final */
+        const int cnt = min(xe - x + 1, (int)blockDim.x);
+        if ((int)threadIdx.x < cnt)
+        {
+            const int xx = x + threadIdx.x, n = row * nmbx + xx;
+            const int has_l = xx > 0, has_t = row > 0, has_tl = row > 0 && xx > 0, has_tr = row > 0 && xx < nmbx - 1;
+            const int f0 = fp->need_reenc[n];
+            const int f1 = fp->changed_pass[has_l ? n - 1 : n];
+            const int f2 = fp->changed_pass[has_t ? n - nmbx : n];
+            const int f3 = fp->changed_pass[has_tl ? n - nmbx - 1 : n];
+            const int f4 = fp->changed_pass[has_tr ? n - nmbx + 1 : n];
+            if ((f0 == REPAIR_TAG(pass, REPAIR_ROUNDS)) | (has_l & (f1 == pass)) | (has_t & (f2 == pass)) | (has_tl & (f3 == pass)) | (has_tr & (f4 == pass)))
+                atomicMin(&s_first, (int)threadIdx.x);
+        }
+        __syncthreads();
+        const int first = s_first;
+        if (first == 0x7fffffff)
+        {
+            x += cnt;
+            publish_row_cta(progress + row, base + x);
+            continue;
+        }
+        x += first;
+        wave_mb_repair(fp, &work, x, row, pass);
+        x++;
+        publish_row_cta(progress + row, base + x);
         mb_store_coefs(fp, &work);
+    }
+}
+
+/* parallel repair round r of pass `pass` (h264_wave.h): every CTA looks at a strip of macroblocks
+ * (one flag per thread), then re-encodes the ones tagged for this round */
+__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_repair_round(const FrameParams *fps, int njobs, int pass, int r)
+{
+    __shared__ MBWork work;
+    __shared__ FrameParams sfp;
+    __shared__ int s_list[MB_WARPS * 32], s_cnt;
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
+        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
+    if (threadIdx.x == 0) { work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; }
+    __syncthreads();
+    const FrameParams *fp = &sfp;
+    if (fp->fsync[FS_STATE] != pass) return;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby, tag = REPAIR_TAG(pass, r);
+    for (int base = 0; base < nmb; base += gridDim.x * blockDim.x)
+    {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int n = base + threadIdx.x * gridDim.x + blockIdx.x;
+        if (n < nmb && fp->need_reenc[n] == tag) s_list[atomicAdd(&s_cnt, 1)] = n;
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int i = 0; i < cnt; i++)
+        {
+            const int m = s_list[i], y = m / nmbx;
+            wave_mb_round(fp, &work, m - y * nmbx, y, pass, r);
+            mb_store_coefs(fp, &work);
+        }
+        __syncthreads();
     }
 }
 
@@ -275,15 +360,17 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
         return;
     }
     item -= njobs;
+    const int part = item & 1;                 /* 0: luma wavefront, 1: chroma wavefront (independent) */
+    item >>= 1;
     const int job = item % njobs, row = item / njobs;
     const FrameParams *fp = fps + job;
     if (row >= fp->nmby || fp->disable_deblock || fp->fsync[FS_STATE] != FS_DONE) return;
     const int nmbx = fp->nmbx;
-    int *progress = fp->row_progress_df;
+    int *progress = part ? fp->row_progress_dfc : fp->row_progress_df;
     for (int x = 0; x < nmbx; x++)
     {
         if (row > 0) wait_row(progress + row - 1, min(x + 2, nmbx));
-        deblock_mb(fp, &tile, x, row);
+        deblock_mb(fp, &tile, x, row, part);
         publish_row(progress + row, x + 1);
     }
 }
@@ -477,7 +564,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_out_info, 64));
     CK(cudaMalloc(&c->d_clusters, 16));
     CK(cudaMemset(c->d_clusters, 0, 16));
-    CK(cudaMalloc(&c->d_progress, sizeof(int) * 3 * c->nmby));
+    CK(cudaMalloc(&c->d_progress, sizeof(int) * 4 * c->nmby));
     CK(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
     CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
     CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
@@ -554,7 +641,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
-    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby; fp->row_clean = c->d_progress + 2 * c->nmby;
+    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby; fp->row_clean = c->d_progress + 2 * c->nmby; fp->row_progress_dfc = c->d_progress + 3 * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
@@ -580,7 +667,7 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
                        cudaEvent_t ev_mid)
 {
     CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
-    k_deblock_rows<<<n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
+    k_deblock_rows<<<2 * n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
     k_hpel<<<dim3(148, n), 256, 0, st>>>(d_fps, n);
     if (ev_mid) CK(cudaEventRecord(ev_mid, st));
@@ -640,7 +727,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     for (int i = 0; i < n; i++)
     {
         h264b200_ctx *c = jobs[i].ctx;
-        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 3 * c->nmby, st));
+        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 4 * c->nmby, st));
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
         CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
@@ -655,12 +742,13 @@ static int encode_impl(int n, h264b200_job *jobs)
      * the device), so that the common case needs no host round trip before the post-processing */
     for (int pass = 1; pass <= 2; pass++)
     {
+        for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass, r);
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
         k_encode_rows<<<n * max_rows, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
         k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
         k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass + 1);
         k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
-        g_launches += 4;
+        g_launches += 4 + REPAIR_ROUNDS;
     }
     CK(cudaEventRecord(g_ev[2], st));
     if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;
@@ -684,12 +772,13 @@ static int encode_impl(int n, h264b200_job *jobs)
             pass = c->h_out_info[4 + FS_STATE];       /* sweeps advance in lock step for all dirty frames */
         }
         CK(cudaMemcpyAsync(d2, h2, sizeof(FrameParams) * m, cudaMemcpyHostToDevice, st));
+        for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, m), MB_WARPS * 32, 0, st>>>(d2, m, pass, r);
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
         k_encode_rows<<<m * rows2, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
         k_check<<<dim3(148, m), MB_WARPS * 32, 0, st>>>(d2, m, pass + 1);
         k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);
-        g_launches += 4;
+        g_launches += 4 + REPAIR_ROUNDS;
         if (launch_post(d2, m, rows2, nmb2, cap, st, NULL)) return -3;
         if (fetch_info(m, jobs, dirty.data(), st)) return -3;
         std::vector<int> still;

@@ -132,6 +132,11 @@ static void run_job(h264b200_job *job)
     if (fp.spec_from_prev) wave_replay(&fp, w, 1);
     for (int pass = 0;;)
     {
+        if (pass > 0)
+            for (int r = 0; r < REPAIR_ROUNDS; r++)
+                for (int y = 0; y < c->nmby; y++)
+                    for (int x = 0; x < c->nmbx; x++)
+                        if (fp.need_reenc[y * c->nmbx + x] == REPAIR_TAG(pass, r)) { wave_mb_round(&fp, w, x, y, pass, r); mb_store_coefs(&fp, w); }
         for (int y = 0; y < c->nmby; y++)
             for (int x = 0; x < c->nmbx; x++)
             {
@@ -175,7 +180,7 @@ static void run_job(h264b200_job *job)
     {
         DeblockTile tile;
         for (int y = 0; y < c->nmby; y++)
-            for (int x = 0; x < c->nmbx; x++) deblock_mb(&fp, &tile, x, y);
+            for (int x = 0; x < c->nmbx; x++) { deblock_mb(&fp, &tile, x, y, 0); deblock_mb(&fp, &tile, x, y, 1); }
     }
     for (int pl = 0; pl < 3; pl++)
     {
