@@ -107,3 +107,42 @@ def test_in_place_recon_and_errors(binding, cuda_lib, ref):
         enc.encode(f, rp)
         assert np.array_equal(f, rrec[i])
     enc.close()
+
+
+def test_many_independent_streams_in_one_batch(binding, cuda_lib, ref):
+    """BASELINE config 5 in small: independent streams (distinct content) batched in one device
+    submission per frame; every stream equals its own reference run."""
+    w, h, n, nstreams = 320, 240, 4, 8
+    clips = [cases.make("panning", w, h, n, seed=100 + s) for s in range(nstreams)]
+    encs = [binding.Encoder(cuda_lib, w, h, 60) for _ in range(nstreams)]
+    rps = [e.run_param(qp=28) for e in encs]
+    outs = [b"" for _ in range(nstreams)]
+    for t in range(n):
+        res = binding.encode_batch(cuda_lib, encs, [c[t].copy() for c in clips], rps)
+        for s in range(nstreams):
+            outs[s] += res[s]
+    for s in range(nstreams):
+        rbs, _, rrec, _ = ref.encode_sequence(clips[s], w, h, 60, qp=28)
+        assert outs[s] == rbs, "stream %d" % s
+        assert np.array_equal(encs[s].recon(), rrec[-1])
+    for e in encs:
+        e.close()
+
+
+def test_rate_controlled_gop_shards(binding, cuda_lib, ref):
+    """BASELINE config 3 in small: rate-controlled closed-GOP segments encoded concurrently, one fresh
+    session per segment (the QP trajectory of every segment must match the reference's)."""
+    w, h, seglen, nseg = 352, 288, 6, 3
+    frames = cases.make("multi", w, h, seglen * nseg)
+    encs = [binding.Encoder(cuda_lib, w, h, seglen) for _ in range(nseg)]
+    rps = [e.run_param(kbps=600) for e in encs]
+    outs = [b"" for _ in range(nseg)]
+    for t in range(seglen):
+        res = binding.encode_batch(cuda_lib, encs, [frames[s * seglen + t].copy() for s in range(nseg)], rps)
+        for s in range(nseg):
+            outs[s] += res[s]
+    for s in range(nseg):
+        rbs, rsizes, _, _ = ref.encode_sequence(frames[s * seglen:(s + 1) * seglen], w, h, seglen, kbps=600)
+        assert outs[s] == rbs, "segment %d" % s
+    for e in encs:
+        e.close()
