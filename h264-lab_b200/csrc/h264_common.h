@@ -301,6 +301,7 @@ struct MBWork
     int32_t intra_res[8];        /* cost16, i16 mode, cost4, nz mask of I4x4                */
     /* chroma prediction, transform / quantisation */
     pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
+    int32_t predc_tag, predc_mv; /* GPU: predc already holds the P16x16 chroma prediction for vector predc_mv (tag = 1) */
     pix_t skip_pred[256];        /* luma prediction at the skip vector                      */
     int16_t dq_y[16][16];        /* transform coefficients / dequantised (quant_t.dq)       */
     int16_t qv_y[16][16];        /* quantised levels (quant_t.qv)                           */

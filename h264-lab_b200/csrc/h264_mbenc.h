@@ -195,7 +195,7 @@ HDN void mb_load(MBState &s)
             else if (lane == 20) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
             else if (lane == 21) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (lane == 22) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; }
+            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; w->predc_tag = 0; }
         } else if (pw == 1)
         {   /* left column: 16 luma + 8 + 8 chroma samples */
             if (lane < 16) w->left_y[lane] = (av & AVAIL_L) ? dy[lane * sy - 1] : 0;
@@ -263,7 +263,7 @@ HDN void mb_load(MBState &s)
             else if (j == 68) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
             else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
             else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; }
+            else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; w->predc_tag = 0; }
             else if (j < 76) w->mvp0_left[j - 72] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 72) + 3] : MV_NA;
             else if (j == 76) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
             else if (j < 80) w->mvp0_tl[j - 76] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 77) + 3] : MV_NA;
@@ -584,6 +584,7 @@ HDN void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
  * (skip test + start candidates, one warp) and one search task per partition mode.
  * ---------------------------------------------------------------------------- */
 /* Candidate stage.  Needs the window loaded around mvp16.  Publishes w->ic[] (lane 0). */
+/* Candidate stage.  Needs the window loaded around mvp16.  Publishes w->ic[] (lane 0). */
 HDN void inter_stage_a(MBState &s, const int32_t cl[2])
 {
     const FrameParams *fp = s.fp;
@@ -774,6 +775,9 @@ HDN void inter_mode_search(MBState &s, int mb_type)
     }
     IF_LANE0
     {
+#if H264_DEVICE
+        __threadfence_block();
+#endif
         if (!mb_type) *(volatile int32_t *)&w->ic[IC_COST0] = part_sad;
         w->mode_cost[mb_type] = part_sad;
         w->mode_pred[mb_type] = (int32_t)(result - (pix_t *)w);
@@ -1717,7 +1721,34 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
             int st;
             while ((st = *(volatile int32_t *)&w->ic[IC_STATE]) == 0) { }
             __threadfence_block();
-            if (st == 2) partition_tasks(s, 3);
+            if (st == 2)
+            {
+                partition_tasks(s, 3);
+                /* P16x16 wins most of the time: when this warp has nothing else to do it prepares that
+                 * mode's chroma prediction, taking the chroma reference fetch off the critical tail */
+                if (*(volatile int32_t *)&w->ic[IC_COST0] >= 0)      /* only when the 16x16 search is already over: never wait for it */
+                {
+                    __threadfence_block();
+                    /* both planes in one pass, every load in flight together (same arithmetic as
+                     * interp_chroma_block for one 8x8 partition) */
+                    const int32_t mv0 = *(volatile int32_t *)&w->part_mv[0][0];
+                    const int scs = fp->stride[1];
+                    const int ax = mv_x(mv0) + mbx * 64, ay = mv_y(mv0) + mby * 64, dx = ax & 7, dy = ay & 7;
+                    const int ca = (8 - dx) * (8 - dy), cb = dx * (8 - dy), cc = (8 - dx) * dy, cd = dx * dy;
+                    const long o = (long)(ay >> 3) * scs + (ax >> 3);
+                    for (int i = LANE_ID; i < 128; i += 32)
+                    {
+                        const int pl = i >> 6, k = i & 63, r = k >> 3, x = k & 7;
+                        const pix_t *p = fp->ref[1 + pl] + o + r * scs + x;
+                        int v;
+                        if (dx | dy) v = (ca * ldpx(p) + cb * ldpx(p + 1) + cc * ldpx(p + scs) + cd * ldpx(p + scs + 1) + 32) >> 6;
+                        else v = ldpx(p);
+                        w->predc[r * 16 + pl * 8 + x] = (pix_t)v;
+                    }
+                    __syncwarp();
+                    IF_LANE0 { w->predc_mv = mv0; w->predc_tag = 1; }
+                }
+            }
         }
 #endif
     }
@@ -1806,14 +1837,15 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
                 FOR_LANES(i, 64) { int r = i >> 2, c = (i & 3) * 4; *(uint32_t *)(decy + r * sy + c) = ld4_sm(w->i4rec + r * 16 + c); }
             }
         }
+        const int have_predc = s.type == 0 && w->predc_tag && w->predc_mv == pmv[0];
         ON_WARP(2)
         {
-            if (s.type >= 5) intra_chroma_plane(s, 0); else mc_chroma_plane(s, 0, s.type, pmv);
+            if (s.type >= 5) intra_chroma_plane(s, 0); else if (!have_predc) mc_chroma_plane(s, 0, s.type, pmv);
             chroma_tq_fast(s, 0);
         }
         ON_WARP(3)
         {
-            if (s.type >= 5) intra_chroma_plane(s, 1); else mc_chroma_plane(s, 1, s.type, pmv);
+            if (s.type >= 5) intra_chroma_plane(s, 1); else if (!have_predc) mc_chroma_plane(s, 1, s.type, pmv);
             chroma_tq_fast(s, 1);
         }
 #else
