@@ -23,7 +23,7 @@
 #if defined(__CUDACC__)
 #  define H264_DEVICE 1
 #  define HD __device__ __forceinline__
-#  define HDN __device__ __noinline__
+#  define HDN static __device__ __noinline__
 #  define H264_TAB static __device__ const
 #else
 #  define H264_DEVICE 0
@@ -69,8 +69,18 @@ HD int wor(int v) { return v; }
  * (16x16 search | 16x8 + 8x16 searches | 8x8 search | intra decision, then luma halves |
  * chroma planes).  ON_WARP(k) guards a task; the host emulation runs the tasks one after
  * the other in program order, which satisfies every producer -> consumer dependency. */
-#define MB_WARPS 4
-#if H264_DEVICE
+#ifndef MB_WARPS
+#define MB_WARPS 4           /* 1: single-warp build of the same code (the candidate re-check kernel): tasks run one after the other */
+#endif
+#if H264_DEVICE && MB_WARPS == 1
+#  define WARP_ID 0
+#  define ON_WARP(k)
+#  define CTA_SYNC() __syncwarp()
+#  define FOR_THREADS(i, n) for (int i = LANE_ID; i < (n); i += 32)
+#  define FOR_SEARCH_THREADS(i, n) for (int i = LANE_ID; i < (n); i += 32)
+#  define IF_THREAD0 if (threadIdx.x == 0)
+HD void bar_sync(int, int) {}
+#elif H264_DEVICE
 /* WARP_ID is the warp's ROLE.  A CTA's warp k always runs on SM sub-partition k, so with the
  * plain numbering every CTA on an SM would put its heaviest task on the same sub-partition
  * (one issue port, one L0 instruction cache); co-resident CTAs therefore rotate the roles. */

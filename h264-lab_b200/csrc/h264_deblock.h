@@ -116,17 +116,32 @@ HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
     }
 }
 
-HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part)
+/* phase 0: everything that does not depend on the row above -- the macroblock's own rows (with the 4
+ * columns to their left, final since the previous macroblock of this row) and the boundary strengths;
+ * phase 1 (once the row above has got far enough): the 4 rows above, the filters, the write-back. */
+HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part, int phase)
 {
     const int sy = fp->stride[0], sc = fp->stride[1];
-    const int alpha = fp->df_alpha[part], beta = fp->df_beta[part];
-    int tc0[4];
-    for (int k = 0; k < 4; k++) tc0[k] = fp->df_tc0[part][k];
     if (part == 0)
     {
         pix_t *py = fp->dec[0] + (mby * 16) * sy + mbx * 16;
-        FOR_LANES(i, 100) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
-        deblock_bs(fp, t, mbx, mby);
+        if (phase == 0)
+        {
+            uint32_t v[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { int i = LANE_ID + 32 * k; if (i < 80) { int r = i / 5, c = i - r * 5; v[k] = *(const uint32_t *)(py + r * sy + c * 4 - 4); } }
+#pragma unroll
+            for (int k = 0; k < 3; k++) { int i = LANE_ID + 32 * k; if (i < 80) { int r = i / 5, c = i - r * 5; t->y[(r + 4) * 6 + c] = v[k]; } }
+#if !H264_DEVICE
+            for (int i = 0; i < 80; i++) { int r = i / 5, c = i - r * 5; t->y[(r + 4) * 6 + c] = *(const uint32_t *)(py + r * sy + c * 4 - 4); }
+#endif
+            deblock_bs(fp, t, mbx, mby);
+            return;
+        }
+        const int alpha = fp->df_alpha[0], beta = fp->df_beta[0];
+        int tc0[4];
+        for (int k = 0; k < 4; k++) tc0[k] = fp->df_tc0[0][k];
+        FOR_LANES(i, 20) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
         WSYNC();
         FOR_LANES(ln, 16)      /* vertical edges: lane owns one row */
         {
@@ -163,8 +178,16 @@ HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int 
         pix_t *pc[2];
         pc[0] = fp->dec[1] + (mby * 8) * sc + mbx * 8;
         pc[1] = fp->dec[2] + (mby * 8) * sc + mbx * 8;
-        FOR_LANES(k, 72) { int pl = k / 36, j = k - pl * 36, r = j / 3, c = j - r * 3; t->c[pl][r * 3 + c] = *(const uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4); }
-        deblock_bs(fp, t, mbx, mby);
+        if (phase == 0)
+        {
+            FOR_LANES(k, 48) { int pl = k / 24, j = k - pl * 24, r = j / 3, c = j - r * 3; t->c[pl][(r + 4) * 3 + c] = *(const uint32_t *)(pc[pl] + r * sc + c * 4 - 4); }
+            deblock_bs(fp, t, mbx, mby);
+            return;
+        }
+        const int alpha = fp->df_alpha[1], beta = fp->df_beta[1];
+        int tc0[4];
+        for (int k = 0; k < 4; k++) tc0[k] = fp->df_tc0[1][k];
+        FOR_LANES(k, 24) { int pl = k / 12, j = k - pl * 12, r = j / 3, c = j - r * 3; t->c[pl][r * 3 + c] = *(const uint32_t *)(pc[pl] + (r - 4) * sc + c * 4 - 4); }
         WSYNC();
         FOR_LANES(ln, 16)      /* lanes 0-7: U lines, 8-15: V lines */
         {
@@ -201,6 +224,7 @@ HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int 
     }
     WSYNC();
 }
+
 
 
 /* a16: replicate the picture edges into the 16 (luma) / 8 (chroma) sample guard band.

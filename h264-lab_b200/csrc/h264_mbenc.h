@@ -175,7 +175,7 @@ HDN void mb_load(MBState &s)
     CTA_SYNC();
     have_inp = w->pf_inp_tag == 1 + mby * nmbx + mbx;
 #endif
-#if H264_DEVICE
+#if H264_DEVICE && MB_WARPS == 4
     if (have_inp && inside)
     {
         /* Fast path: the input is already in shared memory (prefetched); every physical warp

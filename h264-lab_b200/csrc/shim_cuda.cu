@@ -307,24 +307,6 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_repair_round(
     }
 }
 
-/* parallel re-check of the dirty macroblocks of every frame that waits for repair sweep `pass` */
-__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_check(const FrameParams *fps, int njobs, int pass)
-{
-    __shared__ MBWork work;
-    __shared__ FrameParams sfp;
-    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
-        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
-    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; }
-    __syncthreads();
-    const FrameParams *fp = &sfp;
-    if (fp->fsync[FS_STATE] != pass) return;
-    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
-    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
-    {
-        int y = n / nmbx;
-        wave_mb_check(fp, &work, n - y * nmbx, y, pass);
-    }
-}
 __global__ void k_after_check(const FrameParams *fps, int njobs, int pass)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,8 +351,9 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     int *progress = part ? fp->row_progress_dfc : fp->row_progress_df;
     for (int x = 0; x < nmbx; x++)
     {
+        deblock_mb(fp, &tile, x, row, part, 0);
         if (row > 0) wait_row(progress + row - 1, min(x + 2, nmbx));
-        deblock_mb(fp, &tile, x, row, part);
+        deblock_mb(fp, &tile, x, row, part, 1);
         publish_row(progress + row, x + 1);
     }
 }
@@ -484,6 +467,8 @@ struct h264b200_ctx
     uint32_t *h_out_words;        /* pinned */
     int *h_out_info;              /* pinned */
 };
+
+void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st);    /* shim_check.cu */
 
 static long g_launches = 0;
 static cudaStream_t g_stream = 0;
@@ -735,7 +720,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
-    k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, 1);
+    h264b200_launch_check1(g_d_fps, n, 1, st);
     k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
     g_launches += 3;
     /* two repair rounds are queued unconditionally (frames that are already exact skip them on
@@ -746,7 +731,7 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
         k_encode_rows<<<n * max_rows, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
         k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
-        k_check<<<dim3(148, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass + 1);
+        h264b200_launch_check1(g_d_fps, n, pass + 1, st);
         k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
         g_launches += 4 + REPAIR_ROUNDS;
     }
@@ -776,7 +761,7 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
         k_encode_rows<<<m * rows2, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
-        k_check<<<dim3(148, m), MB_WARPS * 32, 0, st>>>(d2, m, pass + 1);
+        h264b200_launch_check1(d2, m, pass + 1, st);
         k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);
         g_launches += 4 + REPAIR_ROUNDS;
         if (launch_post(d2, m, rows2, nmb2, cap, st, NULL)) return -3;

@@ -663,6 +663,19 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
         uint8_t stop_mask = (uint8_t)(0x80 >> (job->out_bits & 7));
         for (i = 0; i < nbytes; i++)
         {
+            /* fast path: a whole word past the header, before the stop bit, without any zero byte and with
+             * fewer than two pending zeros needs no emulation prevention */
+            if (!(i & 3) && i > hdr_full && i + 4 <= stop_byte && zeros < 2)
+            {
+                const uint32_t wv = words[i >> 2];
+                if (!((wv - 0x01010101u) & ~wv & 0x80808080u))
+                {
+                    nal[j] = (uint8_t)(wv >> 24); nal[j + 1] = (uint8_t)(wv >> 16); nal[j + 2] = (uint8_t)(wv >> 8); nal[j + 3] = (uint8_t)wv;
+                    j += 4; i += 3; zeros = 0;
+                    if ((int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+                    continue;
+                }
+            }
             uint8_t byte = (uint8_t)(words[i >> 2] >> (24 - 8 * (i & 3)));
             if (i < hdr_full) byte |= pl->hdr.buf[i];
             else if (i == hdr_full) byte |= (uint8_t)hdr_tail;

@@ -180,7 +180,7 @@ static void run_job(h264b200_job *job)
     {
         DeblockTile tile;
         for (int y = 0; y < c->nmby; y++)
-            for (int x = 0; x < c->nmbx; x++) { deblock_mb(&fp, &tile, x, y, 0); deblock_mb(&fp, &tile, x, y, 1); }
+            for (int x = 0; x < c->nmbx; x++) { for (int part = 0; part < 2; part++) { deblock_mb(&fp, &tile, x, y, part, 0); deblock_mb(&fp, &tile, x, y, part, 1); } }
     }
     for (int pl = 0; pl < 3; pl++)
     {
