@@ -319,6 +319,14 @@ def main():
     p_frames = sum(1 for t in range(Wm, Wm + K) if t % GOP)
     i_frames = K - p_frames
     alg_bytes_step = nseg * ((b_in + b_ref + b_rec) * p_frames + (b_in + b_rec) * i_frames) / K + out_bytes / K
+    # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full capture of this workload
+    traffic = None
+    try:
+        km = json.load(open(os.path.join(ROOT, "profiles", "r01_k_encode_rows_10stream_keymetrics.json")))
+        unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+        traffic = sum(float(km[k][0]) * unit[km[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")) if nseg == NSEG else None
+    except Exception:
+        traffic = None
     k_enc_ms = kern[1] / K
     achieved = alg_bytes_step / (k_enc_ms * 1e-3) / 1e9 if k_enc_ms > 0 else 0.0
     line = {
@@ -332,7 +340,8 @@ def main():
         "kernel_ms_per_step": {"device_total": kern[0] / K, "k_encode_rows": kern[1] / K, "k_deblock_rows+k_borders": kern[2] / K,
                                "k_cavlc+k_scan+k_pack": kern[3] / K},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "kernel": "k_encode_rows", "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                     "traffic": traffic, "traffic_unit": "bytes per k_encode_rows launch (ncu dram__bytes_read+write, profiles/r01_k_encode_rows_10stream_keymetrics.json)",
+                     "algorithmic_bytes_per_launch": alg_bytes_step, "kernel": "k_encode_rows (sweep 0 + repair waves of the step)", "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                      "note": "integer/latency-bound wavefront: HBM is not the limiter (SURVEY 8(d)); "
                              "us per wavefront step = %.2f" % (k_enc_ms * 1e3 / (120 + 2 * 67) if k_enc_ms else 0)},
         "clocks": clocks,

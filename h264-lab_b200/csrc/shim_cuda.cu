@@ -534,9 +534,12 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMemset(c->d_hpel, 0, 3 * ysz + 256));
     c->inp_stride[0] = (width + 63) & ~63;
     c->inp_stride[1] = c->inp_stride[2] = (width / 2 + 63) & ~63;
-    CK(cudaMalloc(&c->d_inp[0], (size_t)c->inp_stride[0] * height + 256));
-    CK(cudaMalloc(&c->d_inp[1], (size_t)c->inp_stride[1] * (height / 2) + 256));
-    CK(cudaMalloc(&c->d_inp[2], (size_t)c->inp_stride[2] * (height / 2) + 256));
+    {   /* one allocation, planes back to back: a tightly packed I420 frame is then a single copy */
+        const size_t s0 = (size_t)c->inp_stride[0] * height, s1 = (size_t)c->inp_stride[1] * (height / 2);
+        CK(cudaMalloc(&c->d_inp[0], s0 + 2 * s1 + 256));
+        c->d_inp[1] = c->d_inp[0] + s0;
+        c->d_inp[2] = c->d_inp[1] + s1;
+    }
     CK(cudaMalloc(&c->d_mbi, sizeof(MBInfo) * c->nmb));
     CK(cudaMemset(c->d_mbi, 0, sizeof(MBInfo) * c->nmb));
     CK(cudaMalloc(&c->d_coef, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
@@ -574,7 +577,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     cudaSetDevice(c->device);
     for (int i = 0; i < 2; i++) cudaFree(c->d_frames[i]);
     cudaFree(c->d_hpel);
-    for (int i = 0; i < 3; i++) cudaFree(c->d_inp[i]);
+    cudaFree(c->d_inp[0]);
     if (c->d_clip) cudaFree(c->d_clip);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
@@ -698,6 +701,14 @@ static int encode_impl(int n, h264b200_job *jobs)
         if (jobs[i].preloaded_index >= 0)
         {
             if (jobs[i].preloaded_index >= c->clip_frames) { jobs[i].status = -3; return -3; }
+            continue;
+        }
+        const size_t ysz = (size_t)c->width * c->height;
+        if (c->inp_stride[0] == c->width && c->inp_stride[1] == c->width / 2 &&
+            jobs[i].stride[0] == c->width && jobs[i].stride[1] == c->width / 2 && jobs[i].stride[2] == c->width / 2 &&
+            jobs[i].yuv[1] == jobs[i].yuv[0] + ysz && jobs[i].yuv[2] == jobs[i].yuv[1] + ysz / 4)
+        {
+            CK(cudaMemcpyAsync(c->d_inp[0], jobs[i].yuv[0], ysz * 3 / 2, cudaMemcpyHostToDevice, st));
             continue;
         }
         for (int pl = 0; pl < 3; pl++)
