@@ -200,6 +200,7 @@ struct MBSpec
 #define FS_LIVE 10        /* [10],[11]: cluster state after the raster-contiguous prefix of finished
                              macroblocks of sweep 0, published while the sweep runs; [12] prefix length */
 #define FS_NFAIL 13       /* dirty macroblocks whose candidate-stage re-check failed (need a re-encode)  */
+#define FS_TRAJ_FIRST 14  /* 0x3fffffff - (first macroblock whose cluster-relevant result changed in the current pass), 0: none */
 #define FS_WORDS 16
 #define FS_DONE 0x40000000
 
@@ -242,6 +243,8 @@ struct FrameParams
     int32_t *clusters;          /* persistent mv_clusters[2] of this encoder (H:766)        */
     MBSpec *spec;               /* [nmb] speculation records                                */
     int32_t *cl_true;           /* [nmb][2] rounded cluster candidates from the last replay */
+    int32_t *cl_ckpt;           /* [(nmb+31)/32][2] raw cluster state before every 32nd macroblock (last replay): a later replay
+                                   resumes at the block of the first macroblock that changed                                    */
     int *changed_pass;          /* [nmb] last pass in which the MB's result changed         */
     int *need_reenc;            /* [nmb] pass for which the parallel re-check asked for a re-encode */
     int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */

@@ -232,7 +232,15 @@ HDN int wave_mb_reencode(const FrameParams *fp, MBWork *w, int x, int y)
 #if !H264_DEVICE
         { extern int g_emu_dbg[8]; g_emu_dbg[6]++; if (diff) g_emu_dbg[7]++; }
 #endif
-        if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES)) atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
+        if (sp.mv0 != old.mv0 || ((sp.flags ^ old.flags) & SPEC_UPDATES))
+        {
+            atomic_add_stat(fp->fsync + FS_TRAJ_CHANGED);
+#if H264_DEVICE
+            atomicMax(fp->fsync + FS_TRAJ_FIRST, 0x3fffffff - n);
+#else
+            if (fp->fsync[FS_TRAJ_FIRST] < 0x3fffffff - n) fp->fsync[FS_TRAJ_FIRST] = 0x3fffffff - n;
+#endif
+        }
     }
     CTA_SYNC();
     return diff;
@@ -279,11 +287,12 @@ HDN void wave_mb_repair(const FrameParams *fp, MBWork *w, int x, int y, int pass
 
 /* Sequential replay of the cluster trajectory by one warp (lane 0 walks, the warp stages
  * 32 records at a time).  Writes cl_true[], the end state, and returns the dirty count. */
-HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
+HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_block = 0)
 {
     const int nmb = fp->nmbx * fp->nmby;
     int32_t c[2];
     c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
+    if (first_block > 0) { c[0] = fp->cl_ckpt[2 * first_block]; c[1] = fp->cl_ckpt[2 * first_block + 1]; }
     int ndirty = 0;
 #if H264_DEVICE
     /* every lane replays the (cheap, strictly sequential) recurrence redundantly; the records of
@@ -292,9 +301,10 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
     {
         const int lane = LANE_ID;
         int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
-        if (lane < nmb) { const MBSpec *sp = fp->spec + lane; mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1]; }
-        for (int base = 0; base < nmb; base += 32)
+        if (32 * first_block + lane < nmb) { const MBSpec *sp = fp->spec + 32 * first_block + lane; mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1]; }
+        for (int base = 32 * first_block; base < nmb; base += 32)
         {
+            if (!predict && lane < 2) fp->cl_ckpt[2 * (base >> 5) + lane] = c[lane];
             int nmv0 = 0, nflags = 0, nu0 = 0, nu1 = 0;
             if (base + 32 + lane < nmb)
             {
@@ -318,8 +328,9 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict)
         }
     }
 #else
-    for (int base = 0; base < nmb; base += 32)
+    for (int base = 32 * first_block; base < nmb; base += 32)
     {
+        if (!predict) { fp->cl_ckpt[2 * (base >> 5)] = c[0]; fp->cl_ckpt[2 * (base >> 5) + 1] = c[1]; }
         FOR_LANES(i, 32)
         {
             int n = base + i;
@@ -389,8 +400,12 @@ HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one wa
     WSYNC();
     if (need_replay)
     {
-        IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; }
-        int nd = wave_replay(fp, w, 0);
+        /* the trajectory is unchanged up to the first macroblock that changed: resume at its block */
+        const int tf = fp->fsync[FS_TRAJ_FIRST];
+        const int first_block = (pass > 0 && tf > 0) ? (0x3fffffff - tf) >> 5 : 0;
+        WSYNC();
+        IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; fp->fsync[FS_TRAJ_FIRST] = 0; }
+        int nd = wave_replay(fp, w, 0, first_block);
         next = nd ? pass + 1 : FS_DONE;
     } else next = FS_DONE;
     if (next == FS_DONE)

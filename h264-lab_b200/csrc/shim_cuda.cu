@@ -121,9 +121,10 @@ __device__ void trajectory_follower(const FrameParams *fp)
             int p;
             while ((p = ld_relaxed(fp->row_progress + row)) <= x) __nanosleep(200);
             fence_acquire();
-            avail = min(p - x, 32);
+            avail = min(p - x, 32 - (n & 31));       /* chunks end at multiples of 32 (checkpoints) */
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
+        if (!(n & 31) && lane < 2) fp->cl_ckpt[2 * (n >> 5) + lane] = c[lane];
         int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
         if (lane < avail)
         {
@@ -460,7 +461,7 @@ struct h264b200_ctx
     int out_cap_words;
     int *d_out_info;
     int32_t *d_clusters;
-    MBSpec *d_spec; int32_t *d_cl_true; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
+    MBSpec *d_spec; int32_t *d_cl_true; int32_t *d_cl_ckpt; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
     int have_traj; int stats[4];
     int *d_prof;
     int *d_progress;              /* 2 * nmby */
@@ -557,6 +558,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
     CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
     CK(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
+    CK(cudaMalloc(&c->d_cl_ckpt, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
+    CK(cudaMemset(c->d_cl_ckpt, 0, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
     CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
     CK(cudaMalloc(&c->d_need_reenc, sizeof(int) * c->nmb));
     CK(cudaMemset(c->d_need_reenc, 0, sizeof(int) * c->nmb));
@@ -581,7 +584,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->d_clip) cudaFree(c->d_clip);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
-    cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
+    cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_cl_ckpt); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
     cudaFreeHost(c->h_out_words); cudaFreeHost(c->h_out_info);
     free(c);
 }
@@ -633,7 +636,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
-    fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->changed_pass = c->d_changed_pass; fp->need_reenc = c->d_need_reenc; fp->fsync = c->d_fsync;
+    fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->cl_ckpt = c->d_cl_ckpt; fp->changed_pass = c->d_changed_pass; fp->need_reenc = c->d_need_reenc; fp->fsync = c->d_fsync;
     fp->max_passes = 4096;
     fp->prof = c->d_prof;
     fp->spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
@@ -651,17 +654,31 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
 }
 
 /* kernels that follow the macroblock sweeps; frames that are not FS_DONE are skipped inside */
+static cudaStream_t g_stream2 = 0;
+static cudaEvent_t g_ev_fork, g_ev_join;
 static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nmb, int cap_words, cudaStream_t st,
                        cudaEvent_t ev_mid)
 {
+    /* the entropy-coding kernels only read the macroblock records: they run on a second stream next to the
+     * in-loop filter (a latency-bound wavefront that leaves most of the chip idle) */
+    if (!g_stream2)
+    {
+        CK(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(g_ev_fork, st));
+    CK(cudaStreamWaitEvent(g_stream2, g_ev_fork, 0));
+    k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, g_stream2>>>(d_fps, n);
+    k_scan<<<n, 1024, 0, g_stream2>>>(d_fps, n, cap_words);
+    k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, g_stream2>>>(d_fps, n);
+    CK(cudaEventRecord(g_ev_join, g_stream2));
     CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
     k_deblock_rows<<<2 * n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
     k_hpel<<<dim3(148, n), 256, 0, st>>>(d_fps, n);
     if (ev_mid) CK(cudaEventRecord(ev_mid, st));
-    k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, st>>>(d_fps, n);
-    k_scan<<<n, 1024, 0, st>>>(d_fps, n, cap_words);
-    k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, st>>>(d_fps, n);
+    CK(cudaStreamWaitEvent(st, g_ev_join, 0));
     g_launches += 6;
     return 0;
 }

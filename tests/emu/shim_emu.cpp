@@ -38,7 +38,7 @@ struct h264b200_ctx
     std::vector<uint32_t> out_words;
     std::vector<pix_t> clip;
     std::vector<MBSpec> spec;
-    std::vector<int32_t> cl_true;
+    std::vector<int32_t> cl_true, cl_ckpt;
     std::vector<int> changed_pass, need_reenc;
     int fsync[FS_WORDS];
     int stats[4];
@@ -68,7 +68,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->coef.resize((size_t)nmb * COEF_PER_MB);
     c->mb_bits.resize((size_t)(nmb + 1) * MB_BITS_WORDS);
     c->mb_nbits.resize(nmb + 2);
-    c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->changed_pass.resize(nmb); c->need_reenc.resize(nmb);
+    c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->cl_ckpt.resize(2 * (nmb / 32 + 2)); c->changed_pass.resize(nmb); c->need_reenc.resize(nmb);
     c->out_words.resize((size_t)nmb * 160 + 1024);
     c->cur = 0;
     c->clusters[0] = c->clusters[1] = 0;
@@ -116,7 +116,7 @@ static void run_job(h264b200_job *job)
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
-    fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
+    fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.cl_ckpt = c->cl_ckpt.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
     memset(c->fsync, 0, sizeof(c->fsync));
     fp.fsync = c->fsync;
     fp.max_passes = 1000;
