@@ -30,13 +30,13 @@
 #include "h264_common.h"
 #include "h264_mbenc.h"
 
-/* Repair of pass p: macroblocks whose re-check failed are re-encoded in REPAIR_ROUNDS fully
+/* Repair of pass p: macroblocks whose re-check failed are re-encoded in REPAIR_ROUNDS (3) fully
  * parallel rounds (round r re-encodes everything tagged REPAIR_TAG(p, r), with whatever
  * neighbour data is current, and tags the causal successors of every macroblock whose
  * neighbour-visible result changed for round r + 1 -- a fixpoint iteration that ends when a round
  * changes nothing); what is still tagged after the last round goes through one wavefront
  * sweep, which follows cascades of any length. */
-#define REPAIR_ROUNDS 6
+#define REPAIR_ROUNDS 3
 #define REPAIR_TAG(pass, r) ((pass) * 8 + (r))
 
 HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
