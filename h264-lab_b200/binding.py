@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "libh264lab_b200.so")
+DEFAULT_LIB = os.environ.get("H264B200_LIB") or os.path.join(HERE, "libh264lab_b200.so")   # H264B200_LIB: developer A/B builds
 
 
 class CreateParam(C.Structure):
