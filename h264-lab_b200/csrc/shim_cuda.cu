@@ -34,7 +34,15 @@
 #include "../../include/h264b200_shim.h"
 
 #ifndef ENC_MIN_BLOCKS
-#define ENC_MIN_BLOCKS 5
+#define ENC_MIN_BLOCKS 3
+#endif
+/* Row progress counters sit PROG_STRIDE ints apart: one 128-byte line (one L2 slice entry) per
+ * row, so that the pollers of neighbouring rows do not queue up on the same line. */
+#ifndef PROG_STRIDE
+#define PROG_STRIDE 32
+#endif
+#ifndef POLL_NS
+#define POLL_NS 20
 #endif
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf(stderr, "h264b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -3; } } while (0)
@@ -78,7 +86,7 @@ __device__ __forceinline__ void publish_row(int *progress, int done)            
 }
 __device__ __forceinline__ void wait_row_cta(const int *progress_above, int need)  /* whole CTA */
 {
-    if (threadIdx.x == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(20); fence_acquire(); }
+    if (threadIdx.x == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(POLL_NS); fence_acquire(); }
     __syncthreads();
 }
 __device__ __forceinline__ void publish_row_cta(int *progress, int done)
@@ -119,7 +127,7 @@ __device__ void trajectory_follower(const FrameParams *fp)
         if (lane == 0)
         {
             int p;
-            while ((p = ld_relaxed(fp->row_progress + row)) <= x) __nanosleep(200);
+            while ((p = ld_relaxed(fp->row_progress + row * PROG_STRIDE)) <= x) __nanosleep(200);
             fence_acquire();
             avail = min(p - x, 32 - (n & 31));       /* chunks end at multiples of 32 (checkpoints) */
         }
@@ -202,12 +210,12 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
                     for (;;)
                     {
                         if (ld_relaxed(fp->row_clean + row - 1) == pass) break;
-                        if (ld_relaxed(progress + row - 1) >= base + 1) { clean = ld_relaxed(fp->row_clean + row - 1) == pass; break; }
+                        if (ld_relaxed(progress + (row - 1) * PROG_STRIDE) >= base + 1) { clean = ld_relaxed(fp->row_clean + row - 1) == pass; break; }
                         __nanosleep(20);
                     }
                 fence_acquire();
                 s_clean = clean;
-                if (clean) { st_release(fp->row_clean + row, pass); st_release(progress + row, base + nmbx); }
+                if (clean) { st_release(fp->row_clean + row, pass); st_release(progress + row * PROG_STRIDE, base + nmbx); }
             }
             __syncthreads();
             if (s_clean) return;
@@ -217,9 +225,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     {
         for (int x = 0; x < nmbx; x++)
         {
-            if (row > 0) wait_row_cta(progress + row - 1, base + min(x + 2, nmbx));
+            if (row > 0) wait_row_cta(progress + (row - 1) * PROG_STRIDE, base + min(x + 2, nmbx));
             wave_mb_first(fp, &work, x, row);
-            publish_row_cta(progress + row, base + x + 1);
+            publish_row_cta(progress + row * PROG_STRIDE, base + x + 1);
             mb_store_coefs(fp, &work);
         }
         return;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
             if (row > 0)
             {
                 const int need = base + min(x + 2, nmbx);
-                while ((p = ld_relaxed(progress + row - 1)) < need) __nanosleep(20);
+                while ((p = ld_relaxed(progress + (row - 1) * PROG_STRIDE)) < need) __nanosleep(20);
                 fence_acquire();
                 p -= base;
             }
@@ -265,13 +273,13 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
         if (first == 0x7fffffff)
         {
             x += cnt;
-            publish_row_cta(progress + row, base + x);
+            publish_row_cta(progress + row * PROG_STRIDE, base + x);
             continue;
         }
         x += first;
         wave_mb_repair(fp, &work, x, row, pass);
         x++;
-        publish_row_cta(progress + row, base + x);
+        publish_row_cta(progress + row * PROG_STRIDE, base + x);
         mb_store_coefs(fp, &work);
     }
 }
@@ -353,9 +361,9 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     for (int x = 0; x < nmbx; x++)
     {
         deblock_mb(fp, &tile, x, row, part, 0);
-        if (row > 0) wait_row(progress + row - 1, min(x + 2, nmbx));
+        if (row > 0) wait_row(progress + (row - 1) * PROG_STRIDE, min(x + 2, nmbx));
         deblock_mb(fp, &tile, x, row, part, 1);
-        publish_row(progress + row, x + 1);
+        publish_row(progress + row * PROG_STRIDE, x + 1);
     }
 }
 
@@ -553,7 +561,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaMalloc(&c->d_out_info, 64));
     CK(cudaMalloc(&c->d_clusters, 16));
     CK(cudaMemset(c->d_clusters, 0, 16));
-    CK(cudaMalloc(&c->d_progress, sizeof(int) * 4 * c->nmby));
+    CK(cudaMalloc(&c->d_progress, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby));
     CK(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
     CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
     CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
@@ -632,7 +640,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
-    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + c->nmby; fp->row_clean = c->d_progress + 2 * c->nmby; fp->row_progress_dfc = c->d_progress + 3 * c->nmby;
+    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 3 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
@@ -740,7 +748,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     for (int i = 0; i < n; i++)
     {
         h264b200_ctx *c = jobs[i].ctx;
-        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * 4 * c->nmby, st));
+        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby, st));
         CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
         CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
