@@ -23,7 +23,11 @@
 #if defined(__CUDACC__)
 #  define H264_DEVICE 1
 #  define HD __device__ __forceinline__
-#  define HDN static __device__ __noinline__
+#  if defined(H264_HDN_AUTO)       /* developer A/B: leave the inlining of the big leaves to the compiler */
+#    define HDN static __device__
+#  else
+#    define HDN static __device__ __noinline__
+#  endif
 #  define H264_TAB static __device__ const
 #else
 #  define H264_DEVICE 0

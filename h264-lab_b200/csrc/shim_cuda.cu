@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
+#include <atomic>
 
 #include "h264_common.h"
 #include "h264_pixel.h"
@@ -479,14 +481,43 @@ struct h264b200_ctx
 
 void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st);    /* shim_check.cu */
 
-static long g_launches = 0;
-static cudaStream_t g_stream = 0;
-static FrameParams *g_d_fps = NULL, *g_h_fps = NULL;
-static int g_fps_cap = 0;
-static int *g_d_tickets = NULL;
-static cudaEvent_t g_ev[6];
-static int g_ev_ok = 0;
-static float g_last_ms[4];
+/* Submission lanes.  Every host thread that submits work gets its own lane: a CUDA stream pair, its
+ * FrameParams staging, tickets and events.  Encoder instances are independent (reference: "distinct
+ * encoders are independent", SURVEY 8(b) Threading), so threads driving different encoders run
+ * concurrently on the device: the latency-bound kernels of one lane (re-check, repair rounds, in-loop
+ * filter) overlap the macroblock sweep of another.  More threads than lanes share lanes (mutex). */
+#define MAX_LANES 64
+struct Lane
+{
+    std::mutex lock;
+    cudaStream_t stream, stream2;
+    FrameParams *d_fps, *h_fps;
+    int fps_cap;
+    int *d_tickets;
+    cudaEvent_t ev[6], ev_fork, ev_join;
+    int ev_ok;
+    float last_ms[4];
+};
+static Lane g_lanes[MAX_LANES];
+static std::atomic<int> g_lane_next(0);
+static std::atomic<long> g_launches(0);
+static thread_local Lane *t_lane = NULL;
+static Lane *lane_get()
+{
+    if (!t_lane) t_lane = &g_lanes[g_lane_next.fetch_add(1) % MAX_LANES];
+    return t_lane;
+}
+#define g_stream (t_lane->stream)
+#define g_stream2 (t_lane->stream2)
+#define g_d_fps (t_lane->d_fps)
+#define g_h_fps (t_lane->h_fps)
+#define g_fps_cap (t_lane->fps_cap)
+#define g_d_tickets (t_lane->d_tickets)
+#define g_ev (t_lane->ev)
+#define g_ev_ok (t_lane->ev_ok)
+#define g_ev_fork (t_lane->ev_fork)
+#define g_ev_join (t_lane->ev_join)
+#define g_last_ms (t_lane->last_ms)
 
 static int g_enc_dyn_smem = 0;     /* developer knob H264B200_ENC_SMEM: extra dynamic shared memory per CTA of k_encode_rows
                                        (limits the CTAs resident per SM, to study cache contention) */
@@ -499,6 +530,7 @@ static int ensure_globals(int njobs)
         const char *e = getenv("H264B200_ENC_SMEM");
         if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
     }
+    lane_get();
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
     if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ok = 1; }
@@ -662,8 +694,6 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
 }
 
 /* kernels that follow the macroblock sweeps; frames that are not FS_DONE are skipped inside */
-static cudaStream_t g_stream2 = 0;
-static cudaEvent_t g_ev_fork, g_ev_join;
 static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nmb, int cap_words, cudaStream_t st,
                        cudaEvent_t ev_mid)
 {
@@ -707,6 +737,7 @@ static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st
 static int encode_impl(int n, h264b200_job *jobs)
 {
     if (n <= 0) return 0;
+    std::lock_guard<std::mutex> guard(lane_get()->lock);
     if (ensure_globals(2 * n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
     cudaStream_t st = g_stream;
     int max_rows = 0, max_nmb = 0, cap = 0x7fffffff;
@@ -854,6 +885,7 @@ extern "C" int h264b200_encode_frames(int n, h264b200_job *jobs) { return encode
 
 extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3], const int strides[3])
 {
+    std::lock_guard<std::mutex> guard(lane_get()->lock);
     if (ensure_globals(1)) return -3;
     for (int pl = 0; pl < 3; pl++)
     {
@@ -865,7 +897,7 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
     return 0;
 }
 
-extern "C" void h264b200_last_timing(float out_ms[4]) { for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
+extern "C" void h264b200_last_timing(float out_ms[4]) { lane_get(); for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
 /* developer builds (-DH264_PROFILE): per-MB phase cycles of the last frame, [nmb][10] ints */
 extern "C" int h264b200_get_profile(h264b200_ctx *c, int *out)
 {
