@@ -16,15 +16,18 @@
 #  define PROF_INIT(s) do { (s).prof_t0 = (s).prof_start = clock64(); for (int k_ = 0; k_ < PROF_N; k_++) (s).prof[k_] = 0; } while (0)
 #  define PROF_MARK(s, k) do { (void)*(volatile int32_t *)&(s).w->scal[15]; long long t_ = clock64(); (s).prof[k] += (int)(t_ - (s).prof_t0); (s).prof_t0 = t_; } while (0)
 #  define PROF_STORE(s, fp, n, type) do { if (threadIdx.x == 0 && (fp)->prof) { for (int k_ = 0; k_ < 12; k_++) (fp)->prof[(n) * 20 + k_] = (s).prof[k_]; \
-        (fp)->prof[(n) * 20 + 16] = (type); } } while (0)
+        (fp)->prof[(n) * 20 + 16] = (type); (fp)->prof[(n) * 20 + 19] = ((s).prof[12] & 0xFFFF) | ((s).prof[13] << 16); } } while (0)
 /* cycles since the start of the macroblock at which warp `wid` reaches this point (slot 12 + wid / 17 + wid) */
 #  define PROF_WARP(s, fp, n, slot) do { (void)*(volatile int32_t *)&(s).w->scal[15]; if ((threadIdx.x & 31) == 0 && (fp)->prof) (fp)->prof[(n) * 20 + (slot)] = (int)(clock64() - (s).prof_start); } while (0)
+/* sub-phase of the phase that is being timed: adds the cycles since the last mark to slot k WITHOUT closing the phase's own slot */
+#  define PROF_SUB(s, k) do { MBState &s_ = const_cast<MBState &>(s); (void)*(volatile int32_t *)&s_.w->scal[15]; long long t_ = clock64(); s_.prof[k] += (int)(t_ - s_.prof_t0); s_.prof_t0 = t_; } while (0)
 #else
 #  define PROF_MEMBERS
 #  define PROF_INIT(s)
 #  define PROF_MARK(s, k)
 #  define PROF_STORE(s, fp, n, type)
 #  define PROF_WARP(s, fp, n, slot)
+#  define PROF_SUB(s, k)
 #endif
 
 struct MBState   /* warp-uniform registers of the macroblock being encoded */
@@ -465,6 +468,7 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
         break;
     }
 
+    if (bw == 16 && bh == 16) PROF_SUB(s, 12);
     rp = ref_at(s, (mv_x(mv) >> 2) + ppx - 1, (mv_y(mv) >> 2) + ppy - 1, bw + 2, bh + 2, &rs);
     rp += rs + 1;                       /* integer sample position of the block */
     copy_block(rp, rs, buf[0], bw, bh);
@@ -506,6 +510,7 @@ HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv
             }
         }
         WSYNC();
+        if (bw == 16 && bh == 16) PROF_SUB(s, 13);
         int sq[7];
         sad_qpel7(I, H1, H2, C, inp, bw, bh, sq);
         int vbest = mv, ibest = -1;
@@ -605,6 +610,12 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
 
     if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
+        if (!((mv_x(mv_skip_a) | mv_y(mv_skip_a)) & 3))
+        {   /* full-pel vector: the prediction is a copy of integer samples, usually inside the search window */
+            int rs;
+            const pix_t *rp = ref_at(s, mv_x(mv_skip_a) >> 2, mv_y(mv_skip_a) >> 2, 16, 16, &rs);
+            copy_block(rp, rs, w->skip_pred, 16, 16);
+        } else
         {
             const int st = fp->stride[0];
             const long o = (long)(mv_y(mv_skip_a) >> 2) * st + (mv_x(mv_skip_a) >> 2);
@@ -644,8 +655,48 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
         }
     }
 
+    PROF_SUB(s, 3);
     if (state != 1)
     {
+#if H264_DEVICE
+        /* candidate start points (H:5370-5386), rounded to full-pel, duplicates dropped keeping first
+         * occurrences (H:5198): one candidate per lane, in the reference's order; the survivors are
+         * visited in lane order */
+        const unsigned FULLM = 0xffffffffu;
+        const int lane = LANE_ID;
+        int cval = 0, cok = 0;
+        if (lane == 0) { cval = mv_skip; cok = ncand; }            /* present when the skip vector was in range */
+        else if (lane == 1) { cval = mvp16; cok = 1; }
+        else if (lane == 2) { cval = 0; cok = 1; }
+        else if (lane == 3) { cval = w->mvp0_left[0]; cok = (s.avail & AVAIL_L) && cval != MV_NA; }
+        else if (lane == 4) { cval = w->mvp0_top[0]; cok = (s.avail & AVAIL_T) && cval != MV_NA; }
+        else if (lane == 5) { cval = w->mvp0_top[4]; cok = (s.avail & AVAIL_TR) && cval != MV_NA; }
+        else if (lane == 6) { cval = mv_pack(8 * 4, 0); cok = s.mbx <= 0; }
+        else if (lane == 7) { cval = mv_pack(0, 8 * 4); cok = s.mby <= 0; }
+        else if (lane == 8) { cval = cl[0]; cok = 1; }
+        else if (lane == 9) { cval = cl[1]; cok = 1; }
+        cval = mv_round_fullpel(cval);
+        const unsigned okm = __ballot_sync(FULLM, cok);
+        const unsigned same = __match_any_sync(FULLM, cval) & okm;
+        unsigned keep = __ballot_sync(FULLM, cok && (same & (0u - same)) == (1u << lane));
+        if (j) keep &= keep - 1;                                    /* full-pel skip vector: its SAD is reused (H:5361) */
+        PROF_SUB(s, 8);
+        while (keep)
+        {
+            const int cj = __shfl_sync(FULLM, cval, __ffs((int)keep) - 1);
+            keep &= keep - 1;
+            int mva = mv_pack(mv_x(cj) + mbqx, mv_y(cj) + mbqy);
+            if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
+            {
+                int cc = mv_cost(cj, mvp16, fp->lambda_mv_q4);
+                int rs;
+                const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
+                int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                if (fp->speed < 1) inter_partition_hint(sad4v, pref);
+                if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cj; }
+            }
+        }
+#else
         /* candidate start points (H:5370-5386) */
         cand[ncand++] = mvp16;
         cand[ncand++] = 0;
@@ -667,6 +718,7 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
             }
             ncand = k;
         }
+        PROF_SUB(s, 8);
 #pragma unroll 1
         for (; j < ncand; j++)
         {
@@ -681,6 +733,8 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
                 if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
             }
         }
+#endif
+        PROF_SUB(s, 9);
     }
     IF_LANE0
     {

@@ -26,12 +26,14 @@ enc = encs[0]
 rps = [e.run_param(qp=28) for e in encs]
 rp = rps[0]
 nmb = ((w + 15) // 16) * ((h + 15) // 16)
-names = ["load", "win", "stage_a", "-", "search16", "wait_tasks", "decide", "tq_w0", "-", "-", "tq_join", "record"]
+names = ["load", "win", "a_publish", "a_skiptest", "s16_qpel7", "wait_tasks", "decide", "tq_w0", "a_candlist", "a_cands", "tq_join", "record"]
 for i in range(n):
     B.encode_batch(L, encs, [fr[i].copy() for _ in encs], rps)
     prof = np.zeros((nmb, 20), np.int32)
     L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
-    tot = prof[:, :12].sum(1)
+    sub = prof[:, 19].astype(np.int64)
+    s16 = np.stack([sub & 0xFFFF, (sub >> 16) & 0xFFFF], 1)      # 16x16 search: integer part (incl. wait for its start), copy + half-sample plane fetch
+    tot = prof[:, :12].sum(1) + s16.sum(1)
     tm = (C.c_float * 4)()
     L.lib.h264b200_last_timing(tm)
     print("frame %d: k_encode %.2f ms; MB cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f  (sum/1.9GHz = %.1f ms serial)" % (
@@ -48,4 +50,5 @@ for i in range(n):
         m = prof[:, 16] == t
         ph = prof[m][:, :12].mean(0)
         print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(12) if names[k] != "-")
+              + " s16_int %.0f s16_fetch %.0f" % tuple(s16[m].mean(0))
               + " | arrive w0..3 %s chroma w2,w3 %s" % (prof[m][:, 12:16].mean(0).astype(int).tolist(), prof[m][:, 17:19].mean(0).astype(int).tolist()))
