@@ -324,14 +324,26 @@ def main():
     alg_bytes_step = nseg * ((b_in + b_ref + b_rec) * p_frames + (b_in + b_rec) * i_frames) / K + out_bytes / K
     # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full capture of this workload
     traffic = None
+    inst = None
     try:
-        km = json.load(open(os.path.join(ROOT, "profiles", "r01_k_encode_rows_10stream_keymetrics.json")))
+        km = json.load(open(os.path.join(ROOT, "profiles", "r01c_k_encode_rows_10stream_keymetrics.json")))
         unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
         traffic = sum(float(km[k][0]) * unit[km[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")) if nseg == NSEG else None
+        # integer-ALU view of the same launch (north_star: ME / transform kernels against the SM issue peak):
+        # warp instructions of the captured launch / the live launch duration, against 4 issue slots x 148 SMs x SM clock
+        inst = float(km["smsp__inst_executed.sum"][0]) if nseg == NSEG and "smsp__inst_executed.sum" in km else None
     except Exception:
         traffic = None
+        inst = None
     k_enc_ms = kern[1] / K
     achieved = alg_bytes_step / (k_enc_ms * 1e-3) / 1e9 if k_enc_ms > 0 else 0.0
+    alu = None
+    if inst and k_enc_ms > 0:
+        sm_mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        peak_ginst = 148 * 4 * sm_mhz * 1e6 / 1e9
+        ach_ginst = inst / (k_enc_ms * 1e-3) / 1e9
+        alu = {"achieved": ach_ginst, "peak": peak_ginst, "unit": "G warp-instructions/s", "frac": ach_ginst / peak_ginst,
+               "source": "smsp__inst_executed.sum of the committed 10-frame capture / live launch time; peak = 148 SMs x 4 issue slots x SM clock"}
     line = {
         "metric": "1080p encode fps, bit-exact to ref", "value": total_frames / dt_res, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dt_res / K * 1e3, "higher_is_better": True,
@@ -343,8 +355,9 @@ def main():
         "kernel_ms_per_step": {"device_total": kern[0] / K, "k_encode_rows": kern[1] / K, "k_deblock_rows+k_borders": kern[2] / K,
                                "k_cavlc+k_scan+k_pack": kern[3] / K},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "traffic_unit": "bytes per k_encode_rows launch (ncu dram__bytes_read+write, profiles/r01_k_encode_rows_10stream_keymetrics.json)",
+                     "traffic": traffic, "traffic_unit": "bytes per k_encode_rows launch (ncu dram__bytes_read+write, profiles/r01c_k_encode_rows_10stream_keymetrics.json)",
                      "algorithmic_bytes_per_launch": alg_bytes_step, "kernel": "k_encode_rows (sweep 0 + repair waves of the step)", "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                     "alu": alu,
                      "note": "integer/latency-bound wavefront: HBM is not the limiter (SURVEY 8(d)); "
                              "us per wavefront step = %.2f" % (k_enc_ms * 1e3 / (120 + 2 * 67) if k_enc_ms else 0)},
         "clocks": clocks,

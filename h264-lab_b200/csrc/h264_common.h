@@ -205,6 +205,8 @@ struct MBSpec
                              macroblocks of sweep 0, published while the sweep runs; [12] prefix length */
 #define FS_NFAIL 13       /* dirty macroblocks whose candidate-stage re-check failed (need a re-encode)  */
 #define FS_TRAJ_FIRST 14  /* 0x3fffffff - (first macroblock whose cluster-relevant result changed in the current pass), 0: none */
+#define FS_REPLAYED 7      /* GPU: repair pass whose trajectory replay the follower of the repair wave has already done */
+#define FS_REPLAY_TF 15    /* GPU: FS_TRAJ_FIRST that replay started from                                   */
 #define FS_WORDS 16
 #define FS_DONE 0x40000000
 

@@ -80,7 +80,13 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     mb_load(s);
     int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
+#if H264_DEVICE && MB_WARPS == 1 && !defined(CHECK_WITH_WINDOW)
+    /* single-warp re-check: the candidate stage reads a handful of 16x16 blocks; fetching them straight
+     * from the reference picture (ref_at() without a window) moves less data than staging a 64x48 window */
+    (void)mvp16;
+#else
     win_load(s, x * 16 + ((mv_x(mvp16) + 1) >> 2), y * 16 + ((mv_y(mvp16) + 1) >> 2));
+#endif
     ON_WARP(0) { inter_stage_a(s, cl); }
     CTA_SYNC();
     int same = 0;
@@ -404,8 +410,12 @@ HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one wa
         const int tf = fp->fsync[FS_TRAJ_FIRST];
         const int first_block = (pass > 0 && tf > 0) ? (0x3fffffff - tf) >> 5 : 0;
         WSYNC();
+        /* GPU: the follower of the repair wave may have replayed already (same resume point) */
+        const int replayed = pass > 0 && fp->fsync[FS_REPLAYED] == pass && fp->fsync[FS_REPLAY_TF] == tf;
+        const int nd_follower = fp->fsync[FS_NDIRTY];
+        WSYNC();
         IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; fp->fsync[FS_TRAJ_FIRST] = 0; }
-        int nd = wave_replay(fp, w, 0, first_block);
+        int nd = replayed ? nd_follower : wave_replay(fp, w, 0, first_block);
         next = nd ? pass + 1 : FS_DONE;
     } else next = FS_DONE;
     if (next == FS_DONE)

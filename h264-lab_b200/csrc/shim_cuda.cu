@@ -166,6 +166,66 @@ __device__ void trajectory_follower(const FrameParams *fp)
     }
 }
 
+/* Trajectory follower of a repair wave (pass > 0, one warp per frame): what k_replay would do after the
+ * wave -- replay the trajectory from the first macroblock whose cluster-relevant result changed -- done
+ * WHILE the wave runs, gated by the row counters like the follower of sweep 0.  Every change of this
+ * pass is a causal successor of a change made by the parallel rounds that ran before the wave, so the
+ * resume point is known when the wave starts; k_replay re-checks that and falls back to its own
+ * replay otherwise (FS_REPLAYED / FS_REPLAY_TF). */
+__device__ void repair_follower(const FrameParams *fp, int pass)
+{
+    const int lane = threadIdx.x;
+    volatile int32_t *fs = (volatile int32_t *)fp->fsync;
+    if (fp->slice_type != SLICE_P || fs[FS_STATE] != pass || fs[FS_TRAJ_CHANGED] == 0) return;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby, base = pass * nmbx;
+    const int tf = fs[FS_TRAJ_FIRST];
+    const int first_block = tf > 0 ? (0x3fffffff - tf) >> 5 : 0;
+    int32_t c[2];
+    c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
+    if (first_block > 0) { c[0] = fp->cl_ckpt[2 * first_block]; c[1] = fp->cl_ckpt[2 * first_block + 1]; }
+    int ndirty = 0, n = 32 * first_block;
+    while (n < nmb)
+    {
+        int row = n / nmbx, x = n - row * nmbx, avail = 0;
+        if (lane == 0)
+        {
+            int p;
+            while ((p = ld_relaxed(fp->row_progress + row * PROG_STRIDE) - base) <= x) __nanosleep(100);
+            fence_acquire();
+            avail = min(p - x, 32 - (n & 31));
+        }
+        avail = __shfl_sync(0xffffffffu, avail, 0);
+        if (!(n & 31) && lane < 2) fp->cl_ckpt[2 * (n >> 5) + lane] = c[lane];
+        int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
+        if (lane < avail)
+        {
+            const MBSpec *sp = fp->spec + n + lane;
+            mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
+        }
+        int t0 = 0, t1 = 0;
+        for (int i = 0; i < avail; i++)
+        {
+            int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+            int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
+            int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
+            if (lane == i) { t0 = r0; t1 = r1; }
+            if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+            if (f & SPEC_UPDATES) clusters_update(c, m);
+        }
+        if (lane < avail) { fp->cl_true[2 * (n + lane)] = t0; fp->cl_true[2 * (n + lane) + 1] = t1; }
+        n += avail;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        fs[FS_CL_END] = c[0]; fs[FS_CL_END + 1] = c[1];
+        fs[FS_NDIRTY] = ndirty;
+        fs[FS_REPLAY_TF] = tf;
+        __threadfence();
+        fs[FS_REPLAYED] = pass;
+    }
+}
+
 __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
@@ -174,11 +234,10 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     if (threadIdx.x == 0) { s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; }
     __syncthreads();
     int item = s_item;
-    if (pass == 0)
-    {   /* the first njobs tickets of sweep 0 are the trajectory followers */
+    {   /* the first njobs tickets are the trajectory followers */
         if (item < njobs)
         {
-            if (threadIdx.x < 32) trajectory_follower(fps + item);
+            if (threadIdx.x < 32) { if (pass == 0) trajectory_follower(fps + item); else repair_follower(fps + item, pass); }
             return;
         }
         item -= njobs;
@@ -796,7 +855,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     {
         for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass, r);
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
-        k_encode_rows<<<n * max_rows, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
+        k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
         k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
         h264b200_launch_check1(g_d_fps, n, pass + 1, st);
         k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
@@ -826,7 +885,7 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemcpyAsync(d2, h2, sizeof(FrameParams) * m, cudaMemcpyHostToDevice, st));
         for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, m), MB_WARPS * 32, 0, st>>>(d2, m, pass, r);
         CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
-        k_encode_rows<<<m * rows2, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
+        k_encode_rows<<<m * rows2 + m, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
         h264b200_launch_check1(d2, m, pass + 1, st);
         k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);

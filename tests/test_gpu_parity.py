@@ -146,3 +146,43 @@ def test_rate_controlled_gop_shards(binding, cuda_lib, ref):
         assert outs[s] == rbs, "segment %d" % s
     for e in encs:
         e.close()
+
+
+def test_concurrent_encoders_from_host_threads(binding, cuda_lib, ref):
+    """Distinct encoders are independent (SURVEY 8(b) Threading): host threads driving their own
+    streams at the same time -- one with H264E_encode, one with H264E_encode_batch -- each get the
+    reference's bytes (every thread submits on its own lane of the shim)."""
+    import threading
+    w, h, n, nthreads = 320, 240, 6, 4
+    clips = [cases.make("multi" if s & 1 else "panning", w, h, n, seed=300 + s) for s in range(nthreads)]
+    outs = [b""] * nthreads
+    recs = [None] * nthreads
+    errs = []
+    start = threading.Barrier(nthreads)
+
+    def worker(s):
+        try:
+            start.wait()
+            if s & 1:
+                bs, _, rec = binding.encode_sequence(cuda_lib, clips[s], w, h, 60, qp=30)
+                outs[s], recs[s] = bs, rec[-1]
+            else:
+                e = binding.Encoder(cuda_lib, w, h, 60)
+                rp = e.run_param(qp=30)
+                for t in range(n):
+                    outs[s] += binding.encode_batch(cuda_lib, [e], [clips[s][t].copy()], [rp])[0]
+                recs[s] = e.recon()
+                e.close()
+        except BaseException as ex:       # reported by the main thread
+            errs.append((s, repr(ex)))
+
+    th = [threading.Thread(target=worker, args=(s,)) for s in range(nthreads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for s in range(nthreads):
+        rbs, _, rrec, _ = ref.encode_sequence(clips[s], w, h, 60, qp=30)
+        assert outs[s] == rbs, "thread %d" % s
+        assert np.array_equal(recs[s], rrec[-1]), "thread %d" % s
