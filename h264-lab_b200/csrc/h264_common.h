@@ -28,11 +28,162 @@
 #  else
 #    define HDN static __device__ __noinline__
 #  endif
+/* Which of the big leaves are inlined into their (single-copy) callers: bit k of H264_INL = function k in
+ * the order of the HDF_ macros below.  A call costs register moves, stack traffic and scheduling freedom;
+ * a copy costs instruction-cache sharing between the warps of a CTA (a function kept out of line is ONE
+ * copy that every search warp runs).  The default is the best set found by A/B runs on B200. */
+#  ifndef H264_INL
+#    define H264_INL 0x7EFFF
+#  endif
+#  if ((H264_INL) >> 0) & 1
+#    define HDF_mb_load static __device__ __forceinline__
+#  else
+#    define HDF_mb_load HDN
+#  endif
+#  if ((H264_INL) >> 1) & 1
+#    define HDF_win_load static __device__ __forceinline__
+#  else
+#    define HDF_win_load HDN
+#  endif
+#  if ((H264_INL) >> 2) & 1
+#    define HDF_inter_stage_a static __device__ __forceinline__
+#  else
+#    define HDF_inter_stage_a HDN
+#  endif
+#  if ((H264_INL) >> 3) & 1
+#    define HDF_luma_tq_fast static __device__ __forceinline__
+#  else
+#    define HDF_luma_tq_fast HDN
+#  endif
+#  if ((H264_INL) >> 4) & 1
+#    define HDF_me_search static __device__ __forceinline__
+#  else
+#    define HDF_me_search HDN
+#  endif
+#  if ((H264_INL) >> 5) & 1
+#    define HDF_sad_qpel7 static __device__ __forceinline__
+#  else
+#    define HDF_sad_qpel7 HDN
+#  endif
+#  if ((H264_INL) >> 6) & 1
+#    define HDF_sad_frame_wh static __device__ __forceinline__
+#  else
+#    define HDF_sad_frame_wh HDN
+#  endif
+#  if ((H264_INL) >> 7) & 1
+#    define HDF_sad_sm_wh static __device__ __forceinline__
+#  else
+#    define HDF_sad_sm_wh HDN
+#  endif
+#  if ((H264_INL) >> 8) & 1
+#    define HDF_interp_luma_planes static __device__ __forceinline__
+#  else
+#    define HDF_interp_luma_planes HDN
+#  endif
+#  if ((H264_INL) >> 9) & 1
+#    define HDF_interp_chroma_block static __device__ __forceinline__
+#  else
+#    define HDF_interp_chroma_block HDN
+#  endif
+#  if ((H264_INL) >> 10) & 1
+#    define HDF_intra16_pred static __device__ __forceinline__
+#  else
+#    define HDF_intra16_pred HDN
+#  endif
+#  if ((H264_INL) >> 11) & 1
+#    define HDF_intra4_choose static __device__ __forceinline__
+#  else
+#    define HDF_intra4_choose HDN
+#  endif
+#  if ((H264_INL) >> 12) & 1
+#    define HDF_wave_mb_first static __device__ __forceinline__
+#  else
+#    define HDF_wave_mb_first HDN
+#  endif
+#  if ((H264_INL) >> 13) & 1
+#    define HDF_sad_nb8 static __device__ __forceinline__
+#  else
+#    define HDF_sad_nb8 HDN
+#  endif
+#  if ((H264_INL) >> 14) & 1
+#    define HDF_copy_block static __device__ __forceinline__
+#  else
+#    define HDF_copy_block HDN
+#  endif
+#  if ((H264_INL) >> 15) & 1
+#    define HDF_average_block static __device__ __forceinline__
+#  else
+#    define HDF_average_block HDN
+#  endif
+#  if ((H264_INL) >> 16) & 1
+#    define HDF_sad_mb_quad static __device__ __forceinline__
+#  else
+#    define HDF_sad_mb_quad HDN
+#  endif
+#  if ((H264_INL) >> 17) & 1
+#    define HDF_mvp_get static __device__ __forceinline__
+#  else
+#    define HDF_mvp_get HDN
+#  endif
+#  if ((H264_INL) >> 18) & 1
+#    define HDF_partition_tasks static __device__ __forceinline__
+#  else
+#    define HDF_partition_tasks HDN
+#  endif
+#  if ((H264_INL) >> 19) & 1
+#    define HDF_mc_chroma_plane static __device__ __forceinline__
+#  else
+#    define HDF_mc_chroma_plane HDN
+#  endif
+#  if ((H264_INL) >> 20) & 1
+#    define HDF_chroma_tq_fast static __device__ __forceinline__
+#  else
+#    define HDF_chroma_tq_fast HDN
+#  endif
+#  if ((H264_INL) >> 21) & 1
+#    define HDF_intra_chroma_plane static __device__ __forceinline__
+#  else
+#    define HDF_intra_chroma_plane HDN
+#  endif
+#  if ((H264_INL) >> 22) & 1
+#    define HDF_mb_store_coefs static __device__ __forceinline__
+#  else
+#    define HDF_mb_store_coefs HDN
+#  endif
+#  if ((H264_INL) >> 23) & 1
+#    define HDF_inter_mode_search static __device__ __forceinline__
+#  else
+#    define HDF_inter_mode_search HDN
+#  endif
 #  define H264_TAB static __device__ const
 #else
 #  define H264_DEVICE 0
 #  define HD static inline
 #  define HDN static
+#  define HDF_mb_load static
+#  define HDF_win_load static
+#  define HDF_inter_stage_a static
+#  define HDF_luma_tq_fast static
+#  define HDF_me_search static
+#  define HDF_sad_qpel7 static
+#  define HDF_sad_frame_wh static
+#  define HDF_sad_sm_wh static
+#  define HDF_interp_luma_planes static
+#  define HDF_interp_chroma_block static
+#  define HDF_intra16_pred static
+#  define HDF_intra4_choose static
+#  define HDF_wave_mb_first static
+#  define HDF_sad_nb8 static
+#  define HDF_copy_block static
+#  define HDF_average_block static
+#  define HDF_sad_mb_quad static
+#  define HDF_mvp_get static
+#  define HDF_partition_tasks static
+#  define HDF_mc_chroma_plane static
+#  define HDF_chroma_tq_fast static
+#  define HDF_intra_chroma_plane static
+#  define HDF_mb_store_coefs static
+#  define HDF_inter_mode_search static
 #  define H264_TAB static const
 #endif
 

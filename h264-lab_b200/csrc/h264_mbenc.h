@@ -158,7 +158,7 @@ HD void win_prefetch(const FrameParams *fp, MBWork *w, int mbx, int mby, int cx,
 }
 #endif
 
-HDN void mb_load(MBState &s)
+HDF_mb_load void mb_load(MBState &s)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -288,7 +288,7 @@ HDN void mb_load(MBState &s)
  * (me_mv_medianpredictor_get H:3720).  x,y,wd,ht in units of 4x4 blocks.
  * ---------------------------------------------------------------------------- */
 HD int med3(int a, int b, int c) { return imax(imin(imax(a, b), c), imin(a, b)); }
-HDN int mvp_get(const int32_t *left, const int32_t *tlv, const int32_t *top, int flag, int x, int y, int wd, int ht)
+HDF_mvp_get int mvp_get(const int32_t *left, const int32_t *tlv, const int32_t *top, int flag, int x, int y, int wd, int ht)
 {
     int a = left[y], b = top[x], c = top[x + wd], d = tlv[y];
     if (!x)
@@ -344,7 +344,7 @@ HD void mvp_put(SearchScratch *w, int x, int y, int wd, int ht, int mv)
  * its block; inside the window (the common case) the samples come from shared memory,
  * otherwise straight from the frame in global memory -- identical values either way.
  * ---------------------------------------------------------------------------- */
-HDN void win_load(MBState &s, int cx, int cy)
+HDF_win_load void win_load(MBState &s, int cx, int cy)
 {
     const FrameParams *fp = s.fp;
     const int stride = fp->stride[0];
@@ -398,7 +398,7 @@ HD const pix_t *ref_at(const MBState &s, int bx, int by, int bw, int bh, int *st
  *   buf[4] : scratch, hpel, hpel1, hpel2 destinations (stride-16 blocks)
  * Returns the best cost; *pbest receives the buffer holding the best prediction.
  * ---------------------------------------------------------------------------- */
-HDN int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv, const int *rng,
+HDF_me_search int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp, int *pmv, const int *rng,
                  int mv_pred, int min_sad, int bw, int bh, pix_t *const buf[4], pix_t **pbest)
 {
     const FrameParams *fp = s.fp;
@@ -566,7 +566,7 @@ HD void inter_partition_hint(const int sad[4], int mode[4])
 
 /* chroma motion compensation of plane pl for every partition of the current MB type
  * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB.  Warp-level. */
-HDN void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
+HDF_mc_chroma_plane void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
 {
     const FrameParams *fp = s.fp;
     int bw = (type & 2) ? 4 : 8, bh = (type & 1) ? 4 : 8;
@@ -590,7 +590,7 @@ HDN void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
  * ---------------------------------------------------------------------------- */
 /* Candidate stage.  Needs the window loaded around mvp16.  Publishes w->ic[] (lane 0). */
 /* Candidate stage.  Needs the window loaded around mvp16.  Publishes w->ic[] (lane 0). */
-HDN void inter_stage_a(MBState &s, const int32_t cl[2])
+HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -758,7 +758,7 @@ HDN void inter_stage_a(MBState &s, const int32_t cl[2])
 
 /* Search of one partition mode (one warp, private scratch s.ss).  The prediction of the
  * whole macroblock for this mode ends up at w->mode_pred[mb_type]. */
-HDN void inter_mode_search(MBState &s, int mb_type)
+HDF_inter_mode_search void inter_mode_search(MBState &s, int mb_type)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -902,7 +902,7 @@ HD int lds_u8(unsigned addr)
  *    partial sums), the mode costs are formed where the sums end up and the strict-'<'-in-
  *    evaluation-order decision is a min-reduction of (cost << 4 | slot);
  *  - residual -> transform -> quantisation -> inverse -> reconstruction stay in registers. */
-HDN int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
+HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -1108,7 +1108,7 @@ HDN int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
     return cost + fp->lambda_i4_q4;
 }
 #else
-HDN int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
+HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -1476,7 +1476,7 @@ HD uint32_t nibble_all(uint32_t m) { m &= m >> 1; m &= m >> 2; return m & 0x1111
 HD uint32_t nibble_any(uint32_t m) { m |= m >> 1; m |= m >> 2; return m & 0x11111111u; }
 
 /* luma of a non-I4x4 macroblock; called by warps 0 and 1 (half = warp) */
-HDN void luma_tq_fast(MBState &s, int half, int intra16)
+HDF_luma_tq_fast void luma_tq_fast(MBState &s, int half, int intra16)
 {
     const unsigned FULL = 0xffffffffu;
     const FrameParams *fp = s.fp;
@@ -1562,7 +1562,7 @@ HDN void luma_tq_fast(MBState &s, int half, int intra16)
 }
 
 /* chroma plane pl; one warp, lanes 16-31 mirror lanes 0-15 */
-HDN void chroma_tq_fast(MBState &s, int pl)
+HDF_chroma_tq_fast void chroma_tq_fast(MBState &s, int pl)
 {
     const unsigned FULL = 0xffffffffu;
     const FrameParams *fp = s.fp;
@@ -1632,7 +1632,7 @@ HDN void chroma_tq_fast(MBState &s, int pl)
 #endif
 
 /* chroma intra prediction of plane pl (warp-level) */
-HDN void intra_chroma_plane(MBState &s, int pl)
+HDF_intra_chroma_plane void intra_chroma_plane(MBState &s, int pl)
 {
     MBWork *w = s.w;
     const pix_t *left = (s.avail & AVAIL_L) ? w->left_c : 0, *top = (s.avail & AVAIL_T) ? w->top_c : 0;
@@ -1679,7 +1679,7 @@ HD void clusters_update(int32_t *cl, int mv)
 /* The hinted partition modes (16x8, 8x16, 8x8) are independent search tasks; the warps that are
  * free (roles 1, 2, and 3 once the intra decision is over) take them from a shared counter, the
  * longest (8x8, four partitions) first.  `slot` selects the warp's private scratch. */
-HDN void partition_tasks(MBState &s, int slot)
+HDF_partition_tasks void partition_tasks(MBState &s, int slot)
 {
     MBWork *w = s.w;
     const int pref = w->ic[IC_PREF];
@@ -2019,7 +2019,7 @@ HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int
 /* Second half of the macroblock record: quantised levels -> HBM (for the CAVLC pass).  Called by
  * the whole CTA after encode_mb(), once the wavefront counters have been advanced; a no-op when
  * no macroblock has been encoded since the last call. */
-HDN void mb_store_coefs(const FrameParams *fp, MBWork *w)
+HDF_mb_store_coefs void mb_store_coefs(const FrameParams *fp, MBWork *w)
 {
     const int tag = w->scal[9];
     if (!tag) return;

@@ -56,7 +56,7 @@ HD uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)
  * MB (stride 16).  (sad_block H:2162, h264e_sad_mb_unlaign_wh H:2189). w, h in {8,16}.
  * Returns the warp-uniform total.
  * ---------------------------------------------------------------------------- */
-HDN int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int h)
+HDF_sad_frame_wh int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int h)
 {
     const int sh = w == 16 ? 2 : 1;      /* words per row: 4 or 2 */
     int acc = 0;
@@ -69,7 +69,7 @@ HDN int sad_frame_wh(const pix_t *a, int a_stride, const pix_t *b16, int w, int 
 }
 
 /* SAD of two stride-16 blocks in the working set */
-HDN int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
+HDF_sad_sm_wh int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
 {
     const int sh = w == 16 ? 2 : 1;
     int acc = 0;
@@ -83,7 +83,7 @@ HDN int sad_sm_wh(const pix_t *a16, const pix_t *b16, int w, int h)
 
 /* a1: four 8x8 quadrant SADs (TL, TR, BL, BR) of a 16x16 block + their sum
  * (h264e_sad_mb_unlaign_8x8 H:2178). */
-HDN int sad_mb_quad(const pix_t *a, int a_stride, const pix_t *b16, int sad4out[4])
+HDF_sad_mb_quad int sad_mb_quad(const pix_t *a, int a_stride, const pix_t *b16, int sad4out[4])
 {
     int q01 = 0, q23 = 0;    /* two 16-bit lanes each: an 8x8 SAD is <= 16320 */
     FOR_LANES(i, 64)
@@ -105,7 +105,7 @@ HDN int sad_mb_quad(const pix_t *a, int a_stride, const pix_t *b16, int sad4out[
  * reference's order, so evaluating more positions than the reference changes nothing).
  * out[0..3] = (+1,0) (-1,0) (0,+1) (0,-1); out[4..7] = (+1,+1) (-1,+1) (+1,-1) (-1,-1).
  * A 16x16 SAD is <= 65280, so two fit one 32-bit accumulator. */
-HDN void sad_nb8(const pix_t *p, int ps, const pix_t *b16, int w, int h, int out[8])
+HDF_sad_nb8 void sad_nb8(const pix_t *p, int ps, const pix_t *b16, int w, int h, int out[8])
 {
     const int sh = w == 16 ? 2 : 1;
     uint32_t a01 = 0, a23 = 0, a45 = 0, a67 = 0;
@@ -131,7 +131,7 @@ HDN void sad_nb8(const pix_t *p, int ps, const pix_t *b16, int w, int h, int out
 /* SADs of the seven sub-pel probes of me_search in one pass, from the integer prediction I
  * and the three half-sample blocks H1 (primary), H2 (secondary), C (diagonal):
  * out = { H1, avg(I,H1), H2, avg(I,H2), avg(H1,H2), C, avg(C,H1) }  (H:5119-5161) */
-HDN void sad_qpel7(const pix_t *I, const pix_t *H1, const pix_t *H2, const pix_t *C, const pix_t *b16, int w, int h, int out[7])
+HDF_sad_qpel7 void sad_qpel7(const pix_t *I, const pix_t *H1, const pix_t *H2, const pix_t *C, const pix_t *b16, int w, int h, int out[7])
 {
     const int sh = w == 16 ? 2 : 1;
     uint32_t a01 = 0, a23 = 0, a45 = 0, a6 = 0;
@@ -158,7 +158,7 @@ HDN void sad_qpel7(const pix_t *I, const pix_t *H1, const pix_t *H2, const pix_t
  * ---------------------------------------------------------------------------- */
 HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-HDN void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
+HDF_copy_block void copy_block(const pix_t *src, int ss, pix_t *dst, int w, int h)
 {
     const int sh = w == 16 ? 2 : 1;
     FOR_LANES(i, h << sh)
@@ -215,7 +215,7 @@ HD void hpel_word(const pix_t *buf, long nwords, int stride, long wi, uint32_t *
 
 /* rounded average of two stride-16 blocks (h264e_qpel_average_wh_align H:2065);
  * dst may alias either source (element-wise) */
-HDN void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int h)
+HDF_average_block void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int h)
 {
     const int sh = w == 16 ? 2 : 1;
     FOR_LANES(i, h << sh)
@@ -229,7 +229,7 @@ HDN void average_block(const pix_t *s0, const pix_t *s1, pix_t *dst, int w, int 
  * the integer plane, any alignment) -> dst (stride 16): the position table of
  * h264e_qpel_interpolate_luma (H:2079-2130) with the filters replaced by the half-sample
  * planes.  hb/hv/hd address the same sample as g in planes b/h/j; all four share `stride`. */
-HDN void interp_luma_planes(const pix_t *g, const pix_t *hb, const pix_t *hv, const pix_t *hd, int stride,
+HDF_interp_luma_planes void interp_luma_planes(const pix_t *g, const pix_t *hb, const pix_t *hv, const pix_t *hd, int stride,
                             int dx, int dy, int w, int h, pix_t *dst)
 {
     const int pos = 1 << (dx + 4 * dy);
@@ -254,7 +254,7 @@ HDN void interp_luma_planes(const pix_t *g, const pix_t *hb, const pix_t *hv, co
 
 /* a3: chroma 1/8-pel bilinear block (h264e_qpel_interpolate_chroma H:2133).
  * src addresses the integer sample of the block's top-left, (dx,dy) in 0..7. */
-HDN void interp_chroma_block(const pix_t *src, int stride, int dx, int dy, int w, int h, pix_t *dst)
+HDF_interp_chroma_block void interp_chroma_block(const pix_t *src, int stride, int dx, int dy, int w, int h, pix_t *dst)
 {
     int a = (8 - dx) * (8 - dy), b = dx * (8 - dy), c = (8 - dx) * dy, d = dx * dy;
     FOR_LANES(i, w * h)
@@ -438,7 +438,7 @@ HD int dc_pred(const pix_t *left, const pix_t *top, int n, int log2n)
 
 /* a7: 16x16 luma prediction, mode 0=V 1=H 2=DC (h264e_intra_predict_16x16 H:1677).
  * left/top are NULL when unavailable. */
-HDN void intra16_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
+HDF_intra16_pred void intra16_pred(pix_t *dst, const pix_t *left, const pix_t *top, int mode)
 {
     int dc = 0;
     if (mode == 2) dc = dc_pred(left, top, 16, 4) * 0x01010101u;

@@ -45,7 +45,7 @@ HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 }
 
 /* pass 0 / I frames */
-HDN void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
+HDF_wave_mb_first void wave_mb_first(const FrameParams *fp, MBWork *w, int x, int y)
 {
     const int n = y * fp->nmbx + x;
     int32_t cl[2] = {0, 0};
