@@ -155,6 +155,36 @@
 #  else
 #    define HDF_inter_mode_search HDN
 #  endif
+#  if ((H264_INL) >> 24) & 1
+#    define HDF_encode_mb static __device__ __forceinline__
+#  else
+#    define HDF_encode_mb HDN
+#  endif
+#  if ((H264_INL) >> 25) & 1
+#    define HDF_quant4x4 static __device__ __forceinline__
+#  else
+#    define HDF_quant4x4 HDN
+#  endif
+#  if ((H264_INL) >> 26) & 1
+#    define HDF_fwd4x4 static __device__ __forceinline__
+#  else
+#    define HDF_fwd4x4 HDN
+#  endif
+#  if ((H264_INL) >> 27) & 1
+#    define HDF_inv4x4_add static __device__ __forceinline__
+#  else
+#    define HDF_inv4x4_add HDN
+#  endif
+#  if ((H264_INL) >> 28) & 1
+#    define HDF_coefs_small static __device__ __forceinline__
+#  else
+#    define HDF_coefs_small HDN
+#  endif
+#  if ((H264_INL) >> 29) & 1
+#    define HDF_wave_mb_reencode static __device__ __forceinline__
+#  else
+#    define HDF_wave_mb_reencode HDN
+#  endif
 #  define H264_TAB static __device__ const
 #else
 #  define H264_DEVICE 0
@@ -184,6 +214,12 @@
 #  define HDF_intra_chroma_plane static
 #  define HDF_mb_store_coefs static
 #  define HDF_inter_mode_search static
+#  define HDF_encode_mb static
+#  define HDF_quant4x4 static
+#  define HDF_fwd4x4 static
+#  define HDF_inv4x4_add static
+#  define HDF_coefs_small static
+#  define HDF_wave_mb_reencode static
 #  define H264_TAB static const
 #endif
 

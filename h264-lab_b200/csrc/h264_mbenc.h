@@ -1717,7 +1717,7 @@ HDF_partition_tasks void partition_tasks(MBState &s, int slot)
  *   warps 0,1: luma halves;  warps 2,3: chroma planes (prediction + transform)
  *   all      : coded block pattern, skip rollback, record
  * ---------------------------------------------------------------------------- */
-HDN void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
+HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
 {
     MBState s;
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;

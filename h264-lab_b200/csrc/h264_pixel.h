@@ -273,7 +273,7 @@ HDF_interp_chroma_block void interp_chroma_block(const pix_t *src, int stride, i
  * out[v + 4u] = coefficient with vertical frequency v and horizontal frequency u
  * (FwdTransformResidual4x42 H:2385, TRANSPOSE_BLOCK 1).
  * ---------------------------------------------------------------------------- */
-HDN void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *out)
+HDF_fwd4x4 void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *out)
 {
     int t[16];
 #pragma unroll
@@ -303,7 +303,7 @@ HDN void fwd4x4(const pix_t *inp, int inp_stride, const pix_t *pred, int16_t *ou
 
 /* a11: inverse core transform of dq[] (same transposed layout) added to pred and
  * clipped (TransformResidual4x4 H:2436 + h264e_transform_add H:2638). */
-HDN void inv4x4_add(const int16_t *dq, const pix_t *pred, pix_t *out, int out_stride)
+HDF_inv4x4_add void inv4x4_add(const int16_t *dq, const pix_t *pred, pix_t *out, int out_stride)
 {
     int t[16];
 #pragma unroll
@@ -341,7 +341,7 @@ HD void copy4x4(const pix_t *pred, pix_t *out, int out_stride)
 HD int quant_class(int i) { return ((i & 1) + ((i >> 2) & 1)) * 2; }
 
 /* "all coefficients from i0 on are small" test against 8 thresholds (is_zero H:2491) */
-HDN int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
+HDF_coefs_small int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
 {
     for (int i = i0; i < 16; i++)
     {
@@ -353,7 +353,7 @@ HDN int coefs_small(const int16_t *c, int i0, const uint16_t *thr)
 
 /* a9: dead-zone quantiser + dequantiser of one 4x4 block, coefficients i0..15
  * (inner loop of quantize(), H:2567-2585).  Returns 1 when any level is non-zero. */
-HDN int quant4x4(int16_t *dq, int16_t *qv, int i0, const uint16_t *qdat)
+HDF_quant4x4 int quant4x4(int16_t *dq, int16_t *qv, int i0, const uint16_t *qdat)
 {
     int nz = 0;
     int rnd = qdat[6];

@@ -185,7 +185,7 @@ HDN void wave_mb_check(const FrameParams *fp, MBWork *w, int x, int y, int pass)
  * macroblock that changed in this sweep */
 /* full re-encode of one macroblock with its true candidates; returns 1 when what its causal
  * successors consume has changed */
-HDN int wave_mb_reencode(const FrameParams *fp, MBWork *w, int x, int y)
+HDF_wave_mb_reencode int wave_mb_reencode(const FrameParams *fp, MBWork *w, int x, int y)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
     const MBSpec old = fp->spec[n];
