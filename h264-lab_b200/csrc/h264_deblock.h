@@ -98,20 +98,29 @@ HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
 {
     const MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     const MBInfo *ml = mi - 1, *mt = mi - fp->nmbx;
-    /* boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg */
+    /* boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg.  Everything a lane
+     * may need is fetched up front with independent loads (one memory round trip instead of a chain of
+     * dependent ones), the decision is taken afterwards. */
     FOR_LANES(j, 32)
     {
         const int horiz = j >> 4, e = (j >> 2) & 3, seg = j & 3;
-        const int intra = mi->type >= 5;
+        const int at_border = (horiz ? mby : mbx) == 0;
+        /* p side: the neighbouring macroblock for edge 0 (this macroblock again at a picture border: unused) */
+        const MBInfo *mp = e ? mi : (at_border ? mi : (horiz ? mt : ml));
+        const int ip = e ? (horiz ? (e - 1) * 4 + seg : seg * 4 + e - 1) : (horiz ? 12 + seg : seg * 4 + 3);
+        const int iq = horiz ? e * 4 + seg : seg * 4 + e;
+        const int type_q = mi->type, type_p = mp->type;
+        const unsigned nz_p = mp->nz_mask, nz_q = mi->nz_mask;
+        const int mv_p = mp->mv[ip], mv_q = mi->mv[iq];
+        const int intra = type_q >= 5;
         int bs;
         if (e == 0)
         {
-            const MBInfo *mn = horiz ? mt : ml;
-            if ((horiz ? mby : mbx) == 0) bs = 0;
-            else if (intra || mn->type >= 5) bs = 4;
-            else bs = horiz ? bs_inter(mn, 12 + seg, mi, seg) : bs_inter(mn, seg * 4 + 3, mi, seg * 4);
+            if (at_border) bs = 0;
+            else if (intra || type_p >= 5) bs = 4;
+            else bs = ((nz_p & (0x8000u >> ip)) || (nz_q & (0x8000u >> iq))) ? 2 : (mv_far(mv_p, mv_q) ? 1 : 0);
         } else if (intra) bs = 3;
-        else bs = horiz ? bs_inter(mi, (e - 1) * 4 + seg, mi, e * 4 + seg) : bs_inter(mi, seg * 4 + e - 1, mi, seg * 4 + e);
+        else bs = ((nz_p & (0x8000u >> ip)) || (nz_q & (0x8000u >> iq))) ? 2 : (mv_far(mv_p, mv_q) ? 1 : 0);
         t->bs[j] = (uint8_t)bs;
     }
 }
@@ -119,6 +128,47 @@ HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
 /* phase 0: everything that does not depend on the row above -- the macroblock's own rows (with the 4
  * columns to their left, final since the previous macroblock of this row) and the boundary strengths;
  * phase 1 (once the row above has got far enough): the 4 rows above, the filters, the write-back. */
+#if H264_DEVICE
+HD void df_cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+HD void df_cp_async_wait()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+/* GPU software pipeline (k_deblock_rows): while macroblock x is being filtered, the samples of macroblock x + 1
+ * that nothing can touch before its own filtering (its 16x16 / 8x8 samples, not the 4 columns to its left) are
+ * already on their way into the other tile, and its boundary strengths are computed. */
+HD void deblock_prefetch(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part)
+{
+    const int sy = fp->stride[0], sc = fp->stride[1];
+    if (part == 0)
+    {
+        const pix_t *py = fp->dec[0] + (mby * 16) * sy + mbx * 16;
+        FOR_LANES(i, 64) { int r = i >> 2, c = 1 + (i & 3); df_cp_async4(&t->y[(r + 4) * 6 + c], py + r * sy + c * 4 - 4); }
+    } else
+    {
+        FOR_LANES(k, 32)
+        {
+            int pl = k >> 4, j = k & 15, r = j >> 1, c = 1 + (j & 1);
+            const pix_t *pc = fp->dec[1 + pl] + (mby * 8) * sc + mbx * 8;
+            df_cp_async4(&t->c[pl][(r + 4) * 3 + c], pc + r * sc + c * 4 - 4);
+        }
+    }
+    deblock_bs(fp, t, mbx, mby);
+}
+/* the 4 columns to the left of macroblock x + 1 = the last 4 columns of macroblock x, final in tile `cur` */
+HD void deblock_handover(const DeblockTile *cur, DeblockTile *nxt, int part)
+{
+    if (part == 0) { FOR_LANES(r, 16) nxt->y[(r + 4) * 6] = cur->y[(r + 4) * 6 + 4]; }
+    else { FOR_LANES(k, 16) { int pl = k >> 3, r = k & 7; nxt->c[pl][(r + 4) * 3] = cur->c[pl][(r + 4) * 3 + 2]; } }
+    df_cp_async_wait();
+    WSYNC();
+}
+#endif
+
 HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part, int phase)
 {
     const int sy = fp->stride[0], sc = fp->stride[1];
@@ -141,7 +191,13 @@ HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int 
         const int alpha = fp->df_alpha[0], beta = fp->df_beta[0];
         int tc0[4];
         for (int k = 0; k < 4; k++) tc0[k] = fp->df_tc0[0][k];
+#if H264_DEVICE
+        /* the 4 rows above are only needed by the horizontal edges: their loads fly while the vertical edges are filtered */
+        uint32_t above = 0;
+        { const int i = LANE_ID; if (i < 20) { int r = i / 5, c = i - r * 5; above = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); } }
+#else
         FOR_LANES(i, 20) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = *(const uint32_t *)(py + (r - 4) * sy + c * 4 - 4); }
+#endif
         WSYNC();
         FOR_LANES(ln, 16)      /* vertical edges: lane owns one row */
         {
@@ -154,6 +210,9 @@ HD void deblock_mb(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int 
 #pragma unroll
             for (int k = 0; k < 5; k++) row[k] = pack4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
+#if H264_DEVICE
+        { const int i = LANE_ID; if (i < 20) { int r = i / 5, c = i - r * 5; t->y[r * 6 + c] = above; } }
+#endif
         WSYNC();
         FOR_LANES(ln, 16)      /* horizontal edges: lane owns one column */
         {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(32) k_replay(const FrameParams *fps, int njobs
 __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int njobs, int *tickets)
 {
     __shared__ int s_item;
-    __shared__ DeblockTile tile;
+    __shared__ DeblockTile tile[2];
     if (threadIdx.x == 0) s_item = atomicAdd(&tickets[1], 1);
     __syncwarp();
     int item = s_item;
@@ -419,11 +419,15 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     if (row >= fp->nmby || fp->disable_deblock || fp->fsync[FS_STATE] != FS_DONE) return;
     const int nmbx = fp->nmbx;
     int *progress = part ? fp->row_progress_dfc : fp->row_progress_df;
+    /* software pipeline over the macroblocks of the row: tile[x & 1] is filtered while tile[(x + 1) & 1] fills */
+    deblock_mb(fp, &tile[0], 0, row, part, 0);
     for (int x = 0; x < nmbx; x++)
     {
-        deblock_mb(fp, &tile, x, row, part, 0);
+        DeblockTile *cur = &tile[x & 1], *nxt = &tile[(x + 1) & 1];
+        if (x + 1 < nmbx) deblock_prefetch(fp, nxt, x + 1, row, part);
         if (row > 0) wait_row(progress + (row - 1) * PROG_STRIDE, min(x + 2, nmbx));
-        deblock_mb(fp, &tile, x, row, part, 1);
+        deblock_mb(fp, cur, x, row, part, 1);
+        if (x + 1 < nmbx) deblock_handover(cur, nxt, part);
         publish_row(progress + row * PROG_STRIDE, x + 1);
     }
 }
