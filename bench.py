@@ -223,6 +223,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = load_binding()
     lib = B.Library()

@@ -142,6 +142,19 @@ __device__ void trajectory_follower(const FrameParams *fp)
             mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
         }
         int t0 = 0, t1 = 0;
+        if (avail == 32)
+        {   /* full chunk: unrolled, the broadcasts of the next records run ahead of the recurrence */
+#pragma unroll 8
+            for (int i = 0; i < 32; i++)
+            {
+                int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+                int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
+                int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
+                if (lane == i) { t0 = r0; t1 = r1; }
+                if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+                if (f & SPEC_UPDATES) clusters_update(c, m);
+            }
+        } else
         for (int i = 0; i < avail; i++)
         {
             int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
@@ -203,6 +216,19 @@ __device__ void repair_follower(const FrameParams *fp, int pass)
             mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
         }
         int t0 = 0, t1 = 0;
+        if (avail == 32)
+        {   /* full chunk: unrolled, the broadcasts of the next records run ahead of the recurrence */
+#pragma unroll 8
+            for (int i = 0; i < 32; i++)
+            {
+                int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
+                int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
+                int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
+                if (lane == i) { t0 = r0; t1 = r1; }
+                if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+                if (f & SPEC_UPDATES) clusters_update(c, m);
+            }
+        } else
         for (int i = 0; i < avail; i++)
         {
             int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
