@@ -8,8 +8,7 @@
  * following argument (T:212); -r sets the INPUT name (T:215); --maxframes only
  * distinguishes zero from non-zero (T:576); --recon and --threads are accepted and
  * ignored; --gen encodes 301 frames of 1024x768 rotating chessboard (T:435-452,
- * T:578-582).  Differences: --denoise is rejected (temporal denoise is not part of the
- * B200 hot path), and --segments N (extension) encodes N closed-GOP segments of the
+ * T:578-582); --denoise sets temporal_denoise_flag (T:525).  Difference: --segments N (extension) encodes N closed-GOP segments of the
  * input concurrently, one fresh encoder session per segment, and concatenates them --
  * the GOP-sharded mode of DESIGN.md; its output equals the reference run once per
  * segment.
@@ -268,7 +267,6 @@ int main(int argc, char **argv)
     struct timespec t0, t1;
 
     if (!parse_args(argc, argv)) return 1;
-    if (opt.denoise) { printf("ERROR: --denoise is not supported by the B200 encoder\n"); return 1; }
     if (!opt.gen)
     {
         guess_size(opt.input_file, &w, &h);
@@ -285,6 +283,7 @@ int main(int argc, char **argv)
     cp.width = w;
     cp.height = h;
     cp.const_input_flag = opt.psnr ? 0 : 1;
+    cp.temporal_denoise_flag = opt.denoise;       /* T:525 */
     cp.vbv_size_bytes = 100000 / 8;
 
     if (opt.segments > 1 && fin)

@@ -454,6 +454,11 @@ struct FrameParams
     int *prof;                  /* developer builds: per-MB phase cycle counts [nmb][10]    */
     int max_passes;             /* safety bound on verification sweeps                      */
     int spec_from_prev;         /* 1: speculate with the previous P frame's replayed trajectory */
+    /* temporal noise suppressor (h264_denoise.h); dn_out[0] == NULL: not used for this frame */
+    const pix_t *dn_src[3];     /* picture as submitted                                       */
+    const pix_t *dn_prev[3];    /* previous output of the filter                              */
+    pix_t *dn_out[3];           /* new output = inp[] of the macroblock path                  */
+    int dn_src_stride[3], dn_stride[3];
 };
 
 /* shared-memory search window of one macroblock (luma): WIN_W x WIN_H samples */

@@ -33,6 +33,7 @@
 #include "h264_wave.h"
 #include "h264_cavlc.h"
 #include "h264_deblock.h"
+#include "h264_denoise.h"
 #include "../../include/h264b200_shim.h"
 
 #ifndef ENC_MIN_BLOCKS
@@ -470,6 +471,26 @@ __global__ void k_borders(const FrameParams *fps, int njobs)
     }
 }
 
+/* temporal noise suppressor (h264_denoise.h): thread = 4 samples of one plane; blockIdx.y = job.  Jobs that do not
+ * ask for it have dn_out == NULL. */
+__global__ void __launch_bounds__(256) k_denoise(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    if (!fp->dn_out[0]) return;
+    for (int pl = 0; pl < 3; pl++)
+    {
+        const int w = pl ? fp->width >> 1 : fp->width, h = pl ? fp->height >> 1 : fp->height;
+        if (w <= 2 || h <= 2) continue;
+        const int wpr = (w + 3) >> 2;
+        const long n = (long)wpr * h;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        {
+            const int y = (int)(i / wpr), x0 = (int)(i - (long)y * wpr) * 4;
+            denoise_word(fp->dn_src[pl], fp->dn_src_stride[pl], fp->dn_prev[pl], fp->dn_out[pl], fp->dn_stride[pl], w, h, x0, y);
+        }
+    }
+}
+
 /* half-sample planes of the new reference picture (after deblocking and border extension) */
 __global__ void __launch_bounds__(256) k_hpel(const FrameParams *fps, int njobs)
 {
@@ -551,6 +572,7 @@ struct h264b200_ctx
     size_t plane_off[3];
     pix_t *d_inp[3];
     pix_t *d_clip; int clip_frames;
+    pix_t *d_dn[2]; int dn_cur;   /* temporal noise suppressor: previous / new filtered picture (layout of d_inp), allocated on first use */
     int cur;
     MBInfo *d_mbi;
     int16_t *d_coef;
@@ -711,6 +733,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     cudaFree(c->d_hpel);
     cudaFree(c->d_inp[0]);
     if (c->d_clip) cudaFree(c->d_clip);
+    for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
     cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_cl_ckpt); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
@@ -724,6 +747,9 @@ extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
     cudaMemset(c->d_clusters, 0, 16);
     c->cur = 0;
     c->have_traj = 0;
+    /* the noise suppressor starts from an all-zero "previous picture" (H:6345-6349) */
+    for (int i = 0; i < 2; i++) if (c->d_dn[i]) { cudaFree(c->d_dn[i]); c->d_dn[i] = NULL; }
+    c->dn_cur = 0;
 }
 
 static void build_fp(const h264b200_job *job, FrameParams *fp)
@@ -752,6 +778,16 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
             fp->inp[i] = i == 0 ? b : (i == 1 ? b + ys : b + ys + ys / 4);
             fp->inp_stride[i] = i ? c->width / 2 : c->width;
         } else { fp->inp[i] = c->d_inp[i]; fp->inp_stride[i] = c->inp_stride[i]; }
+        if (p.denoise && c->d_dn[0])
+        {   /* the macroblock path reads the filtered picture (H:6692-6693); the filter reads what was the input */
+            const size_t s0 = (size_t)c->inp_stride[0] * c->height, s1 = (size_t)c->inp_stride[1] * (c->height / 2);
+            const size_t off = i == 0 ? 0 : (i == 1 ? s0 : s0 + s1);
+            fp->dn_src[i] = fp->inp[i]; fp->dn_src_stride[i] = fp->inp_stride[i];
+            fp->dn_prev[i] = c->d_dn[c->dn_cur] + off;
+            fp->dn_out[i] = c->d_dn[c->dn_cur ^ 1] + off;
+            fp->dn_stride[i] = c->inp_stride[i];
+            fp->inp[i] = fp->dn_out[i]; fp->inp_stride[i] = c->inp_stride[i];
+        }
         fp->dec[i] = c->d_frames[c->cur] + c->plane_off[i];
         fp->ref[i] = c->d_frames[c->cur ^ 1] + c->plane_off[i];
     }
@@ -829,11 +865,22 @@ static int encode_impl(int n, h264b200_job *jobs)
     std::lock_guard<std::mutex> guard(lane_get()->lock);
     if (ensure_globals(2 * n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
     cudaStream_t st = g_stream;
-    int max_rows = 0, max_nmb = 0, cap = 0x7fffffff;
+    int max_rows = 0, max_nmb = 0, cap = 0x7fffffff, any_denoise = 0;
     for (int i = 0; i < n; i++)
     {
         h264b200_ctx *c = jobs[i].ctx;
         jobs[i].status = 0;
+        if (jobs[i].p.denoise)
+        {
+            any_denoise = 1;
+            for (int k = 0; k < 2; k++)
+                if (!c->d_dn[k])
+                {
+                    const size_t sz = (size_t)c->inp_stride[0] * c->height + 2 * (size_t)c->inp_stride[1] * (c->height / 2) + 256;
+                    CK(cudaMalloc(&c->d_dn[k], sz));
+                    CK(cudaMemset(c->d_dn[k], 0, sz));
+                }
+        }
         build_fp(&jobs[i], &g_h_fps[i]);
         max_rows = c->nmby > max_rows ? c->nmby : max_rows;
         max_nmb = c->nmb > max_nmb ? c->nmb : max_nmb;
@@ -873,6 +920,7 @@ static int encode_impl(int n, h264b200_job *jobs)
         CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
         CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
     }
+    if (any_denoise) { k_denoise<<<dim3(296, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
@@ -963,6 +1011,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     CK(cudaEventRecord(g_ev[5], st));
     CK(cudaStreamSynchronize(st));
     for (int i = 0; i < n; i++) if (jobs[i].update_ref && jobs[i].status == 0) jobs[i].ctx->cur ^= 1;
+    for (int i = 0; i < n; i++) if (jobs[i].p.denoise && jobs[i].ctx->d_dn[0]) jobs[i].ctx->dn_cur ^= 1;
     cudaEventElapsedTime(&g_last_ms[0], g_ev[0], g_ev[5]);
     cudaEventElapsedTime(&g_last_ms[1], g_ev[1], g_ev[2]);
     cudaEventElapsedTime(&g_last_ms[2], g_ev[2], g_ev[3]);

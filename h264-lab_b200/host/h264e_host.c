@@ -456,7 +456,7 @@ int H264E_sizeof(const H264E_create_param_t *par, int *sizeof_persist, int *size
 
 static int unsupported_create(const H264E_create_param_t *p)
 {
-    return p->fine_rate_control_flag || p->max_long_term_reference_frames || p->temporal_denoise_flag ||
+    return p->fine_rate_control_flag || p->max_long_term_reference_frames ||
            p->num_layers > 1 || p->vbv_overflow_empty_frame_flag;
 }
 
@@ -563,6 +563,7 @@ static void fill_frame_params(h264e_host_t *e, h264b200_frame_params *p, int sli
     }
     build_qdat(p->qdat, e->rc.qp, slice_type);
     p->hdr_bits = hdr_bits;
+    p->denoise = e->param.temporal_denoise_flag && e->run.encode_speed < 2;      /* H:6686 */
 }
 
 /* everything H264E_encode does before the macroblock loop (H:6654-6811, H:6477-6486) */

@@ -64,7 +64,7 @@ typedef struct H264E_create_param_tag
     int const_input_flag;                 /* 0: input planes are overwritten with the reconstruction */
     int max_long_term_reference_frames;   /* must be 0                                             */
     int enableNEON;                       /* ignored                                               */
-    int temporal_denoise_flag;            /* must be 0                                             */
+    int temporal_denoise_flag;            /* 1: temporal noise suppression of the input (H:122-125); applied when encode_speed < 2 */
     int sps_id;
     int num_layers;                       /* 1 (0 is accepted as 1); SVC is not supported          */
     int inter_layer_pred_flag;

@@ -34,6 +34,8 @@ typedef struct
     int df_alpha[2], df_beta[2], df_tc0[2][4];
     unsigned short qdat[2][42];   /* quantiser tables of rc_set_qp  (H:5839-5912)        */
     int hdr_bits;            /* bit position inside the NAL at which slice_data() starts */
+    int denoise;             /* 1: run the temporal noise suppressor on the input first and encode its output
+                                (temporal_denoise_flag && encode_speed < 2, H:6686; h264e_denoise_run H:1547) */
 } h264b200_frame_params;
 
 /* One frame of one encoder instance. */

@@ -614,3 +614,34 @@ void orc_extend_borders(uint8_t *pic, int w, int h, int guard)
         memcpy(pic - guard + (h + y) * stride, pic - guard + (h - 1) * stride, (size_t)stride);
     }
 }
+
+/* ---------------- temporal noise suppressor (h264e_denoise_run H:1547-1620) -------- */
+#include "../h264-lab_b200/csrc/h264_denoise_tab.h"       /* 255 - gain(d), 255 - min(4 gain(d), 255): data only (H:1122) */
+/* In place like the reference: `prev` (the previous output, w x h at prev_stride) becomes the new output.
+ * The reference parks every output row one row up while it works and shifts the rows back afterwards
+ * (H:1561-1619); with a scratch copy of the old picture that is simply: border samples = current picture,
+ * inner samples blended by the weight of the sample's own and its 4-neighbourhood's temporal difference. */
+void orc_denoise_run(const uint8_t *cur, uint8_t *prev, int w, int h, int cur_stride, int prev_stride)
+{
+    int x, y;
+    uint8_t *old;
+    if (w <= 2 || h <= 2) return;                                         /* H:1550 */
+    old = (uint8_t *)malloc((size_t)w * h);
+    for (y = 0; y < h; y++) memcpy(old + (size_t)y * w, prev + (size_t)y * prev_stride, (size_t)w);
+    for (y = 0; y < h; y++)
+        for (x = 0; x < w; x++)
+        {
+            const uint8_t *c = cur + (size_t)y * cur_stride + x;
+            const uint8_t *p = old + (size_t)y * w + x;
+            int v = c[0];
+            if (x > 0 && y > 0 && x < w - 1 && y < h - 1)
+            {
+                int d = iabs_(c[0] - p[0]);                                                         /* H:1572, 1578 */
+                int nb = iabs_((c[-1] - p[-1]) + (c[1] - p[1]) + (c[-cur_stride] - p[-w]) + (c[cur_stride] - p[w])) >> 2;   /* H:1573-1582 */
+                unsigned g = (unsigned)denoise_weight[d][0] * (unsigned)denoise_weight[nb][1];       /* H:1584-1594 */
+                v = (int)(((unsigned)p[0] * g + (0xffffu - g) * (unsigned)c[0] + (1u << 15)) >> 16); /* H:1598 */
+            }
+            prev[(size_t)y * prev_stride + x] = (uint8_t)v;
+        }
+    free(old);
+}

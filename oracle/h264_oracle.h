@@ -25,6 +25,7 @@ void orc_deblock_luma(uint8_t *pix, int stride, const uint8_t *strength, const u
 void orc_deblock_chroma(uint8_t *pix, int stride, const uint8_t *strength, const uint8_t *tc0,
                         const uint8_t *alpha, const uint8_t *beta);
 void orc_extend_borders(uint8_t *pic, int w, int h, int guard);
+void orc_denoise_run(const uint8_t *cur, uint8_t *prev, int w, int h, int cur_stride, int prev_stride);
 #ifdef __cplusplus
 }
 #endif

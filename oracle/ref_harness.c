@@ -97,7 +97,31 @@ EXPORT void ref_get_state(void *venc, int *out /* [8] */)
  *  returns total bytes or -(error code)
  *  *seconds   : wall time of the H264E_encode loop only (CLOCK_MONOTONIC)
  */
+static long ref_encode_sequence_impl(int width, int height, int gop, int qp, int kbps, int speed, int flags,
+                                int nframes, const unsigned char *yuv_in,
+                                unsigned char *out, long out_cap, int *out_sizes,
+                                unsigned char *recon, double *seconds);
 EXPORT long ref_encode_sequence(int width, int height, int gop, int qp, int kbps, int speed,
+                                int nframes, const unsigned char *yuv_in,
+                                unsigned char *out, long out_cap, int *out_sizes,
+                                unsigned char *recon, double *seconds)
+{
+    return ref_encode_sequence_impl(width, height, gop, qp, kbps, speed, 0, nframes, yuv_in, out, out_cap, out_sizes, recon, seconds);
+}
+/* same with create-time options: flags bit 0 = temporal_denoise_flag (H:122) */
+EXPORT long ref_encode_sequence_ex(int width, int height, int gop, int qp, int kbps, int speed, int flags,
+                                   int nframes, const unsigned char *yuv_in,
+                                   unsigned char *out, long out_cap, int *out_sizes,
+                                   unsigned char *recon, double *seconds)
+{
+    return ref_encode_sequence_impl(width, height, gop, qp, kbps, speed, flags, nframes, yuv_in, out, out_cap, out_sizes, recon, seconds);
+}
+/* the reference's temporal noise suppressor on caller buffers (known-answer tests) */
+EXPORT void ref_denoise_run(unsigned char *frm, unsigned char *frmprev, int w, int h, int stride_frm, int stride_frmprev)
+{
+    h264e_denoise_run(frm, frmprev, w, h, stride_frm, stride_frmprev);
+}
+static long ref_encode_sequence_impl(int width, int height, int gop, int qp, int kbps, int speed, int flags,
                                 int nframes, const unsigned char *yuv_in,
                                 unsigned char *out, long out_cap, int *out_sizes,
                                 unsigned char *recon, double *seconds)
@@ -122,6 +146,7 @@ EXPORT long ref_encode_sequence(int width, int height, int gop, int qp, int kbps
     cp.height = height;
     cp.const_input_flag = 1;
     cp.vbv_size_bytes = 100000 / 8;
+    cp.temporal_denoise_flag = flags & 1;
     err = H264E_sizeof(&cp, &sp, &ss);
     if (err) return -err;
     enc = aligned_alloc(64, ((size_t)sp + 63) & ~(size_t)63);

@@ -20,6 +20,7 @@ extern "C" int *emu_dbg(void) { return g_emu_dbg; }
 #include "../../h264-lab_b200/csrc/h264_wave.h"
 #include "../../h264-lab_b200/csrc/h264_cavlc.h"
 #include "../../h264-lab_b200/csrc/h264_deblock.h"
+#include "../../h264-lab_b200/csrc/h264_denoise.h"
 #include "../../include/h264b200_shim.h"
 
 struct h264b200_ctx
@@ -37,6 +38,7 @@ struct h264b200_ctx
     std::vector<int> mb_nbits;
     std::vector<uint32_t> out_words;
     std::vector<pix_t> clip;
+    std::vector<pix_t> dn[2]; int dn_cur;   /* temporal noise suppressor: previous / new filtered picture */
     std::vector<MBSpec> spec;
     std::vector<int32_t> cl_true, cl_ckpt;
     std::vector<int> changed_pass, need_reenc;
@@ -78,7 +80,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     return 0;
 }
 extern "C" void h264b200_ctx_destroy(h264b200_ctx *c) { delete c; }
-extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->have_traj = 0; }
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->have_traj = 0; c->dn[0].clear(); c->dn[1].clear(); c->dn_cur = 0; }
 
 static void run_job(h264b200_job *job)
 {
@@ -107,6 +109,18 @@ static void run_job(h264b200_job *job)
             fp.inp[i] = i == 0 ? b : (i == 1 ? b + ys : b + ys + ys / 4);
             fp.inp_stride[i] = i ? c->width / 2 : c->width;
         } else { fp.inp[i] = job->yuv[i]; fp.inp_stride[i] = job->stride[i]; }
+        if (p.denoise)
+        {   /* filter the submitted picture, encode the filter's output (same flow as shim_cuda.cu) */
+            const int w = i ? c->width >> 1 : c->width, h = i ? c->height >> 1 : c->height;
+            const size_t s0 = (size_t)c->width * c->height, s1 = s0 / 4, off = i == 0 ? 0 : (i == 1 ? s0 : s0 + s1);
+            for (int k = 0; k < 2; k++) if (c->dn[k].empty()) c->dn[k].assign(s0 + 2 * s1 + 16, 0);
+            const pix_t *prev = c->dn[c->dn_cur].data() + off;
+            pix_t *out = c->dn[c->dn_cur ^ 1].data() + off;
+            if (w > 2 && h > 2)
+                for (int y = 0; y < h; y++)
+                    for (int x0 = 0; x0 < w; x0 += 4) denoise_word(fp.inp[i], fp.inp_stride[i], prev, out, w, w, h, x0, y);
+            fp.inp[i] = out; fp.inp_stride[i] = w;
+        }
         fp.dec[i] = c->frame[c->cur].data() + c->plane_off[i];
         fp.ref[i] = c->frame[c->cur ^ 1].data() + c->plane_off[i];
     }
@@ -197,6 +211,7 @@ static void run_job(h264b200_job *job)
             for (int r = 0; r < hh; r++) memcpy(job->recon[pl] + (size_t)r * job->recon_stride[pl], fp.dec[pl] + (size_t)r * fp.stride[pl != 0], ww);
         }
     if (job->update_ref) c->cur ^= 1;
+    if (p.denoise) c->dn_cur ^= 1;
     job->status = 0;
 }
 

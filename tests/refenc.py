@@ -52,11 +52,15 @@ def lib(variant=""):
         l.ref_encode_sequence.restype = C.c_long
         l.ref_encode_sequence.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
                                                          C.c_void_p, C.POINTER(C.c_double)]
+        if hasattr(l, "ref_encode_sequence_ex"):
+            l.ref_encode_sequence_ex.restype = C.c_long
+            l.ref_encode_sequence_ex.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
+                                                                C.c_void_p, C.POINTER(C.c_double)]
         _libs[variant] = l
     return _libs[variant]
 
 
-def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, variant=""):
+def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, variant="", denoise=0):
     """frames: uint8 [n, w*h*3/2].  Returns (bitstream bytes, sizes[n], recon [n, W16*H16*3/2] or None, seconds)."""
     l = lib(variant)
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
@@ -67,8 +71,12 @@ def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_rec
     sizes = np.zeros(n, dtype=np.int32)
     recon = np.zeros((n, w16 * h16 * 3 // 2), dtype=np.uint8) if want_recon else None
     secs = C.c_double(0)
-    tot = l.ref_encode_sequence(width, height, gop, qp, kbps, speed, n, frames.ctypes.data, out.ctypes.data, cap,
-                                sizes.ctypes.data, recon.ctypes.data if want_recon else None, C.byref(secs))
+    if denoise:
+        tot = l.ref_encode_sequence_ex(width, height, gop, qp, kbps, speed, 1, n, frames.ctypes.data, out.ctypes.data, cap,
+                                       sizes.ctypes.data, recon.ctypes.data if want_recon else None, C.byref(secs))
+    else:
+        tot = l.ref_encode_sequence(width, height, gop, qp, kbps, speed, n, frames.ctypes.data, out.ctypes.data, cap,
+                                    sizes.ctypes.data, recon.ctypes.data if want_recon else None, C.byref(secs))
     if tot < 0:
         raise RuntimeError("reference encoder error %d" % -tot)
     return out[:tot].tobytes(), sizes, recon, secs.value

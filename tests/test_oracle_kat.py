@@ -260,3 +260,27 @@ def test_borders(orc, rl):
         orc.orc_extend_borders(C.c_void_p(a.ctypes.data + off), w, h, g)
         rl.ref_copy_borders(C.c_void_p(b.ctypes.data + off), w, h, g)
         assert np.array_equal(a, b)
+
+
+def test_denoise(orc, rl):
+    """Temporal noise suppressor (h264e_denoise_run H:1547): the restatement against the reference on
+    random, static, saturated and tiny pictures, over several pictures in a row (the filter is recursive)."""
+    if not hasattr(rl, "ref_denoise_run"):
+        pytest.skip("oracle/_ref predates ref_denoise_run")
+    rng = np.random.default_rng(11)
+    for (w, h, cs, ps) in ((64, 48, 64, 96), (183, 125, 183, 200), (5, 3, 8, 8), (3, 7, 3, 5), (2, 9, 2, 2), (16, 2, 16, 16)):
+        p1 = np.zeros(h * ps + 16, np.uint8)
+        p2 = p1.copy()
+        base = rng.integers(0, 256, size=h * cs, dtype=np.uint8)
+        for it in range(5):
+            if it == 3:
+                cur = np.full(h * cs, 255, np.uint8)
+            elif it == 4:
+                cur = np.zeros(h * cs, np.uint8)
+            else:
+                cur = np.clip(base.astype(np.int32) + rng.integers(-6, 7, size=h * cs), 0, 255).astype(np.uint8)
+            c2 = cur.copy()
+            orc.orc_denoise_run(P(cur), P(p1), w, h, cs, ps)
+            rl.ref_denoise_run(P(c2), P(p2), w, h, cs, ps)
+            assert np.array_equal(p1, p2), (w, h, it)
+            assert np.array_equal(cur, c2)
