@@ -135,10 +135,18 @@ class Encoder:
             pass
 
 
-def encode_sequence(library, frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, denoise=0):
+def encode_sequence(library, frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, denoise=0,
+                    empty_frames=0, stuffing=0):
     """Mirror of tests/refenc.encode_sequence on the B200 library: one session, frame by frame."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
-    enc = Encoder(library, width, height, gop, temporal_denoise_flag=1) if denoise else Encoder(library, width, height, gop)
+    extra = {}
+    if denoise:
+        extra["temporal_denoise_flag"] = 1
+    if empty_frames:
+        extra["vbv_overflow_empty_frame_flag"] = 1
+    if stuffing:
+        extra["vbv_underflow_stuffing_flag"] = 1
+    enc = Encoder(library, width, height, gop, **extra)
     rp = enc.run_param(qp=qp, kbps=kbps, speed=speed)
     out, sizes, recon = [], [], []
     for i in range(frames.shape[0]):

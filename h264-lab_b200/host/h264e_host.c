@@ -456,8 +456,7 @@ int H264E_sizeof(const H264E_create_param_t *par, int *sizeof_persist, int *size
 
 static int unsupported_create(const H264E_create_param_t *p)
 {
-    return p->fine_rate_control_flag || p->max_long_term_reference_frames ||
-           p->num_layers > 1 || p->vbv_overflow_empty_frame_flag;
+    return p->fine_rate_control_flag || p->max_long_term_reference_frames || p->num_layers > 1;
 }
 
 int H264E_init(H264E_persist_t *penc, const H264E_create_param_t *opt)
@@ -539,6 +538,8 @@ typedef struct
     int slice_type, is_key;
     hbits_t hdr;
     int status;
+    int transparent;     /* VBV overflow: the frame is coded as one run of skipped macroblocks, no device work (H:6497-6508) */
+    H264E_io_yuv_t inplace;   /* caller planes that receive the reconstruction when const_input_flag == 0 */
 } frame_plan_t;
 
 static void fill_frame_params(h264e_host_t *e, h264b200_frame_params *p, int slice_type, int hdr_bits)
@@ -625,6 +626,17 @@ static int plan_frame(h264e_host_t *e, H264E_scratch_t *scratch, const H264E_run
     rc_frame_start(e, pl->long_term_idx_use < 0);
     write_slice_header(e, &pl->hdr, pl->slice_type, pl->is_key, pl->long_term_idx_update);
 
+    /* VBV overflow: a "transparent" frame -- slice header, one mb_skip_run covering the picture, and the
+     * reconstruction is the reference picture as it is (H:6497-6508).  Never an I / KEY frame
+     * (long_term_idx_use is -1 for those), never a frame that updates a long-term buffer. */
+    if (e->param.vbv_size_bytes && !pl->long_term_idx_use && pl->long_term_idx_update <= 0 &&
+        e->rc.vbv_bits - e->run.desired_frame_bytes * 8 > e->param.vbv_size_bytes * 8)
+    {
+        pl->transparent = 1;
+        memset(&pl->inplace, 0, sizeof(pl->inplace));
+        if (!e->param.const_input_flag && in->yuv[0]) pl->inplace = *in;
+        return H264E_STATUS_SUCCESS;
+    }
     memset(job, 0, sizeof(*job));
     job->ctx = e->ctx;
     fill_frame_params(e, &job->p, pl->slice_type, hb_bits(&pl->hdr));
@@ -646,7 +658,33 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
     int nbits, nbytes, i, filler;
     uint8_t *d, *nal;
     int zeros = 0, j = 0;
-    const uint32_t *words = job->out_words;
+    const uint32_t *words;
+    if (pl->transparent)
+    {
+        hb_ue(&pl->hdr, (uint32_t)e->nmb);
+        hb_trailing(&pl->hdr);
+        if ((int)e->out_pos + 4 + 2 * pl->hdr.nbytes + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+        emit_nal(e, pl->hdr.buf, pl->hdr.nbytes);
+        if (pl->inplace.yuv[0])
+        {   /* in-place mode: the caller's frame receives the reconstruction = the unchanged reference picture */
+            unsigned char *planes[3];
+            int strides[3], w16 = e->w16, h16 = e->h16, c, r;
+            unsigned char *tmp = (unsigned char *)malloc((size_t)w16 * h16 * 3 / 2);
+            if (!tmp) return H264E_STATUS_DEVICE_ERROR;
+            planes[0] = tmp; planes[1] = tmp + (size_t)w16 * h16; planes[2] = planes[1] + (size_t)w16 * h16 / 4;
+            strides[0] = w16; strides[1] = strides[2] = w16 / 2;
+            if (h264b200_get_recon(e->ctx, planes, strides)) { free(tmp); return H264E_STATUS_DEVICE_ERROR; }
+            for (c = 0; c < 3; c++)
+            {
+                int cw = c ? e->param.width / 2 : e->param.width, ch = c ? e->param.height / 2 : e->param.height;
+                for (r = 0; r < ch; r++) memcpy(pl->inplace.yuv[c] + (size_t)r * pl->inplace.stride[c], planes[c] + (size_t)r * strides[c], (size_t)cw);
+            }
+            free(tmp);
+        }
+        filler = rc_frame_end(e, 0, 1);
+        goto after_rc;
+    }
+    words = job->out_words;
     if (job->status) return job->status == -1 ? H264E_STATUS_NO_DEVICE : H264E_STATUS_DEVICE_ERROR;
 
     /* the device left hdr_bits of room at the front of the payload: merge the header,
@@ -691,6 +729,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
     e->out_pos += 4 + j;
 
     filler = rc_frame_end(e, pl->long_term_idx_use == -1, job->trailing_skip_run == e->nmb);
+after_rc:
     if (filler)
     {   /* filler_data NAL (H:6113-6122) */
         uint8_t *f = (uint8_t *)malloc((size_t)filler + 2);
@@ -727,14 +766,14 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
         plans[i].status = plan_frame((h264e_host_t *)enc[i], scratch[i], run_param ? run_param[i] : NULL, frame[i],
                                      &plans[i], &jobs[njobs]);
         if (plans[i].status) { if (!err) err = plans[i].status; }
-        else njobs++;
+        else if (!plans[i].transparent) njobs++;
     }
     if (njobs) h264b200_encode_frames(njobs, jobs);
     njobs = 0;
     for (i = 0; i < n; i++)
     {
         if (plans[i].status) { coded_data[i] = NULL; sizeof_coded_data[i] = 0; continue; }
-        plans[i].status = finish_frame(&plans[i], &jobs[njobs++]);
+        plans[i].status = plans[i].transparent ? finish_frame(&plans[i], NULL) : finish_frame(&plans[i], &jobs[njobs++]);
         if (plans[i].status && !err) err = plans[i].status;
         coded_data[i] = plans[i].e->out;
         sizeof_coded_data[i] = (int)plans[i].e->out_pos;
@@ -753,7 +792,7 @@ int H264E_encode(H264E_persist_t *enc, H264E_scratch_t *scratch, const H264E_run
     if (!coded_data || !sizeof_coded_data) return H264E_STATUS_BAD_ARGUMENT;
     err = plan_frame((h264e_host_t *)enc, scratch, opt, in, &plan, &job);
     if (err) return err;
-    h264b200_encode_frames(1, &job);
+    if (!plan.transparent) h264b200_encode_frames(1, &job);
     err = finish_frame(&plan, &job);
     if (err) return err;
     *sizeof_coded_data = (int)plan.e->out_pos;

@@ -108,7 +108,8 @@ EXPORT long ref_encode_sequence(int width, int height, int gop, int qp, int kbps
 {
     return ref_encode_sequence_impl(width, height, gop, qp, kbps, speed, 0, nframes, yuv_in, out, out_cap, out_sizes, recon, seconds);
 }
-/* same with create-time options: flags bit 0 = temporal_denoise_flag (H:122) */
+/* same with create-time options: flags bit 0 = temporal_denoise_flag (H:122), bit 1 = vbv_overflow_empty_frame_flag
+ * (H:96), bit 2 = vbv_underflow_stuffing_flag (H:101) */
 EXPORT long ref_encode_sequence_ex(int width, int height, int gop, int qp, int kbps, int speed, int flags,
                                    int nframes, const unsigned char *yuv_in,
                                    unsigned char *out, long out_cap, int *out_sizes,
@@ -147,6 +148,8 @@ static long ref_encode_sequence_impl(int width, int height, int gop, int qp, int
     cp.const_input_flag = 1;
     cp.vbv_size_bytes = 100000 / 8;
     cp.temporal_denoise_flag = flags & 1;
+    cp.vbv_overflow_empty_frame_flag = (flags >> 1) & 1;
+    cp.vbv_underflow_stuffing_flag = (flags >> 2) & 1;
     err = H264E_sizeof(&cp, &sp, &ss);
     if (err) return -err;
     enc = aligned_alloc(64, ((size_t)sp + 63) & ~(size_t)63);

@@ -60,7 +60,8 @@ def lib(variant=""):
     return _libs[variant]
 
 
-def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, variant="", denoise=0):
+def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_recon=True, variant="", denoise=0,
+                    empty_frames=0, stuffing=0):
     """frames: uint8 [n, w*h*3/2].  Returns (bitstream bytes, sizes[n], recon [n, W16*H16*3/2] or None, seconds)."""
     l = lib(variant)
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
@@ -71,8 +72,9 @@ def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_rec
     sizes = np.zeros(n, dtype=np.int32)
     recon = np.zeros((n, w16 * h16 * 3 // 2), dtype=np.uint8) if want_recon else None
     secs = C.c_double(0)
-    if denoise:
-        tot = l.ref_encode_sequence_ex(width, height, gop, qp, kbps, speed, 1, n, frames.ctypes.data, out.ctypes.data, cap,
+    flags = (1 if denoise else 0) | (2 if empty_frames else 0) | (4 if stuffing else 0)
+    if flags:
+        tot = l.ref_encode_sequence_ex(width, height, gop, qp, kbps, speed, flags, n, frames.ctypes.data, out.ctypes.data, cap,
                                        sizes.ctypes.data, recon.ctypes.data if want_recon else None, C.byref(secs))
     else:
         tot = l.ref_encode_sequence(width, height, gop, qp, kbps, speed, n, frames.ctypes.data, out.ctypes.data, cap,

@@ -17,3 +17,30 @@ def test_emu_matches_reference(case, binding, emu_lib, ref):
     assert list(sizes) == list(rsizes)
     assert bs == rbs
     assert np.array_equal(rec, rrec)
+
+
+def test_emu_in_place_transparent_frames(binding, emu_lib, ref):
+    """Host logic of the VBV-overflow transparent frames (H:6497-6508) incl. in-place reconstruction and the batch entry."""
+    import numpy as np
+    w, h, n = 352, 288, 6
+    frames = cases.make("noise", w, h, n)
+    rbs, rsizes, rrec, _ = ref.encode_sequence(frames, w, h, n, kbps=2500, empty_frames=1)
+    assert list(rsizes[1:4]) == [10, 10, 10]
+    enc = binding.Encoder(emu_lib, w, h, n, const_input=0, vbv_overflow_empty_frame_flag=1)
+    rp = enc.run_param(kbps=2500)
+    out = b""
+    for i in range(n):
+        f = frames[i].copy()
+        out += enc.encode(f, rp)
+        assert np.array_equal(f, rrec[i]), i
+    enc.close()
+    assert out == rbs
+    encs = [binding.Encoder(emu_lib, w, h, n, vbv_overflow_empty_frame_flag=1) for _ in range(2)]
+    rps = [e.run_param(kbps=2500) for e in encs]
+    outs = [b"", b""]
+    for i in range(n):
+        res = binding.encode_batch(emu_lib, encs, [frames[i].copy(), frames[i].copy()], rps)
+        outs = [o + r for o, r in zip(outs, res)]
+    assert outs[0] == rbs and outs[1] == rbs
+    for e in encs:
+        e.close()

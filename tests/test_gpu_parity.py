@@ -109,6 +109,33 @@ def test_in_place_recon_and_errors(binding, cuda_lib, ref):
     enc.close()
 
 
+def test_in_place_transparent_frames(binding, cuda_lib, ref):
+    """VBV overflow with vbv_overflow_empty_frame_flag: transparent frames (one skip run, H:6497-6508); in in-place mode
+    the caller's planes receive the unchanged reference picture.  Also through H264E_encode_batch."""
+    w, h, n = 352, 288, 6
+    frames = cases.make("noise", w, h, n)
+    rbs, rsizes, rrec, _ = ref.encode_sequence(frames, w, h, n, kbps=2500, empty_frames=1)
+    assert list(rsizes[1:4]) == [10, 10, 10]          # the case does produce transparent frames
+    enc = binding.Encoder(cuda_lib, w, h, n, const_input=0, vbv_overflow_empty_frame_flag=1)
+    rp = enc.run_param(kbps=2500)
+    out = b""
+    for i in range(n):
+        f = frames[i].copy()
+        out += enc.encode(f, rp)
+        assert np.array_equal(f, rrec[i]), i
+    enc.close()
+    assert out == rbs
+    encs = [binding.Encoder(cuda_lib, w, h, n, vbv_overflow_empty_frame_flag=1) for _ in range(2)]
+    rps = [e.run_param(kbps=2500) for e in encs]
+    outs = [b"", b""]
+    for i in range(n):
+        res = binding.encode_batch(cuda_lib, encs, [frames[i].copy(), frames[i].copy()], rps)
+        outs = [o + r for o, r in zip(outs, res)]
+    assert outs[0] == rbs and outs[1] == rbs
+    for e in encs:
+        e.close()
+
+
 def test_many_independent_streams_in_one_batch(binding, cuda_lib, ref):
     """BASELINE config 5 in small: independent streams (distinct content) batched in one device
     submission per frame; every stream equals its own reference run."""

@@ -8,8 +8,9 @@ B = importlib.util.module_from_spec(spec); spec.loader.exec_module(B)
 L = B.Library()
 L.lib.H264E_b200_ctx.restype = C.c_void_p
 w, h, nseg, nfr = 1920, 1080, int(sys.argv[1]), int(sys.argv[2])
+denoise = len(sys.argv) > 3 and sys.argv[3] == "denoise"      # temporal noise suppressor in front of the encoder
 clips = [content.panning(w, h, nfr, seed=1000 + s) for s in range(nseg)]
-encs = [B.Encoder(L, w, h, 60) for _ in range(nseg)]
+encs = [B.Encoder(L, w, h, 60, temporal_denoise_flag=1) if denoise else B.Encoder(L, w, h, 60) for _ in range(nseg)]
 rps = [e.run_param(qp=28) for e in encs]
 for t in range(nfr):
     fr = [clips[s][t].copy() for s in range(nseg)]
