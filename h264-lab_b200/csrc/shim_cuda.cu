@@ -2,20 +2,31 @@
  * shim_cuda.cu -- sm_100a kernels + the C-ABI shim (include/h264b200_shim.h).
  *
  * One submission encodes one frame for each of n independent encoder instances
- * (closed-GOP segments or streams).  Per submission, on one CUDA stream:
+ * (closed-GOP segments or streams).  Per submission, on the submitting thread's lane
+ * (a CUDA stream pair; see `Lane`):
  *
- *   H2D inputs -> k_encode_rows  : macroblock decisions + transform/quant/recon.
- *                                  Persistent-style wavefront: one warp per macroblock
+ *   H2D inputs [-> k_denoise     : optional temporal noise suppressor in front of the encoder]
+ *              -> k_encode_rows  : sweep 0: macroblock decisions + transform/quant/recon.
+ *                                  Persistent-style wavefront: one CTA of 4 warps per macroblock
  *                                  ROW; rows are claimed from an atomic ticket so that a
  *                                  claimed row's predecessor is always running; a row may
  *                                  process macroblock x when the row above has finished
  *                                  x+2 macroblocks (acquire/release on per-row counters).
- *              -> k_deblock_rows : in-loop filter, same wavefront on its own counters.
+ *                                  The first n tickets follow the mv_clusters trajectory.
+ *              -> k_check1, k_after_check, k_repair_round x3, k_encode_rows (repair wave),
+ *                 k_replay       : the exact-wavefront machinery of h264_wave.h (twice, more
+ *                                  passes only after a host check)
+ *              -> k_deblock_rows : in-loop filter, same wavefront on its own counters, luma and
+ *                                  chroma as independent wavefronts;   || on the lane's second stream:
+ *                 k_cavlc        : one thread per macroblock: syntax + CAVLC bit strings,
+ *                 k_scan         : per frame, exclusive prefix sum of the bit lengths,
+ *                 k_pack         : scatter the strings into the slice payload.
  *              -> k_borders      : guard-band replication of the new reference picture.
- *              -> k_cavlc        : one thread per macroblock: syntax + CAVLC bit strings.
- *              -> k_scan         : per frame, exclusive prefix sum of the bit lengths.
- *              -> k_pack         : scatter the strings into the slice payload.
+ *              -> k_hpel         : its three half-sample planes.
  *   D2H payload.
+ *
+ * Build-time knobs (A/B-tested on B200): ENC_MIN_BLOCKS (CTAs per SM of k_encode_rows,
+ * i.e. its register budget), H264_INL (h264_common.h: which big leaves are inlined), PROG_STRIDE, POLL_NS.
  *
  * The per-macroblock code is in h264_*.h (shared with the test-only host emulation).
  */
