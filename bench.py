@@ -15,7 +15,8 @@ barrier and the max-over-ranks time).
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM;
 `e2e` = frames/s through the public C API with pinned host buffers (H2D of every input,
-D2H of every payload inside the timed region).  `roofline` is for the dominant kernel
+D2H of every payload inside the timed region; the copy of frame t + 1 is started with
+H264E_prefetch before frame t is encoded, so it overlaps the kernels of frame t).  `roofline` is for the dominant kernel
 (k_encode_rows): algorithmic HBM bytes / measured kernel time against the measured HBM
 peak -- the path is latency/ALU bound, not HBM bound, and the fraction says so.
 `cpu_baseline` = the unmodified reference (oracle/_ref) on the host cores, one process per
@@ -258,6 +259,7 @@ def main():
                 assert err == 0
         n = nseg
         yuvs = [B.IoYuv() for _ in range(n)]
+        nxt = [B.IoYuv() for _ in range(n)]
         P = (C.c_void_p * n)(*[e.persist for e in encs])
         S = (C.c_void_p * n)(*[e.scratch for e in encs])
         R = (C.c_void_p * n)(*[C.addressof(r) for r in rps])
@@ -278,6 +280,14 @@ def main():
                     base = clips[i].data_ptr() + (t % nframes) * FRAME_BYTES
                     yuvs[i].yuv[0], yuvs[i].yuv[1], yuvs[i].yuv[2] = base, base + W * H, base + W * H * 5 // 4
                     yuvs[i].stride[0], yuvs[i].stride[1], yuvs[i].stride[2] = W, W // 2, W // 2
+            if not resident and t + 1 < Wm + K:
+                # double buffering through the public API: the copy of frame t + 1 overlaps the encoding of frame t
+                for i in range(n):
+                    base = clips[i].data_ptr() + ((t + 1) % nframes) * FRAME_BYTES
+                    nxt[i].yuv[0], nxt[i].yuv[1], nxt[i].yuv[2] = base, base + W * H, base + W * H * 5 // 4
+                    nxt[i].stride[0], nxt[i].stride[1], nxt[i].stride[2] = W, W // 2, W // 2
+                    err = lib.lib.H264E_prefetch(C.c_void_p(encs[i].persist), C.byref(nxt[i]))
+                    assert err == 0, "H264E_prefetch error %d" % err
             err = lib.lib.H264E_encode_batch(n, P, S, R, Y, D, N)
             assert err == 0, "H264E_encode_batch error %d" % err
             out_bytes += sum(N[i] for i in range(n))
@@ -304,7 +314,10 @@ def main():
     sampler.start()
     dt_res, kern, launches, _ = run(resident=True)
     clocks = sampler.stop()
-    dt_e2e, _, _, out_bytes = run(resident=False)
+    lib.lib.h264b200_prefetch_hits.restype = C.c_long
+    hits0 = lib.lib.h264b200_prefetch_hits()
+    dt_e2e, kern_e2e, _, out_bytes = run(resident=False)
+    prefetch_hits = int(lib.lib.h264b200_prefetch_hits() - hits0)
     dt_res = max_over_ranks(dt_res)
     dt_e2e = max_over_ranks(dt_e2e)
     if rank != 0:
@@ -351,8 +364,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
         "megapixels_per_s": total_frames / dt_res * W * H / 1e6,
         "e2e": {"value": total_frames / dt_e2e, "unit": "frames/s", "h2d_bytes_per_step": nseg * FRAME_BYTES,
-                "d2h_bytes_per_step": int(out_bytes / K), "ms_per_step": dt_e2e / K * 1e3},
-        "gpu_launches": launches,
+                "d2h_bytes_per_step": int(out_bytes / K), "ms_per_step": dt_e2e / K * 1e3,
+                "device_ms_per_step": kern_e2e[0] / K, "k_encode_rows_ms_per_step": kern_e2e[1] / K},
+        "gpu_launches": launches, "e2e_prefetch_hits": prefetch_hits,
         "kernel_ms_per_step": {"device_total": kern[0] / K, "k_encode_rows": kern[1] / K, "k_deblock_rows+k_borders": kern[2] / K,
                                "k_cavlc+k_scan+k_pack": kern[3] / K},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

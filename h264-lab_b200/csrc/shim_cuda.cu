@@ -582,6 +582,13 @@ struct h264b200_ctx
     size_t luma_bytes;
     size_t plane_off[3];
     pix_t *d_inp[3];
+    /* two input buffers (d_inp points at the one the current frame uses).  h264b200_prefetch_input names the NEXT frame;
+     * its copy into the other buffer is issued by the submission of the current frame, behind that submission's own
+     * (small) uploads, on a copy stream: it overlaps the current frame's kernels. */
+    pix_t *d_inb[2][3]; int inb_cur;
+    struct { const unsigned char *yuv[3]; int stride[3]; } want;   /* named by prefetch_input, not copied yet */
+    int want_valid;
+    struct { const unsigned char *yuv[3]; int stride[3]; cudaEvent_t ev; int ttl; } stg;   /* staged in d_inb[1 - inb_cur] */
     pix_t *d_clip; int clip_frames;
     pix_t *d_dn[2]; int dn_cur;   /* temporal noise suppressor: previous / new filtered picture (layout of d_inp), allocated on first use */
     int cur;
@@ -699,9 +706,14 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->inp_stride[1] = c->inp_stride[2] = (width / 2 + 63) & ~63;
     {   /* one allocation, planes back to back: a tightly packed I420 frame is then a single copy */
         const size_t s0 = (size_t)c->inp_stride[0] * height, s1 = (size_t)c->inp_stride[1] * (height / 2);
-        CK(cudaMalloc(&c->d_inp[0], s0 + 2 * s1 + 256));
-        c->d_inp[1] = c->d_inp[0] + s0;
-        c->d_inp[2] = c->d_inp[1] + s1;
+        for (int b = 0; b < 2; b++)
+        {
+            CK(cudaMalloc(&c->d_inb[b][0], s0 + 2 * s1 + 256));
+            c->d_inb[b][1] = c->d_inb[b][0] + s0;
+            c->d_inb[b][2] = c->d_inb[b][1] + s1;
+        }
+        CK(cudaEventCreateWithFlags(&c->stg.ev, cudaEventDisableTiming));
+        for (int k = 0; k < 3; k++) c->d_inp[k] = c->d_inb[0][k];
     }
     CK(cudaMalloc(&c->d_mbi, sizeof(MBInfo) * c->nmb));
     CK(cudaMemset(c->d_mbi, 0, sizeof(MBInfo) * c->nmb));
@@ -742,7 +754,8 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     cudaSetDevice(c->device);
     for (int i = 0; i < 2; i++) cudaFree(c->d_frames[i]);
     cudaFree(c->d_hpel);
-    cudaFree(c->d_inp[0]);
+    for (int b = 0; b < 2; b++) cudaFree(c->d_inb[b][0]);
+    cudaEventDestroy(c->stg.ev);
     if (c->d_clip) cudaFree(c->d_clip);
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
@@ -758,6 +771,7 @@ extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
     cudaMemset(c->d_clusters, 0, 16);
     c->cur = 0;
     c->have_traj = 0;
+    c->stg.ttl = 0; c->want_valid = 0;
     /* the noise suppressor starts from an all-zero "previous picture" (H:6345-6349) */
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) { cudaFree(c->d_dn[i]); c->d_dn[i] = NULL; }
     c->dn_cur = 0;
@@ -870,6 +884,37 @@ static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st
     return 0;
 }
 
+/* host planes -> the ctx's device input layout (rows padded to 64 bytes), one copy when the frame is tightly packed */
+static int upload_input(h264b200_ctx *c, pix_t *const dst[3], const unsigned char *const yuv[3], const int stride[3], cudaStream_t st)
+{
+    const size_t ysz = (size_t)c->width * c->height;
+    if (c->inp_stride[0] == c->width && c->inp_stride[1] == c->width / 2 &&
+        stride[0] == c->width && stride[1] == c->width / 2 && stride[2] == c->width / 2 &&
+        yuv[1] == yuv[0] + ysz && yuv[2] == yuv[1] + ysz / 4)
+    {
+        CK(cudaMemcpyAsync(dst[0], yuv[0], ysz * 3 / 2, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    for (int pl = 0; pl < 3; pl++)
+    {
+        int w = pl ? c->width / 2 : c->width, h = pl ? c->height / 2 : c->height;
+        CK(cudaMemcpy2DAsync(dst[pl], c->inp_stride[pl], yuv[pl], stride[pl], w, h, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+static std::atomic<long> g_prefetch_hits(0);
+extern "C" long h264b200_prefetch_hits(void) { return g_prefetch_hits; }      /* frames whose staged copy was used */
+static cudaStream_t g_copy_stream = 0;
+static std::mutex g_copy_lock;
+extern "C" int h264b200_prefetch_input(h264b200_ctx *c, const unsigned char *const yuv[3], const int stride[3])
+{
+    if (!c || !yuv || !yuv[0]) return -3;
+    for (int i = 0; i < 3; i++) { c->want.yuv[i] = yuv[i]; c->want.stride[i] = stride[i]; }
+    c->want_valid = 1;
+    return 0;
+}
+
 static int encode_impl(int n, h264b200_job *jobs)
 {
     if (n <= 0) return 0;
@@ -892,6 +937,21 @@ static int encode_impl(int n, h264b200_job *jobs)
                     CK(cudaMemset(c->d_dn[k], 0, sz));
                 }
         }
+        jobs[i].status = 0;
+        if (jobs[i].preloaded_index < 0 && c->stg.ttl > 0)
+        {   /* the frame staged while the previous one was encoded: switch to its buffer, wait for its copy, no H2D here */
+            const int hit = c->stg.yuv[0] == jobs[i].yuv[0] && c->stg.yuv[1] == jobs[i].yuv[1] && c->stg.yuv[2] == jobs[i].yuv[2] &&
+                            c->stg.stride[0] == jobs[i].stride[0] && c->stg.stride[1] == jobs[i].stride[1] && c->stg.stride[2] == jobs[i].stride[2];
+            c->stg.ttl = 0;
+            if (hit)
+            {
+                g_prefetch_hits++;
+                c->inb_cur ^= 1;
+                for (int k = 0; k < 3; k++) c->d_inp[k] = c->d_inb[c->inb_cur][k];
+                CK(cudaStreamWaitEvent(st, c->stg.ev, 0));
+                jobs[i].status = 1;      /* "input already on the device" until the copy loop below */
+            } else CK(cudaStreamWaitEvent(st, c->stg.ev, 0));    /* unused copy: let it finish before its buffer can be reused */
+        }
         build_fp(&jobs[i], &g_h_fps[i]);
         max_rows = c->nmby > max_rows ? c->nmby : max_rows;
         max_nmb = c->nmb > max_nmb ? c->nmb : max_nmb;
@@ -906,20 +966,8 @@ static int encode_impl(int n, h264b200_job *jobs)
             if (jobs[i].preloaded_index >= c->clip_frames) { jobs[i].status = -3; return -3; }
             continue;
         }
-        const size_t ysz = (size_t)c->width * c->height;
-        if (c->inp_stride[0] == c->width && c->inp_stride[1] == c->width / 2 &&
-            jobs[i].stride[0] == c->width && jobs[i].stride[1] == c->width / 2 && jobs[i].stride[2] == c->width / 2 &&
-            jobs[i].yuv[1] == jobs[i].yuv[0] + ysz && jobs[i].yuv[2] == jobs[i].yuv[1] + ysz / 4)
-        {
-            CK(cudaMemcpyAsync(c->d_inp[0], jobs[i].yuv[0], ysz * 3 / 2, cudaMemcpyHostToDevice, st));
-            continue;
-        }
-        for (int pl = 0; pl < 3; pl++)
-        {
-            int w = pl ? c->width / 2 : c->width, h = pl ? c->height / 2 : c->height;
-            CK(cudaMemcpy2DAsync(c->d_inp[pl], c->inp_stride[pl], jobs[i].yuv[pl], jobs[i].stride[pl], w, h,
-                                 cudaMemcpyHostToDevice, st));
-        }
+        if (jobs[i].status == 1) { jobs[i].status = 0; continue; }          /* staged ahead of time */
+        if (upload_input(c, c->d_inp, jobs[i].yuv, jobs[i].stride, st)) { jobs[i].status = -3; return -3; }
     }
     CK(cudaMemcpyAsync(g_d_fps, g_h_fps, sizeof(FrameParams) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(g_d_tickets, 0, 64, st));
@@ -935,6 +983,21 @@ static int encode_impl(int n, h264b200_job *jobs)
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
+    {   /* inputs of the NEXT frames named by h264b200_prefetch_input: their copies start now, behind this submission's
+         * own uploads, and run under its kernels */
+        std::lock_guard<std::mutex> cguard(g_copy_lock);
+        for (int i = 0; i < n; i++)
+        {
+            h264b200_ctx *c = jobs[i].ctx;
+            if (!c->want_valid) continue;
+            c->want_valid = 0;
+            if (!g_copy_stream) CK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+            if (upload_input(c, c->d_inb[c->inb_cur ^ 1], c->want.yuv, c->want.stride, g_copy_stream)) return -3;
+            CK(cudaEventRecord(c->stg.ev, g_copy_stream));
+            for (int k = 0; k < 3; k++) { c->stg.yuv[k] = c->want.yuv[k]; c->stg.stride[k] = c->want.stride[k]; }
+            c->stg.ttl = 1;
+        }
+    }
     h264b200_launch_check1(g_d_fps, n, 1, st);
     k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
     g_launches += 3;

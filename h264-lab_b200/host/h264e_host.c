@@ -811,6 +811,16 @@ int H264E_get_recon(H264E_persist_t *penc, unsigned char *y, unsigned char *u, u
     return h264b200_get_recon(e->ctx, planes, strides) ? H264E_STATUS_DEVICE_ERROR : H264E_STATUS_SUCCESS;
 }
 
+int H264E_prefetch(H264E_persist_t *penc, const H264E_io_yuv_t *next)
+{
+    h264e_host_t *e = (h264e_host_t *)penc;
+    const unsigned char *yuv[3];
+    int i;
+    if (!e || e->magic != H264E_MAGIC || !e->ctx || !next || !next->yuv[0]) return H264E_STATUS_BAD_ARGUMENT;
+    for (i = 0; i < 3; i++) yuv[i] = next->yuv[i];
+    return h264b200_prefetch_input(e->ctx, yuv, next->stride) ? H264E_STATUS_DEVICE_ERROR : H264E_STATUS_SUCCESS;
+}
+
 int H264E_preload(H264E_persist_t *penc, int nframes, const unsigned char *frames)
 {
     h264e_host_t *e = (h264e_host_t *)penc;

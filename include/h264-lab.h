@@ -124,6 +124,12 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
                        const H264E_run_param_t *const *run_param, H264E_io_yuv_t *const *frame,
                        unsigned char **coded_data, int *sizeof_coded_data);
 
+/* Double buffering of the input: name the frame that will be passed to the NEXT H264E_encode / H264E_encode_batch call
+ * of this session; the call that encodes the CURRENT frame then also starts the host->device copy of that next frame,
+ * which overlaps the current frame's kernels.  The next call recognises the frame by its plane pointers and strides and
+ * skips its own copy.  The planes must stay untouched until then.  Optional: output is identical with or without it. */
+int H264E_prefetch(H264E_persist_t *enc, const H264E_io_yuv_t *next_frame);
+
 /* Device-resident input: upload nframes tightly packed I420 frames (stride == width) to the
  * session's GPU; a frame whose io_yuv has yuv[0] == NULL is then taken from clip frame
  * number stride[0].  Used to measure the hot path with inputs already in HBM. */

@@ -82,6 +82,14 @@ void h264b200_last_timing(float out_ms[4]);
  * host->device copy inside the call).  Replaces any previously preloaded clip. */
 int h264b200_preload(h264b200_ctx *ctx, int nframes, const unsigned char *frames);
 
+/* Name the NEXT frame of ctx (same plane / stride meaning as h264b200_job.yuv) before submitting the current one: the
+ * submission of the current frame then also starts the host->device copy of that next frame, on a copy stream, behind
+ * its own small uploads, so that the copy runs under the current frame's kernels.  The next job of ctx whose yuv /
+ * stride equal these pointers uses the staged copy instead of copying inside h264b200_encode_frames.  The caller must
+ * leave the planes untouched until that job has been submitted.  Purely an optimisation: results are identical with
+ * or without it. */
+int h264b200_prefetch_input(h264b200_ctx *ctx, const unsigned char *const yuv[3], const int stride[3]);
+
 /* Copy the most recent reconstruction (W16 x H16 luma, W16/2 x H16/2 chroma) to host. */
 int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const int strides[3]);
 
@@ -89,6 +97,8 @@ int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const 
  * created: [0] sweeps, [1] macroblocks re-encoded, [2] candidate-stage re-checks, [3] frames. */
 void h264b200_ctx_stats(h264b200_ctx *ctx, int out[4]);
 
+/* Number of frames that found their input staged by h264b200_prefetch_input. */
+long h264b200_prefetch_hits(void);
 /* Number of kernel launches issued since the library was loaded. */
 long h264b200_launch_count(void);
 const char *h264b200_backend_name(void);

@@ -231,6 +231,9 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
     }
     return 0;
 }
+/* the emulation reads host memory directly: nothing to stage */
+extern "C" int h264b200_prefetch_input(h264b200_ctx *, const unsigned char *const *, const int *) { return 0; }
+extern "C" long h264b200_prefetch_hits(void) { return 0; }
 extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
 {
     size_t fs = (size_t)c->width * c->height * 3 / 2;

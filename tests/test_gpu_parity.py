@@ -213,3 +213,28 @@ def test_concurrent_encoders_from_host_threads(binding, cuda_lib, ref):
         rbs, _, rrec, _ = ref.encode_sequence(clips[s], w, h, 60, qp=30)
         assert outs[s] == rbs, "thread %d" % s
         assert np.array_equal(recs[s], rrec[-1]), "thread %d" % s
+
+
+def test_prefetch_is_transparent(binding, cuda_lib, ref):
+    """H264E_prefetch (double-buffered input upload): same bytes whether the next frame was staged, staged but a
+    different frame is then encoded (miss), or not staged at all."""
+    import ctypes as C
+    w, h, n = 366, 250, 6                      # odd chroma width: the staged copy goes through the 2-D path
+    frames = cases.make("panning", w, h, n)
+    rbs, _, rrec, _ = ref.encode_sequence(frames, w, h, n, qp=26)
+    enc = binding.Encoder(cuda_lib, w, h, n)
+    rp = enc.run_param(qp=26)
+    keep = [frames[i].copy() for i in range(n)]
+    decoy = frames[0].copy()
+    out = b""
+    for i in range(n):
+        if i + 1 < n and i != 2:
+            nxt = enc.io_yuv(keep[i + 1])
+            assert cuda_lib.lib.H264E_prefetch(C.c_void_p(enc.persist), C.byref(nxt)) == 0
+        elif i == 2:
+            nxt = enc.io_yuv(decoy)             # staged, never encoded: must be ignored
+            assert cuda_lib.lib.H264E_prefetch(C.c_void_p(enc.persist), C.byref(nxt)) == 0
+        out += enc.encode(keep[i], rp)
+    assert out == rbs
+    assert np.array_equal(enc.recon(), rrec[-1])
+    enc.close()
