@@ -482,6 +482,21 @@ __global__ void k_borders(const FrameParams *fps, int njobs)
     }
 }
 
+/* start-of-frame state: row progress counters (encode, deblock luma / chroma, clean flags), out_info, fsync with the
+ * cluster state the trajectory starts from (FS_LIVE), and the tickets of the submission */
+__global__ void __launch_bounds__(256) k_frame_init(const FrameParams *fps, int njobs, int *tickets)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    const int nprog = (3 * PROG_STRIDE + 1) * fp->nmby;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) fp->row_progress[i] = 0;
+    if (blockIdx.x == 0)
+    {
+        if (threadIdx.x < 16) fp->out_info[threadIdx.x] = 0;
+        if (threadIdx.x < FS_WORDS) fp->fsync[threadIdx.x] = (threadIdx.x == FS_LIVE || threadIdx.x == FS_LIVE + 1) ? fp->clusters[threadIdx.x - FS_LIVE] : 0;
+        if (blockIdx.y == 0 && threadIdx.x < 16) tickets[threadIdx.x] = 0;
+    }
+}
+
 /* temporal noise suppressor (h264_denoise.h): thread = 4 samples of one plane; blockIdx.y = job.  Jobs that do not
  * ask for it have dn_out == NULL. */
 __global__ void __launch_bounds__(256) k_denoise(const FrameParams *fps, int njobs)
@@ -623,6 +638,7 @@ struct Lane
     FrameParams *d_fps, *h_fps;
     int fps_cap;
     int *d_tickets;
+    int *d_info, *h_info;         /* gathered per-job results of a submission (device / pinned host), 12 ints per job */
     cudaEvent_t ev[6], ev_fork, ev_join;
     int ev_ok;
     float last_ms[4];
@@ -642,6 +658,8 @@ static Lane *lane_get()
 #define g_h_fps (t_lane->h_fps)
 #define g_fps_cap (t_lane->fps_cap)
 #define g_d_tickets (t_lane->d_tickets)
+#define g_d_info (t_lane->d_info)
+#define g_h_info (t_lane->h_info)
 #define g_ev (t_lane->ev)
 #define g_ev_ok (t_lane->ev_ok)
 #define g_ev_fork (t_lane->ev_fork)
@@ -670,6 +688,10 @@ static int ensure_globals(int njobs)
         int cap = njobs < 16 ? 16 : njobs * 2;
         CK(cudaMalloc(&g_d_fps, sizeof(FrameParams) * cap));
         CK(cudaMallocHost(&g_h_fps, sizeof(FrameParams) * cap));
+        if (g_d_info) cudaFree(g_d_info);
+        if (g_h_info) cudaFreeHost(g_h_info);
+        CK(cudaMalloc(&g_d_info, sizeof(int) * 12 * cap));
+        CK(cudaMallocHost(&g_h_info, sizeof(int) * 12 * cap));
         g_fps_cap = cap;
     }
     return 0;
@@ -861,7 +883,7 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
     k_scan<<<n, 1024, 0, g_stream2>>>(d_fps, n, cap_words);
     k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, g_stream2>>>(d_fps, n);
     CK(cudaEventRecord(g_ev_join, g_stream2));
-    CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));
+    if (!ev_mid) CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));      /* host-driven extra passes: the slot was used before */
     k_deblock_rows<<<2 * n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
     k_borders<<<dim3(64, n), 256, 0, st>>>(d_fps, n);
     k_hpel<<<dim3(148, n), 256, 0, st>>>(d_fps, n);
@@ -871,16 +893,21 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
     return 0;
 }
 
-static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st)
+/* out_info[0..3] and fsync[0..7] of every job of the submission, gathered into one buffer: ONE device->host copy
+ * instead of two tiny ones per job (every small transfer on a stream costs ~10 us of latency) */
+__global__ void k_gather_info(const FrameParams *fps, int n, int *out)
 {
-    for (int k = 0; k < n; k++)
-    {
-        h264b200_ctx *c = jobs[idx ? idx[k] : k].ctx;
-        CK(cudaMemcpyAsync(c->h_out_info, c->d_out_info, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->h_out_info + 4, c->d_fsync, 32, cudaMemcpyDeviceToHost, st));
-    }
+    const int j = blockIdx.x, t = threadIdx.x;
+    if (j < n && t < 12) out[j * 12 + t] = t < 4 ? fps[j].out_info[t] : fps[j].fsync[t - 4];
+}
+static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st, const FrameParams *d_fps)
+{
+    k_gather_info<<<n, 32, 0, st>>>(d_fps, n, g_d_info);
+    CK(cudaMemcpyAsync(g_h_info, g_d_info, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    for (int k = 0; k < n; k++) memcpy(jobs[idx ? idx[k] : k].ctx->h_out_info, g_h_info + 12 * k, sizeof(int) * 12);
+    g_launches += 1;
     return 0;
 }
 
@@ -970,15 +997,10 @@ static int encode_impl(int n, h264b200_job *jobs)
         if (upload_input(c, c->d_inp, jobs[i].yuv, jobs[i].stride, st)) { jobs[i].status = -3; return -3; }
     }
     CK(cudaMemcpyAsync(g_d_fps, g_h_fps, sizeof(FrameParams) * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(g_d_tickets, 0, 64, st));
-    for (int i = 0; i < n; i++)
-    {
-        h264b200_ctx *c = jobs[i].ctx;
-        CK(cudaMemsetAsync(c->d_progress, 0, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby, st));
-        CK(cudaMemsetAsync(c->d_out_info, 0, 64, st));
-        CK(cudaMemsetAsync(c->d_fsync, 0, sizeof(int) * FS_WORDS, st));
-        CK(cudaMemcpyAsync(c->d_fsync + FS_LIVE, c->d_clusters, 8, cudaMemcpyDeviceToDevice, st));
-    }
+    /* per-frame synchronisation state of every job (row counters, output info, fsync + the live cluster state) and the
+     * tickets: one small kernel instead of four memsets / copies per job */
+    k_frame_init<<<dim3(8, n), 256, 0, st>>>(g_d_fps, n, g_d_tickets);
+    g_launches += 1;
     if (any_denoise) { k_denoise<<<dim3(296, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
@@ -1006,8 +1028,8 @@ static int encode_impl(int n, h264b200_job *jobs)
     for (int pass = 1; pass <= 2; pass++)
     {
         for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass, r);
-        CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
-        k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, pass);
+        /* ticket slots: [0] sweep 0, [1] in-loop filter, [2], [3] the two repair waves queued here, [4] host-driven passes */
+        k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets + 1 + pass, pass);
         k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
         h264b200_launch_check1(g_d_fps, n, pass + 1, st);
         k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
@@ -1016,7 +1038,7 @@ static int encode_impl(int n, h264b200_job *jobs)
     CK(cudaEventRecord(g_ev[2], st));
     if (launch_post(g_d_fps, n, max_rows, max_nmb, cap, st, g_ev[3])) return -3;
     CK(cudaEventRecord(g_ev[4], st));
-    if (fetch_info(n, jobs, NULL, st)) return -3;
+    if (fetch_info(n, jobs, NULL, st, g_d_fps)) return -3;
 
     /* frames whose speculated mv_clusters candidates did not verify: repair sweeps (h264_wave.h) */
     std::vector<int> dirty;
@@ -1036,14 +1058,14 @@ static int encode_impl(int n, h264b200_job *jobs)
         }
         CK(cudaMemcpyAsync(d2, h2, sizeof(FrameParams) * m, cudaMemcpyHostToDevice, st));
         for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, m), MB_WARPS * 32, 0, st>>>(d2, m, pass, r);
-        CK(cudaMemsetAsync(g_d_tickets, 0, 4, st));
-        k_encode_rows<<<m * rows2 + m, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets, pass);
+        CK(cudaMemsetAsync(g_d_tickets + 4, 0, 4, st));
+        k_encode_rows<<<m * rows2 + m, MB_WARPS * 32, g_enc_dyn_smem, st>>>(d2, m, g_d_tickets + 4, pass);
         k_replay<<<m, 32, 0, st>>>(d2, m, pass);
         h264b200_launch_check1(d2, m, pass + 1, st);
         k_after_check<<<(m + 63) / 64, 64, 0, st>>>(d2, m, pass + 1);
         g_launches += 4 + REPAIR_ROUNDS;
         if (launch_post(d2, m, rows2, nmb2, cap, st, NULL)) return -3;
-        if (fetch_info(m, jobs, dirty.data(), st)) return -3;
+        if (fetch_info(m, jobs, dirty.data(), st, d2)) return -3;
         std::vector<int> still;
         for (int k = 0; k < m; k++)
         {
