@@ -238,3 +238,16 @@ def test_prefetch_is_transparent(binding, cuda_lib, ref):
     assert out == rbs
     assert np.array_equal(enc.recon(), rrec[-1])
     enc.close()
+
+
+def test_full_gop_and_idr_at_bench_size(binding, cuda_lib, ref):
+    """BASELINE config 2's shape on one session: 1080p, GOP 60, 62 frames (a whole GOP, the IDR that follows it and one
+    more P frame), byte for byte -- the trajectory speculation / repair machinery over 60 consecutive P frames."""
+    import content
+    w, h, n, gop = 1920, 1080, 62, 60
+    frames = content.panning(w, h, n, seed=4242)
+    variant = "_fast" if ref.have_ref("_fast") else ""
+    rbs, rsz, _, _ = ref.encode_sequence(frames, w, h, gop, qp=28, want_recon=False, variant=variant)
+    bs, sz, _ = binding.encode_sequence(cuda_lib, frames, w, h, gop, qp=28, want_recon=False)
+    assert list(sz) == list(rsz)
+    assert bs == rbs
