@@ -89,6 +89,9 @@ typedef struct h264e_host_tag
 } h264e_host_t;
 
 static pthread_mutex_t g_live_lock = PTHREAD_MUTEX_INITIALIZER;
+#include <time.h>
+static double g_host_ms[3], g_host_t_finish0;       /* developer statistic, see H264E_b200_host_timing (not thread-exact) */
+static double host_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static h264e_host_t *g_live = NULL;
 static int g_atexit_registered = 0;
 
@@ -761,6 +764,8 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
     plans = (frame_plan_t *)calloc((size_t)n, sizeof(*plans));
     jobs = (h264b200_job *)calloc((size_t)n, sizeof(*jobs));
     if (!plans || !jobs) { free(plans); free(jobs); return H264E_STATUS_BAD_ARGUMENT; }
+    {
+    double t0 = host_now(), t1, t2;
     for (i = 0; i < n; i++)
     {
         plans[i].status = plan_frame((h264e_host_t *)enc[i], scratch[i], run_param ? run_param[i] : NULL, frame[i],
@@ -768,7 +773,11 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
         if (plans[i].status) { if (!err) err = plans[i].status; }
         else if (!plans[i].transparent) njobs++;
     }
+    t1 = host_now();
     if (njobs) h264b200_encode_frames(njobs, jobs);
+    t2 = host_now();
+    g_host_ms[0] += (t1 - t0) * 1e3; g_host_ms[1] += (t2 - t1) * 1e3; g_host_t_finish0 = t2;
+    }
     njobs = 0;
     for (i = 0; i < n; i++)
     {
@@ -778,10 +787,15 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
         coded_data[i] = plans[i].e->out;
         sizeof_coded_data[i] = (int)plans[i].e->out_pos;
     }
+    g_host_ms[2] += (host_now() - g_host_t_finish0) * 1e3;
     free(plans);
     free(jobs);
     return err;
 }
+
+/* developer statistic: accumulated host milliseconds of H264E_encode_batch: [0] planning (RC, headers), [1] the device
+ * submission (h264b200_encode_frames, blocking), [2] NAL assembly + RC update */
+void H264E_b200_host_timing(double out[3]) { int i; for (i = 0; i < 3; i++) out[i] = g_host_ms[i]; }
 
 int H264E_encode(H264E_persist_t *enc, H264E_scratch_t *scratch, const H264E_run_param_t *opt,
                  H264E_io_yuv_t *in, unsigned char **coded_data, int *sizeof_coded_data)

@@ -135,6 +135,10 @@ int H264E_prefetch(H264E_persist_t *enc, const H264E_io_yuv_t *next_frame);
  * number stride[0].  Used to measure the hot path with inputs already in HBM. */
 int H264E_preload(H264E_persist_t *enc, int nframes, const unsigned char *frames);
 
+/* Developer statistic: accumulated host milliseconds spent by H264E_encode_batch in [0] planning (rate control, headers),
+ * [1] the blocking device submission, [2] NAL assembly and rate-control update. */
+void H264E_b200_host_timing(double out_ms[3]);
+
 /* Copy the reconstruction of the last encoded frame (W16 x H16, planes tightly packed
  * with strides W16, W16/2, W16/2) to host memory. */
 int H264E_get_recon(H264E_persist_t *enc, unsigned char *y, unsigned char *u, unsigned char *v);
