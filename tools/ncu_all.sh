@@ -5,8 +5,8 @@
 #   tools/ncu_all.sh <tag> step  : EVERY kernel launch of one P-frame step of the bench workload (10 concurrent 1080p frames)
 tag=${1:-x}; what=${2:-enc}
 if [ "$what" = step ]; then
-  # a step launches 23 kernels (3 + 2 x (3 repair rounds + 4) + 6); step 3 is a P frame with a predicted trajectory
-  ncu --set full --clock-control none --launch-skip 69 --launch-count 23 \
+  # a step launches 25 kernels (init + 3 + 2 x (3 repair rounds + 4) + 6 + gather); step 3 is a P frame with a predicted trajectory
+  ncu --set full --clock-control none --launch-skip 75 --launch-count 25 \
       -o gpurun_out/${tag}_step_allkernels -f python tools/batch_probe.py 10 4 > gpurun_out/${tag}_ncu_all.log 2>&1
 else
   ncu --set full --import-source on --clock-control none --kernel-name k_encode_rows --launch-skip 9 --launch-count 1 \
