@@ -1,10 +1,10 @@
-"""Developer tool (GPU box): parity + throughput of the other BASELINE configs at reduced frame counts.
+"""Checker-side developer tool (GPU box; lives under tests/ because it runs the oracle): parity + throughput of the other BASELINE configs at reduced frame counts.
   config 3: 2160p rate-controlled closed-GOP segments in one batch
   config 4: 1080p all-intra
   config 5: 64 concurrent 720p streams
 Each result is compared byte for byte with the compiled reference (oracle/_ref) on the first streams."""
 import importlib.util, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import content, refenc

@@ -1,7 +1,7 @@
-"""Developer tool (GPU box): byte-for-byte parity over a whole GOP and across an IDR at the bench's size:
+"""Checker-side developer tool (GPU box; lives under tests/ because it runs the oracle): byte-for-byte parity over a whole GOP and across an IDR at the bench's size:
 1080p, GOP 60, 62 frames, one session; and the same with the temporal noise suppressor."""
 import hashlib, importlib.util, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import content, refenc, numpy as np
 spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "h264-lab_b200", "binding.py"))
