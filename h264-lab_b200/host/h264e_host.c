@@ -703,18 +703,22 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
         uint32_t hdr_tail = hdr_rem ? (uint32_t)((pl->hdr.acc & ((1u << hdr_rem) - 1)) << (8 - hdr_rem)) : 0;
         int stop_byte = job->out_bits >> 3;
         uint8_t stop_mask = (uint8_t)(0x80 >> (job->out_bits & 7));
+        /* room for the worst case (an emulation-prevention byte after every second byte) is checked once; only a
+         * nearly full buffer pays for the per-byte checks */
+        const int roomy = (long)e->out_pos + 4 + nbytes + nbytes / 2 + 16 <= (long)e->out_cap;
         for (i = 0; i < nbytes; i++)
         {
             /* fast path: a whole word past the header, before the stop bit, without any zero byte and with
-             * fewer than two pending zeros needs no emulation prevention */
+             * fewer than two pending zeros needs no emulation prevention: one byte-swapped 32-bit store */
             if (!(i & 3) && i > hdr_full && i + 4 <= stop_byte && zeros < 2)
             {
                 const uint32_t wv = words[i >> 2];
                 if (!((wv - 0x01010101u) & ~wv & 0x80808080u))
                 {
-                    nal[j] = (uint8_t)(wv >> 24); nal[j + 1] = (uint8_t)(wv >> 16); nal[j + 2] = (uint8_t)(wv >> 8); nal[j + 3] = (uint8_t)wv;
+                    const uint32_t be = __builtin_bswap32(wv);
+                    memcpy(nal + j, &be, 4);
                     j += 4; i += 3; zeros = 0;
-                    if ((int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+                    if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
                     continue;
                 }
             }
@@ -725,7 +729,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
             if (zeros == 2 && byte <= 3) { nal[j++] = 3; zeros = 0; }
             zeros = byte ? 0 : zeros + 1;
             nal[j++] = byte;
-            if ((int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+            if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
         }
     }
     if (e->run.nalu_callback) e->run.nalu_callback(nal, j, e->run.nalu_callback_token);
