@@ -117,6 +117,36 @@ __device__ __forceinline__ void publish_row_cta(int *progress, int done)
  * no co-residency assumption, no deadlock.  Row progress counters are monotonic: sweep p of
  * a row counts from p*nmbx.  k_replay then replays the cluster trajectory of every frame and
  * publishes FS_DONE or the number of the repair sweep the host has to launch. */
+/* The mv_clusters recurrence (clusters_update, H:5263-5278) over `avail` consecutive records held one per lane.  The
+ * serial chain is kept as short as it can be: the state stays unpacked in four registers, every lane prepares x, y and
+ * the norm of ITS record once, and all broadcasts are independent of the state, so they run ahead of the chain
+ * (cluster -> norms -> tests -> selects).  Same arithmetic as clusters_update, including the 16-bit wrap of mv_pack. */
+__device__ __forceinline__ void replay_chunk(int32_t c[2], int avail, int mv0, int flags, int u0, int u1, int &t0, int &t1, int &ndirty)
+{
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int mx = mv_x(mv0), my = mv_y(mv0), mn = mx * mx + my * my;
+    int c0x = mv_x(c[0]), c0y = mv_y(c[0]), c1x = mv_x(c[1]), c1y = mv_y(c[1]);
+#pragma unroll 8
+    for (int i = 0; i < 32; i++)
+    {
+        if (i >= avail) break;
+        const int f = __shfl_sync(FULLM, flags, i), a0 = __shfl_sync(FULLM, u0, i), a1 = __shfl_sync(FULLM, u1, i);
+        const int x = __shfl_sync(FULLM, mx, i), y = __shfl_sync(FULLM, my, i), norm = __shfl_sync(FULLM, mn, i);
+        const int r0 = mv_pack((c0x + 1) & ~3, (c0y + 1) & ~3), r1 = mv_pack((c1x + 1) & ~3, (c1y + 1) & ~3);
+        if (lane == i) { t0 = r0; t1 = r1; }
+        if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
+        const int n0 = c0x * c0x + c0y * c0y, n1 = c1x * c1x + c1y * c1y;
+        const int upd = f & SPEC_UPDATES;
+        const int lo = upd && norm < n1, hi = upd && norm >= n0;
+        const int b0x = (int)(int16_t)((63 * c0x + x + 32) >> 6), b0y = (int)(int16_t)((63 * c0y + y + 32) >> 6);
+        const int b1x = (int)(int16_t)((63 * c1x + x + 32) >> 6), b1y = (int)(int16_t)((63 * c1y + y + 32) >> 6);
+        c0x = lo ? b0x : c0x; c0y = lo ? b0y : c0y;
+        c1x = hi ? b1x : c1x; c1y = hi ? b1y : c1y;
+    }
+    c[0] = mv_pack(c0x, c0y); c[1] = mv_pack(c1x, c1y);
+}
+
 /* Trajectory follower of sweep 0 (one warp per frame): consumes the macroblocks of the frame in
  * raster order as they finish, replays mv_clusters_update, publishes the running state for
  * the macroblocks still to start (their speculation) and, at the end, does what
@@ -154,28 +184,7 @@ __device__ void trajectory_follower(const FrameParams *fp)
             mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
         }
         int t0 = 0, t1 = 0;
-        if (avail == 32)
-        {   /* full chunk: unrolled, the broadcasts of the next records run ahead of the recurrence */
-#pragma unroll 8
-            for (int i = 0; i < 32; i++)
-            {
-                int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
-                int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
-                int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
-                if (lane == i) { t0 = r0; t1 = r1; }
-                if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
-                if (f & SPEC_UPDATES) clusters_update(c, m);
-            }
-        } else
-        for (int i = 0; i < avail; i++)
-        {
-            int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
-            int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
-            int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
-            if (lane == i) { t0 = r0; t1 = r1; }
-            if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
-            if (f & SPEC_UPDATES) clusters_update(c, m);
-        }
+        replay_chunk(c, avail, mv0, flags, u0, u1, t0, t1, ndirty);
         if (lane < avail) { fp->cl_true[2 * (n + lane)] = t0; fp->cl_true[2 * (n + lane) + 1] = t1; }
         n += avail;
         if (lane == 0) { fs[FS_LIVE] = c[0]; fs[FS_LIVE + 1] = c[1]; fs[FS_LIVE + 2] = n; }
@@ -228,28 +237,7 @@ __device__ void repair_follower(const FrameParams *fp, int pass)
             mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1];
         }
         int t0 = 0, t1 = 0;
-        if (avail == 32)
-        {   /* full chunk: unrolled, the broadcasts of the next records run ahead of the recurrence */
-#pragma unroll 8
-            for (int i = 0; i < 32; i++)
-            {
-                int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
-                int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
-                int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
-                if (lane == i) { t0 = r0; t1 = r1; }
-                if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
-                if (f & SPEC_UPDATES) clusters_update(c, m);
-            }
-        } else
-        for (int i = 0; i < avail; i++)
-        {
-            int r0 = mv_round_fullpel(c[0]), r1 = mv_round_fullpel(c[1]);
-            int f = __shfl_sync(0xffffffffu, flags, i), m = __shfl_sync(0xffffffffu, mv0, i);
-            int a0 = __shfl_sync(0xffffffffu, u0, i), a1 = __shfl_sync(0xffffffffu, u1, i);
-            if (lane == i) { t0 = r0; t1 = r1; }
-            if ((f & SPEC_USED_CL) && (r0 != a0 || r1 != a1)) ndirty++;
-            if (f & SPEC_UPDATES) clusters_update(c, m);
-        }
+        replay_chunk(c, avail, mv0, flags, u0, u1, t0, t1, ndirty);
         if (lane < avail) { fp->cl_true[2 * (n + lane)] = t0; fp->cl_true[2 * (n + lane) + 1] = t1; }
         n += avail;
     }
