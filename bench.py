@@ -190,6 +190,10 @@ def main():
     ap.add_argument("--segments", type=int, default=NSEG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,7 +218,8 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": min(cores, nref), "kind": "reference",
                                  "sample": "%d steps x %d segments, one process per segment on %d host cores" % (K, nref, cores)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return
 
     import numpy as np
@@ -224,7 +229,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = load_binding()
     lib = B.Library()
@@ -386,7 +390,8 @@ def main():
                                               % (cpu_steps, nseg, cores)}
         except Exception as ex:      # the oracle always exists; report loudly if it does not run
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
