@@ -394,7 +394,8 @@ struct MBSpec
 #define FS_TRAJ_FIRST 14  /* 0x3fffffff - (first macroblock whose cluster-relevant result changed in the current pass), 0: none */
 #define FS_REPLAYED 7      /* GPU: repair pass whose trajectory replay the follower of the repair wave has already done */
 #define FS_REPLAY_TF 15    /* GPU: FS_TRAJ_FIRST that replay started from                                   */
-#define FS_WORDS 16
+#define FS_WAVE_TAGS 16    /* macroblocks tagged for the repair WAVE of the current pass (successors of changes of the last parallel round) */
+#define FS_WORDS 24
 #define FS_DONE 0x40000000
 
 /* Quantised levels of one macroblock (int16), written by the encode pass and read

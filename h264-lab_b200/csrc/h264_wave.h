@@ -261,6 +261,7 @@ HDN void wave_mb_round(const FrameParams *fp, MBWork *w, int x, int y, int pass,
         IF_THREAD0
         {
             const int tag = REPAIR_TAG(pass, r + 1);
+            if (r + 1 == REPAIR_ROUNDS) atomic_add_stat(fp->fsync + FS_WAVE_TAGS);     /* the wave has something to do */
             if (x < nmbx - 1) fp->need_reenc[n + 1] = tag;
             if (y < fp->nmby - 1)
             {
@@ -414,7 +415,7 @@ HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one wa
         const int replayed = pass > 0 && fp->fsync[FS_REPLAYED] == pass && fp->fsync[FS_REPLAY_TF] == tf;
         const int nd_follower = fp->fsync[FS_NDIRTY];
         WSYNC();
-        IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; fp->fsync[FS_TRAJ_FIRST] = 0; }
+        IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; fp->fsync[FS_TRAJ_FIRST] = 0; fp->fsync[FS_WAVE_TAGS] = 0; }
         int nd = replayed ? nd_follower : wave_replay(fp, w, 0, first_block);
         next = nd ? pass + 1 : FS_DONE;
     } else next = FS_DONE;

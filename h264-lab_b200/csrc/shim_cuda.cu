@@ -278,6 +278,12 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     const int nmbx = fp->nmbx;
     int *progress = fp->row_progress;
     const int base = pass * nmbx;
+    if (pass > 0 && fp->fsync[FS_WAVE_TAGS] == 0)
+    {   /* nothing was tagged for this wave (the last parallel round changed nothing): no macroblock can change in it,
+         * every row says so at once -- no chain of round trips down the frame -- and leaves */
+        if (threadIdx.x == 0) { st_release(fp->row_clean + row, pass); st_release(progress + row * PROG_STRIDE, base + nmbx); }
+        return;
+    }
     if (pass > 0)
     {
         /* Repair sweeps touch few macroblocks.  A row in which nothing is queued, below a row that
