@@ -36,7 +36,9 @@
  * neighbour-visible result changed for round r + 1 -- a fixpoint iteration that ends when a round
  * changes nothing); what is still tagged after the last round goes through one wavefront
  * sweep, which follows cascades of any length. */
+#ifndef REPAIR_ROUNDS
 #define REPAIR_ROUNDS 3
+#endif
 #define REPAIR_TAG(pass, r) ((pass) * 8 + (r))
 
 HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
