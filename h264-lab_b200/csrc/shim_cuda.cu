@@ -601,6 +601,8 @@ struct h264b200_ctx
     pix_t *d_clip; int clip_frames;
     pix_t *d_dn[2]; int dn_cur;   /* temporal noise suppressor: previous / new filtered picture (layout of d_inp), allocated on first use */
     int cur;
+    int last_dec;                 /* index (into d_frames) of the picture the last encoded frame was reconstructed into */
+    cudaStream_t copy_stream;     /* stream of the staged input copies (per context: it belongs to the context's device) */
     MBInfo *d_mbi;
     int16_t *d_coef;
     uint32_t *d_mb_bits;
@@ -634,18 +636,27 @@ struct Lane
     int *d_tickets;
     int *d_info, *h_info;         /* gathered per-job results of a submission (device / pinned host), 12 ints per job */
     cudaEvent_t ev[6], ev_fork, ev_join;
+    cudaEvent_t ev_x[4];           /* [0], [1]: around the entropy-coding kernels on stream2; [2], [3]: around the pre-pass */
     int ev_ok;
-    float last_ms[4];
+    float last_ms[8];
 };
 static Lane g_lanes[MAX_LANES];
 static std::atomic<int> g_lane_next(0);
 static std::atomic<long> g_launches(0);
+/* a lane's streams, events and staging belong to ONE device: a thread gets one lane per device it submits to */
+#define MAX_DEVICES 16
+static thread_local Lane *t_lanes[MAX_DEVICES];
 static thread_local Lane *t_lane = NULL;
-static Lane *lane_get()
+static Lane *lane_get(int device)
 {
-    if (!t_lane) t_lane = &g_lanes[g_lane_next.fetch_add(1) % MAX_LANES];
-    return t_lane;
+    Lane *&l = t_lanes[device & (MAX_DEVICES - 1)];
+    if (!l) l = &g_lanes[g_lane_next.fetch_add(1) % MAX_LANES];
+    t_lane = l;
+    return l;
 }
+/* every entry point binds the calling thread to the context's device first (contexts are created on the device that
+ * is current or named at creation; the caller's current device may be anything afterwards) */
+static Lane *lane_enter(const h264b200_ctx *c);
 #define g_stream (t_lane->stream)
 #define g_stream2 (t_lane->stream2)
 #define g_d_fps (t_lane->d_fps)
@@ -659,22 +670,20 @@ static Lane *lane_get()
 #define g_ev_fork (t_lane->ev_fork)
 #define g_ev_join (t_lane->ev_join)
 #define g_last_ms (t_lane->last_ms)
+#define g_ev_x (t_lane->ev_x)
 
 static int g_enc_dyn_smem = 0;     /* developer knob H264B200_ENC_SMEM: extra dynamic shared memory per CTA of k_encode_rows
                                        (limits the CTAs resident per SM, to study cache contention) */
+static std::once_flag g_knob_once;
 static int ensure_globals(int njobs)
 {
-    static int once = 0;
-    if (!once)
-    {
-        once = 1;
+    std::call_once(g_knob_once, []() {
         const char *e = getenv("H264B200_ENC_SMEM");
         if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
-    }
-    lane_get();
+    });
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
-    if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ok = 1; }
+    if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); for (int i = 0; i < 4; i++) CK(cudaEventCreate(&g_ev_x[i])); g_ev_ok = 1; }
     if (njobs > g_fps_cap)
     {
         if (g_d_fps) cudaFree(g_d_fps);
@@ -691,6 +700,7 @@ static int ensure_globals(int njobs)
     return 0;
 }
 
+extern "C" void h264b200_ctx_destroy(h264b200_ctx *c);
 extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, int device)
 {
     int ndev = 0;
@@ -701,6 +711,9 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CK(cudaGetDevice(&dev));
     h264b200_ctx *c = (h264b200_ctx *)calloc(1, sizeof(*c));
     if (!c) return -3;
+    /* a failed allocation releases everything allocated before it (h264b200_ctx_destroy copes with NULL members) */
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "h264b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); h264b200_ctx_destroy(c); return -3; } } while (0)
     c->device = dev;
     c->width = width; c->height = height;
     c->nmbx = (width + 15) >> 4; c->nmby = (height + 15) >> 4; c->nmb = c->nmbx * c->nmby;
@@ -712,54 +725,55 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->plane_off[2] = ysz + csz + (size_t)c->stride[1] * 8 + 8;
     for (int i = 0; i < 2; i++)
     {
-        CK(cudaMalloc(&c->d_frames[i], ysz + 2 * csz + 256));
-        CK(cudaMemset(c->d_frames[i], 0, ysz + 2 * csz + 256));
+        CKC(cudaMalloc(&c->d_frames[i], ysz + 2 * csz + 256));
+        CKC(cudaMemset(c->d_frames[i], 0, ysz + 2 * csz + 256));
     }
     c->luma_bytes = ysz;
-    CK(cudaMalloc(&c->d_hpel, 3 * ysz + 256));
-    CK(cudaMemset(c->d_hpel, 0, 3 * ysz + 256));
+    CKC(cudaMalloc(&c->d_hpel, 3 * ysz + 256));
+    CKC(cudaMemset(c->d_hpel, 0, 3 * ysz + 256));
     c->inp_stride[0] = (width + 63) & ~63;
     c->inp_stride[1] = c->inp_stride[2] = (width / 2 + 63) & ~63;
     {   /* one allocation, planes back to back: a tightly packed I420 frame is then a single copy */
         const size_t s0 = (size_t)c->inp_stride[0] * height, s1 = (size_t)c->inp_stride[1] * (height / 2);
         for (int b = 0; b < 2; b++)
         {
-            CK(cudaMalloc(&c->d_inb[b][0], s0 + 2 * s1 + 256));
+            CKC(cudaMalloc(&c->d_inb[b][0], s0 + 2 * s1 + 256));
             c->d_inb[b][1] = c->d_inb[b][0] + s0;
             c->d_inb[b][2] = c->d_inb[b][1] + s1;
         }
-        CK(cudaEventCreateWithFlags(&c->stg.ev, cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&c->stg.ev, cudaEventDisableTiming));
         for (int k = 0; k < 3; k++) c->d_inp[k] = c->d_inb[0][k];
     }
-    CK(cudaMalloc(&c->d_mbi, sizeof(MBInfo) * c->nmb));
-    CK(cudaMemset(c->d_mbi, 0, sizeof(MBInfo) * c->nmb));
-    CK(cudaMalloc(&c->d_coef, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
-    CK(cudaMemset(c->d_coef, 0, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
-    CK(cudaMalloc(&c->d_mb_bits, sizeof(uint32_t) * MB_BITS_WORDS * (size_t)(c->nmb + 1)));
-    CK(cudaMalloc(&c->d_mb_nbits, sizeof(int) * (c->nmb + 2)));
-    CK(cudaMalloc(&c->d_mb_bitoff, sizeof(int) * (c->nmb + 2)));
+    CKC(cudaMalloc(&c->d_mbi, sizeof(MBInfo) * c->nmb));
+    CKC(cudaMemset(c->d_mbi, 0, sizeof(MBInfo) * c->nmb));
+    CKC(cudaMalloc(&c->d_coef, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
+    CKC(cudaMemset(c->d_coef, 0, sizeof(int16_t) * COEF_PER_MB * (size_t)c->nmb));
+    CKC(cudaMalloc(&c->d_mb_bits, sizeof(uint32_t) * MB_BITS_WORDS * (size_t)(c->nmb + 1)));
+    CKC(cudaMalloc(&c->d_mb_nbits, sizeof(int) * (c->nmb + 2)));
+    CKC(cudaMalloc(&c->d_mb_bitoff, sizeof(int) * (c->nmb + 2)));
     c->out_cap_words = c->nmb * 160 + 1024;
-    CK(cudaMalloc(&c->d_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
-    CK(cudaMalloc(&c->d_out_info, 64));
-    CK(cudaMalloc(&c->d_clusters, 16));
-    CK(cudaMemset(c->d_clusters, 0, 16));
-    CK(cudaMalloc(&c->d_progress, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby));
-    CK(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
-    CK(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
-    CK(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
-    CK(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
-    CK(cudaMalloc(&c->d_cl_ckpt, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
-    CK(cudaMemset(c->d_cl_ckpt, 0, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
-    CK(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
-    CK(cudaMalloc(&c->d_need_reenc, sizeof(int) * c->nmb));
-    CK(cudaMemset(c->d_need_reenc, 0, sizeof(int) * c->nmb));
-    CK(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
+    CKC(cudaMalloc(&c->d_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
+    CKC(cudaMalloc(&c->d_out_info, 64));
+    CKC(cudaMalloc(&c->d_clusters, 16));
+    CKC(cudaMemset(c->d_clusters, 0, 16));
+    CKC(cudaMalloc(&c->d_progress, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby));
+    CKC(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
+    CKC(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
+    CKC(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
+    CKC(cudaMemset(c->d_cl_true, 0, sizeof(int32_t) * 2 * c->nmb));
+    CKC(cudaMalloc(&c->d_cl_ckpt, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
+    CKC(cudaMemset(c->d_cl_ckpt, 0, sizeof(int32_t) * 2 * (c->nmb / 32 + 2)));
+    CKC(cudaMalloc(&c->d_changed_pass, sizeof(int) * c->nmb));
+    CKC(cudaMalloc(&c->d_need_reenc, sizeof(int) * c->nmb));
+    CKC(cudaMemset(c->d_need_reenc, 0, sizeof(int) * c->nmb));
+    CKC(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
 #ifdef H264_PROFILE
-    CK(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
-    CK(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
+    CKC(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
+    CKC(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
 #endif
-    CK(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
-    CK(cudaMallocHost(&c->h_out_info, 64));
+    CKC(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
+    CKC(cudaMallocHost(&c->h_out_info, 64));
+#undef CKC
     *out = c;
     return 0;
 }
@@ -771,21 +785,25 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     for (int i = 0; i < 2; i++) cudaFree(c->d_frames[i]);
     cudaFree(c->d_hpel);
     for (int b = 0; b < 2; b++) cudaFree(c->d_inb[b][0]);
-    cudaEventDestroy(c->stg.ev);
+    if (c->stg.ev) cudaEventDestroy(c->stg.ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d_prof) cudaFree(c->d_prof);
     if (c->d_clip) cudaFree(c->d_clip);
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
     cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
     cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_cl_ckpt); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
-    cudaFreeHost(c->h_out_words); cudaFreeHost(c->h_out_info);
+    if (c->h_out_words) cudaFreeHost(c->h_out_words);
+    if (c->h_out_info) cudaFreeHost(c->h_out_info);
     free(c);
 }
 
 extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
 {
     if (!c) return;
+    cudaSetDevice(c->device);
     cudaMemset(c->d_clusters, 0, 16);
-    c->cur = 0;
+    c->cur = 0; c->last_dec = 0;
     c->have_traj = 0;
     c->stg.ttl = 0; c->want_valid = 0;
     /* the noise suppressor starts from an all-zero "previous picture" (H:6345-6349) */
@@ -850,6 +868,8 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
 
 extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
 {
+    if (!c) return -3;
+    std::lock_guard<std::mutex> guard(lane_enter(c)->lock);
     if (ensure_globals(1)) return -3;
     size_t fs = (size_t)c->width * c->height * 3 / 2;
     if (c->d_clip) { cudaFree(c->d_clip); c->d_clip = NULL; c->clip_frames = 0; }
@@ -873,9 +893,11 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
     }
     CK(cudaEventRecord(g_ev_fork, st));
     CK(cudaStreamWaitEvent(g_stream2, g_ev_fork, 0));
+    if (ev_mid) CK(cudaEventRecord(g_ev_x[0], g_stream2));
     k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, g_stream2>>>(d_fps, n);
     k_scan<<<n, 1024, 0, g_stream2>>>(d_fps, n, cap_words);
     k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, g_stream2>>>(d_fps, n);
+    if (ev_mid) CK(cudaEventRecord(g_ev_x[1], g_stream2));
     CK(cudaEventRecord(g_ev_join, g_stream2));
     if (!ev_mid) CK(cudaMemsetAsync(g_d_tickets + 1, 0, 4, st));      /* host-driven extra passes: the slot was used before */
     k_deblock_rows<<<2 * n * max_rows + n, 32, 0, st>>>(d_fps, n, g_d_tickets);
@@ -926,8 +948,6 @@ static int upload_input(h264b200_ctx *c, pix_t *const dst[3], const unsigned cha
 
 static std::atomic<long> g_prefetch_hits(0);
 extern "C" long h264b200_prefetch_hits(void) { return g_prefetch_hits; }      /* frames whose staged copy was used */
-static cudaStream_t g_copy_stream = 0;
-static std::mutex g_copy_lock;
 extern "C" int h264b200_prefetch_input(h264b200_ctx *c, const unsigned char *const yuv[3], const int stride[3])
 {
     if (!c || !yuv || !yuv[0]) return -3;
@@ -936,11 +956,16 @@ extern "C" int h264b200_prefetch_input(h264b200_ctx *c, const unsigned char *con
     return 0;
 }
 
-static int encode_impl(int n, h264b200_job *jobs)
+static Lane *lane_enter(const h264b200_ctx *c)
 {
-    if (n <= 0) return 0;
-    std::lock_guard<std::mutex> guard(lane_get()->lock);
-    if (ensure_globals(2 * n)) { for (int i = 0; i < n; i++) jobs[i].status = -3; return -3; }
+    cudaSetDevice(c->device);
+    return lane_get(c->device);
+}
+
+/* one submission: n <= max_jobs_per_submission() frames of contexts that live on the lane's device */
+static int encode_chunk(int n, h264b200_job *jobs)
+{
+    if (ensure_globals(2 * n)) return -3;
     cudaStream_t st = g_stream;
     int max_rows = 0, max_nmb = 0, cap = 0x7fffffff, any_denoise = 0;
     for (int i = 0; i < n; i++)
@@ -1001,15 +1026,14 @@ static int encode_impl(int n, h264b200_job *jobs)
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
     {   /* inputs of the NEXT frames named by h264b200_prefetch_input: their copies start now, behind this submission's
          * own uploads, and run under its kernels */
-        std::lock_guard<std::mutex> cguard(g_copy_lock);
         for (int i = 0; i < n; i++)
         {
             h264b200_ctx *c = jobs[i].ctx;
             if (!c->want_valid) continue;
             c->want_valid = 0;
-            if (!g_copy_stream) CK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-            if (upload_input(c, c->d_inb[c->inb_cur ^ 1], c->want.yuv, c->want.stride, g_copy_stream)) return -3;
-            CK(cudaEventRecord(c->stg.ev, g_copy_stream));
+            if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            if (upload_input(c, c->d_inb[c->inb_cur ^ 1], c->want.yuv, c->want.stride, c->copy_stream)) return -3;
+            CK(cudaEventRecord(c->stg.ev, c->copy_stream));
             for (int k = 0; k < 3; k++) { c->stg.yuv[k] = c->want.yuv[k]; c->stg.stride[k] = c->want.stride[k]; }
             c->stg.ttl = 1;
         }
@@ -1100,12 +1124,108 @@ static int encode_impl(int n, h264b200_job *jobs)
     }
     CK(cudaEventRecord(g_ev[5], st));
     CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < n; i++) if (jobs[i].update_ref && jobs[i].status == 0) jobs[i].ctx->cur ^= 1;
+    for (int i = 0; i < n; i++) if (jobs[i].status == 0) { jobs[i].ctx->last_dec = jobs[i].ctx->cur; if (jobs[i].update_ref) jobs[i].ctx->cur ^= 1; }
     for (int i = 0; i < n; i++) if (jobs[i].p.denoise && jobs[i].ctx->d_dn[0]) jobs[i].ctx->dn_cur ^= 1;
     cudaEventElapsedTime(&g_last_ms[0], g_ev[0], g_ev[5]);
     cudaEventElapsedTime(&g_last_ms[1], g_ev[1], g_ev[2]);
     cudaEventElapsedTime(&g_last_ms[2], g_ev[2], g_ev[3]);
-    cudaEventElapsedTime(&g_last_ms[3], g_ev[3], g_ev[4]);
+    cudaEventElapsedTime(&g_last_ms[3], g_ev_x[0], g_ev_x[1]);      /* entropy coding: events on ITS stream (it runs beside the in-loop filter) */
+    return rc;
+}
+
+/* Frames that are not encoded (VBV-overflow "transparent" frames, H:6497-6508) but whose session runs the temporal
+ * noise suppressor: the reference filters EVERY submitted picture before it decides what to do with it (H:6686), so
+ * the filter's state has to advance: upload, k_denoise, flip -- nothing else. */
+static int denoise_only_chunk(int n, h264b200_job *jobs)
+{
+    if (ensure_globals(2 * n)) return -3;
+    cudaStream_t st = g_stream;
+    for (int i = 0; i < n; i++)
+    {
+        h264b200_ctx *c = jobs[i].ctx;
+        for (int k = 0; k < 2; k++)
+            if (!c->d_dn[k])
+            {
+                const size_t sz = (size_t)c->inp_stride[0] * c->height + 2 * (size_t)c->inp_stride[1] * (c->height / 2) + 256;
+                CK(cudaMalloc(&c->d_dn[k], sz));
+                CK(cudaMemset(c->d_dn[k], 0, sz));
+            }
+        if (c->stg.ttl > 0) { c->stg.ttl = 0; CK(cudaStreamWaitEvent(st, c->stg.ev, 0)); }    /* a staged copy is not used here */
+        if (jobs[i].preloaded_index >= 0) { if (jobs[i].preloaded_index >= c->clip_frames) return -3; }
+        else if (upload_input(c, c->d_inp, jobs[i].yuv, jobs[i].stride, st)) return -3;
+        h264b200_job tmp = jobs[i];
+        tmp.p.denoise = 1;
+        build_fp(&tmp, &g_h_fps[i]);
+    }
+    CK(cudaMemcpyAsync(g_d_fps, g_h_fps, sizeof(FrameParams) * n, cudaMemcpyHostToDevice, st));
+    k_denoise<<<dim3(296, n), 256, 0, st>>>(g_d_fps, n);
+    g_launches += 1;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int i = 0; i < n; i++) { jobs[i].ctx->dn_cur ^= 1; jobs[i].status = 0; jobs[i].out_words = NULL; jobs[i].out_bits = 0; }
+    return 0;
+}
+
+/* k_encode_rows gives its first n tickets to trajectory followers that spin until the rows of their frame have
+ * finished, so a submission must leave resident CTA slots for the rows: at most half of the slots the device can hold
+ * are ever followers.  Larger batches are split into consecutive submissions (results are identical: the jobs of a
+ * batch are independent). */
+static int max_jobs_per_submission()
+{
+    static std::atomic<int> cached(0);
+    int v = cached.load();
+    if (v) return v;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_rows, MB_WARPS * 32, g_enc_dyn_smem) != cudaSuccess) per_sm = 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 1;
+    v = per_sm * sms / 2;
+    if (v < 1) v = 1;
+    cached.store(v);
+    return v;
+}
+
+static int encode_impl(int n, h264b200_job *jobs)
+{
+    if (n <= 0) return 0;
+    if (!jobs) return -3;
+    for (int i = 0; i < n; i++)
+    {
+        jobs[i].status = -3; jobs[i].out_words = NULL; jobs[i].out_bits = 0; jobs[i].trailing_skip_run = 0;
+        if (!jobs[i].ctx || jobs[i].ctx->device != jobs[0].ctx->device) return -3;       /* one device per submission */
+    }
+    Lane *lane = lane_enter(jobs[0].ctx);
+    std::lock_guard<std::mutex> guard(lane->lock);
+    const int cap = max_jobs_per_submission();
+    std::vector<h264b200_job> enc, dn;
+    std::vector<int> enc_idx, dn_idx;
+    for (int i = 0; i < n; i++)
+    {
+        if (jobs[i].p.denoise == 2) { dn.push_back(jobs[i]); dn_idx.push_back(i); }
+        else { enc.push_back(jobs[i]); enc_idx.push_back(i); }
+    }
+    int rc = 0;
+    for (int pass = 0; pass < 2; pass++)
+    {
+        std::vector<h264b200_job> &v = pass ? enc : dn;
+        std::vector<int> &idx = pass ? enc_idx : dn_idx;
+        for (size_t b = 0; b < v.size(); b += (size_t)cap)
+        {
+            const int m = (int)(v.size() - b < (size_t)cap ? v.size() - b : (size_t)cap);
+            for (int k = 0; k < m; k++) v[b + k].status = 0;
+            const int r = pass ? encode_chunk(m, &v[b]) : denoise_only_chunk(m, &v[b]);
+            if (r == -3)
+            {   /* a CUDA call failed somewhere in the submission: nothing of it can be trusted.  Every job of the chunk
+                 * reports the error, queued work is drained so that the pinned staging can be reused */
+                cudaStreamSynchronize(g_stream);
+                if (g_stream2) cudaStreamSynchronize(g_stream2);
+                cudaGetLastError();
+                for (int k = 0; k < m; k++) { v[b + k].status = -3; v[b + k].out_words = NULL; }
+            }
+            if (r && !rc) rc = r;
+            for (int k = 0; k < m; k++) jobs[idx[b + k]] = v[b + k];
+        }
+    }
     return rc;
 }
 
@@ -1113,19 +1233,33 @@ extern "C" int h264b200_encode_frames(int n, h264b200_job *jobs) { return encode
 
 extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3], const int strides[3])
 {
-    std::lock_guard<std::mutex> guard(lane_get()->lock);
+    if (!c) return -3;
+    std::lock_guard<std::mutex> guard(lane_enter(c)->lock);
     if (ensure_globals(1)) return -3;
+    /* the picture the last encoded frame was reconstructed into: after a frame that updated the reference (or a transparent
+     * frame, whose reconstruction IS the reference picture) that is the current reference; after a droppable frame
+     * (update_ref == 0) the reference did not move and the reconstruction sits in the other picture */
     for (int pl = 0; pl < 3; pl++)
     {
         int w = c->nmbx * (pl ? 8 : 16), h = c->nmby * (pl ? 8 : 16);
-        CK(cudaMemcpy2DAsync(planes[pl], strides[pl], c->d_frames[c->cur ^ 1] + c->plane_off[pl], c->stride[pl != 0], w, h,
+        CK(cudaMemcpy2DAsync(planes[pl], strides[pl], c->d_frames[c->last_dec] + c->plane_off[pl], c->stride[pl != 0], w, h,
                              cudaMemcpyDeviceToHost, g_stream));
     }
     CK(cudaStreamSynchronize(g_stream));
     return 0;
 }
 
-extern "C" void h264b200_last_timing(float out_ms[4]) { lane_get(); for (int i = 0; i < 4; i++) out_ms[i] = g_last_ms[i]; }
+extern "C" void h264b200_note_transparent(h264b200_ctx *c) { if (c) c->last_dec = c->cur ^ 1; }
+
+extern "C" int h264b200_last_timing_ex(float *out_ms, int n)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    lane_get(dev);
+    for (int i = 0; i < n; i++) out_ms[i] = i < 8 ? g_last_ms[i] : 0.f;
+    return 8;
+}
+extern "C" void h264b200_last_timing(float out_ms[4]) { h264b200_last_timing_ex(out_ms, 4); }
 /* developer builds (-DH264_PROFILE): per-MB phase cycles of the last frame, [nmb][10] ints */
 extern "C" int h264b200_get_profile(h264b200_ctx *c, int *out)
 {

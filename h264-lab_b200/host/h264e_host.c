@@ -541,7 +541,10 @@ typedef struct
     int slice_type, is_key;
     hbits_t hdr;
     int status;
-    int transparent;     /* VBV overflow: the frame is coded as one run of skipped macroblocks, no device work (H:6497-6508) */
+    int transparent;     /* VBV overflow: the frame is coded as one run of skipped macroblocks, no macroblock work (H:6497-6508) */
+    int dn_only;         /* ... but the temporal noise suppressor still sees the picture (H:6686 runs before the decision):
+                            the device job of such a frame only advances the filter state */
+    int job;             /* index of the frame's device job in the submission, -1: none */
     H264E_io_yuv_t inplace;   /* caller planes that receive the reconstruction when const_input_flag == 0 */
 } frame_plan_t;
 
@@ -638,6 +641,15 @@ static int plan_frame(h264e_host_t *e, H264E_scratch_t *scratch, const H264E_run
         pl->transparent = 1;
         memset(&pl->inplace, 0, sizeof(pl->inplace));
         if (!e->param.const_input_flag && in->yuv[0]) pl->inplace = *in;
+        if (e->param.temporal_denoise_flag && e->run.encode_speed < 2)
+        {   /* H:6686-6696: the filter has already consumed this picture when the reference gets here */
+            memset(job, 0, sizeof(*job));
+            job->ctx = e->ctx;
+            job->p.denoise = 2;
+            for (i = 0; i < 3; i++) { job->yuv[i] = in->yuv[i]; job->stride[i] = in->stride[i]; }
+            job->preloaded_index = in->yuv[0] ? -1 : in->stride[0];
+            pl->dn_only = 1;
+        }
         return H264E_STATUS_SUCCESS;
     }
     memset(job, 0, sizeof(*job));
@@ -664,6 +676,8 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
     const uint32_t *words;
     if (pl->transparent)
     {
+        if (pl->dn_only && (!job || job->status)) return H264E_STATUS_DEVICE_ERROR;
+        h264b200_note_transparent(e->ctx);
         hb_ue(&pl->hdr, (uint32_t)e->nmb);
         hb_trailing(&pl->hdr);
         if ((int)e->out_pos + 4 + 2 * pl->hdr.nbytes + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
@@ -687,8 +701,10 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
         filler = rc_frame_end(e, 0, 1);
         goto after_rc;
     }
-    words = job->out_words;
+    if (!job) return H264E_STATUS_DEVICE_ERROR;
     if (job->status) return job->status == -1 ? H264E_STATUS_NO_DEVICE : H264E_STATUS_DEVICE_ERROR;
+    words = job->out_words;
+    if (!words) return H264E_STATUS_DEVICE_ERROR;      /* a failed submission never hands out a payload */
 
     /* the device left hdr_bits of room at the front of the payload: merge the header,
      * add the RBSP stop bit and convert MSB-first words to escaped bytes */
@@ -774,20 +790,22 @@ int H264E_encode_batch(int n, H264E_persist_t *const *enc, H264E_scratch_t *cons
     {
         plans[i].status = plan_frame((h264e_host_t *)enc[i], scratch[i], run_param ? run_param[i] : NULL, frame[i],
                                      &plans[i], &jobs[njobs]);
+        plans[i].job = -1;
         if (plans[i].status) { if (!err) err = plans[i].status; }
-        else if (!plans[i].transparent) njobs++;
+        else if (!plans[i].transparent || plans[i].dn_only) plans[i].job = njobs++;
     }
     t1 = host_now();
-    if (njobs) h264b200_encode_frames(njobs, jobs);
+    /* a failed submission leaves status != 0 / out_words == NULL in every job it could not finish: finish_frame turns
+     * that into H264E_STATUS_DEVICE_ERROR for the sessions concerned */
+    if (njobs) (void)h264b200_encode_frames(njobs, jobs);
     t2 = host_now();
     g_host_ms[0] += (t1 - t0) * 1e3; g_host_ms[1] += (t2 - t1) * 1e3; g_host_t_finish0 = t2;
     }
-    njobs = 0;
     for (i = 0; i < n; i++)
     {
         if (plans[i].status) { coded_data[i] = NULL; sizeof_coded_data[i] = 0; continue; }
-        plans[i].status = plans[i].transparent ? finish_frame(&plans[i], NULL) : finish_frame(&plans[i], &jobs[njobs++]);
-        if (plans[i].status && !err) err = plans[i].status;
+        plans[i].status = finish_frame(&plans[i], plans[i].job >= 0 ? &jobs[plans[i].job] : NULL);
+        if (plans[i].status) { if (!err) err = plans[i].status; coded_data[i] = NULL; sizeof_coded_data[i] = 0; continue; }
         coded_data[i] = plans[i].e->out;
         sizeof_coded_data[i] = (int)plans[i].e->out_pos;
     }
@@ -810,8 +828,12 @@ int H264E_encode(H264E_persist_t *enc, H264E_scratch_t *scratch, const H264E_run
     if (!coded_data || !sizeof_coded_data) return H264E_STATUS_BAD_ARGUMENT;
     err = plan_frame((h264e_host_t *)enc, scratch, opt, in, &plan, &job);
     if (err) return err;
-    if (!plan.transparent) h264b200_encode_frames(1, &job);
-    err = finish_frame(&plan, &job);
+    if (!plan.transparent || plan.dn_only)
+    {
+        const int rc = h264b200_encode_frames(1, &job);
+        if (rc && !job.status) job.status = rc;       /* never assemble a NAL from a failed submission */
+    }
+    err = finish_frame(&plan, (!plan.transparent || plan.dn_only) ? &job : NULL);
     if (err) return err;
     *sizeof_coded_data = (int)plan.e->out_pos;
     *coded_data = plan.e->out;

@@ -16,6 +16,14 @@
 #ifndef H264_LAB_B200_API_H
 #define H264_LAB_B200_API_H
 
+/* the reference header pulls these in for its users (H:325-329); its CLI (minih264e_test.c) relies on uint8_t,
+ * assert and memset through it, so a drop-in header has to provide them as well */
+#include <assert.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -35,7 +35,10 @@ typedef struct
     unsigned short qdat[2][42];   /* quantiser tables of rc_set_qp  (H:5839-5912)        */
     int hdr_bits;            /* bit position inside the NAL at which slice_data() starts */
     int denoise;             /* 1: run the temporal noise suppressor on the input first and encode its output
-                                (temporal_denoise_flag && encode_speed < 2, H:6686; h264e_denoise_run H:1547) */
+                                (temporal_denoise_flag && encode_speed < 2, H:6686; h264e_denoise_run H:1547);
+                                2: ONLY run the suppressor (the frame itself is coded by the host as a "transparent"
+                                all-skip frame, H:6497-6508, yet the reference has filtered it by then): every other
+                                field of p is ignored, the job produces no payload */
 } h264b200_frame_params;
 
 /* One frame of one encoder instance. */
@@ -56,7 +59,9 @@ typedef struct
                                         before it are zero.  Valid until the next call on this ctx. */
     int out_bits;                    /* [out] end of the payload incl. the trailing mb_skip_run */
     int trailing_skip_run;           /* [out] skipped macroblocks at the end of the slice   */
-    int status;                      /* [out] 0 = ok, -1 no device, -2 payload overflow, -3 CUDA error */
+    int status;                      /* [out] 0 = ok, -1 no device, -2 payload overflow (per-MB string or slice buffer),
+                                        -3 CUDA error or bad argument (then EVERY job of the submission reports -3 and
+                                        out_words is NULL), -4 the exact-wavefront verification did not converge */
 } h264b200_job;
 
 /* Create / destroy the device state for a width x height encoder.  device = CUDA
@@ -69,13 +74,19 @@ void h264b200_ctx_reset(h264b200_ctx *ctx);
 /* Encode one frame for each of n independent encoder instances concurrently
  * (host->device copy of the inputs, macroblock pass, deblocking, CAVLC + pack,
  * device->host copy of the payload).  Blocks until every job has finished.
- * Returns 0, or the first failing job's negative status. */
+ * All contexts of one call must live on the same device (else -3); the call binds the calling thread to that
+ * device.  Any n is accepted: batches larger than the device can hold as one wavefront submission are run as
+ * consecutive submissions.  Returns 0, or the first failing job's negative status. */
 int h264b200_encode_frames(int n, h264b200_job *jobs);
 
 /* Timing of the kernels of the last h264b200_encode_frames call, in milliseconds,
  * measured with CUDA events on the launch stream: [0] whole call on device,
  * [1] macroblock pass, [2] deblock + border, [3] CAVLC + pack.  */
 void h264b200_last_timing(float out_ms[4]);
+/* Same, n slots (returns how many are defined): [0] whole submission on the device, [1] macroblock sweep incl. the
+ * verification / repair passes, [2] in-loop filter + guard bands + half-sample planes, [3] entropy coding (CAVLC, prefix
+ * sum, pack; measured on the second stream it runs on, beside [2]), [4] SAD-map pre-pass, [5..7] reserved (0). */
+int h264b200_last_timing_ex(float *out_ms, int n);
 
 /* Upload a clip of nframes tightly packed I420 frames (stride == width) to device memory
  * owned by ctx; jobs with preloaded_index >= 0 then read their input from HBM (no
@@ -90,8 +101,13 @@ int h264b200_preload(h264b200_ctx *ctx, int nframes, const unsigned char *frames
  * or without it. */
 int h264b200_prefetch_input(h264b200_ctx *ctx, const unsigned char *const yuv[3], const int stride[3]);
 
-/* Copy the most recent reconstruction (W16 x H16 luma, W16/2 x H16/2 chroma) to host. */
+/* Copy the reconstruction of the last frame of ctx (W16 x H16 luma, W16/2 x H16/2 chroma) to host: the picture the
+ * last h264b200_encode_frames job wrote (also when that frame was droppable and did not become the reference), or the
+ * reference picture after h264b200_note_transparent(). */
 int h264b200_get_recon(h264b200_ctx *ctx, unsigned char *const planes[3], const int strides[3]);
+/* The host coded a frame of ctx without a device job (transparent frame, H:6497-6508): its reconstruction is the
+ * current reference picture, unchanged. */
+void h264b200_note_transparent(h264b200_ctx *ctx);
 
 /* Statistics of the exact-wavefront scheme (csrc/h264_wave.h), accumulated since the ctx was
  * created: [0] sweeps, [1] macroblocks re-encoded, [2] candidate-stage re-checks, [3] frames. */

@@ -28,6 +28,13 @@ static void ref_mb_hook(struct H264E_persist_tag *enc);
 #define REF_MB_HOOK(enc) ref_mb_hook(enc)
 #endif
 
+#ifdef REF_OPCOUNT_ENABLED
+/* Only defined for the measurement build (Makefile target _ref/libh264ref_count.so): opcount.sed adds one
+ * REF_CNT(category, n) statement at the top of the reference's leaf functions in a temporary copy of the header. */
+static long long g_ref_ops[16];
+#define REF_CNT(k, n) (g_ref_ops[k] += (n))
+#endif
+
 #include "h264-lab.h"
 
 #define EXPORT __attribute__((visibility("default")))
@@ -81,6 +88,11 @@ EXPORT void ref_get_state(void *venc, int *out /* [8] */)
     out[6] = enc->rc.prev_qp;
     out[7] = enc->next_idr_pic_id;
 }
+
+#ifdef REF_OPCOUNT_ENABLED
+EXPORT void ref_reset_opcounts(void) { memset(g_ref_ops, 0, sizeof(g_ref_ops)); }
+EXPORT void ref_get_opcounts(long long *out /* [16] */) { memcpy(out, g_ref_ops, sizeof(g_ref_ops)); }
+#endif
 
 /* ------------------------------------------------------------------ */
 /* (2) whole-sequence helper                                           */

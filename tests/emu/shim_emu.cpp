@@ -31,7 +31,7 @@ struct h264b200_ctx
     std::vector<pix_t> hpel;         /* half-sample planes b, h, j of the reference picture */
     size_t luma_bytes;
     size_t plane_off[3];
-    int cur;
+    int cur, last_dec;
     std::vector<MBInfo> mbi;
     std::vector<int16_t> coef;
     std::vector<uint32_t> mb_bits;
@@ -72,7 +72,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->mb_nbits.resize(nmb + 2);
     c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->cl_ckpt.resize(2 * (nmb / 32 + 2)); c->changed_pass.resize(nmb); c->need_reenc.resize(nmb);
     c->out_words.resize((size_t)nmb * 160 + 1024);
-    c->cur = 0;
+    c->cur = 0; c->last_dec = 0;
     c->clusters[0] = c->clusters[1] = 0;
     c->have_traj = 0;
     memset(c->stats, 0, sizeof(c->stats));
@@ -80,7 +80,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     return 0;
 }
 extern "C" void h264b200_ctx_destroy(h264b200_ctx *c) { delete c; }
-extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->have_traj = 0; c->dn[0].clear(); c->dn[1].clear(); c->dn_cur = 0; }
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->last_dec = 0; c->have_traj = 0; c->dn[0].clear(); c->dn[1].clear(); c->dn_cur = 0; }
 
 static void run_job(h264b200_job *job)
 {
@@ -123,6 +123,12 @@ static void run_job(h264b200_job *job)
         }
         fp.dec[i] = c->frame[c->cur].data() + c->plane_off[i];
         fp.ref[i] = c->frame[c->cur ^ 1].data() + c->plane_off[i];
+    }
+    if (p.denoise == 2)
+    {   /* transparent frame of a session with the noise suppressor: only the filter state advances (see shim_cuda.cu) */
+        c->dn_cur ^= 1;
+        job->status = 0; job->out_words = NULL; job->out_bits = 0;
+        return;
     }
     for (int i = 0; i < 3; i++) fp.hp[i] = c->hpel.data() + i * c->luma_bytes + c->plane_off[0];
     fp.hp_out = c->hpel.data(); fp.dec_base = c->frame[c->cur].data(); fp.luma_bytes = (int)c->luma_bytes;
@@ -210,6 +216,7 @@ static void run_job(h264b200_job *job)
             int ww = c->nmbx * (pl ? 8 : 16), hh = c->nmby * (pl ? 8 : 16);
             for (int r = 0; r < hh; r++) memcpy(job->recon[pl] + (size_t)r * job->recon_stride[pl], fp.dec[pl] + (size_t)r * fp.stride[pl != 0], ww);
         }
+    c->last_dec = c->cur;
     if (job->update_ref) c->cur ^= 1;
     if (p.denoise) c->dn_cur ^= 1;
     job->status = 0;
@@ -226,7 +233,7 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
     for (int pl = 0; pl < 3; pl++)
     {
         int ww = c->nmbx * (pl ? 8 : 16), hh = c->nmby * (pl ? 8 : 16);
-        const pix_t *src = c->frame[c->cur ^ 1].data() + c->plane_off[pl];
+        const pix_t *src = c->frame[c->last_dec].data() + c->plane_off[pl];
         for (int r = 0; r < hh; r++) memcpy(planes[pl] + (size_t)r * strides[pl], src + (size_t)r * c->stride[pl != 0], ww);
     }
     return 0;
@@ -240,6 +247,8 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
     c->clip.assign(frames, frames + fs * nframes);
     return 0;
 }
+extern "C" void h264b200_note_transparent(h264b200_ctx *c) { if (c) c->last_dec = c->cur ^ 1; }
+extern "C" int h264b200_last_timing_ex(float *out_ms, int n) { for (int i = 0; i < n; i++) out_ms[i] = 0; return 8; }
 extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }

@@ -82,3 +82,43 @@ def encode_sequence(frames, width, height, gop, qp=28, kbps=0, speed=0, want_rec
     if tot < 0:
         raise RuntimeError("reference encoder error %d" % -tot)
     return out[:tot].tobytes(), sizes, recon, secs.value
+
+
+class RefSession:
+    """The reference's public API driven frame by frame (ref_sizeof / ref_init / ref_encode), for tests that need
+    per-frame run parameters (frame types) or in-place reconstruction (const_input_flag = 0)."""
+
+    def __init__(self, width, height, gop, const_input=1, variant="", **extra):
+        self.l = lib(variant)
+        self.width, self.height = width, height
+        self.cp = CreateParam(width=width, height=height, gop=gop, const_input_flag=const_input,
+                              vbv_size_bytes=100000 // 8, enableNEON=1, num_layers=1, **extra)
+        sp, ss = C.c_int(), C.c_int()
+        err = self.l.ref_sizeof(C.byref(self.cp), C.byref(sp), C.byref(ss))
+        if err:
+            raise RuntimeError("ref_sizeof error %d" % err)
+        self._persist = np.zeros(sp.value + 64, np.uint8)
+        self._scratch = np.zeros(ss.value + 64, np.uint8)
+        self.persist = (self._persist.ctypes.data + 63) & ~63
+        self.scratch = (self._scratch.ctypes.data + 63) & ~63
+        self.l.ref_init(C.c_void_p(self.persist), C.byref(self.cp))
+
+    def encode(self, frame, qp=28, kbps=0, speed=0, frame_type=0):
+        """frame: contiguous uint8 I420 array (overwritten with the reconstruction when const_input_flag = 0)."""
+        w, h = self.width, self.height
+        rp = RunParam()
+        rp.frame_type, rp.encode_speed = frame_type, speed
+        if kbps:
+            rp.desired_frame_bytes, rp.qp_min, rp.qp_max = kbps * 1000 // 8 // 30, 10, 50
+        else:
+            rp.qp_min = rp.qp_max = qp
+        yuv = IoYuv()
+        base = frame.ctypes.data
+        yuv.yuv[0], yuv.yuv[1], yuv.yuv[2] = base, base + w * h, base + w * h * 5 // 4
+        yuv.stride[0], yuv.stride[1], yuv.stride[2] = w, w // 2, w // 2
+        data, n = C.c_void_p(0), C.c_int(0)
+        err = self.l.ref_encode(C.c_void_p(self.persist), C.c_void_p(self.scratch), C.byref(rp), C.byref(yuv),
+                                C.byref(data), C.byref(n))
+        if err:
+            raise RuntimeError("ref_encode error %d" % err)
+        return C.string_at(data.value, n.value)

@@ -44,3 +44,27 @@ def test_emu_in_place_transparent_frames(binding, emu_lib, ref):
     assert outs[0] == rbs and outs[1] == rbs
     for e in encs:
         e.close()
+
+
+def _droppable_sequence(binding, lib, ref):
+    """KEY, P, DROPPABLE, P, DROPPABLE, P in in-place mode (const_input_flag = 0): the caller's planes receive the
+    reconstruction of EVERY frame, also of the droppable ones that never become the reference (H:6598-6623), and
+    H264E_get_recon returns the reconstruction of the last encoded frame, droppable or not."""
+    w, h, n = 352, 288, 6
+    types = [0, 0, 1, 0, 1, 0]                 # H264E_FRAME_TYPE_DROPPABLE = 1
+    frames = cases.make("panning", w, h, n)
+    rs = ref.RefSession(w, h, 0, const_input=0)
+    enc = binding.Encoder(lib, w, h, 0, const_input=0)
+    for i in range(n):
+        fr, fo = frames[i].copy(), frames[i].copy()
+        rbs = rs.encode(fr, qp=28, frame_type=types[i])
+        rp = enc.run_param(qp=28, frame_type=types[i])
+        bs = enc.encode(fo, rp)
+        assert bs == rbs, "frame %d" % i
+        assert np.array_equal(fo, fr), "in-place reconstruction of frame %d" % i
+        assert np.array_equal(enc.recon(), fr), "H264E_get_recon after frame %d" % i
+    enc.close()
+
+
+def test_emu_droppable_frames(binding, emu_lib, ref):
+    _droppable_sequence(binding, emu_lib, ref)

@@ -251,3 +251,101 @@ def test_full_gop_and_idr_at_bench_size(binding, cuda_lib, ref):
     bs, sz, _ = binding.encode_sequence(cuda_lib, frames, w, h, gop, qp=28, want_recon=False)
     assert list(sz) == list(rsz)
     assert bs == rbs
+
+
+def test_droppable_frames(binding, cuda_lib, ref):
+    """Droppable frames in in-place mode + H264E_get_recon after them (see tests/test_emu_parity.py)."""
+    from test_emu_parity import _droppable_sequence
+    _droppable_sequence(binding, cuda_lib, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs at their STATED geometry (SURVEY 8(d) C2, C3, C5), every unit compared with oracle/_ref
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_units(ref, clips, w, h, gop, **kw):
+    """The reference run once per unit (fresh instance per closed-GOP segment / stream), on the host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    variant = "_fast" if ref.have_ref("_fast") else ""
+    want_recon = kw.pop("want_recon", True)
+
+    def one(c):
+        return ref.encode_sequence(c, w, h, gop, variant=variant, want_recon=want_recon, **kw)[:3]
+    with ThreadPoolExecutor(max_workers=min(len(clips), os.cpu_count() or 4)) as ex:      # ctypes releases the GIL
+        return list(ex.map(one, clips))
+
+
+def _batch_units(binding, cuda_lib, clips, w, h, gop, **kw):
+    """frame t of every unit in ONE device submission (H264E_encode_batch); returns per unit (bytes, sizes, last recon)."""
+    n = len(clips)
+    encs = [binding.Encoder(cuda_lib, w, h, gop) for _ in range(n)]
+    rps = [e.run_param(**kw) for e in encs]
+    outs, sizes = [b""] * n, [[] for _ in range(n)]
+    for t in range(clips[0].shape[0]):
+        res = binding.encode_batch(cuda_lib, encs, [c[t].copy() for c in clips], rps)
+        for i in range(n):
+            outs[i] += res[i]
+            sizes[i].append(len(res[i]))
+    recs = [e.recon() for e in encs]
+    for e in encs:
+        e.close()
+    return outs, sizes, recs
+
+
+def test_c3_2160p_rate_controlled_segments(binding, cuda_lib, ref):
+    """BASELINE config 3 at its stated geometry: 3840x2160, --kbps 20000, GOP 30, closed-GOP segments with one fresh
+    session each, encoded concurrently in one batch: bytes, per-frame sizes (the QP trajectory) and reconstruction."""
+    import content
+    w, h, gop, nseg, nfr = 3840, 2160, 30, 2, 8
+    clips = [content.panning(w, h, nfr, seed=3000 + s) for s in range(nseg)]
+    refs = _ref_units(ref, clips, w, h, gop, kbps=20000)
+    outs, sizes, recs = _batch_units(binding, cuda_lib, clips, w, h, gop, kbps=20000)
+    for s in range(nseg):
+        assert sizes[s] == [int(x) for x in refs[s][1]], "segment %d: frame sizes (QP trajectory)" % s
+        assert outs[s] == refs[s][0], "segment %d: bit stream" % s
+        assert np.array_equal(recs[s], refs[s][2][-1]), "segment %d: reconstruction" % s
+
+
+def test_c5_64_streams_720p(binding, cuda_lib, ref):
+    """BASELINE config 5 at its stated geometry: 64 independent 1280x720 streams (distinct seeds), GOP 60, QP 28, one
+    frame of every stream per submission; EVERY stream is compared with its own reference run."""
+    import content
+    w, h, gop, nstreams, nfr = 1280, 720, 60, 64, 4
+    clips = [content.panning(w, h, nfr, seed=s) for s in range(nstreams)]
+    refs = _ref_units(ref, clips, w, h, gop, qp=28)
+    outs, sizes, recs = _batch_units(binding, cuda_lib, clips, w, h, gop, qp=28)
+    for s in range(nstreams):
+        assert outs[s] == refs[s][0], "stream %d: bit stream" % s
+        assert np.array_equal(recs[s], refs[s][2][-1]), "stream %d: reconstruction" % s
+
+
+def test_bench_shape_10x1080p_all_streams_and_determinism(binding, cuda_lib, ref):
+    """The bench workload itself (BASELINE config 2: ten 1080p closed-GOP segments, QP 28, one submission per frame
+    index): ALL ten streams compared with the reference, and the whole run repeated three times with identical
+    digests -- 690 row CTAs over the resident slots in ticket order is the regime where an ordering bug of the
+    wavefront protocol would show (the determinism soak stands in for compute-sanitizer, closed on this pool)."""
+    import content
+    w, h, gop, nseg, nfr = 1920, 1080, 60, 10, 8
+    clips = [content.panning(w, h, nfr, seed=1000 + s) for s in range(nseg)]      # bench.py's clips
+    refs = _ref_units(ref, clips, w, h, gop, qp=28)
+    digests = []
+    for rep in range(3):
+        outs, sizes, recs = _batch_units(binding, cuda_lib, clips, w, h, gop, qp=28)
+        for s in range(nseg):
+            assert outs[s] == refs[s][0], "run %d segment %d: bit stream" % (rep, s)
+            assert np.array_equal(recs[s], refs[s][2][-1]), "run %d segment %d: reconstruction" % (rep, s)
+        digests.append(hashlib.md5(b"".join(outs) + b"".join(r.tobytes() for r in recs)).hexdigest())
+    assert digests[0] == digests[1] == digests[2]
+
+
+def test_batch_larger_than_one_submission(binding, cuda_lib, ref):
+    """Any batch size is accepted: more jobs than the device holds as one wavefront submission are run as
+    consecutive submissions (h264b200_encode_frames), results unchanged."""
+    w, h, n = 64, 48, 3
+    nstreams = 300
+    clips = [cases.make("panning", w, h, n, seed=500 + (s % 7)) for s in range(nstreams)]
+    refs = {}
+    for k in range(7):
+        refs[k] = ref.encode_sequence(clips[k], w, h, 60, qp=30)[0]
+    outs, _, _ = _batch_units(binding, cuda_lib, clips, w, h, 60, qp=30)
+    for s in range(nstreams):
+        assert outs[s] == refs[s % 7], "stream %d" % s

@@ -21,7 +21,9 @@ def _load(name, path):
     return mod
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, cuda=False):
+    if cuda:
+        os.environ["CUDA_VISIBLE_DEVICES"] = str(rank)       # one rank per GPU; H264E_init takes the current device
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,7 +31,8 @@ def _worker(rank, world, port, q):
     import cases
     S = _load("h264lab_shard", os.path.join(ROOT, "h264-lab_b200", "shard.py"))
     B = S.binding()
-    lib = B.Library(os.path.join(ROOT, "tests", "_emu", "libh264lab_emu.so"))
+    lib = B.Library(os.path.join(ROOT, "h264-lab_b200", "libh264lab_b200.so") if cuda
+                    else os.path.join(ROOT, "tests", "_emu", "libh264lab_emu.so"))
     w, h, gop, n = 176, 144, 4, 14
     frames = cases.make("panning", w, h, n)
     units = [frames[s:s + k] for s, k in S.split_closed_gops(n, gop)]
@@ -41,6 +44,19 @@ def _worker(rank, world, port, q):
 
 
 def test_two_ranks_shard_segments(ref, emu_lib):
+    _run_two_ranks(ref, cuda=False)
+
+
+@pytest.mark.gpu
+def test_two_ranks_shard_segments_cuda(ref, cuda_lib):
+    """The same two-rank run on the PRODUCT library, one rank per GPU (skipped on a one-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run_two_ranks(ref, cuda=True)
+
+
+def _run_two_ranks(ref, cuda):
     import torch.multiprocessing as mp
     S = _load("h264lab_shard", os.path.join(ROOT, "h264-lab_b200", "shard.py"))
     assert S.units_of_rank(5, 0, 2) == [0, 2, 4] and S.units_of_rank(5, 1, 2) == [1, 3]
@@ -50,7 +66,7 @@ def test_two_ranks_shard_segments(ref, emu_lib):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, cuda)) for r in range(2)]
     for p in procs:
         p.start()
     out = None
