@@ -168,6 +168,21 @@ def _ref_worker(cfg, unit, nframes, conn, core):
         if cmd == "digests":
             conn.send(digests)
             continue
+        if isinstance(cmd, tuple):          # ("run", k): k frames back to back, free-running (no lock step with the others)
+            t0 = time.perf_counter()
+            err_any = 0
+            for _ in range(cmd[1]):
+                f = clip[t % nframes].copy()
+                yuv = refenc.IoYuv()
+                base = f.ctypes.data
+                yuv.yuv[0], yuv.yuv[1], yuv.yuv[2] = base, base + W * H, base + W * H * 5 // 4
+                yuv.stride[0], yuv.stride[1], yuv.stride[2] = W, W // 2, W // 2
+                data, n = C.c_void_p(), C.c_int()
+                err_any |= l.ref_encode(C.c_void_p(pp), C.c_void_p(sc), C.byref(rp), C.byref(yuv), C.byref(data), C.byref(n))
+                digests.append(hashlib.md5(C.string_at(data.value, n.value)).hexdigest() if not err_any else None)
+                t += 1
+            conn.send((err_any, time.perf_counter() - t0))
+            continue
         f = clip[t % nframes].copy()
         yuv = refenc.IoYuv()
         base = f.ctypes.data
@@ -181,14 +196,31 @@ def _ref_worker(cfg, unit, nframes, conn, core):
         t += 1
 
 
+def _core_order():
+    """logical CPUs this process may use, one hardware thread of every physical core first, their siblings after"""
+    allowed = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+    first, rest, seen = [], [], set()
+    for c in allowed:
+        try:
+            sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+        except Exception:
+            sib = str(c)
+        if sib in seen:
+            rest.append(c)
+        else:
+            seen.add(sib)
+            first.append(c)
+    return first + rest
+
+
 class RefPool:
     def __init__(self, cfg, units, nframes):
         ctx = mp.get_context("spawn")
         self.conns, self.procs = [], []
-        cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+        cores = _core_order()
         for k, u in enumerate(units):
             a, b = ctx.Pipe()
-            core = cores[k % len(cores)] if cores and len(units) <= len(cores) else None     # one core each when they fit
+            core = cores[k] if len(units) <= len(cores) else None     # one core each when they fit, else the OS schedules
             p = ctx.Process(target=_ref_worker, args=(cfg, u, nframes, b, core), daemon=True)
             p.start()
             self.conns.append(a)
@@ -206,6 +238,16 @@ class RefPool:
         assert all(e == 0 for e, _ in out)
         return sum(n for _, n in out)
 
+    def run(self, k):
+        """every process encodes its next k frames at its own pace; returns the wall time until the last one is done"""
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(("run", k))
+        out = [c.recv() for c in self.conns]
+        dt = time.perf_counter() - t0
+        assert all(e == 0 for e, _ in out)
+        return dt
+
     def digests(self):
         for c in self.conns:
             c.send("digests")
@@ -222,12 +264,9 @@ def run_reference(cfg, units, steps, warmup, want_digests=False):
     """steps x len(units) frames of the workload on the host cores (one process per unit)."""
     nframes = min(max(cfg["gop"], 1) if cfg["gop"] > 1 else 8, steps + warmup)
     pool = RefPool(cfg, units, nframes)
-    for _ in range(warmup):
-        pool.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        pool.step()
-    dt = time.perf_counter() - t0
+    if warmup:
+        pool.run(warmup)
+    dt = pool.run(steps)
     dig = pool.digests() if want_digests else None
     variant = pool.variant
     pool.close()
@@ -459,7 +498,7 @@ def main():
     achieved_hbm = alg_bytes_step / (k_main_ms * 1e-3) / 1e9 if k_main_ms > 0 else 0.0
     # algorithmic integer work (SURVEY 8(d) counting rules), measured on this workload with the reference's own counters
     opc = load_json(os.path.join(ROOT, "profiles", "r02_opcount.json"), {}).get(args.config)
-    peak_rows, peak_source = int_peak()
+    peak_rows, peak_source = int_peak(live=not os.environ.get("H264B200_NO_LIVE_PEAK"))
     roof = {"bound": "issue (integer ALU) / wavefront latency -- not hbm, not tensor", "kernel": "macroblock sweep (motion search + mode decision + transform/quant/recon kernels of the step)",
             "achieved": None, "peak": None, "unit": "G int-ops/s", "frac": None, "traffic": None}
     if opc and peak_rows.get("vsadu4") and k_main_ms > 0:
@@ -479,7 +518,7 @@ def main():
                    "algorithmic_bytes_per_launch": alg_bytes_step, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
     steps_wave = (w16 // 16) + 2 * ((h16 // 16) - 1)
     roof["us_per_wavefront_step"] = k_main_ms * 1e3 / steps_wave if k_main_ms else None
-    names = ["device_total", "macroblock_sweep", "deblock+borders+hpel", "cavlc+scan+pack (second stream)", "sad_maps", "extra5", "extra6", "extra7"]
+    names = ["device_total", "macroblock_sweep", "deblock+borders+hpel", "cavlc+scan+pack (second stream)", "sad_maps", "me_prepass", "intra_check", "extra7"]
     line = {
         "metric": metric, "value": total_frames / dt_res, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dt_res / K * 1e3, "higher_is_better": True,

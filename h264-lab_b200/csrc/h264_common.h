@@ -374,10 +374,11 @@ struct MBSpec
     int32_t cand_sig[4]; /* candidate-stage outcome: mv_best, sad_best, cost_best, partition hints */
     int32_t mode_cost[4];/* cost of every partition mode that was searched                   */
     int32_t inter_best;  /* partition mode that won the inter decision                      */
-    int32_t pad[3];
+    int32_t pad[3];      /* [0] cost of the inter decision                                   */
 };
 #define SPEC_UPDATES 1
 #define SPEC_USED_CL 2
+#define SPEC_NO_INTRA 4       /* decided without looking at the intra modes (sweep 0 of a P frame): wave_mb_intra_check has to confirm */
 
 /* per-frame synchronisation words of the wavefront / verification passes */
 #define FS_ARRIVE 0       /* rows that finished the current pass (monotonic)                 */
@@ -455,6 +456,19 @@ struct FrameParams
     int *prof;                  /* developer builds: per-MB phase cycle counts [nmb][10]    */
     int max_passes;             /* safety bound on verification sweeps                      */
     int spec_from_prev;         /* 1: speculate with the previous P frame's replayed trajectory */
+    /* SAD maps of the frame's macroblocks (h264_sadmap.h), [nmb][SM_WORDS]; use_sadmap: the pre-pass ran for this frame */
+    uint32_t *sadmap;
+    int use_sadmap;
+    /* speculative motion estimation ahead of the wavefront (h264_wave.h): use_me = the pre-pass ran for this frame;
+     * me_field = [nmb][16] motion field the pre-pass predicts for THIS frame (input of its refinement rounds) */
+    int use_me;
+    int32_t *me_field;
+    /* 1: sweep 0 of this P frame decides every macroblock among the inter modes only; the intra costs of all macroblocks are
+     * verified afterwards, in parallel, against the finished sweep (h264_wave.h, wave_mb_intra_check) */
+    int spec_no_intra;
+    /* [0]: inter cost from which a macroblock of this frame evaluates its intra modes inside sweep 0 after all (11/8 of the
+     * mean inter cost of the previous P frame, written by wave_replay(predict)); only read when spec_from_prev */
+    int *cost_stat;
     /* temporal noise suppressor (h264_denoise.h); dn_out[0] == NULL: not used for this frame */
     const pix_t *dn_src[3];     /* picture as submitted                                       */
     const pix_t *dn_prev[3];    /* previous output of the filter                              */
@@ -467,6 +481,27 @@ struct FrameParams
 #define WIN_H 48
 
 #define MB_BITS_WORDS 512       /* 2048 bytes per macroblock */
+
+/* SAD-map record of one macroblock (h264_sadmap.h) */
+#define SM_R 7
+#define SM_N (2 * SM_R + 1)
+#define SM_QR 6
+#define SM_QN (2 * SM_QR + 1)
+#define SM_INT_ENTRIES (SM_N * SM_N)
+#define SM_Q_ENTRIES (SM_QN * SM_QN)
+#define SM_INT_OFF 4
+#define SM_Q_OFF (SM_INT_OFF + 2 * SM_INT_ENTRIES)
+#define SM_ME_OFF (SM_Q_OFF + 2 * SM_Q_ENTRIES)
+/* ... followed by the macroblock's speculative motion-estimation record (h264_wave.h, me_prepass_mb): the inputs the
+ * estimation was run with (the key) and everything it produced */
+#define ME_KEY 0          /* [0..3] MV context left, [4..7] top-left, [8..12] top (+ top-right), [13], [14] cluster candidates, [15] 1 = valid */
+#define ME_IC 16          /* MBWork::ic[16] as the candidate stage / 16x16 search left it */
+#define ME_COST 32        /* mode_cost[4] */
+#define ME_MV 36          /* part_mv[4][4] */
+#define ME_MVD 52         /* part_mvd[4][4] */
+#define ME_WORDS 80
+#define SM_WORDS (SM_ME_OFF + ME_WORDS)
+#define SM_INVALID 0xFFFFFFFFu
 
 /* ---- per-macroblock working set (shared memory on the GPU) --------------------- */
 /* private scratch of one motion-search warp */
@@ -527,6 +562,17 @@ struct MBWork
     uint32_t old_mbi[40];        /* previous record / reconstruction of an MB being repaired */
     uint32_t old_rec[96];
     int32_t rp_mv0[32], rp_flags[32], rp_used0[32], rp_used1[32], rp_true0[32], rp_true1[32];   /* replay staging */
+    /* SAD maps (h264_sadmap.h): the record of the current macroblock and, while it is encoded, the one of the next macroblock
+     * of the row (bulk copy, double buffered); map_tag = 1 + macroblock index a buffer holds / was asked to hold,
+     * map_cnt = copies issued into a buffer so far (phase of its barrier) */
+#if MB_WARPS == 1
+    uint32_t __attribute__((aligned(16))) maps[2][4];          /* single-warp build: records are read where they lie */
+#else
+    uint32_t __attribute__((aligned(16))) maps[2][SM_WORDS];
+#endif
+    unsigned long long map_bar[2];
+    int32_t map_tag[2], map_cnt[2];
+    int32_t pf_enable;           /* 1: the row loop of sweep 0 runs: stage the next macroblock's record while this one is encoded */
 };
 
 HD int mb_avail(int mbx, int mby, int nmbx)   /* single slice per frame: H:3605-3622 */

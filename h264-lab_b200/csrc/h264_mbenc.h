@@ -8,6 +8,7 @@
 #pragma once
 #include "h264_common.h"
 #include "h264_pixel.h"
+#include "h264_sadmap.h"
 
 /* optional per-macroblock phase timing (developer builds with -DH264_PROFILE) */
 #if defined(H264_PROFILE) && H264_DEVICE
@@ -44,7 +45,24 @@ struct MBState   /* warp-uniform registers of the macroblock being encoded */
     SearchScratch *ss;   /* private scratch of the search warp running this code */
     int win_x0, win_y0;  /* luma coordinates of the search window's first sample; win_x0 % 4 == 0 */
     int win_ok;
+    /* SAD-map record of the macroblock (h264_sadmap.h; shared-memory copy or the record in global memory, NULL: none) */
+    const uint32_t *map;
+    int map_cx, map_cy, map_qcx, map_qcy;
+    int lut;             /* 1: the searches of this macroblock look their SADs up and build no prediction blocks; the
+                            prediction of the winning mode is made from its vectors at the end (luma_pred_half) */
 };
+
+/* bind the macroblock's SAD-map record (h264_sadmap.h) */
+HD void lut_bind(MBState &s, const uint32_t *rec)
+{
+    s.map = rec;
+    s.map_cx = s.map_cy = s.map_qcx = s.map_qcy = 0;
+    if (rec)
+    {
+        s.map_cx = mv_x((int)rec[0]); s.map_cy = mv_y((int)rec[0]);
+        s.map_qcx = mv_x((int)rec[1]); s.map_qcy = mv_y((int)rec[1]);
+    }
+}
 
 /* slots of MBWork::ic, the outcome of the candidate stage (inter_stage_a) */
 #define IC_STATE 0        /* 0 not known yet, 1 early skip, 2 continue with the searches */
@@ -156,6 +174,36 @@ HD void win_prefetch(const FrameParams *fp, MBWork *w, int mbx, int mby, int cx,
     }
     IF_THREAD0 { w->pf_win_tag = 1 + mby * fp->nmbx + mbx; w->pf_win_x0 = x0; w->pf_win_y0 = y0; }
 }
+/* ---- bulk copy (TMA engine, cp.async.bulk) of a SAD-map record into shared memory, completion on an mbarrier ---- */
+HD unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+HD void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+HD void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tMAP_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MAP_DONE;\n\tbra MAP_WAIT;\n\tMAP_DONE:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* one thread: start the copy of macroblock (mbx, mby)'s record into buffer mbx & 1 */
+HD void map_prefetch(const FrameParams *fp, MBWork *w, int mbx, int mby)
+{
+    IF_THREAD0
+    {
+        if (fp->use_sadmap && fp->slice_type == SLICE_P && mbx < fp->nmbx)
+        {
+            const int n = mby * fp->nmbx + mbx, b = mbx & 1;
+            const unsigned bar = smem_u32(&w->map_bar[b]), dst = smem_u32(w->maps[b]);
+            const uint32_t *src = fp->sadmap + (size_t)n * SM_WORDS;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* earlier reads of the buffer before the engine overwrites it */
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(SM_WORDS * 4)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"((unsigned)(SM_WORDS * 4)), "r"(bar) : "memory");
+            w->map_cnt[b]++;
+            w->map_tag[b] = 1 + n;
+        }
+    }
+}
 #endif
 
 HDF_mb_load void mb_load(MBState &s)
@@ -177,6 +225,18 @@ HDF_mb_load void mb_load(MBState &s)
     cp_async_commit_wait_all();
     CTA_SYNC();
     have_inp = w->pf_inp_tag == 1 + mby * nmbx + mbx;
+    {   /* SAD-map record: the staged copy when there is one for this macroblock, else the record where it lies */
+        const uint32_t *rec = 0;
+        if (fp->use_sadmap && fp->slice_type == SLICE_P)
+        {
+            const int b = mbx & 1;
+            rec = fp->sadmap + (size_t)(mby * nmbx + mbx) * SM_WORDS;
+            if (w->map_tag[b] == 1 + mby * nmbx + mbx) { mbar_wait(&w->map_bar[b], (unsigned)(w->map_cnt[b] - 1) & 1u); rec = w->maps[b]; }
+        }
+        lut_bind(s, rec);
+    }
+#else
+    lut_bind(s, (fp->use_sadmap && fp->slice_type == SLICE_P) ? fp->sadmap + (size_t)(mby * nmbx + mbx) * SM_WORDS : 0);
 #endif
 #if H264_DEVICE && MB_WARPS == 4
     if (have_inp && inside)
@@ -279,7 +339,10 @@ HDF_mb_load void mb_load(MBState &s)
     }
     CTA_SYNC();
 #if H264_DEVICE
+#if MB_WARPS == 4
     mb_prefetch_input(fp, w, mbx + 1, mby);      /* for the next macroblock of the row */
+    if (w->pf_enable) map_prefetch(fp, w, mbx + 1, mby);
+#endif
 #endif
 }
 
@@ -539,6 +602,261 @@ HDF_me_search int me_search(const MBState &s, int ppx, int ppy, const pix_t *inp
     return min_sad;
 }
 
+/* ------------------------------------------------------------------------------
+ * Look-up flavour of the searches (h264_sadmap.h).  The record is bound by mb_load(); lut_decide() picks the flavour
+ * for the whole macroblock.  lut_part_sad() is the one place that turns "SAD of partition (ppx, ppy, bw, bh) at absolute
+ * quarter-sample vector v" into a number: from the maps when the position is tabulated, from the pictures otherwise
+ * (integer position: the reference picture; sub-sample position: interp_luma_planes on the half-sample planes) --
+ * the same value either way.
+ * ---------------------------------------------------------------------------- */
+HD int lut_decide(const MBState &s, int mvp16)
+{
+    if (!s.map || s.fp->slice_type != SLICE_P || s.map[2] != 1u) return 0;
+    const int px = (mv_x(mvp16) + 2) >> 2, py = (mv_y(mvp16) + 2) >> 2;
+    return iabs(px - s.map_cx) <= SM_R - 2 && iabs(py - s.map_cy) <= SM_R - 2;
+}
+HD int lut_quads(const MBState &s, int vrel, uint32_t *lo, uint32_t *hi)
+{
+    return sadmap_lookup(s.map, s.map_cx, s.map_cy, s.map_qcx, s.map_qcy, mv_x(vrel), mv_y(vrel), lo, hi);
+}
+HDN int part_sad_pixels(const MBState &s, int vabs, int ppx, int ppy, int bw, int bh)
+{
+    const FrameParams *fp = s.fp;
+    const int st = fp->stride[0];
+    const pix_t *inp = s.w->inp_y + ppy * 16 + ppx;
+    const long o = (long)((mv_y(vabs) >> 2) + ppy) * st + (mv_x(vabs) >> 2) + ppx;
+    if (!((mv_x(vabs) | mv_y(vabs)) & 3)) return sad_frame_wh(fp->ref[0] + o, st, inp, bw, bh);
+    interp_luma_planes(fp->ref[0] + o, fp->hp[0] + o, fp->hp[1] + o, fp->hp[2] + o, st, mv_x(vabs) & 3, mv_y(vabs) & 3, bw, bh, s.ss->tmpblk);
+    WSYNC();
+    const int v = sad_sm_wh(s.ss->tmpblk, inp, bw, bh);
+    WSYNC();
+    return v;
+}
+#if !H264_DEVICE
+extern long g_emu_lut[8];       /* emulation statistics: [0] P macroblocks, [1] of them in the look-up flavour, [2] look-ups, [3] misses */
+#define LUT_STAT(k) (g_emu_lut[k]++)
+#else
+#define LUT_STAT(k) ((void)0)
+#endif
+HD int lut_part_sad(const MBState &s, int vabs, int ppx, int ppy, int bw, int bh)
+{
+    uint32_t lo, hi;
+    LUT_STAT(2);
+    if (lut_quads(s, mv_pack(mv_x(vabs) - s.mbx * 64, mv_y(vabs) - s.mby * 64), &lo, &hi)) return quads_part(lo, hi, ppx, ppy, bw, bh);
+    LUT_STAT(3);
+    return part_sad_pixels(s, vabs, ppx, ppy, bw, bh);
+}
+
+/* me_search() with look-ups: the same walk (H:4973-5176) -- greedy diamond with the 16-bit cost cache, one diagonal
+ * probe + restart, seven ordered sub-sample probes -- but every SAD is one lut_part_sad() and no prediction block is built. */
+HDN int me_search_lut(const MBState &s, int ppx, int ppy, int *pmv, const int *rng, int mv_pred, int min_sad, int bw, int bh)
+{
+    const FrameParams *fp = s.fp;
+    const int lam = fp->lambda_mv_q4;
+    int mv = *pmv;
+    uint32_t c0, c1, c2, c3, p0, p1, p2, p3;      /* cache[0..3], cache[4..7] of the reference, kept in registers */
+    int dir, cloop, dir_prev, cost, v;
+    for (;;)
+    {
+        dir = 0; cloop = 4; dir_prev = -1;
+        c0 = c1 = c2 = c3 = p0 = p1 = p2 = p3 = 0xffffu;
+        do
+        {
+            const int dx = dir == 0 ? 4 : (dir == 1 ? -4 : 0), dy = dir == 2 ? 4 : (dir == 3 ? -4 : 0);
+            v = mv_pack(mv_x(mv) + dx, mv_y(mv) + dy);
+            const uint32_t cd = dir == 0 ? c0 : (dir == 1 ? c1 : (dir == 2 ? c2 : c3));
+            if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]) && cd == 0xffffu)
+            {
+                cost = lut_part_sad(s, v, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+                const uint32_t cc = (uint32_t)cost & 0xffffu;
+                if (dir == 0) c0 = cc; else if (dir == 1) c1 = cc; else if (dir == 2) c2 = cc; else c3 = cc;
+                if (cost < min_sad)
+                {
+                    uint32_t corner = 0xffffu;
+                    if (dir_prev >= 0) corner = dir == 0 ? p0 : (dir == 1 ? p1 : (dir == 2 ? p2 : p3));
+                    p0 = c0; p1 = c1; p2 = c2; p3 = c3;
+                    c0 = c1 = c2 = c3 = 0xffffu;
+                    if (dir_prev >= 0) { const int k = dir_prev ^ 1; if (k == 0) c0 = corner; else if (k == 1) c1 = corner; else if (k == 2) c2 = corner; else c3 = corner; }
+                    { const int k = dir ^ 1; const uint32_t m = (uint32_t)min_sad & 0xffffu; if (k == 0) c0 = m; else if (k == 1) c1 = m; else if (k == 2) c2 = m; else c3 = m; }
+                    dir_prev = dir;
+                    dir--;
+                    cloop = 4 + 1;
+                    mv = v;
+                    min_sad = cost;
+                }
+            }
+            dir = (dir + 1) & 3;
+        } while (--cloop);
+        {
+            const int pdy = c3 >= c2 ? 4 : -4, sdx = c1 >= c0 ? 4 : -4;
+            v = mv_pack(mv_x(mv) + sdx, mv_y(mv) + pdy);
+            if (mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]))
+            {
+                cost = lut_part_sad(s, v, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+                if (cost < min_sad) { mv = v; min_sad = cost; continue; }
+            }
+        }
+        break;
+    }
+    if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
+    {
+        uint32_t minsad1 = c1, minsad2 = c3;
+        int sqx = -1, sqy = 0, pqx = 0, pqy = -1;
+        if (c3 >= c2) { pqy = 1; minsad2 = c2; }
+        if (c1 >= c0) { sqx = 1; minsad1 = c0; }
+        if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
+        const int dgx = pqx + sqx, dgy = pqy + sqy;
+        int vbest = mv;
+#pragma unroll 1
+        for (int i = 0; i < 7; i++)
+        {
+            const int ox = i == 0 ? 2 * pqx : (i == 1 ? pqx : (i == 2 ? 2 * sqx : (i == 3 ? sqx : (i == 4 ? dgx : (i == 5 ? 2 * dgx : pqx + dgx)))));
+            const int oy = i == 0 ? 2 * pqy : (i == 1 ? pqy : (i == 2 ? 2 * sqy : (i == 3 ? sqy : (i == 4 ? dgy : (i == 5 ? 2 * dgy : pqy + dgy)))));
+            v = mv_pack(mv_x(mv) + ox, mv_y(mv) + oy);
+            const int sad_test = lut_part_sad(s, v, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+            if (sad_test < min_sad) { min_sad = sad_test; vbest = v; }
+        }
+        mv = vbest;
+    }
+    *pmv = mv;
+    return min_sad;
+}
+
+
+#if H264_DEVICE
+/* ------------------------------------------------------------------------------
+ * sm_100a execution of the look-up flavour: ONE position per lane.  The host emulation runs me_search_lut() /
+ * the serial candidate loop above (which document the walk); here the eight neighbours of a search centre, the seven
+ * sub-sample probes and the start candidates are each costed by their own lane (look-up + MV cost), and only the
+ * order-dependent replay of the reference's comparisons runs warp-uniform on the gathered costs.
+ * ---------------------------------------------------------------------------- */
+/* SAD of the lane's own vector v (lanes with valid == 0 return 0); positions that are not tabulated are computed from
+ * the pictures by the whole warp, one after the other (rare) */
+HD int lut_sad_lanes(const MBState &s, int v, int valid, int ppx, int ppy, int bw, int bh)
+{
+    const unsigned FULLM = 0xffffffffu;
+    uint32_t lo = 0, hi = 0;
+    int hit = 0;
+    if (valid) hit = lut_quads(s, mv_pack(mv_x(v) - s.mbx * 64, mv_y(v) - s.mby * 64), &lo, &hi);
+    int sad = hit ? quads_part(lo, hi, ppx, ppy, bw, bh) : 0;
+    unsigned miss = __ballot_sync(FULLM, valid && !hit);
+    while (miss)
+    {
+        const int l = __ffs((int)miss) - 1;
+        miss &= miss - 1;
+        const int sv = part_sad_pixels(s, __shfl_sync(FULLM, v, l), ppx, ppy, bw, bh);
+        if (LANE_ID == l) sad = sv;
+    }
+    return sad;
+}
+
+HDN int me_search_par(const MBState &s, int ppx, int ppy, int *pmv, const int *rng, int mv_pred, int min_sad, int bw, int bh)
+{
+    const unsigned FULLM = 0xffffffffu;
+    const FrameParams *fp = s.fp;
+    const int lam = fp->lambda_mv_q4, lane = LANE_ID;
+    int mv = *pmv;
+    /* neighbour k = lane & 7 of a centre: 0 (+1,0) 1 (-1,0) 2 (0,+1) 3 (0,-1) 4 (+1,+1) 5 (-1,+1) 6 (+1,-1) 7 (-1,-1) */
+    const int k = lane & 7;
+    const int ox = (k == 0 || k == 4 || k == 6) ? 4 : ((k == 2 || k == 3) ? 0 : -4);
+    const int oy = (k == 2 || k == 4 || k == 5) ? 4 : ((k == 0 || k == 1) ? 0 : -4);
+    uint32_t c0, c1, c2, c3, p0, p1, p2, p3;
+    int dir, cloop, dir_prev;
+    for (;;)
+    {
+        dir = 0; cloop = 4; dir_prev = -1;
+        c0 = c1 = c2 = c3 = p0 = p1 = p2 = p3 = 0xffffu;
+        int nb4, nb5, nb6, nb7;
+        unsigned inmask;
+        for (;;)
+        {
+            const int v = mv_pack(mv_x(mv) + ox, mv_y(mv) + oy);
+            const int inr = mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]);
+            const int cst = lut_sad_lanes(s, v, lane < 8 && inr, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+            inmask = __ballot_sync(FULLM, inr) & 0xffu;
+            const int nb0 = __shfl_sync(FULLM, cst, 0), nb1 = __shfl_sync(FULLM, cst, 1), nb2 = __shfl_sync(FULLM, cst, 2), nb3 = __shfl_sync(FULLM, cst, 3);
+            nb4 = __shfl_sync(FULLM, cst, 4); nb5 = __shfl_sync(FULLM, cst, 5); nb6 = __shfl_sync(FULLM, cst, 6); nb7 = __shfl_sync(FULLM, cst, 7);
+            int moved = 0;
+            do
+            {
+                const uint32_t cd = dir == 0 ? c0 : (dir == 1 ? c1 : (dir == 2 ? c2 : c3));
+                if (((inmask >> dir) & 1u) && cd == 0xffffu)
+                {
+                    const int cost = dir == 0 ? nb0 : (dir == 1 ? nb1 : (dir == 2 ? nb2 : nb3));
+                    const uint32_t cc = (uint32_t)cost & 0xffffu;
+                    if (dir == 0) c0 = cc; else if (dir == 1) c1 = cc; else if (dir == 2) c2 = cc; else c3 = cc;
+                    if (cost < min_sad)
+                    {
+                        uint32_t corner = 0xffffu;
+                        if (dir_prev >= 0) corner = dir == 0 ? p0 : (dir == 1 ? p1 : (dir == 2 ? p2 : p3));
+                        p0 = c0; p1 = c1; p2 = c2; p3 = c3;
+                        c0 = c1 = c2 = c3 = 0xffffu;
+                        if (dir_prev >= 0) { const int q = dir_prev ^ 1; if (q == 0) c0 = corner; else if (q == 1) c1 = corner; else if (q == 2) c2 = corner; else c3 = corner; }
+                        { const int q = dir ^ 1; const uint32_t m = (uint32_t)min_sad & 0xffffu; if (q == 0) c0 = m; else if (q == 1) c1 = m; else if (q == 2) c2 = m; else c3 = m; }
+                        mv = mv_pack(mv_x(mv) + (dir == 0 ? 4 : (dir == 1 ? -4 : 0)), mv_y(mv) + (dir == 2 ? 4 : (dir == 3 ? -4 : 0)));
+                        min_sad = cost;
+                        dir_prev = dir;
+                        dir--;
+                        cloop = 4 + 1;
+                        moved = 1;
+                    }
+                }
+                dir = (dir + 1) & 3;
+            } while (--cloop && !moved);
+            if (!moved) break;          /* the walk has settled on this centre; after a move its neighbours are costed anew */
+        }
+        {
+            const int pneg = c3 >= c2 ? 0 : 1, sneg = c1 >= c0 ? 0 : 1, kk = 4 + sneg + 2 * pneg;
+            if ((inmask >> kk) & 1u)
+            {
+                const int cost = kk == 4 ? nb4 : (kk == 5 ? nb5 : (kk == 6 ? nb6 : nb7));
+                if (cost < min_sad) { mv = mv_pack(mv_x(mv) + (sneg ? -4 : 4), mv_y(mv) + (pneg ? -4 : 4)); min_sad = cost; continue; }
+            }
+        }
+        break;
+    }
+    if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
+    {
+        uint32_t minsad1 = c1, minsad2 = c3;
+        int sqx = -1, sqy = 0, pqx = 0, pqy = -1;
+        if (c3 >= c2) { pqy = 1; minsad2 = c2; }
+        if (c1 >= c0) { sqx = 1; minsad1 = c0; }
+        if (minsad2 > minsad1) { int t; t = sqx; sqx = pqx; pqx = t; t = sqy; sqy = pqy; pqy = t; }
+        const int dgx = pqx + sqx, dgy = pqy + sqy;
+        /* probe i = lane: 0 2p, 1 p, 2 2s, 3 s, 4 p+s, 5 2(p+s), 6 2p+s (H:5119-5161); strict '<' in that order == the
+         * smallest (cost, i) */
+        const int i = lane & 7;
+        const int qx = i == 0 ? 2 * pqx : (i == 1 ? pqx : (i == 2 ? 2 * sqx : (i == 3 ? sqx : (i == 4 ? dgx : (i == 5 ? 2 * dgx : pqx + dgx)))));
+        const int qy = i == 0 ? 2 * pqy : (i == 1 ? pqy : (i == 2 ? 2 * sqy : (i == 3 ? sqy : (i == 4 ? dgy : (i == 5 ? 2 * dgy : pqy + dgy)))));
+        const int v = mv_pack(mv_x(mv) + qx, mv_y(mv) + qy);
+        const int cst = lut_sad_lanes(s, v, lane < 7, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+        int key = lane < 7 ? ((cst << 3) | i) : 0x7FFFFFFF;
+        key = min(key, __shfl_xor_sync(FULLM, key, 4));
+        key = min(key, __shfl_xor_sync(FULLM, key, 2));
+        key = min(key, __shfl_xor_sync(FULLM, key, 1));
+        key = __shfl_sync(FULLM, key, 0);
+        if ((key >> 3) < min_sad) { min_sad = key >> 3; mv = __shfl_sync(FULLM, v, key & 7); }
+    }
+    *pmv = mv;
+    return min_sad;
+}
+#endif
+
+/* rows 8 * half .. 8 * half + 7 of the luma prediction of an inter macroblock, made from its final vectors (one warp):
+ * what the reference has in its buffers after the winning probe (H:5116-5170) or re-interpolates (H:5520) */
+HDN void luma_pred_half(const MBState &s, int half, int type, const int32_t *pmv, pix_t *dst)
+{
+    const FrameParams *fp = s.fp;
+    FOR_LANES(i, 32)
+    {
+        const int r = 8 * half + (i >> 2), c = (i & 3) * 4;
+        const int part = type <= 0 ? 0 : (type == 1 ? (r >> 3) : (type == 2 ? (c >> 3) : (r >> 3) * 2 + (c >> 3)));
+        const int mv = pmv[part];
+        *(uint32_t *)(dst + r * 16 + c) = interp_luma_word(fp, mv_x(mv) + (s.mbx * 16 + c) * 4, mv_y(mv) + (s.mby * 16 + r) * 4);
+    }
+    WSYNC();
+}
+
 /* me_mv_set_range H:5181 */
 HD void me_set_range(const FrameParams *fp, int *pnt, int *rng, int mby_q)
 {
@@ -610,6 +928,14 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
 
     if (mv_in_rect(mv_skip_a, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
+        uint32_t qlo, qhi;
+        if (s.lut && lut_quads(s, mv_skip, &qlo, &qhi))
+        {   /* the skip position is tabulated: no prediction block is needed for the test (encode_mb makes it if the
+             * macroblock ends up using it) */
+            sad4v[0] = (int)(qlo & 0xFFFF); sad4v[1] = (int)(qlo >> 16); sad4v[2] = (int)(qhi & 0xFFFF); sad4v[3] = (int)(qhi >> 16);
+            sad_skip = sad4v[0] + sad4v[1] + sad4v[2] + sad4v[3];
+        } else
+        {
         if (!((mv_x(mv_skip_a) | mv_y(mv_skip_a)) & 3))
         {   /* full-pel vector: the prediction is a copy of integer samples, usually inside the search window */
             int rs;
@@ -624,6 +950,7 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
         }
         WSYNC();
         sad_skip = sad_mb_quad(w->inp_y, 16, w->skip_pred, sad4v);
+        }
         if (imax(imax(sad4v[0], sad4v[1]), imax(sad4v[2], sad4v[3])) < fp->skip_thr_inter)
         {
             int32_t one_mv = mv_skip;
@@ -679,8 +1006,45 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
         const unsigned okm = __ballot_sync(FULLM, cok);
         const unsigned same = __match_any_sync(FULLM, cval) & okm;
         unsigned keep = __ballot_sync(FULLM, cok && (same & (0u - same)) == (1u << lane));
+        const unsigned keep_all = keep;
         if (j) keep &= keep - 1;                                    /* full-pel skip vector: its SAD is reused (H:5361) */
         PROF_SUB(s, 8);
+        if (s.lut)
+        {
+            /* look-up flavour: every surviving candidate is costed by its own lane.  A full-pel skip vector is simply
+             * costed again on lane 0 (same position, same numbers as the reused ones); the reference's "first strictly
+             * smaller sum in list order" is the smallest (sum, lane). */
+            const int mva = mv_pack(mv_x(cval) + mbqx, mv_y(cval) + mbqy);
+            const int inr = ((keep_all >> lane) & 1u) && mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1);
+            uint32_t qlo = 0, qhi = 0;
+            const int hit = inr && lut_quads(s, cval, &qlo, &qhi);
+            unsigned miss = __ballot_sync(FULLM, inr && !hit);
+            while (miss)
+            {   /* not tabulated: from the reference picture, by the whole warp */
+                const int l = __ffs((int)miss) - 1;
+                miss &= miss - 1;
+                const int ma = __shfl_sync(FULLM, mva, l);
+                int q4[4];
+                sad_mb_quad(fp->ref[0] + (long)(mv_y(ma) >> 2) * fp->stride[0] + (mv_x(ma) >> 2), fp->stride[0], w->inp_y, q4);
+                if (lane == l) { qlo = (uint32_t)q4[0] | ((uint32_t)q4[1] << 16); qhi = (uint32_t)q4[2] | ((uint32_t)q4[3] << 16); }
+            }
+            int q4[4], pl[4] = {0, 0, 0, 0};
+            q4[0] = (int)(qlo & 0xFFFF); q4[1] = (int)(qlo >> 16); q4[2] = (int)(qhi & 0xFFFF); q4[3] = (int)(qhi >> 16);
+            const int sad = q4[0] + q4[1] + q4[2] + q4[3], cc = mv_cost(cval, mvp16, fp->lambda_mv_q4);
+            if (inr && fp->speed < 1) inter_partition_hint(q4, pl);
+            if (__ballot_sync(FULLM, pl[1])) pref[1] = 1;
+            if (__ballot_sync(FULLM, pl[2])) pref[2] = 1;
+            if (__ballot_sync(FULLM, pl[3])) pref[3] = 1;
+            int key = inr ? (((sad + cc) << 5) | lane) : 0x7FFFFFFF;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(FULLM, key, o));
+            if (key != 0x7FFFFFFF)
+            {
+                const int wl = key & 31;
+                mv_best = __shfl_sync(FULLM, cval, wl); sad_best = __shfl_sync(FULLM, sad, wl); cand_cost_best = __shfl_sync(FULLM, cc, wl);
+            }
+            keep = 0;
+        }
         while (keep)
         {
             const int cj = __shfl_sync(FULLM, cval, __ffs((int)keep) - 1);
@@ -689,9 +1053,18 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
             if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
             {
                 int cc = mv_cost(cj, mvp16, fp->lambda_mv_q4);
-                int rs;
-                const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
-                int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                int sad;
+                uint32_t qlo, qhi;
+                if (s.lut && lut_quads(s, cj, &qlo, &qhi))
+                {
+                    sad4v[0] = (int)(qlo & 0xFFFF); sad4v[1] = (int)(qlo >> 16); sad4v[2] = (int)(qhi & 0xFFFF); sad4v[3] = (int)(qhi >> 16);
+                    sad = sad4v[0] + sad4v[1] + sad4v[2] + sad4v[3];
+                } else
+                {
+                    int rs;
+                    const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
+                    sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                }
                 if (fp->speed < 1) inter_partition_hint(sad4v, pref);
                 if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cj; }
             }
@@ -726,9 +1099,18 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
             if (mv_in_rect(mva, fp->mvlim_x0, fp->mvlim_y0, fp->mvlim_x1, fp->mvlim_y1))
             {
                 int cc = mv_cost(cand[j], mvp16, fp->lambda_mv_q4);
-                int rs;
-                const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
-                int sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                int sad;
+                uint32_t qlo, qhi;
+                if (s.lut && lut_quads(s, cand[j], &qlo, &qhi))
+                {
+                    sad4v[0] = (int)(qlo & 0xFFFF); sad4v[1] = (int)(qlo >> 16); sad4v[2] = (int)(qhi & 0xFFFF); sad4v[3] = (int)(qhi >> 16);
+                    sad = sad4v[0] + sad4v[1] + sad4v[2] + sad4v[3];
+                } else
+                {
+                    int rs;
+                    const pix_t *rp = ref_at(s, mv_x(mva) >> 2, mv_y(mva) >> 2, 16, 16, &rs);
+                    sad = sad_mb_quad(rp, rs, w->inp_y, sad4v);
+                }
                 if (fp->speed < 1) inter_partition_hint(sad4v, pref);
                 if (sad + cc < sad_best + cand_cost_best) { cand_cost_best = cc; sad_best = sad; mv_best = cand[j]; }
             }
@@ -793,18 +1175,29 @@ HDF_inter_mode_search void inter_mode_search(MBState &s, int mb_type)
         {
             mvabs = mv_round_fullpel(mv_pred_a);
             me_set_range(fp, &mvabs, rng, mbqy + py * 4);
+            if (s.lut) sad_best = lut_part_sad(s, mvabs, px, py, bw, bh) + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
+            else
+            {
             int rs;
             const pix_t *rp = ref_at(s, (mv_x(mvabs) >> 2) + px, (mv_y(mvabs) >> 2) + py, bw, bh, &rs);
             sad_best = sad_frame_wh(rp, rs, w->inp_y + py * 16 + px, bw, bh)
                      + mv_cost(mvabs, mv_pred_a, fp->lambda_mv_q4);
+            }
         }
         int sb = mb_type ? (mb_type == 2 ? 8 : 128) : 256;
         pix_t *bufs[4];
         bufs[0] = store; bufs[1] = store + sb; bufs[2] = store + (sb == 8 ? 256 : 2 * sb); bufs[3] = bufs[2] + sb;
-        pix_t *dout;
+        pix_t *dout = store;
+#if H264_DEVICE
+        if (s.lut) part_sad += me_search_par(s, px, py, &mvabs, rng, mv_pred_a, sad_best, bw, bh);
+#else
+        if (s.lut) part_sad += me_search_lut(s, px, py, &mvabs, rng, mv_pred_a, sad_best, bw, bh);
+#endif
+        else
         part_sad += me_search(s, px, py, w->inp_y + py * 16 + px, &mvabs, rng, mv_pred_a, sad_best,
                               bw, bh, bufs, &dout);
-        if (!mb_type) result = dout;
+        if (s.lut) { }                  /* no prediction blocks in the look-up flavour (luma_pred_half makes the winner's) */
+        else if (!mb_type) result = dout;
         else
         {
             const int sh = bw == 16 ? 2 : 1;
@@ -902,7 +1295,7 @@ HD int lds_u8(unsigned addr)
  *    partial sums), the mode costs are formed where the sums end up and the strict-'<'-in-
  *    evaluation-order decision is a min-reduction of (cost << 4 | slot);
  *  - residual -> transform -> quantisation -> inverse -> reconstruction stay in registers. */
-HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
+HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16, int fixed_bound = -1)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -913,7 +1306,7 @@ HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
     int nz_mask = 0;
     const int penalty = (3 * fp->lambda_q4) >> 4;
     const int skip_thr = fp->skip_thr_i4x4;
-    const int poll_skip = fp->slice_type == SLICE_P;
+    const int poll_skip = fp->slice_type == SLICE_P && fixed_bound < 0;
 
     /* padded reconstruction R[17][24]: row 0 = row above (TL at col 3, 16 + 4 samples from col 4),
      * col 3 = left column; sample (x,y) of the MB at R[(y+1)*24 + x+4] */
@@ -982,6 +1375,7 @@ HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
             /* exact pruning: the blocks decided so far already cost as much as a competitor */
             int bound = cost16;
             if (st == 2) bound = imin(bound, inter_final_bound(fp, w));
+            if (fixed_bound >= 0) bound = imin(bound, fixed_bound);
             if (cost + __shfl_xor_sync(FULL, cost, 16) + fp->lambda_i4_q4 >= bound) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         }
         const int nA = t < 2 ? t : 4 * (t >> 1) + (t & 1) - 2;
@@ -1108,7 +1502,7 @@ HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
     return cost + fp->lambda_i4_q4;
 }
 #else
-HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
+HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16, int fixed_bound = -1)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -1120,10 +1514,11 @@ HDF_intra4_choose int intra4_choose(MBState &s, int *nz_mask_out, int cost16)
 
     for (int n = 0; n < 16; n++)
     {
-        if (fp->slice_type == SLICE_P && w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
+        if (fixed_bound < 0 && fp->slice_type == SLICE_P && w->ic[IC_STATE] == 1) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         {   /* exact pruning (see inter_cost_bound) */
             int bound = cost16;
-            if (fp->slice_type == SLICE_P && w->ic[IC_STATE] == 2) bound = imin(bound, inter_final_bound(fp, w));
+            if (fixed_bound < 0 && fp->slice_type == SLICE_P && w->ic[IC_STATE] == 2) bound = imin(bound, inter_final_bound(fp, w));
+            if (fixed_bound >= 0) bound = imin(bound, fixed_bound);
             if (cost >= bound) { *nz_mask_out = 0; return 0x7FFFFFFF; }
         }
         /* which neighbours exist for block n (block2avail H:4750) */
@@ -1702,6 +2097,80 @@ HDF_partition_tasks void partition_tasks(MBState &s, int slot)
     }
 }
 
+/* The motion-estimation phase of a P macroblock: candidate stage on warp 0, then the 16x16 search there and the hinted
+ * partition modes on warps 1 and 2 (single-warp build: one after the other).  Leaves its results in w->ic[],
+ * w->mode_cost[], w->part_mv[][], w->part_mvd[][] (+ prediction blocks in the pixel flavour). */
+HD void me_phase(MBState &s, const int32_t cl[2])
+{
+    MBWork *w = s.w;
+    ON_WARP(0)
+    {
+        s.ss = &w->ss[0];
+        inter_stage_a(s, cl);
+        PROF_MARK(s, 2);
+        bar_sync(1, 96);
+        if (w->ic[IC_STATE] != 1) inter_mode_search(s, 0);
+        PROF_MARK(s, 4);
+    }
+    ON_WARP(1) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 1); }
+    ON_WARP(2) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 2); }
+}
+
+/* Inter decision over the results of me_phase() (H:5500-5522): early skip, else the cheapest searched mode in ascending
+ * order with strict '<', else P16x16 at the skip vector when the raw skip SAD is smaller.  Every thread, same values.
+ * Returns the winning partition mode of the search (what MBSpec::inter_best records). */
+HD int inter_decide(const FrameParams *fp, const MBWork *w, int *ptype, int *pcost, int32_t pmv[4], int32_t pmvd[4], int *use_skip_pred)
+{
+    const int mvp16 = w->ic[IC_MVP16], mv_skip = w->ic[IC_MV_SKIP];
+    *use_skip_pred = 0;
+    if (w->ic[IC_STATE] == 1)
+    {
+        *ptype = MBT_SKIP; *pcost = 0;
+        pmv[0] = mv_skip;
+        *use_skip_pred = 1;
+        return 0;
+    }
+    int cost = 0xffffff, best_type = 0;
+    for (int t = 0; t < 4; t++)
+        if ((w->ic[IC_PREF] >> t) & 1)
+            if (w->mode_cost[t] < cost) { cost = w->mode_cost[t]; best_type = t; }
+    int type = best_type;
+    for (int i = 0; i < 4; i++) { pmv[i] = w->part_mv[best_type][i]; pmvd[i] = w->part_mvd[best_type][i]; }
+    if (cost > w->ic[IC_SAD_SKIP])     /* P16x16 at the skip vector is cheaper (H:5512) */
+    {
+        type = 0;
+        cost = w->ic[IC_SAD_SKIP] + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+        pmv[0] = mv_skip;
+        pmvd[0] = mv_sub2(mv_skip, mvp16);
+        *use_skip_pred = 1;      /* same samples the reference re-interpolates (H:5520) */
+    }
+    *ptype = type; *pcost = cost;
+    return best_type;
+}
+
+/* Does the speculative motion-estimation record of the macroblock (h264_wave.h, me_prepass_mb) belong to exactly the
+ * inputs the macroblock really has -- the 13 context vectors and the two cluster candidates?  Then running the
+ * estimation again would reproduce the record word for word.  Every warp evaluates it (same answer in all). */
+HD int me_record_matches(const MBState &s, const uint32_t *mr, const int32_t cl[2])
+{
+    const MBWork *w = s.w;
+    int ok = 1;
+    FOR_LANES(i, 16)
+    {
+        int32_t have;
+        if (i < 4) have = w->mvp0_left[i];
+        else if (i < 8) have = w->mvp0_tl[i - 4];
+        else if (i < 13) have = w->mvp0_top[i - 8];
+        else if (i < 15) have = cl[i - 13];
+        else have = 1;
+        if ((int32_t)mr[ME_KEY + i] != have) ok = 0;
+    }
+#if H264_DEVICE
+    ok = __all_sync(0xffffffffu, ok);
+#endif
+    return ok;
+}
+
 /* ------------------------------------------------------------------------------
  * a17: encode one macroblock (mb_encode H:5724 + the pixel/coefficient half of
  * mb_write H:4378) with the whole CTA.  cl[] = rounded mv_clusters candidates.
@@ -1717,7 +2186,7 @@ HDF_partition_tasks void partition_tasks(MBState &s, int slot)
  *   warps 0,1: luma halves;  warps 2,3: chroma planes (prediction + transform)
  *   all      : coded block pattern, skip rollback, record
  * ---------------------------------------------------------------------------- */
-HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out)
+HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby, const int32_t cl[2], MBSpec *spec_out, int with_intra = 1)
 {
     MBState s;
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
@@ -1725,9 +2194,9 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
     s.pbest = w->skip_pred; s.ss = &w->ss[WARP_ID < 3 ? WARP_ID : 0];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
+    s.map = 0; s.lut = 0;
     const int is_p = fp->slice_type == SLICE_P;
     MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
-    int16_t *coef = fp->coef + (size_t)(mby * fp->nmbx + mbx) * COEF_PER_MB;
     int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
     PROF_INIT(s);
 
@@ -1736,25 +2205,53 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
     if (is_p)
     {
         int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
-        win_load(s, mbx * 16 + ((mv_x(mvp16) + 1) >> 2), mby * 16 + ((mv_y(mvp16) + 1) >> 2));
+        /* searches by look-up (h264_sadmap.h) when the macroblock's record covers where its predictor points; else the
+         * pixel flavour with its shared-memory window.  Same decisions either way. */
+        s.lut = lut_decide(s, mvp16);
+        LUT_STAT(0); if (s.lut) LUT_STAT(1);
+        if (!s.lut) win_load(s, mbx * 16 + ((mv_x(mvp16) + 1) >> 2), mby * 16 + ((mv_y(mvp16) + 1) >> 2));
     }
     PROF_MARK(s, 1);
 
-    /* ---- concurrent tasks ---- */
-    if (is_p)
+    /* ---- motion estimation: already done ahead of the wavefront?  (h264_wave.h, me_prepass_mb) ---- */
+    int me_hit = 0;
+    if (is_p && s.lut && fp->use_me)
     {
-        ON_WARP(0)
+        const uint32_t *mr = s.map + SM_ME_OFF;
+        me_hit = me_record_matches(s, mr, cl);
+        if (me_hit)
         {
-            s.ss = &w->ss[0];
-            inter_stage_a(s, cl);
-            PROF_MARK(s, 2);
-            bar_sync(1, 96);
-            if (w->ic[IC_STATE] != 1) inter_mode_search(s, 0);
-            PROF_MARK(s, 4);
+            FOR_THREADS(i, 52)
+            {
+                if (i < 16) w->ic[i] = (int32_t)mr[ME_IC + i];
+                else if (i < 20) w->mode_cost[i - 16] = (int32_t)mr[ME_COST + i - 16];
+                else if (i < 36) (&w->part_mv[0][0])[i - 20] = (int32_t)mr[ME_MV + i - 20];
+                else (&w->part_mvd[0][0])[i - 36] = (int32_t)mr[ME_MVD + i - 36];
+            }
+            CTA_SYNC();
         }
-        ON_WARP(1) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 1); }
-        ON_WARP(2) { bar_sync(1, 96); if (w->ic[IC_STATE] != 1) partition_tasks(s, 2); }
+        LUT_STAT(4); if (me_hit) LUT_STAT(5);
     }
+    /* Intra modes inside this sweep?  Always, unless the sweep speculates that none wins (with_intra == 0, sweep 0 of a P
+     * frame); even then when the inter cost is already known (record) and so far above the usual that an intra mode
+     * probably does win -- evaluating it here saves the repair -- and when the estimation has to run in place anyway. */
+    int do_intra = with_intra;
+    if (!do_intra)
+    {
+        do_intra = 1;
+        if (me_hit)
+        {
+            int t_, c_, u_; int32_t m_[4], d_[4];
+            inter_decide(fp, w, &t_, &c_, m_, d_, &u_);
+            do_intra = t_ != MBT_SKIP && c_ >= (fp->spec_from_prev ? fp->cost_stat[0] : 0);
+        }
+    }
+    /* ---- concurrent tasks ---- */
+    if (is_p && !me_hit) me_phase(s, cl);
+    if (!do_intra)
+    {   /* sweep 0 of a P frame speculates "no intra mode wins" (h264_wave.h, wave_mb_intra_check verifies afterwards) */
+        ON_WARP(3) { IF_LANE0 { w->intra_res[0] = 0x7FFFFFFF; w->intra_res[1] = 2; w->intra_res[2] = 0x7FFFFFFF; w->intra_res[3] = 0; } }
+    } else
     ON_WARP(3)
     {
         /* Intra16x16: heuristic mode, one prediction, SAD cost (intra_choose_16x16 H:4876) */
@@ -1777,7 +2274,7 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
             __threadfence_block();
             if (st == 2)
             {
-                partition_tasks(s, 3);
+                if (!me_hit) partition_tasks(s, 3);
                 /* P16x16 wins most of the time: when this warp has nothing else to do it prepares that
                  * mode's chroma prediction, taking the chroma reference fetch off the critical tail */
                 if (*(volatile int32_t *)&w->ic[IC_COST0] >= 0)      /* only when the 16x16 search is already over: never wait for it */
@@ -1817,39 +2314,20 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
     for (int k = 0; k < 4; k++) spec_out->mode_cost[k] = 0x7FFFFFFF;
     if (is_p)
     {
-        const int mvp16 = w->ic[IC_MVP16], mv_skip = w->ic[IC_MV_SKIP];
-        s.mv_skip_pred = mv_skip;
-        if (w->ic[IC_STATE] == 1)
-        {
-            s.type = MBT_SKIP; s.cost = 0;
-            pmv[0] = mv_skip;
-            s.pbest = w->skip_pred;
-        } else
+        s.mv_skip_pred = w->ic[IC_MV_SKIP];
+        int use_skip_pred;
+        const int best_type = inter_decide(fp, w, &s.type, &s.cost, pmv, pmvd, &use_skip_pred);
+        if (w->ic[IC_STATE] != 1)
         {
             used_cl = 1;
             for (int k = 0; k < 4; k++) cand_sig[k] = w->ic[IC_SIG + k];
-            s.cost = 0xffffff;
-            int best_type = 0;
-            for (int t = 0; t < 4; t++)
-                if ((w->ic[IC_PREF] >> t) & 1)
-                {
-                    spec_out->mode_cost[t] = w->mode_cost[t];
-                    if (w->mode_cost[t] < s.cost) { s.cost = w->mode_cost[t]; best_type = t; }
-                }
+            for (int t = 0; t < 4; t++) if ((w->ic[IC_PREF] >> t) & 1) spec_out->mode_cost[t] = w->mode_cost[t];
             spec_out->inter_best = best_type;
-            s.type = best_type;
-            s.pbest = (pix_t *)w + w->mode_pred[best_type];
-            for (int i = 0; i < 4; i++) { pmv[i] = w->part_mv[best_type][i]; pmvd[i] = w->part_mvd[best_type][i]; }
-            if (s.cost > w->ic[IC_SAD_SKIP])     /* P16x16 at the skip vector is cheaper (H:5512) */
-            {
-                s.type = 0;
-                s.cost = w->ic[IC_SAD_SKIP] + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
-                pmv[0] = mv_skip;
-                pmvd[0] = mv_sub2(mv_skip, mvp16);
-                s.pbest = w->skip_pred;      /* same samples the reference re-interpolates (H:5520) */
-            }
         }
+        /* pixel flavour: the prediction block the search (or the skip test) left behind; look-up flavour: made below */
+        s.pbest = use_skip_pred ? w->skip_pred : (s.lut ? w->mode_store[0] : (pix_t *)w + w->mode_pred[best_type]);
     }
+    spec_out->pad[0] = s.cost;           /* cost of the inter decision: what an intra mode has to beat (wave_mb_intra_check) */
     if (s.type >= 0)
     {
         s.i16_mode = w->intra_res[1];
@@ -1858,14 +2336,14 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
     }
 
     spec_out->mv0 = pmv[0];
-    spec_out->flags = ((is_p && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0);
+    spec_out->flags = ((is_p && s.type < 5) ? SPEC_UPDATES : 0) | (used_cl ? SPEC_USED_CL : 0) | (do_intra ? 0 : SPEC_NO_INTRA);
     spec_out->cl_used[0] = mv_round_fullpel(cl[0]); spec_out->cl_used[1] = mv_round_fullpel(cl[1]);
     for (int k = 0; k < 4; k++) spec_out->cand_sig[k] = cand_sig[k];
 
 #if H264_DEVICE
     /* the searches are over: the window buffer is free for the next macroblock of the row, whose
      * MV predictor will most likely be this macroblock's vector */
-    if (is_p && mbx + 1 < fp->nmbx)
+    if (is_p && mbx + 1 < fp->nmbx && !s.lut)
     {
         const int mvn = s.type >= 5 ? 0 : (s.type <= 1 ? pmv[0] : pmv[1]);
         win_prefetch(fp, w, mbx + 1, mby, (mbx + 1) * 16 + ((mv_x(mvn) + 1) >> 2), mby * 16 + ((mv_y(mvn) + 1) >> 2));
@@ -1873,6 +2351,19 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
 #endif
     /* ---- prediction of chroma, transform, quantisation, reconstruction ---- */
     PROF_MARK(s, 6);
+    if (s.lut && s.type <= 3)
+    {   /* look-up flavour: the luma prediction of the chosen inter mode (or of the skip vector) is made now, from the
+         * final vectors; each of the two luma warps makes the half it transforms */
+        ON_WARP(0) { luma_pred_half(s, 0, s.type, pmv, w->mode_store[0]); }
+        ON_WARP(1) { luma_pred_half(s, 1, s.type, pmv, w->mode_store[0]); }
+        if (me_hit && s.type == MBT_SKIP)
+        {   /* early skip taken from the record: the chroma prediction the skip test would have left in predc */
+            ON_WARP(2) { mc_chroma_plane(s, 0, MBT_SKIP, pmv); }
+            ON_WARP(3) { mc_chroma_plane(s, 1, MBT_SKIP, pmv); }
+        }
+        s.pbest = w->mode_store[0];
+        if (s.type == MBT_SKIP) CTA_SYNC();
+    }
     int cbpl = 0, cbpc = 0;
     const int sy = fp->stride[0], sc = fp->stride[1];
     pix_t *decy = fp->dec[0] + (mby * 16) * sy + mbx * 16;

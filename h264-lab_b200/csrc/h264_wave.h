@@ -40,10 +40,165 @@
 #define REPAIR_ROUNDS 3
 #endif
 #define REPAIR_TAG(pass, r) ((pass) * 8 + (r))
+/* rounds of the speculative motion-estimation pre-pass (me_prepass_mb): round 0 + refinements */
+#ifndef ME_ROUNDS
+#define ME_ROUNDS 3
+#endif
 
 HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 {
     IF_THREAD0 { fp->spec[n] = sp; }
+}
+
+
+/* ------------------------------------------------------------------------------
+ * Speculative motion estimation AHEAD of the wavefront.
+ *
+ * What the motion estimation of a macroblock (candidate stage + searches, me_phase) depends on, besides the pictures, is
+ * small: the 13 vectors of its MV-predictor context and the two cluster candidates.  With the SAD maps in place
+ * the estimation is pure table work, so it can be run for EVERY macroblock of the frame at once, before the wavefront
+ * starts, on PREDICTED inputs: round 0 takes the context from the previous frame's motion field (the record array
+ * still holds it), every further round takes it from the field the previous round predicted for this frame (a Jacobi
+ * iteration that settles after a round or two where motion is coherent) and only re-runs macroblocks whose
+ * context has changed.  Each result is stored next to the macroblock's SAD maps together with the inputs it was
+ * computed from.  The wavefront (encode_mb) compares those inputs with the real ones: equal -- identical inputs,
+ * identical function -- means the record IS what the estimation would produce now, and the macroblock skips it;
+ * different means the estimation runs in place, as before.  Nothing is ever trusted without that comparison, so the
+ * decisions stay the reference's; only the critical path of the wavefront gets shorter.
+ * ---------------------------------------------------------------------------- */
+HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round)
+{
+    const int nmbx = fp->nmbx, n = y * nmbx + x;
+    MBState s;
+    s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
+    s.avail = mb_avail(x, y, nmbx);
+    s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
+    s.pbest = w->skip_pred; s.ss = &w->ss[0];
+    s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
+    s.map = 0; s.lut = 0;
+    mb_load(s);                                  /* input samples, SAD maps, MV context from the record array = the PREVIOUS frame's field */
+    uint32_t *mr = fp->sadmap + (size_t)n * SM_WORDS + SM_ME_OFF;
+    if (round > 0)
+    {   /* context from the field predicted for this frame (same availability rules as mb_load) */
+        const int av = s.avail;
+        const int32_t *f = fp->me_field;
+        FOR_THREADS(i, 13)
+        {
+            if (i < 4) w->mvp0_left[i] = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * i + 3] : MV_NA;
+            else if (i == 4) w->mvp0_tl[0] = (av & AVAIL_TL) ? f[(n - nmbx - 1) * 16 + 15] : MV_NA;
+            else if (i < 8) w->mvp0_tl[i - 4] = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * (i - 5) + 3] : MV_NA;
+            else if (i < 12) w->mvp0_top[i - 8] = (av & AVAIL_T) ? f[(n - nmbx) * 16 + 12 + (i - 8)] : MV_NA;
+            else w->mvp0_top[4] = (av & AVAIL_TR) ? f[(n - nmbx + 1) * 16 + 12] : MV_NA;
+        }
+        CTA_SYNC();
+    }
+    int32_t cl[2];
+    if (fp->spec_from_prev) { cl[0] = fp->cl_true[2 * n]; cl[1] = fp->cl_true[2 * n + 1]; }         /* what sweep 0 will use (wave_mb_first) */
+    else { cl[0] = mv_round_fullpel(fp->clusters[0]); cl[1] = mv_round_fullpel(fp->clusters[1]); }
+    if (round > 0 && me_record_matches(s, mr, cl)) return;      /* the record already belongs to this context */
+    const int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
+    s.lut = lut_decide(s, mvp16);
+    int32_t pmv[4] = {0, 0, 0, 0}, pmvd[4] = {0, 0, 0, 0};
+    int type = 0;
+    if (s.lut)
+    {
+        me_phase(s, cl);
+        CTA_SYNC();
+        FOR_THREADS(i, 68)
+        {
+            int32_t v;
+            if (i < 4) v = w->mvp0_left[i];
+            else if (i < 8) v = w->mvp0_tl[i - 4];
+            else if (i < 13) v = w->mvp0_top[i - 8];
+            else if (i < 15) v = cl[i - 13];
+            else if (i == 15) v = 1;
+            else if (i < 32) v = w->ic[i - 16];
+            else if (i < 36) v = w->mode_cost[i - 32];
+            else if (i < 52) v = (&w->part_mv[0][0])[i - 36];
+            else v = (&w->part_mvd[0][0])[i - 52];
+            mr[i] = (uint32_t)v;
+        }
+        int cost, usp;
+        inter_decide(fp, w, &type, &cost, pmv, pmvd, &usp);
+    } else
+    {   /* no estimation by look-up here: no record; the field keeps the previous frame's vectors for the neighbours' context */
+        IF_THREAD0 { mr[ME_KEY + 15] = 0; }
+        type = -2;
+    }
+    /* the motion field this macroblock is predicted to end up with (an intra outcome cannot be known here) */
+    FOR_THREADS(i, 16)
+    {
+        int v;
+        if (type == -2) v = fp->mbi[n].mv[i];
+        else if (type <= 0) v = pmv[0];
+        else
+        {
+            const int bx = i & 3, by = i >> 2;
+            v = pmv[type == 1 ? (by >> 1) : (type == 2 ? (bx >> 1) : (by >> 1) * 2 + (bx >> 1))];
+        }
+        fp->me_field[n * 16 + i] = v;
+    }
+    CTA_SYNC();
+}
+
+/* ------------------------------------------------------------------------------
+ * Intra modes verified AFTER sweep 0 (P frames, fp->spec_no_intra).
+ *
+ * The Intra16x16 / Intra4x4 costs of a macroblock (H:4876, H:4723) need the unfiltered reconstruction of its left and
+ * upper neighbours, and Intra4x4 is a chain of 16 dependent block decisions: on the wavefront that chain was the
+ * longest thing a P macroblock did, although an intra mode wins for about one macroblock in a hundred.  Sweep 0
+ * therefore decides every macroblock among the inter modes only and records the cost to beat; once the sweep is
+ * over, the neighbours' reconstruction exists everywhere and this check -- independent per macroblock, so fully
+ * parallel -- evaluates the intra costs exactly as encode_mb would (same exact pruning against the inter cost).  Where
+ * an intra mode wins, the macroblock is queued for a full re-encode in repair pass 1; the repair machinery above
+ * re-encodes it with all modes and follows every consequence (successors whose context changed, the cluster
+ * trajectory).  A macroblock whose neighbours change later is re-encoded in full anyway (it is their causal
+ * successor), so every final decision has seen the intra modes with the final neighbours.
+ * ---------------------------------------------------------------------------- */
+HDN void wave_mb_intra_check(const FrameParams *fp, MBWork *w, int x, int y)
+{
+    const int n = y * fp->nmbx + x;
+    const int flags = fp->spec[n].flags;
+    /* early skips never look at intra modes (H:5767); only macroblocks decided without them need the check */
+    if (!(flags & SPEC_NO_INTRA) || !(flags & SPEC_USED_CL)) return;
+    const int inter_cost = fp->spec[n].pad[0];
+    MBState s;
+    s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
+    s.avail = mb_avail(x, y, fp->nmbx);
+    s.type = 0; s.cost = inter_cost; s.i16_mode = 2; s.mv_skip_pred = 0;
+    s.pbest = w->skip_pred; s.ss = &w->ss[0];
+    s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
+    s.map = 0; s.lut = 0;
+    mb_load(s);
+    int win = 0;
+    ON_WARP(0)
+    {
+        const pix_t *left = (s.avail & AVAIL_L) ? w->left_y : 0;
+        const pix_t *top = (s.avail & AVAIL_T) ? w->top_y : 0;
+        const int m16 = intra16_estimate(w->inp_y, s.avail, fp->qp);
+        intra16_pred(w->i16pred, left, top, m16);
+        WSYNC();
+        const int cost16 = sad_sm_wh(w->inp_y, w->i16pred, 16, 16) + ((bitsize_ue(m16 + 1) * fp->lambda_q4) >> 4) + fp->lambda_i16_q4;
+        win = cost16 < inter_cost;
+        if (!win && fp->speed < 2)
+        {
+            int nz4 = 0;
+            const int cost4 = intra4_choose(s, &nz4, cost16, inter_cost);
+            win = cost4 < inter_cost;
+        }
+        IF_LANE0 { w->scal[4] = win; }
+    }
+    CTA_SYNC();
+    win = w->scal[4];
+    IF_THREAD0
+    {
+        if (win)
+        {
+            fp->need_reenc[n] = REPAIR_TAG(1, 0);
+            atomic_add_stat(fp->fsync + FS_NFAIL);
+        }
+    }
+    CTA_SYNC();
 }
 
 /* pass 0 / I frames */
@@ -63,7 +218,7 @@ HDF_wave_mb_first void wave_mb_first(const FrameParams *fp, MBWork *w, int x, in
         if (fp->spec_from_prev) { cl[0] = fp->cl_true[2 * n]; cl[1] = fp->cl_true[2 * n + 1]; }
         else { cl[0] = mv_round_fullpel(fp->clusters[0]); cl[1] = mv_round_fullpel(fp->clusters[1]); }
     }
-    encode_mb(fp, w, x, y, cl, &sp);
+    encode_mb(fp, w, x, y, cl, &sp, !(fp->slice_type == SLICE_P && fp->spec_no_intra));
     if (fp->slice_type == SLICE_P)
     {
         spec_store(fp, n, sp);
@@ -80,14 +235,16 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
     s.pbest = w->skip_pred; s.ss = &w->ss[0];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
+    s.map = 0; s.lut = 0;
     mb_load(s);
     int mvp16 = mvp_get(w->mvp0_left, w->mvp0_tl, w->mvp0_top, s.avail, 0, 0, 4, 4);
+    s.lut = lut_decide(s, mvp16);
 #if H264_DEVICE && MB_WARPS == 1 && !defined(CHECK_WITH_WINDOW)
     /* single-warp re-check: the candidate stage reads a handful of 16x16 blocks; fetching them straight
      * from the reference picture (ref_at() without a window) moves less data than staging a 64x48 window */
     (void)mvp16;
 #else
-    win_load(s, x * 16 + ((mv_x(mvp16) + 1) >> 2), y * 16 + ((mv_y(mvp16) + 1) >> 2));
+    if (!s.lut) win_load(s, x * 16 + ((mv_x(mvp16) + 1) >> 2), y * 16 + ((mv_y(mvp16) + 1) >> 2));
 #endif
     ON_WARP(0) { inter_stage_a(s, cl); }
     CTA_SYNC();
@@ -310,7 +467,8 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
     {
         const int lane = LANE_ID;
         int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
-        if (32 * first_block + lane < nmb) { const MBSpec *sp = fp->spec + 32 * first_block + lane; mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1]; }
+        long long csum = 0; int ccnt = 0;        /* predict: mean inter cost of the frame (see FrameParams::cost_stat) */
+        if (32 * first_block + lane < nmb) { const MBSpec *sp = fp->spec + 32 * first_block + lane; mv0 = sp->mv0; flags = sp->flags; u0 = sp->cl_used[0]; u1 = sp->cl_used[1]; if (predict && (flags & SPEC_USED_CL)) { csum += sp->pad[0]; ccnt++; } }
         for (int base = 32 * first_block; base < nmb; base += 32)
         {
             if (!predict && lane < 2) fp->cl_ckpt[2 * (base >> 5) + lane] = c[lane];
@@ -319,6 +477,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
             {
                 const MBSpec *sp = fp->spec + base + 32 + lane;
                 nmv0 = sp->mv0; nflags = sp->flags; nu0 = sp->cl_used[0]; nu1 = sp->cl_used[1];
+                if (predict && (nflags & SPEC_USED_CL)) { csum += sp->pad[0]; ccnt++; }
             }
             const int cnt = imin(32, nmb - base);
             int t0 = 0, t1 = 0;
@@ -335,8 +494,20 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
             if (lane < cnt) { fp->cl_true[2 * (base + lane)] = t0; fp->cl_true[2 * (base + lane) + 1] = t1; }
             mv0 = nmv0; flags = nflags; u0 = nu0; u1 = nu1;
         }
+        if (predict && fp->cost_stat)
+        {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(0xffffffffu, csum, o); ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o); }
+            if (lane == 0) fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0;
+        }
     }
 #else
+    if (predict && fp->cost_stat)
+    {
+        long long csum = 0; int ccnt = 0;
+        for (int n = 0; n < nmb; n++) if (fp->spec[n].flags & SPEC_USED_CL) { csum += fp->spec[n].pad[0]; ccnt++; }
+        fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0;
+    }
     for (int base = 32 * first_block; base < nmb; base += 32)
     {
         if (!predict) { fp->cl_ckpt[2 * (base >> 5)] = c[0]; fp->cl_ckpt[2 * (base >> 5) + 1] = c[1]; }
@@ -420,6 +591,7 @@ HDN int wave_end_of_pass(const FrameParams *fp, MBWork *w, int pass)   /* one wa
         IF_LANE0 { fp->fsync[FS_TRAJ_CHANGED] = 0; fp->fsync[FS_TRAJ_FIRST] = 0; fp->fsync[FS_WAVE_TAGS] = 0; }
         int nd = replayed ? nd_follower : wave_replay(fp, w, 0, first_block);
         next = nd ? pass + 1 : FS_DONE;
+        if (pass == 0 && fp->spec_no_intra) next = 1;       /* the intra verification may still queue re-encodes: wave_after_check(1) decides */
     } else next = FS_DONE;
     if (next == FS_DONE)
     {

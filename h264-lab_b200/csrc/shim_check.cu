@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(32) k_check1(const FrameParams *fps, int njobs
     __shared__ FrameParams sfp;
     for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
         ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
-    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; }
+    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; work.map_tag[0] = work.map_tag[1] = 0; work.pf_enable = 0; }
     __syncwarp();
     const FrameParams *fp = &sfp;
     if (fp->fsync[FS_STATE] != pass) return;
@@ -29,6 +29,57 @@ __global__ void __launch_bounds__(32) k_check1(const FrameParams *fps, int njobs
         int y = n / nmbx;
         wave_mb_check(fp, &work, n - y * nmbx, y, pass);
     }
+}
+
+/* Speculative motion estimation ahead of the wavefront (h264_wave.h, me_prepass_mb): one warp per macroblock, every
+ * macroblock of every P frame of the submission, no dependencies between them.  round 0 predicts the context from the
+ * previous frame's motion field, later rounds from the field the round before predicted. */
+__global__ void __launch_bounds__(32) k_me(const FrameParams *fps, int njobs, int round)
+{
+    __shared__ MBWork work;
+    __shared__ FrameParams sfp;
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
+        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
+    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; work.map_tag[0] = work.map_tag[1] = 0; work.pf_enable = 0; }
+    __syncwarp();
+    const FrameParams *fp = &sfp;
+    if (!fp->use_me || fp->slice_type != SLICE_P) return;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
+    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+    {
+        int y = n / nmbx;
+        me_prepass_mb(fp, &work, n - y * nmbx, y, round);
+    }
+}
+
+/* Intra modes of every macroblock of a finished sweep 0 (h264_wave.h, wave_mb_intra_check): one warp per macroblock,
+ * independent of each other; winners are queued for repair pass 1. */
+__global__ void __launch_bounds__(32) k_intra_check(const FrameParams *fps, int njobs)
+{
+    __shared__ MBWork work;
+    __shared__ FrameParams sfp;
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
+        ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
+    if (threadIdx.x == 0) { work.pf_inp_tag = 0; work.pf_win_tag = 0; work.map_tag[0] = work.map_tag[1] = 0; work.pf_enable = 0; }
+    __syncwarp();
+    const FrameParams *fp = &sfp;
+    if (!fp->spec_no_intra || fp->slice_type != SLICE_P || fp->fsync[FS_STATE] != 1) return;
+    const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
+    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+    {
+        int y = n / nmbx;
+        wave_mb_intra_check(fp, &work, n - y * nmbx, y);
+    }
+}
+
+void h264b200_launch_intra_check(const FrameParams *fps, int njobs, int max_nmb, cudaStream_t st)
+{
+    k_intra_check<<<dim3((max_nmb + 3) / 4, njobs), 32, 0, st>>>(fps, njobs);
+}
+
+void h264b200_launch_me(const FrameParams *fps, int njobs, int max_nmb, int round, cudaStream_t st)
+{
+    k_me<<<dim3((max_nmb + 3) / 4, njobs), 32, 0, st>>>(fps, njobs, round);
 }
 
 void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st)

@@ -194,9 +194,12 @@ __device__ void trajectory_follower(const FrameParams *fp)
     {
         fs[FS_CL_END] = c[0]; fs[FS_CL_END + 1] = c[1];
         fs[FS_NDIRTY] = ndirty;
-        if (!ndirty) { fp->clusters[0] = c[0]; fp->clusters[1] = c[1]; fs[FS_PASSES] = 1; }
+        /* a frame whose sweep 0 left the intra modes out is never finished here: k_intra_check may still queue re-encodes,
+         * k_after_check(1) finishes the frame when neither it nor the candidate re-check found anything */
+        const int more = ndirty || fp->spec_no_intra;
+        if (!more) { fp->clusters[0] = c[0]; fp->clusters[1] = c[1]; fs[FS_PASSES] = 1; }
         __threadfence();
-        fs[FS_STATE] = ndirty ? 1 : FS_DONE;
+        fs[FS_STATE] = more ? 1 : FS_DONE;
     }
 }
 
@@ -257,7 +260,14 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
     __shared__ int s_item;
-    if (threadIdx.x == 0) { s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; }
+    if (threadIdx.x == 0)
+    {
+        s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0;
+        /* SAD-map staging (bulk copies into work.maps[], h264_mbenc.h map_prefetch): only the row loop of sweep 0 stages ahead */
+        work.map_tag[0] = work.map_tag[1] = 0; work.map_cnt[0] = work.map_cnt[1] = 0; work.pf_enable = pass == 0;
+        mbar_init(&work.map_bar[0], 1); mbar_init(&work.map_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     int item = s_item;
     {   /* the first njobs tickets are the trajectory followers */
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_repair_round(
     __shared__ int s_list[MB_WARPS * 32], s_cnt;
     for (int i = threadIdx.x; i < (int)(sizeof(FrameParams) / 4); i += blockDim.x)
         ((uint32_t *)&sfp)[i] = ((const uint32_t *)(fps + blockIdx.y))[i];
-    if (threadIdx.x == 0) { work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; }
+    if (threadIdx.x == 0) { work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0; work.map_tag[0] = work.map_tag[1] = 0; work.pf_enable = 0; }
     __syncthreads();
     const FrameParams *fp = &sfp;
     if (fp->fsync[FS_STATE] != pass) return;
@@ -578,6 +588,132 @@ __global__ void k_pack(const FrameParams *fps, int njobs)
 }
 
 /* ------------------------------------------------------------------------------ */
+/* SAD-map pre-pass (h264_sadmap.h)                                                 */
+/* ------------------------------------------------------------------------------ */
+/* One CTA per macroblock, one THREAD per tabulated position: 225 full-sample offsets around the centre, then 169
+ * quarter-sample positions around the best of them.  The reference window (30 rows x 36 bytes) and, for the second part,
+ * the windows of the planes G, b, h, j (20 rows x 24 bytes each) sit in shared memory; a thread walks the 16 rows of its
+ * block: five aligned words per row and source, four funnel shifts, four packed-byte SADs against the input row
+ * (one 16-byte broadcast load).  No shuffles, no divergence, ~250 / ~500 instructions per thread. */
+#define SMW_STRIDE 10
+#define SMP_STRIDE 7
+__global__ void __launch_bounds__(256) k_sadmap(const FrameParams *fps, int njobs)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    if (!fp->use_sadmap || fp->slice_type != SLICE_P) return;
+    const int nmbx = fp->nmbx, nmb = nmbx * fp->nmby, st = fp->stride[0];
+    const int xmax = nmbx * 16 + 12, ymax = fp->nmby * 16 + 15;
+    __shared__ __align__(16) uint32_t s_inp[64];
+    __shared__ uint32_t s_win[30 * SMW_STRIDE];
+    __shared__ uint32_t s_pl[4][20 * SMP_STRIDE];
+    __shared__ int s_red[8];
+    const int t = threadIdx.x;
+    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+    {
+        const int mby = n / nmbx, mbx = n - mby * nmbx;
+        uint32_t *rec = fp->sadmap + (size_t)n * SM_WORDS;
+        int cx, cy;
+        sadmap_center(fp, n, &cx, &cy);
+        if (t < 64) s_inp[t] = sadmap_inp_word(fp, mbx, mby, t >> 2, t & 3);
+        const int wx0 = mbx * 16 + cx - SM_R, wy0 = mby * 16 + cy - SM_R, ax0 = wx0 & ~3, sh0 = wx0 - ax0;
+        for (int i = t; i < 30 * 9; i += 256)
+        {
+            const int r = i / 9, wd = i - r * 9;
+            const int y = min(max(wy0 + r, -16), ymax), x = min(max(ax0 + 4 * wd, -16), xmax);
+            s_win[r * SMW_STRIDE + wd] = *(const uint32_t *)(fp->ref[0] + (long)y * st + x);
+        }
+        __syncthreads();
+        int key = 0x7FFFFFFF;
+        if (t < SM_INT_ENTRIES)
+        {
+            const int dy = t / SM_N, dx = t - dy * SM_N;
+            uint32_t lo = SM_INVALID, hi = SM_INVALID;
+            if (sadmap_block_inside(fp, wx0 + dx, wy0 + dy))
+            {
+                const int col = sh0 + dx, sh = (col & 3) * 8;
+                const uint32_t *row = s_win + dy * SMW_STRIDE + (col >> 2);
+                int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll
+                for (int r = 0; r < 16; r++)
+                {
+                    const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
+                    const uint4 in = *(const uint4 *)(s_inp + 4 * r);
+                    const int l = (int)(__vsadu4(__funnelshift_r(w0, w1, sh), in.x) + __vsadu4(__funnelshift_r(w1, w2, sh), in.y));
+                    const int rr = (int)(__vsadu4(__funnelshift_r(w2, w3, sh), in.z) + __vsadu4(__funnelshift_r(w3, w4, sh), in.w));
+                    if (r < 8) { q0 += l; q1 += rr; } else { q2 += l; q3 += rr; }
+                    row += SMW_STRIDE;
+                }
+                lo = (uint32_t)q0 | ((uint32_t)q1 << 16); hi = (uint32_t)q2 | ((uint32_t)q3 << 16);
+                key = ((q0 + q1 + q2 + q3) << 8) | t;
+            }
+            *(uint2 *)(rec + SM_INT_OFF + 2 * t) = make_uint2(lo, hi);
+        }
+        /* position with the smallest 16x16 SAD (first in scan order on ties): centre of the quarter map */
+#pragma unroll
+        for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        if ((t & 31) == 0) s_red[t >> 5] = key;
+        __syncthreads();
+        int bt = s_red[0];
+#pragma unroll
+        for (int k = 1; k < 8; k++) bt = min(bt, s_red[k]);
+        bt = bt == 0x7FFFFFFF ? SM_R * SM_N + SM_R : (bt & 255);
+        const int bx = cx + (bt % SM_N) - SM_R, by = cy + (bt / SM_N) - SM_R;
+        const int ox = mbx * 16 + bx - 2, oy = mby * 16 + by - 2, pax0 = ox & ~3, psh0 = ox - pax0;
+        for (int i = t; i < 4 * 20 * 6; i += 256)
+        {
+            const int pl = i / 120, k = i - pl * 120, r = k / 6, wd = k - r * 6;
+            const int y = min(max(oy + r, -16), ymax), x = min(max(pax0 + 4 * wd, -16), xmax);
+            const pix_t *plane = pl == 0 ? fp->ref[0] : fp->hp[pl - 1];
+            s_pl[pl][r * SMP_STRIDE + wd] = *(const uint32_t *)(plane + (long)y * st + x);
+        }
+        __syncthreads();
+        if (t < SM_Q_ENTRIES)
+        {
+            const int qyi = t / SM_QN, qxi = t - qyi * SM_QN, qx = qxi - SM_QR, qy = qyi - SM_QR;
+            const int aqx = (mbx * 16 + bx) * 4 + qx, aqy = (mby * 16 + by) * 4 + qy;
+            uint32_t lo = SM_INVALID, hi = SM_INVALID;
+            if (sadmap_block_inside(fp, aqx >> 2, aqy >> 2))
+            {
+                /* the two sources of the position (interp_luma_word): plane, column / row offset inside the staged windows */
+                const int dx = qx & 3, dy = qy & 3, fx = (qx >> 2) + 2, fy = (qy >> 2) + 2, pos = 1 << (dx + 4 * dy);
+                int pa = 0, ca = fx, ra = fy, pb = -1, cb = 0, rb = 0;
+                if (pos != 1)
+                {
+                    pa = -1;
+                    if (pos & 0xe0ee) { pa = 1; ca = fx; ra = fy + ((pos & 0xe000) ? 1 : 0); }
+                    if (pos & 0xbbb0) { const int c2 = fx + ((pos & 0x8880) ? 1 : 0); if (pa >= 0) { pb = 2; cb = c2; rb = fy; } else { pa = 2; ca = c2; ra = fy; } }
+                    if (pos & 0x4e40) { if (pa >= 0) { pb = 3; cb = fx; rb = fy; } else { pa = 3; ca = fx; ra = fy; } }
+                    if ((pos & 0xfafa) && pb < 0) { pb = 0; cb = fx + ((dx + 1) >> 2); rb = fy + ((dy + 1) >> 2); }
+                }
+                const int cola = psh0 + ca, sha = (cola & 3) * 8, colb = psh0 + cb, shb = (colb & 3) * 8;
+                const uint32_t *rowa = s_pl[pa] + ra * SMP_STRIDE + (cola >> 2);
+                const uint32_t *rowb = s_pl[pb < 0 ? 0 : pb] + rb * SMP_STRIDE + (colb >> 2);
+                int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll 4
+                for (int r = 0; r < 16; r++)
+                {
+                    uint32_t a0 = __funnelshift_r(rowa[0], rowa[1], sha), a1 = __funnelshift_r(rowa[1], rowa[2], sha);
+                    uint32_t a2 = __funnelshift_r(rowa[2], rowa[3], sha), a3 = __funnelshift_r(rowa[3], rowa[4], sha);
+                    if (pb >= 0)
+                    {
+                        a0 = __vavgu4(a0, __funnelshift_r(rowb[0], rowb[1], shb)); a1 = __vavgu4(a1, __funnelshift_r(rowb[1], rowb[2], shb));
+                        a2 = __vavgu4(a2, __funnelshift_r(rowb[2], rowb[3], shb)); a3 = __vavgu4(a3, __funnelshift_r(rowb[3], rowb[4], shb));
+                    }
+                    const uint4 in = *(const uint4 *)(s_inp + 4 * r);
+                    const int l = (int)(__vsadu4(a0, in.x) + __vsadu4(a1, in.y)), rr = (int)(__vsadu4(a2, in.z) + __vsadu4(a3, in.w));
+                    if (r < 8) { q0 += l; q1 += rr; } else { q2 += l; q3 += rr; }
+                    rowa += SMP_STRIDE; rowb += SMP_STRIDE;
+                }
+                lo = (uint32_t)q0 | ((uint32_t)q1 << 16); hi = (uint32_t)q2 | ((uint32_t)q3 << 16);
+            }
+            *(uint2 *)(rec + SM_Q_OFF + 2 * t) = make_uint2(lo, hi);
+        }
+        if (t == 0) { rec[0] = (uint32_t)mv_pack(cx, cy); rec[1] = (uint32_t)mv_pack(bx, by); rec[2] = 1; rec[3] = 0; rec[SM_ME_OFF + ME_KEY + 15] = 0; }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------ */
 /* host side                                                                        */
 /* ------------------------------------------------------------------------------ */
 struct h264b200_ctx
@@ -614,12 +750,16 @@ struct h264b200_ctx
     MBSpec *d_spec; int32_t *d_cl_true; int32_t *d_cl_ckpt; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
     int have_traj; int stats[4];
     int *d_prof;
+    uint32_t *d_sadmap;           /* [nmb][SM_WORDS] SAD-map records of the frame being encoded (h264_sadmap.h) */
+    int32_t *d_me_field;          /* [nmb][16] motion field predicted by the motion-estimation pre-pass (h264_wave.h) */
     int *d_progress;              /* 2 * nmby */
     uint32_t *h_out_words;        /* pinned */
     int *h_out_info;              /* pinned */
 };
 
 void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st);    /* shim_check.cu */
+void h264b200_launch_me(const FrameParams *fps, int njobs, int max_nmb, int round, cudaStream_t st);
+void h264b200_launch_intra_check(const FrameParams *fps, int njobs, int max_nmb, cudaStream_t st);
 
 /* Submission lanes.  Every host thread that submits work gets its own lane: a CUDA stream pair, its
  * FrameParams staging, tickets and events.  Encoder instances are independent (reference: "distinct
@@ -636,7 +776,7 @@ struct Lane
     int *d_tickets;
     int *d_info, *h_info;         /* gathered per-job results of a submission (device / pinned host), 12 ints per job */
     cudaEvent_t ev[6], ev_fork, ev_join;
-    cudaEvent_t ev_x[4];           /* [0], [1]: around the entropy-coding kernels on stream2; [2], [3]: around the pre-pass */
+    cudaEvent_t ev_x[7];           /* [0], [1]: around the entropy-coding kernels on stream2; [2], [3], [4]: around the two pre-passes */
     int ev_ok;
     float last_ms[8];
 };
@@ -675,15 +815,23 @@ static Lane *lane_enter(const h264b200_ctx *c);
 static int g_enc_dyn_smem = 0;     /* developer knob H264B200_ENC_SMEM: extra dynamic shared memory per CTA of k_encode_rows
                                        (limits the CTAs resident per SM, to study cache contention) */
 static std::once_flag g_knob_once;
+static int g_no_sadmap = 0;        /* developer knob H264B200_NO_SADMAP: pixel flavour of the searches everywhere (A/B runs) */
+static int g_no_me = 0;            /* developer knob H264B200_NO_ME_PREPASS: no speculative motion estimation ahead of the wavefront */
+static int g_me_rounds = ME_ROUNDS; /* developer knob H264B200_ME_ROUNDS */
+static int g_no_intra_spec = 0;    /* developer knob H264B200_NO_INTRA_SPEC: intra modes evaluated inside sweep 0 as the reference does */
 static int ensure_globals(int njobs)
 {
     std::call_once(g_knob_once, []() {
+        g_no_sadmap = getenv("H264B200_NO_SADMAP") != NULL;
+        g_no_me = getenv("H264B200_NO_ME_PREPASS") != NULL;
+        g_no_intra_spec = getenv("H264B200_NO_INTRA_SPEC") != NULL;
+        if (getenv("H264B200_ME_ROUNDS")) g_me_rounds = atoi(getenv("H264B200_ME_ROUNDS"));
         const char *e = getenv("H264B200_ENC_SMEM");
         if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
     });
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
-    if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); for (int i = 0; i < 4; i++) CK(cudaEventCreate(&g_ev_x[i])); g_ev_ok = 1; }
+    if (!g_ev_ok) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); for (int i = 0; i < 7; i++) CK(cudaEventCreate(&g_ev_x[i])); g_ev_ok = 1; }
     if (njobs > g_fps_cap)
     {
         if (g_d_fps) cudaFree(g_d_fps);
@@ -767,6 +915,10 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CKC(cudaMalloc(&c->d_need_reenc, sizeof(int) * c->nmb));
     CKC(cudaMemset(c->d_need_reenc, 0, sizeof(int) * c->nmb));
     CKC(cudaMalloc(&c->d_fsync, sizeof(int) * FS_WORDS));
+    CKC(cudaMalloc(&c->d_sadmap, sizeof(uint32_t) * SM_WORDS * (size_t)c->nmb + 256));
+    CKC(cudaMemset(c->d_sadmap, 0, sizeof(uint32_t) * SM_WORDS * (size_t)c->nmb + 256));
+    CKC(cudaMalloc(&c->d_me_field, sizeof(int32_t) * 16 * (size_t)c->nmb));
+    CKC(cudaMemset(c->d_me_field, 0, sizeof(int32_t) * 16 * (size_t)c->nmb));
 #ifdef H264_PROFILE
     CKC(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
     CKC(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
@@ -788,6 +940,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->stg.ev) cudaEventDestroy(c->stg.ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d_prof) cudaFree(c->d_prof);
+    cudaFree(c->d_sadmap); cudaFree(c->d_me_field);
     if (c->d_clip) cudaFree(c->d_clip);
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
@@ -856,6 +1009,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
+    fp->cost_stat = c->d_clusters + 2;       /* the allocation holds 4 ints */
     fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 3 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
@@ -864,6 +1018,11 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->max_passes = 4096;
     fp->prof = c->d_prof;
     fp->spec_from_prev = (p.slice_type == SLICE_P && c->have_traj && !getenv("H264B200_NO_PREV_TRAJ"));
+    fp->sadmap = c->d_sadmap;
+    fp->use_sadmap = p.slice_type == SLICE_P && !g_no_sadmap;
+    fp->use_me = fp->use_sadmap && !g_no_me;
+    fp->spec_no_intra = p.slice_type == SLICE_P && !g_no_intra_spec;
+    fp->me_field = c->d_me_field;
 }
 
 extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
@@ -1021,6 +1180,17 @@ static int encode_chunk(int n, h264b200_job *jobs)
     k_frame_init<<<dim3(8, n), 256, 0, st>>>(g_d_fps, n, g_d_tickets);
     g_launches += 1;
     if (any_denoise) { k_denoise<<<dim3(296, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
+    /* SAD maps of every macroblock of every P frame of the submission: dependency-free, ahead of the wavefront */
+    int any_p = 0;
+    for (int i = 0; i < n; i++) any_p |= g_h_fps[i].use_sadmap;
+    CK(cudaEventRecord(g_ev_x[2], st));
+    if (any_p) { k_sadmap<<<dim3(max_nmb, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
+    CK(cudaEventRecord(g_ev_x[3], st));
+    /* ... and the motion estimation itself on predicted contexts (round 0 + refinement rounds); the wavefront verifies */
+    int any_me = 0;
+    for (int i = 0; i < n; i++) any_me |= g_h_fps[i].use_me;
+    if (any_me) for (int r = 0; r < g_me_rounds; r++) { h264b200_launch_me(g_d_fps, n, max_nmb, r, st); g_launches += 1; }
+    CK(cudaEventRecord(g_ev_x[4], st));
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
     k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
@@ -1037,6 +1207,13 @@ static int encode_chunk(int n, h264b200_job *jobs)
             for (int k = 0; k < 3; k++) { c->stg.yuv[k] = c->want.yuv[k]; c->stg.stride[k] = c->want.stride[k]; }
             c->stg.ttl = 1;
         }
+    }
+    {   /* P frames: sweep 0 decided among the inter modes only; the intra modes of every macroblock are verified now */
+        int any_spec = 0;
+        for (int i = 0; i < n; i++) any_spec |= g_h_fps[i].spec_no_intra;
+        CK(cudaEventRecord(g_ev_x[5], st));
+        if (any_spec) { h264b200_launch_intra_check(g_d_fps, n, max_nmb, st); g_launches += 1; }
+        CK(cudaEventRecord(g_ev_x[6], st));
     }
     h264b200_launch_check1(g_d_fps, n, 1, st);
     k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
@@ -1129,6 +1306,9 @@ static int encode_chunk(int n, h264b200_job *jobs)
     cudaEventElapsedTime(&g_last_ms[0], g_ev[0], g_ev[5]);
     cudaEventElapsedTime(&g_last_ms[1], g_ev[1], g_ev[2]);
     cudaEventElapsedTime(&g_last_ms[2], g_ev[2], g_ev[3]);
+    cudaEventElapsedTime(&g_last_ms[4], g_ev_x[2], g_ev_x[3]);
+    cudaEventElapsedTime(&g_last_ms[5], g_ev_x[3], g_ev_x[4]);
+    cudaEventElapsedTime(&g_last_ms[6], g_ev_x[5], g_ev_x[6]);
     cudaEventElapsedTime(&g_last_ms[3], g_ev_x[0], g_ev_x[1]);      /* entropy coding: events on ITS stream (it runs beside the in-loop filter) */
     return rc;
 }

@@ -85,7 +85,7 @@ int h264b200_encode_frames(int n, h264b200_job *jobs);
 void h264b200_last_timing(float out_ms[4]);
 /* Same, n slots (returns how many are defined): [0] whole submission on the device, [1] macroblock sweep incl. the
  * verification / repair passes, [2] in-loop filter + guard bands + half-sample planes, [3] entropy coding (CAVLC, prefix
- * sum, pack; measured on the second stream it runs on, beside [2]), [4] SAD-map pre-pass, [5..7] reserved (0). */
+ * sum, pack; measured on the second stream it runs on, beside [2]), [4] SAD-map pre-pass, [5] speculative motion-estimation pre-pass, [6] intra verification after sweep 0 (part of [1]), [7] reserved (0). */
 int h264b200_last_timing_ex(float *out_ms, int n);
 
 /* Upload a clip of nframes tightly packed I420 frames (stride == width) to device memory

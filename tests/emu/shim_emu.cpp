@@ -9,10 +9,13 @@
  * tested on CPU.  The product library (libh264lab_b200.so) never links this file
  * and has no CPU fallback.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 int g_emu_dbg[8];
+long g_emu_lut[8];
+extern "C" long *emu_lut_stats(void) { return g_emu_lut; }
 extern "C" int *emu_dbg(void) { return g_emu_dbg; }
 #include "../../h264-lab_b200/csrc/h264_common.h"
 #include "../../h264-lab_b200/csrc/h264_pixel.h"
@@ -42,9 +45,12 @@ struct h264b200_ctx
     std::vector<MBSpec> spec;
     std::vector<int32_t> cl_true, cl_ckpt;
     std::vector<int> changed_pass, need_reenc;
+    std::vector<uint32_t> sadmap;
+    std::vector<int32_t> me_field;
     int fsync[FS_WORDS];
     int stats[4];
     int32_t clusters[2];
+    int cost_stat[2];
     int have_traj;
 };
 
@@ -72,6 +78,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     c->mb_nbits.resize(nmb + 2);
     c->spec.resize(nmb); c->cl_true.resize(2 * nmb); c->cl_ckpt.resize(2 * (nmb / 32 + 2)); c->changed_pass.resize(nmb); c->need_reenc.resize(nmb);
     c->out_words.resize((size_t)nmb * 160 + 1024);
+    c->sadmap.assign((size_t)nmb * SM_WORDS, 0);
+    c->me_field.assign((size_t)nmb * 16, 0);
     c->cur = 0; c->last_dec = 0;
     c->clusters[0] = c->clusters[1] = 0;
     c->have_traj = 0;
@@ -136,6 +144,7 @@ static void run_job(h264b200_job *job)
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
+    fp.cost_stat = c->cost_stat;
     fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.cl_ckpt = c->cl_ckpt.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
     memset(c->fsync, 0, sizeof(c->fsync));
     fp.fsync = c->fsync;
@@ -148,8 +157,23 @@ static void run_job(h264b200_job *job)
     fp.hdr_bits = p.hdr_bits;
     const int nmb = c->nmbx * c->nmby;
 
+    /* SAD-map pre-pass (h264_sadmap.h): before the sweep, while the record array still holds the previous frame */
+    fp.sadmap = c->sadmap.data();
+    fp.use_sadmap = p.slice_type == SLICE_P && !getenv("H264B200_NO_SADMAP");
+    if (fp.use_sadmap)
+        for (int y = 0; y < c->nmby; y++)
+            for (int x = 0; x < c->nmbx; x++) sadmap_build_mb(&fp, x, y);
+
     MBWork *w = new MBWork();
     if (fp.spec_from_prev) wave_replay(&fp, w, 1);
+    /* speculative motion estimation ahead of the wavefront (h264_wave.h): round 0 + refinement rounds */
+    fp.me_field = c->me_field.data();
+    fp.use_me = fp.use_sadmap && !getenv("H264B200_NO_ME_PREPASS");
+    fp.spec_no_intra = p.slice_type == SLICE_P && !getenv("H264B200_NO_INTRA_SPEC");
+    if (fp.use_me)
+        for (int round = 0; round < (getenv("H264B200_ME_ROUNDS") ? atoi(getenv("H264B200_ME_ROUNDS")) : ME_ROUNDS); round++)
+            for (int y = 0; y < c->nmby; y++)
+                for (int x = 0; x < c->nmbx; x++) me_prepass_mb(&fp, w, x, y, round);
     for (int pass = 0;;)
     {
         if (pass > 0)
@@ -168,6 +192,9 @@ static void run_job(h264b200_job *job)
         if (next == FS_DONE) break;
         /* parallel re-check of the dirty macroblocks before the repair sweep */
         c->fsync[FS_STATE] = next;
+        if (pass == 0 && fp.spec_no_intra)      /* sweep 0 left the intra modes out: verify them now, everywhere */
+            for (int y = 0; y < c->nmby; y++)
+                for (int x = 0; x < c->nmbx; x++) wave_mb_intra_check(&fp, w, x, y);
         for (int y = 0; y < c->nmby; y++)
             for (int x = 0; x < c->nmbx; x++) wave_mb_check(&fp, w, x, y, next);
         if (wave_after_check(&fp, next) == FS_DONE) break;
@@ -175,6 +202,13 @@ static void run_job(h264b200_job *job)
         if (pass > fp.max_passes) { job->status = -4; delete w; return; }
     }
     delete w;
+    if (getenv("H264B200_DUMP") && p.slice_type == SLICE_P)
+    {   /* developer statistic: inter cost vs final type of every macroblock */
+        FILE *f = fopen(getenv("H264B200_DUMP"), "a");
+        for (int n = 0; n < nmb; n++) fprintf(f, "%d %d %d %d\n", n, c->spec[n].pad[0], (int)c->mbi[n].type, c->spec[n].flags);
+        fprintf(f, "-1 0 0 0\n");
+        fclose(f);
+    }
     c->have_traj = (p.slice_type == SLICE_P);
     c->stats[0] += c->fsync[FS_PASSES]; c->stats[1] += c->fsync[FS_REENC]; c->stats[2] += c->fsync[FS_CHECKS]; c->stats[3]++;
     g_launches++;

@@ -2,7 +2,6 @@
 // micro-benchmarked on the box").  Every kernel keeps 8 independent dependency chains per thread so that the pipes,
 // not latencies, are the limit; 148 x 8 CTAs of 256 threads.  Prints G-ops/s for the whole chip:
 //   imad      32-bit multiply-add                      (1 op  = 1 IMAD)
-//   iadd3     32-bit add                               (1 op  = 1 IADD3)
 //   vsadu4    packed-byte sum of absolute differences  (1 op  = 1 VABSDIFF4 with accumulate = 4 samples)
 //   dp4a      packed-byte dot product                  (1 op  = 1 IDP4A = 4 MACs)
 //   vavgu4    packed-byte rounded average              (lowered by the compiler to a LOP3/IADD sequence)
@@ -26,7 +25,6 @@ template <int OP> __global__ void __launch_bounds__(256) k(unsigned *out, unsign
             for (int c = 0; c < CHAINS; c++)
             {
                 if (OP == 0) x[c] = x[c] * a + b;
-                else if (OP == 1) x[c] = x[c] + a + (b ^ j);
                 else if (OP == 2) x[c] = __vsadu4(x[c] ^ (unsigned)j, a) + x[c];
                 else if (OP == 3) x[c] = (unsigned)__dp4a((int)(x[c] ^ (unsigned)j), (int)a, (int)x[c]);
                 else if (OP == 4) x[c] = __vavgu4(x[c], a ^ (unsigned)j);
@@ -65,7 +63,6 @@ int main()
     unsigned *d;
     cudaMalloc(&d, 148 * 8 * 256 * 4);
     run<0>("imad", d, 1);
-    run<1>("iadd3", d, 1);
     run<2>("vsadu4", d, 4);
     run<3>("dp4a", d, 4);
     run<4>("vavgu4", d, 4);
