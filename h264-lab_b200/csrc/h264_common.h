@@ -396,6 +396,8 @@ struct MBSpec
 #define FS_REPLAYED 7      /* GPU: repair pass whose trajectory replay the follower of the repair wave has already done */
 #define FS_REPLAY_TF 15    /* GPU: FS_TRAJ_FIRST that replay started from                                   */
 #define FS_WAVE_TAGS 16    /* macroblocks tagged for the repair WAVE of the current pass (successors of changes of the last parallel round) */
+#define FS_FAST 17         /* statistics: macroblocks of sweep 0 taken by the decide / work fast path (h264_fast.h) */
+#define FS_SLOW 18         /* statistics: macroblocks of sweep 0 encoded by the complete path */
 #define FS_WORDS 24
 #define FS_DONE 0x40000000
 
@@ -444,6 +446,8 @@ struct FrameParams
     int *need_reenc;            /* [nmb] pass for which the parallel re-check asked for a re-encode */
     int *fsync;                 /* [FS_WORDS] frame synchronisation words                   */
     int *row_progress;          /* [nmby] macroblocks finished per row (encode pass)        */
+    int *row_progress_mv;       /* [nmby] sweep 0: macroblocks DECIDED per row (vectors, types, speculation records written; the
+                                   reconstruction may still be in the works), >= row_progress                     */
     int *row_progress_df;       /* [nmby] same for the deblock pass                         */
     int *row_progress_dfc;      /* [nmby] deblock pass, chroma wavefront                     */
     int *row_clean;             /* [nmby] last repair sweep the row went through without anything to do */
@@ -467,7 +471,8 @@ struct FrameParams
      * verified afterwards, in parallel, against the finished sweep (h264_wave.h, wave_mb_intra_check) */
     int spec_no_intra;
     /* [0]: inter cost from which a macroblock of this frame evaluates its intra modes inside sweep 0 after all (11/8 of the
-     * mean inter cost of the previous P frame, written by wave_replay(predict)); only read when spec_from_prev */
+     * mean inter cost of the previous P frame, written by wave_replay(predict)); [1]: inter cost from which the
+     * motion-estimation pre-pass predicts an intra outcome (15/8 of that mean); only read when spec_from_prev */
     int *cost_stat;
     /* temporal noise suppressor (h264_denoise.h); dn_out[0] == NULL: not used for this frame */
     const pix_t *dn_src[3];     /* picture as submitted                                       */
@@ -512,11 +517,38 @@ struct SearchScratch
     int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */
 };
 
-struct MBWork
+/* What prediction + transform / quantisation / reconstruction of one macroblock work on.  MBWork starts with one (its
+ * members are used as w->inp_y ... everywhere); the fast path of P frames (h264_fast.h) gives every warp a private one,
+ * and the functions that only touch these members (luma_tq_*, chroma_tq_*, mc_chroma_plane) are handed such a buffer
+ * through MBState::w. */
+struct TQBuf
 {
-    /* inputs, read-only after mb_load */
     pix_t inp_y[256];            /* input MB, stride 16 (mb_pix_inp, H:566)                 */
     pix_t inp_c[128];            /* U at +0, V at +8, stride 16                             */
+    pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
+    int16_t dq_y[16][16];        /* transform coefficients / dequantised (quant_t.dq)       */
+    int16_t qv_y[16][16];        /* quantised levels (quant_t.qv)                           */
+    int16_t dq_c[8][16];
+    int16_t qv_c[8][16];
+    int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
+    int16_t dc_c[8], qdc_c[8];
+    int8_t  zflag1[16], zflag2[16], zflagc[8];
+    int32_t tq_res[8];           /* luma nz bits of the two halves, chroma nz bits / dc flags */
+};
+
+/* decision of one macroblock of a fast-path batch (h264_fast.h) */
+struct FastDec
+{
+    int32_t type, mv_skip;
+    int32_t pmv[4];
+    int32_t x, pad;
+};
+#define FAST_BATCH 8          /* motion-estimation records staged per bulk-copy group */
+#define FAST_RING 16          /* decided macroblocks the deciding warp may be ahead of the working warps */
+
+struct MBWork : TQBuf
+{
+    /* inputs, read-only after mb_load (inp_y, inp_c: TQBuf) */
     pix_t top_y[24];             /* unfiltered row above: 16 + 4 of the top-right MB        */
     pix_t left_y[16];
     pix_t top_c[16];             /* U 0..7, V 8..15                                         */
@@ -546,18 +578,9 @@ struct MBWork
     int16_t i4t[16], i4u[16];    /* residual / butterfly exchange of the current 4x4 block  */
     int8_t  i4_mode[16], i4_code[16];
     int32_t intra_res[8];        /* cost16, i16 mode, cost4, nz mask of I4x4                */
-    /* chroma prediction, transform / quantisation */
-    pix_t predc[128];            /* chroma prediction: U at +0, V at +8, stride 16         */
+    /* chroma prediction, transform / quantisation (predc, dq_*, qv_*, ...: TQBuf) */
     int32_t predc_tag, predc_mv; /* GPU: predc already holds the P16x16 chroma prediction for vector predc_mv (tag = 1) */
     pix_t skip_pred[256];        /* luma prediction at the skip vector                      */
-    int16_t dq_y[16][16];        /* transform coefficients / dequantised (quant_t.dq)       */
-    int16_t qv_y[16][16];        /* quantised levels (quant_t.qv)                           */
-    int16_t dq_c[8][16];
-    int16_t qv_c[8][16];
-    int16_t dc_y[16], qdc_y[16]; /* luma DC: transform values / quantised levels            */
-    int16_t dc_c[8], qdc_c[8];
-    int8_t  zflag1[16], zflag2[16], zflagc[8];
-    int32_t tq_res[8];           /* luma nz bits of the two halves, chroma nz bits / dc flags */
     int32_t scal[16];            /* scalars produced by one lane for everybody              */
     uint32_t old_mbi[40];        /* previous record / reconstruction of an MB being repaired */
     uint32_t old_rec[96];
@@ -573,6 +596,21 @@ struct MBWork
     unsigned long long map_bar[2];
     int32_t map_tag[2], map_cnt[2];
     int32_t pf_enable;           /* 1: the row loop of sweep 0 runs: stage the next macroblock's record while this one is encoded */
+#if MB_WARPS != 1
+    /* fast path of P frames (h264_fast.h): private buffers of the warps, the decisions of the current batch, the final
+     * vectors of the previous macroblock of the row, the motion-estimation records of the batch (bulk copies) */
+    TQBuf wb[MB_WARPS];
+    pix_t wpred[MB_WARPS][256];
+    FastDec fd[FAST_RING];
+    int32_t last_mv[16];
+    int32_t batch_n;
+    int32_t q_dec;               /* decisions handed to the working warps so far (monotonic within the row) */
+    int32_t q_done[MB_WARPS];    /* [k]: decisions worked off by warp k (it takes q = k - 1, k - 1 + 3, ...) */
+    int32_t cmd, slow_x;         /* 0: run; 1: all warps meet to encode macroblock slow_x by the complete path; 2: row finished */
+    uint32_t __attribute__((aligned(16))) me_stage[FAST_BATCH][ME_WORDS];
+    unsigned long long me_bar;
+    int32_t me_cnt, me_first, me_num;      /* copies completed on me_bar so far; first macroblock / number of records staged */
+#endif
 };
 
 HD int mb_avail(int mbx, int mby, int nmbx)   /* single slice per frame: H:3605-3622 */

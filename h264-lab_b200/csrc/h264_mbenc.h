@@ -2119,11 +2119,12 @@ HD void me_phase(MBState &s, const int32_t cl[2])
 /* Inter decision over the results of me_phase() (H:5500-5522): early skip, else the cheapest searched mode in ascending
  * order with strict '<', else P16x16 at the skip vector when the raw skip SAD is smaller.  Every thread, same values.
  * Returns the winning partition mode of the search (what MBSpec::inter_best records). */
-HD int inter_decide(const FrameParams *fp, const MBWork *w, int *ptype, int *pcost, int32_t pmv[4], int32_t pmvd[4], int *use_skip_pred)
+HD int inter_decide_p(const FrameParams *fp, const int32_t *ic, const int32_t *mode_cost, const int32_t *part_mv, const int32_t *part_mvd,
+                      int *ptype, int *pcost, int32_t pmv[4], int32_t pmvd[4], int *use_skip_pred)
 {
-    const int mvp16 = w->ic[IC_MVP16], mv_skip = w->ic[IC_MV_SKIP];
+    const int mvp16 = ic[IC_MVP16], mv_skip = ic[IC_MV_SKIP];
     *use_skip_pred = 0;
-    if (w->ic[IC_STATE] == 1)
+    if (ic[IC_STATE] == 1)
     {
         *ptype = MBT_SKIP; *pcost = 0;
         pmv[0] = mv_skip;
@@ -2132,20 +2133,24 @@ HD int inter_decide(const FrameParams *fp, const MBWork *w, int *ptype, int *pco
     }
     int cost = 0xffffff, best_type = 0;
     for (int t = 0; t < 4; t++)
-        if ((w->ic[IC_PREF] >> t) & 1)
-            if (w->mode_cost[t] < cost) { cost = w->mode_cost[t]; best_type = t; }
+        if ((ic[IC_PREF] >> t) & 1)
+            if (mode_cost[t] < cost) { cost = mode_cost[t]; best_type = t; }
     int type = best_type;
-    for (int i = 0; i < 4; i++) { pmv[i] = w->part_mv[best_type][i]; pmvd[i] = w->part_mvd[best_type][i]; }
-    if (cost > w->ic[IC_SAD_SKIP])     /* P16x16 at the skip vector is cheaper (H:5512) */
+    for (int i = 0; i < 4; i++) { pmv[i] = part_mv[best_type * 4 + i]; pmvd[i] = part_mvd[best_type * 4 + i]; }
+    if (cost > ic[IC_SAD_SKIP])     /* P16x16 at the skip vector is cheaper (H:5512) */
     {
         type = 0;
-        cost = w->ic[IC_SAD_SKIP] + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
+        cost = ic[IC_SAD_SKIP] + mv_cost(mv_skip, mvp16, fp->lambda_mv_q4);
         pmv[0] = mv_skip;
         pmvd[0] = mv_sub2(mv_skip, mvp16);
         *use_skip_pred = 1;      /* same samples the reference re-interpolates (H:5520) */
     }
     *ptype = type; *pcost = cost;
     return best_type;
+}
+HD int inter_decide(const FrameParams *fp, const MBWork *w, int *ptype, int *pcost, int32_t pmv[4], int32_t pmvd[4], int *use_skip_pred)
+{
+    return inter_decide_p(fp, w->ic, w->mode_cost, &w->part_mv[0][0], &w->part_mvd[0][0], ptype, pcost, pmv, pmvd, use_skip_pred);
 }
 
 /* Does the speculative motion-estimation record of the macroblock (h264_wave.h, me_prepass_mb) belong to exactly the

@@ -69,6 +69,29 @@ HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
 HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
+    uint32_t *mr = fp->sadmap + (size_t)n * SM_WORDS + SM_ME_OFF;
+    if (round > 0 && mr[ME_KEY + 15] == 1u)
+    {   /* refinement rounds: most records already belong to the context the field now predicts -- check that first, it
+         * takes 15 loads and no macroblock set-up */
+        const int av = mb_avail(x, y, nmbx);
+        const int32_t *f = fp->me_field;
+        int same = 1;
+        FOR_LANES(i, 15)
+        {
+            int32_t have;
+            if (i < 4) have = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * i + 3] : MV_NA;
+            else if (i == 4) have = (av & AVAIL_TL) ? f[(n - nmbx - 1) * 16 + 15] : MV_NA;
+            else if (i < 8) have = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * (i - 5) + 3] : MV_NA;
+            else if (i < 12) have = (av & AVAIL_T) ? f[(n - nmbx) * 16 + 12 + (i - 8)] : MV_NA;
+            else if (i == 12) have = (av & AVAIL_TR) ? f[(n - nmbx + 1) * 16 + 12] : MV_NA;
+            else have = fp->spec_from_prev ? fp->cl_true[2 * n + (i - 13)] : mv_round_fullpel(fp->clusters[i - 13]);
+            if ((int32_t)mr[ME_KEY + i] != have) same = 0;
+        }
+#if H264_DEVICE
+        same = __all_sync(0xffffffffu, same);          /* the pre-pass runs one warp per macroblock */
+#endif
+        if (same) return;
+    }
     MBState s;
     s.fp = fp; s.w = w; s.mbx = x; s.mby = y;
     s.avail = mb_avail(x, y, nmbx);
@@ -77,7 +100,6 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     s.map = 0; s.lut = 0;
     mb_load(s);                                  /* input samples, SAD maps, MV context from the record array = the PREVIOUS frame's field */
-    uint32_t *mr = fp->sadmap + (size_t)n * SM_WORDS + SM_ME_OFF;
     if (round > 0)
     {   /* context from the field predicted for this frame (same availability rules as mb_load) */
         const int av = s.avail;
@@ -120,6 +142,9 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
         }
         int cost, usp;
         inter_decide(fp, w, &type, &cost, pmv, pmvd, &usp);
+        /* an inter cost nearly twice the usual: the macroblock will most likely end up intra, i.e. without vectors
+         * for its neighbours' context (only a prediction -- the wavefront checks every context) */
+        if (type != MBT_SKIP && fp->spec_from_prev && cost >= fp->cost_stat[1]) type = -3;
     } else
     {   /* no estimation by look-up here: no record; the field keeps the previous frame's vectors for the neighbours' context */
         IF_THREAD0 { mr[ME_KEY + 15] = 0; }
@@ -130,6 +155,7 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
     {
         int v;
         if (type == -2) v = fp->mbi[n].mv[i];
+        else if (type == -3) v = MV_NA;
         else if (type <= 0) v = pmv[0];
         else
         {
@@ -498,7 +524,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
         {
 #pragma unroll
             for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(0xffffffffu, csum, o); ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o); }
-            if (lane == 0) fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0;
+            if (lane == 0) { fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0; fp->cost_stat[1] = ccnt ? (int)((csum / ccnt) * 15 / 8) : 0x7FFFFFFF; }
         }
     }
 #else
@@ -507,6 +533,7 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
         long long csum = 0; int ccnt = 0;
         for (int n = 0; n < nmb; n++) if (fp->spec[n].flags & SPEC_USED_CL) { csum += fp->spec[n].pad[0]; ccnt++; }
         fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0;
+        fp->cost_stat[1] = ccnt ? (int)((csum / ccnt) * 15 / 8) : 0x7FFFFFFF;
     }
     for (int base = 32 * first_block; base < nmb; base += 32)
     {

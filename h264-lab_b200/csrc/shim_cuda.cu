@@ -42,6 +42,7 @@
 #include "h264_pixel.h"
 #include "h264_mbenc.h"
 #include "h264_wave.h"
+#include "h264_fast.h"
 #include "h264_cavlc.h"
 #include "h264_deblock.h"
 #include "h264_denoise.h"
@@ -164,18 +165,33 @@ __device__ void trajectory_follower(const FrameParams *fp)
     int32_t c[2];
     c[0] = fp->clusters[0]; c[1] = fp->clusters[1];
     int ndirty = 0, n = 0;
+    /* the fast path publishes a macroblock's vectors and speculation record ("decided") before its pixel work is done */
+    const int *prog = fp->use_me ? fp->row_progress_mv : fp->row_progress;
+#ifdef H264_FASTPROF
+    unsigned long long fgt0, fwait = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(fgt0));
+#endif
     while (n < nmb)
     {
+#ifdef H264_FASTPROF
+        unsigned long long fa_, fb_;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(fa_));
+#endif
         /* how many macroblocks of the raster order are finished from n on (at most 32) */
         int row = n / nmbx, x = n - row * nmbx, avail = 0;
         if (lane == 0)
         {
             int p;
-            while ((p = ld_relaxed(fp->row_progress + row * PROG_STRIDE)) <= x) __nanosleep(200);
+            while ((p = ld_relaxed(prog + row * PROG_STRIDE)) <= x) __nanosleep(200);
             fence_acquire();
             avail = min(p - x, 32 - (n & 31));       /* chunks end at multiples of 32 (checkpoints) */
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
+#ifdef H264_FASTPROF
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(fb_));
+        fwait += fb_ - fa_;
+        if (lane == 0 && fp->prof && (n % nmbx) == 0) fp->prof[68 * 8 + 2 * (n / nmbx)] = (int)(fb_ - fgt0);
+#endif
         if (!(n & 31) && lane < 2) fp->cl_ckpt[2 * (n >> 5) + lane] = c[lane];
         int mv0 = 0, flags = 0, u0 = 0, u1 = 0;
         if (lane < avail)
@@ -190,6 +206,9 @@ __device__ void trajectory_follower(const FrameParams *fp)
         if (lane == 0) { fs[FS_LIVE] = c[0]; fs[FS_LIVE + 1] = c[1]; fs[FS_LIVE + 2] = n; }
     }
     __syncwarp();
+#ifdef H264_FASTPROF
+    if (lane == 0 && fp->prof) { unsigned long long fe_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(fe_)); fp->prof[68 * 8 + 200] = (int)(fe_ - fgt0); fp->prof[68 * 8 + 201] = (int)fwait; }
+#endif
     if (lane == 0)
     {
         fs[FS_CL_END] = c[0]; fs[FS_CL_END + 1] = c[1];
@@ -255,6 +274,26 @@ __device__ void repair_follower(const FrameParams *fp, int pass)
     }
 }
 
+__device__ int g_d_no_fast = 0;      /* developer knob H264B200_NO_FAST (set from the host): no decide / work fast path */
+/* one thread: bulk copies (TMA engine) of the motion-estimation records of macroblocks x0 .. x0 + FAST_BATCH - 1 of row y into
+ * work.me_stage[], all completing on one barrier phase */
+__device__ __forceinline__ void me_stage_issue(const FrameParams *fp, MBWork *w, int x0, int y)
+{
+    const int num = min(FAST_BATCH, fp->nmbx - x0);
+    w->me_first = x0; w->me_num = num > 0 ? num : 0;
+    if (num <= 0) return;
+    const unsigned bar = smem_u32(&w->me_bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(num * ME_WORDS * 4)) : "memory");
+    for (int k = 0; k < num; k++)
+    {
+        const uint32_t *src = fp->sadmap + (size_t)(y * fp->nmbx + x0 + k) * SM_WORDS + SM_ME_OFF;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(w->me_stage[k])), "l"(src), "r"((unsigned)(ME_WORDS * 4)), "r"(bar) : "memory");
+    }
+    w->me_cnt++;
+}
+
 __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
@@ -265,7 +304,8 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
         s_item = atomicAdd(&tickets[0], 1); work.scal[9] = 0; work.pf_inp_tag = 0; work.pf_win_tag = 0;
         /* SAD-map staging (bulk copies into work.maps[], h264_mbenc.h map_prefetch): only the row loop of sweep 0 stages ahead */
         work.map_tag[0] = work.map_tag[1] = 0; work.map_cnt[0] = work.map_cnt[1] = 0; work.pf_enable = pass == 0;
-        mbar_init(&work.map_bar[0], 1); mbar_init(&work.map_bar[1], 1);
+        work.me_cnt = 0; work.me_first = -1; work.me_num = 0; work.batch_n = 0;
+        mbar_init(&work.map_bar[0], 1); mbar_init(&work.map_bar[1], 1); mbar_init(&work.me_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -324,13 +364,148 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
             if (s_clean) return;
         }
     }
+    if (pass == 0 && fp->slice_type == SLICE_P && fp->use_me && fp->spec_no_intra && !g_d_no_fast)
+    {
+        /* Fast path of P frames (h264_fast.h) as a pipeline inside the CTA.  Warp 0 DECIDES macroblock after macroblock from
+         * the motion-estimation records (staged by bulk copies), publishing "decided" progress for the row below and
+         * handing every decision to the ring work.fd[]; warps 1..3 WORK the ring off, one macroblock each (decision q goes
+         * to warp 1 + q % 3).  The wavefront's serial chain is the decide step alone.  A macroblock that cannot be decided
+         * from its record is encoded by the whole CTA (wave_mb_first) once the ring has drained. */
+        int *prog_mv = fp->row_progress_mv;
+        const int pw = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+        volatile int32_t *v_qdec = &work.q_dec, *v_cmd = &work.cmd;
+        volatile int32_t *v_done = work.q_done;
+        if (threadIdx.x == 0) { work.pf_enable = 0; work.q_dec = 0; work.cmd = 0; work.slow_x = 0; for (int k = 0; k < MB_WARPS; k++) work.q_done[k] = 0; }
+        __syncthreads();
+        /* state of the deciding warp */
+        int x = 0, q = 0, seen_mv = 0, x_base = 0, q_base = 0, pub_full = 0;
+        int my = pw - 1;                                   /* next decision of a working warp */
+#ifdef H264_FASTPROF
+        unsigned long long gt0, gt_poll = 0, gt_ring = 0, gt_dec = 0, gt_slow = 0, gt_tmp;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+#define GT(v) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v))
+#else
+#define GT(v) do { } while (0)
+#endif
+        for (;;)
+        {
+            if (pw == 0)
+            {
+                /* decisions worked off completely: everything below the smallest decision still open at one of the three warps */
+#define FAST_PREFIX() min(q, min(min(0 + 3 * v_done[1], 1 + 3 * v_done[2]), 2 + 3 * v_done[3]))
+#define FAST_PUBLISH_FULL() do { const int xf_ = x_base + (FAST_PREFIX() - q_base); if (xf_ > pub_full) { pub_full = xf_; __threadfence(); if (lane == 0) st_release(progress + row * PROG_STRIDE, xf_); } } while (0)
+                int go_slow = 0;
+                while (x < nmbx && !go_slow)
+                {
+                    if (x < work.me_first || x >= work.me_first + work.me_num) { if (lane == 0) me_stage_issue(fp, &work, x, row); __syncwarp(); }
+                    const int first = work.me_first, num = work.me_num;
+                    mbar_wait(&work.me_bar, (unsigned)(work.me_cnt - 1) & 1u);
+                    for (int nb = x - first; nb < num; nb++)
+                    {
+                        const int need = min(x + 2, nmbx);
+                        if (row > 0 && seen_mv < need)
+                        {
+                            int p = 0;
+#ifdef H264_FASTPROF
+                            unsigned long long a_, b_; GT(a_);
+#endif
+                            if (lane == 0) p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
+                            p = __shfl_sync(0xffffffffu, p, 0);
+                            while (p < need)
+                            {
+                                FAST_PUBLISH_FULL();
+                                __nanosleep(POLL_NS);
+                                if (lane == 0) p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
+                                p = __shfl_sync(0xffffffffu, p, 0);
+                            }
+                            if (lane == 0) fence_acquire();
+                            __syncwarp();
+                            seen_mv = p;
+#ifdef H264_FASTPROF
+                            GT(b_); gt_poll += b_ - a_;
+#endif
+                        }
+#ifdef H264_FASTPROF
+                        { unsigned long long a_, b_; GT(a_);
+#endif
+                        while (q - FAST_PREFIX() >= FAST_RING - 1) { FAST_PUBLISH_FULL(); __nanosleep(32); }
+#ifdef H264_FASTPROF
+                        GT(b_); gt_ring += b_ - a_; }
+#endif
+                        if (!fast_decide(fp, &work, x, row, work.me_stage[x - first], q % FAST_RING)) { go_slow = 1; break; }
+                        q++;
+                        __threadfence_block();
+                        if (lane == 0) *v_qdec = q;
+                        x++;
+                        publish_row(prog_mv + row * PROG_STRIDE, x);
+                        FAST_PUBLISH_FULL();
+                    }
+                }
+                /* drain the ring: the complete path (or the end of the row) needs every earlier macroblock finished */
+                while (FAST_PREFIX() < q) { FAST_PUBLISH_FULL(); __nanosleep(32); }
+                FAST_PUBLISH_FULL();
+                if (lane == 0) { work.slow_x = x; __threadfence_block(); *v_cmd = go_slow ? 1 : 2; }
+            } else
+            {
+                const int k = pw - 1;
+                int cnt = v_done[pw];
+                for (;;)
+                {
+                    int have;
+                    while (!(have = (*v_qdec > my)) && *v_cmd == 0) __nanosleep(32);
+                    if (!have) have = *v_qdec > my;          /* a decision made just before the command was raised */
+                    if (!have) break;
+                    __threadfence_block();
+                    fast_work(fp, &work, work.fd[my % FAST_RING].x, row, my % FAST_RING, pw);
+                    __threadfence();                        /* reconstruction and records before the completion is seen */
+                    cnt++;
+                    if (lane == 0) v_done[pw] = cnt;
+                    my += 3;
+                    (void)k;
+                }
+            }
+            __syncthreads();
+            const int cmd = work.cmd, sx = work.slow_x;
+            if (cmd == 2) break;
+#ifdef H264_FASTPROF
+            GT(gt_tmp);
+#endif
+            /* complete path for macroblock sx, whole CTA */
+            if (row > 0) wait_row_cta(progress + (row - 1) * PROG_STRIDE, min(sx + 2, nmbx));
+            wave_mb_first(fp, &work, sx, row);
+            if (threadIdx.x < 16) work.last_mv[threadIdx.x] = fp->mbi[row * nmbx + sx].mv[threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                st_release(prog_mv + row * PROG_STRIDE, sx + 1); st_release(progress + row * PROG_STRIDE, sx + 1);
+                work.cmd = 0;
+                atomicAdd(fp->fsync + FS_SLOW, 1);
+            }
+            mb_store_coefs(fp, &work);
+            if (pw == 0) { x = sx + 1; x_base = x; q_base = q; pub_full = x; }
+#ifdef H264_FASTPROF
+            { unsigned long long b_; GT(b_); gt_slow += b_ - gt_tmp; }
+#endif
+        }
+#ifdef H264_FASTPROF
+        if (threadIdx.x == 0 && fp->prof)
+        {
+            unsigned long long b_; GT(b_);
+            int *pr = fp->prof + row * 8;
+            pr[0] = (int)(gt0 & 0x7fffffff); pr[1] = (int)(b_ - gt0); pr[2] = (int)gt_poll; pr[3] = (int)gt_ring; pr[4] = (int)gt_slow; pr[5] = q;
+        }
+#endif
+        if (threadIdx.x == 0) { st_release(progress + row * PROG_STRIDE, nmbx); atomicAdd(fp->fsync + FS_FAST, q); }
+        return;
+    }
     if (pass == 0)
     {
         for (int x = 0; x < nmbx; x++)
         {
             if (row > 0) wait_row_cta(progress + (row - 1) * PROG_STRIDE, base + min(x + 2, nmbx));
             wave_mb_first(fp, &work, x, row);
-            publish_row_cta(progress + row * PROG_STRIDE, base + x + 1);
+            __syncthreads();
+            if (threadIdx.x == 0) { st_release(fp->row_progress_mv + row * PROG_STRIDE, x + 1); st_release(progress + row * PROG_STRIDE, base + x + 1); }
             mb_store_coefs(fp, &work);
         }
         return;
@@ -491,7 +666,7 @@ __global__ void k_borders(const FrameParams *fps, int njobs)
 __global__ void __launch_bounds__(256) k_frame_init(const FrameParams *fps, int njobs, int *tickets)
 {
     const FrameParams *fp = fps + blockIdx.y;
-    const int nprog = (3 * PROG_STRIDE + 1) * fp->nmby;
+    const int nprog = (4 * PROG_STRIDE + 1) * fp->nmby;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) fp->row_progress[i] = 0;
     if (blockIdx.x == 0)
     {
@@ -748,7 +923,7 @@ struct h264b200_ctx
     int *d_out_info;
     int32_t *d_clusters;
     MBSpec *d_spec; int32_t *d_cl_true; int32_t *d_cl_ckpt; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
-    int have_traj; int stats[4];
+    int have_traj; int stats[8]; long long dbg[8];
     int *d_prof;
     uint32_t *d_sadmap;           /* [nmb][SM_WORDS] SAD-map records of the frame being encoded (h264_sadmap.h) */
     int32_t *d_me_field;          /* [nmb][16] motion field predicted by the motion-estimation pre-pass (h264_wave.h) */
@@ -825,6 +1000,7 @@ static int ensure_globals(int njobs)
         g_no_sadmap = getenv("H264B200_NO_SADMAP") != NULL;
         g_no_me = getenv("H264B200_NO_ME_PREPASS") != NULL;
         g_no_intra_spec = getenv("H264B200_NO_INTRA_SPEC") != NULL;
+        if (getenv("H264B200_NO_FAST")) { int one = 1; cudaMemcpyToSymbol(g_d_no_fast, &one, sizeof(one)); }
         if (getenv("H264B200_ME_ROUNDS")) g_me_rounds = atoi(getenv("H264B200_ME_ROUNDS"));
         const char *e = getenv("H264B200_ENC_SMEM");
         if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
@@ -841,8 +1017,8 @@ static int ensure_globals(int njobs)
         CK(cudaMallocHost(&g_h_fps, sizeof(FrameParams) * cap));
         if (g_d_info) cudaFree(g_d_info);
         if (g_h_info) cudaFreeHost(g_h_info);
-        CK(cudaMalloc(&g_d_info, sizeof(int) * 12 * cap));
-        CK(cudaMallocHost(&g_h_info, sizeof(int) * 12 * cap));
+        CK(cudaMalloc(&g_d_info, sizeof(int) * 20 * cap));
+        CK(cudaMallocHost(&g_h_info, sizeof(int) * 20 * cap));
         g_fps_cap = cap;
     }
     return 0;
@@ -904,7 +1080,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CKC(cudaMalloc(&c->d_out_info, 64));
     CKC(cudaMalloc(&c->d_clusters, 16));
     CKC(cudaMemset(c->d_clusters, 0, 16));
-    CKC(cudaMalloc(&c->d_progress, sizeof(int) * (3 * PROG_STRIDE + 1) * c->nmby));
+    CKC(cudaMalloc(&c->d_progress, sizeof(int) * (4 * PROG_STRIDE + 1) * c->nmby));
     CKC(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
     CKC(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
     CKC(cudaMalloc(&c->d_cl_true, sizeof(int32_t) * 2 * c->nmb));
@@ -919,12 +1095,12 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CKC(cudaMemset(c->d_sadmap, 0, sizeof(uint32_t) * SM_WORDS * (size_t)c->nmb + 256));
     CKC(cudaMalloc(&c->d_me_field, sizeof(int32_t) * 16 * (size_t)c->nmb));
     CKC(cudaMemset(c->d_me_field, 0, sizeof(int32_t) * 16 * (size_t)c->nmb));
-#ifdef H264_PROFILE
+#if defined(H264_PROFILE) || defined(H264_FASTPROF)
     CKC(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
     CKC(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
 #endif
     CKC(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
-    CKC(cudaMallocHost(&c->h_out_info, 64));
+    CKC(cudaMallocHost(&c->h_out_info, 128));
 #undef CKC
     *out = c;
     return 0;
@@ -1010,7 +1186,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
     fp->cost_stat = c->d_clusters + 2;       /* the allocation holds 4 ints */
-    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 3 * PROG_STRIDE * c->nmby;
+    fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_progress_mv = c->d_progress + 3 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 4 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
@@ -1073,15 +1249,15 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
 __global__ void k_gather_info(const FrameParams *fps, int n, int *out)
 {
     const int j = blockIdx.x, t = threadIdx.x;
-    if (j < n && t < 12) out[j * 12 + t] = t < 4 ? fps[j].out_info[t] : fps[j].fsync[t - 4];
+    if (j < n && t < 20) out[j * 20 + t] = t < 4 ? fps[j].out_info[t] : (t < 12 ? fps[j].fsync[t - 4] : fps[j].fsync[FS_FAST + t - 12]);
 }
 static int fetch_info(int n, h264b200_job *jobs, const int *idx, cudaStream_t st, const FrameParams *d_fps)
 {
     k_gather_info<<<n, 32, 0, st>>>(d_fps, n, g_d_info);
-    CK(cudaMemcpyAsync(g_h_info, g_d_info, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(g_h_info, g_d_info, sizeof(int) * 20 * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    for (int k = 0; k < n; k++) memcpy(jobs[idx ? idx[k] : k].ctx->h_out_info, g_h_info + 12 * k, sizeof(int) * 12);
+    for (int k = 0; k < n; k++) memcpy(jobs[idx ? idx[k] : k].ctx->h_out_info, g_h_info + 20 * k, sizeof(int) * 20);
     g_launches += 1;
     return 0;
 }
@@ -1284,6 +1460,8 @@ static int encode_chunk(int n, h264b200_job *jobs)
         jobs[i].out_words = c->h_out_words;
         c->stats[0] += c->h_out_info[4 + FS_PASSES]; c->stats[1] += c->h_out_info[4 + FS_REENC];
         c->stats[2] += c->h_out_info[4 + FS_CHECKS]; c->stats[3]++;
+        c->stats[4] += c->h_out_info[12]; c->stats[5] += c->h_out_info[13];
+        for (int k = 0; k < 5; k++) c->dbg[k] = c->h_out_info[14 + k];
         c->have_traj = jobs[i].p.slice_type == SLICE_P;
         if (jobs[i].status) { if (!rc) rc = jobs[i].status; continue; }
         if (c->h_out_info[1] & 4) { jobs[i].status = -4; if (!rc) rc = -4; continue; }
@@ -1448,5 +1626,6 @@ extern "C" int h264b200_get_profile(h264b200_ctx *c, int *out)
     return 0;
 }
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
+extern "C" int h264b200_ctx_stats_ex(h264b200_ctx *c, int *out, int n) { for (int i = 0; i < n; i++) out[i] = i < 8 ? c->stats[i] : (i < 13 ? (int)c->dbg[i - 8] : 0); return 13; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "cuda-sm_100a"; }

@@ -112,6 +112,9 @@ void h264b200_note_transparent(h264b200_ctx *ctx);
 /* Statistics of the exact-wavefront scheme (csrc/h264_wave.h), accumulated since the ctx was
  * created: [0] sweeps, [1] macroblocks re-encoded, [2] candidate-stage re-checks, [3] frames. */
 void h264b200_ctx_stats(h264b200_ctx *ctx, int out[4]);
+/* same, n slots (returns how many are defined): [4] macroblocks of P-frame sweeps taken by the decide / work fast path
+ * (csrc/h264_fast.h), [5] macroblocks of those sweeps encoded by the complete path, [6], [7] reserved */
+int h264b200_ctx_stats_ex(h264b200_ctx *ctx, int *out, int n);
 
 /* Number of frames that found their input staged by h264b200_prefetch_input. */
 long h264b200_prefetch_hits(void);

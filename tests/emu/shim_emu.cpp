@@ -15,12 +15,15 @@
 #include <vector>
 int g_emu_dbg[8];
 long g_emu_lut[8];
+long g_emu_miss[20];
+extern "C" long *emu_miss_stats(void) { return g_emu_miss; }
 extern "C" long *emu_lut_stats(void) { return g_emu_lut; }
 extern "C" int *emu_dbg(void) { return g_emu_dbg; }
 #include "../../h264-lab_b200/csrc/h264_common.h"
 #include "../../h264-lab_b200/csrc/h264_pixel.h"
 #include "../../h264-lab_b200/csrc/h264_mbenc.h"
 #include "../../h264-lab_b200/csrc/h264_wave.h"
+#include "../../h264-lab_b200/csrc/h264_fast.h"
 #include "../../h264-lab_b200/csrc/h264_cavlc.h"
 #include "../../h264-lab_b200/csrc/h264_deblock.h"
 #include "../../h264-lab_b200/csrc/h264_denoise.h"
@@ -174,6 +177,7 @@ static void run_job(h264b200_job *job)
         for (int round = 0; round < (getenv("H264B200_ME_ROUNDS") ? atoi(getenv("H264B200_ME_ROUNDS")) : ME_ROUNDS); round++)
             for (int y = 0; y < c->nmby; y++)
                 for (int x = 0; x < c->nmbx; x++) me_prepass_mb(&fp, w, x, y, round);
+    const int use_fast = fp.use_me && fp.spec_no_intra && !getenv("H264B200_NO_FAST");
     for (int pass = 0;;)
     {
         if (pass > 0)
@@ -184,7 +188,14 @@ static void run_job(h264b200_job *job)
         for (int y = 0; y < c->nmby; y++)
             for (int x = 0; x < c->nmbx; x++)
             {
-                if (pass == 0) wave_mb_first(&fp, w, x, y);
+                if (pass == 0)
+                {
+                    /* fast path of P frames (h264_fast.h): decide from the motion-estimation record, then the pixel work */
+                    const int n = y * c->nmbx + x;
+                    if (use_fast && fast_decide(&fp, w, x, y, fp.sadmap + (size_t)n * SM_WORDS + SM_ME_OFF, 0)) { fast_work(&fp, w, x, y, 0, 0); g_emu_lut[6]++; continue; }
+                    wave_mb_first(&fp, w, x, y);
+                    for (int i = 0; i < 16; i++) w->last_mv[i] = fp.mbi[n].mv[i];
+                }
                 else wave_mb_repair(&fp, w, x, y, pass);
                 mb_store_coefs(&fp, w);
             }
@@ -285,6 +296,7 @@ extern "C" void h264b200_note_transparent(h264b200_ctx *c) { if (c) c->last_dec 
 extern "C" int h264b200_last_timing_ex(float *out_ms, int n) { for (int i = 0; i < n; i++) out_ms[i] = 0; return 8; }
 extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
 extern "C" void h264b200_ctx_stats(h264b200_ctx *c, int out[4]) { for (int i = 0; i < 4; i++) out[i] = c->stats[i]; }
+extern "C" int h264b200_ctx_stats_ex(h264b200_ctx *c, int *out, int n) { for (int i = 0; i < n; i++) out[i] = i < 4 ? c->stats[i] : 0; return 8; }
 extern "C" long h264b200_launch_count(void) { return g_launches; }
 extern "C" const char *h264b200_backend_name(void) { return "host-emulation (test only)"; }
 extern "C" void emu_get_cl_true(h264b200_ctx *c, int32_t *out) { memcpy(out, c->cl_true.data(), c->cl_true.size() * 4); }

@@ -1,0 +1,24 @@
+"""developer helper (GPU box, -DH264_FASTPROF variant): per-row timeline of sweep 0 of the last frame (ns)"""
+import ctypes as C, importlib.util, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import content
+spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "h264-lab_b200", "binding.py")); B = importlib.util.module_from_spec(spec); spec.loader.exec_module(B)
+L = B.Library(os.environ.get("H264B200_LIB"))
+L.lib.H264E_b200_ctx.restype = C.c_void_p
+w, h, n = 1920, 1080, 4
+fr = content.panning(w, h, n, seed=1000)
+enc = B.Encoder(L, w, h, 60); rp = enc.run_param(qp=28)
+nmb = 120 * 68
+for i in range(n):
+    enc.encode(fr[i].copy(), rp)
+prof = np.zeros((nmb * 20,), np.int32)
+L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
+r = prof[:68 * 8].reshape(68, 8).astype(np.int64)
+t0 = r[:, 0].min()
+print("row  start_us  dur_us  poll_us  ring_us  slow_us  fast")
+for y in range(68):
+    print("%3d %9.1f %7.1f %8.1f %8.1f %8.1f %5d" % (y, ((r[y, 0] - t0) & 0x7fffffff) / 1e3, r[y, 1] / 1e3, r[y, 2] / 1e3, r[y, 3] / 1e3, r[y, 4] / 1e3, r[y, 5]))
+f = prof[68 * 8:68 * 8 + 210].astype(np.int64)
+print("follower: end %.1f us, waiting %.1f us; reaches row r at (us):" % (f[200] / 1e3, f[201] / 1e3), " ".join("%d:%.0f" % (y, f[2 * y] / 1e3) for y in range(0, 68, 6)))
