@@ -510,6 +510,8 @@ struct FrameParams
 
 /* ---- per-macroblock working set (shared memory on the GPU) --------------------- */
 /* private scratch of one motion-search warp */
+/* scratch slot of search task k: the single-warp build runs the tasks one after the other in one slot */
+#define SS_SLOT(k) (MB_WARPS == 1 ? 0 : (k))
 struct SearchScratch
 {
     pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)    */
@@ -556,14 +558,18 @@ struct MBWork : TQBuf
     pix_t tl[4];                 /* top-left Y, U, V                                        */
     int32_t mvp0_left[4], mvp0_tl[4], mvp0_top[5];   /* MV predictor context at MB start    */
     int32_t nb_i4mode[8];        /* I4x4 modes of the left MB's right column / top MB's bottom row */
+#if MB_WARPS == 1 && !defined(CHECK_WITH_WINDOW)
+    uint32_t win[4];             /* single-warp build (pre-passes, re-checks): no search window, blocks are read where they lie */
+#else
     uint32_t win[(WIN_W * WIN_H + 32) / 4];   /* search window: copy of the reference picture around the MV predictor */
+#endif
     /* GPU: asynchronous prefetch for the NEXT macroblock of the row (cp.async): its input samples,
      * and -- once this macroblock's searches are over -- its search window, placed where this
      * macroblock's motion vector points.  Tags = 1 + macroblock index the data belongs to. */
     uint32_t pf_inp[96];         /* 64 luma words (stride 16) + 32 chroma words (U | V, stride 16) */
     int32_t pf_inp_tag, pf_win_tag, pf_win_x0, pf_win_y0;
     /* motion search */
-    SearchScratch ss[4];         /* one per warp that may run a partition-mode search */
+    SearchScratch ss[MB_WARPS == 1 ? 1 : 4];   /* one per warp that may run a partition-mode search (SS_SLOT) */
     int32_t task_next;           /* partition-mode search tasks handed out so far (encode_mb) */
     pix_t mode_store[3][256];    /* assembled prediction of partition modes 1..3 (whichever warp searched them) */
     int32_t ic[16];              /* result of the candidate stage, see IC_* in h264_mbenc.h  */
@@ -582,9 +588,14 @@ struct MBWork : TQBuf
     int32_t predc_tag, predc_mv; /* GPU: predc already holds the P16x16 chroma prediction for vector predc_mv (tag = 1) */
     pix_t skip_pred[256];        /* luma prediction at the skip vector                      */
     int32_t scal[16];            /* scalars produced by one lane for everybody              */
+#if MB_WARPS == 1
+    uint32_t old_mbi[4], old_rec[4];      /* single-warp build: no re-encodes, no staged replay */
+    int32_t rp_mv0[1], rp_flags[1], rp_used0[1], rp_used1[1], rp_true0[1], rp_true1[1];
+#else
     uint32_t old_mbi[40];        /* previous record / reconstruction of an MB being repaired */
     uint32_t old_rec[96];
     int32_t rp_mv0[32], rp_flags[32], rp_used0[32], rp_used1[32], rp_true0[32], rp_true1[32];   /* replay staging */
+#endif
     /* SAD maps (h264_sadmap.h): the record of the current macroblock and, while it is encoded, the one of the next macroblock
      * of the row (bulk copy, double buffered); map_tag = 1 + macroblock index a buffer holds / was asked to hold,
      * map_cnt = copies issued into a buffer so far (phase of its barrier) */

@@ -760,39 +760,36 @@ HDN int me_search_par(const MBState &s, int ppx, int ppy, int *pmv, const int *r
     const int k = lane & 7;
     const int ox = (k == 0 || k == 4 || k == 6) ? 4 : ((k == 2 || k == 3) ? 0 : -4);
     const int oy = (k == 2 || k == 4 || k == 5) ? 4 : ((k == 0 || k == 1) ? 0 : -4);
-    uint32_t c0, c1, c2, c3, p0, p1, p2, p3;
-    int dir, cloop, dir_prev;
+    /* the reference's cost cache: cache[0..3] (this centre) and cache[4..7] (the previous one), 16 bits each, packed */
+    unsigned long long cc, pc;
+#define CGET(v, d) ((uint32_t)((v) >> (16 * (d))) & 0xffffu)
+#define CSET(v, d, x) (v) = ((v) & ~(0xffffULL << (16 * (d)))) | ((unsigned long long)((x) & 0xffffu) << (16 * (d)))
+    int dir, cloop, dir_prev, cst;
+    unsigned inmask;
     for (;;)
     {
         dir = 0; cloop = 4; dir_prev = -1;
-        c0 = c1 = c2 = c3 = p0 = p1 = p2 = p3 = 0xffffu;
-        int nb4, nb5, nb6, nb7;
-        unsigned inmask;
+        cc = pc = ~0ULL;
         for (;;)
         {
             const int v = mv_pack(mv_x(mv) + ox, mv_y(mv) + oy);
             const int inr = mv_in_rect(v, rng[0], rng[1], rng[2], rng[3]);
-            const int cst = lut_sad_lanes(s, v, lane < 8 && inr, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
+            cst = lut_sad_lanes(s, v, lane < 8 && inr, ppx, ppy, bw, bh) + mv_cost(v, mv_pred, lam);
             inmask = __ballot_sync(FULLM, inr) & 0xffu;
-            const int nb0 = __shfl_sync(FULLM, cst, 0), nb1 = __shfl_sync(FULLM, cst, 1), nb2 = __shfl_sync(FULLM, cst, 2), nb3 = __shfl_sync(FULLM, cst, 3);
-            nb4 = __shfl_sync(FULLM, cst, 4); nb5 = __shfl_sync(FULLM, cst, 5); nb6 = __shfl_sync(FULLM, cst, 6); nb7 = __shfl_sync(FULLM, cst, 7);
             int moved = 0;
             do
             {
-                const uint32_t cd = dir == 0 ? c0 : (dir == 1 ? c1 : (dir == 2 ? c2 : c3));
-                if (((inmask >> dir) & 1u) && cd == 0xffffu)
+                if (((inmask >> dir) & 1u) && CGET(cc, dir) == 0xffffu)
                 {
-                    const int cost = dir == 0 ? nb0 : (dir == 1 ? nb1 : (dir == 2 ? nb2 : nb3));
-                    const uint32_t cc = (uint32_t)cost & 0xffffu;
-                    if (dir == 0) c0 = cc; else if (dir == 1) c1 = cc; else if (dir == 2) c2 = cc; else c3 = cc;
+                    const int cost = __shfl_sync(FULLM, cst, dir);
+                    CSET(cc, dir, (uint32_t)cost);
                     if (cost < min_sad)
                     {
-                        uint32_t corner = 0xffffu;
-                        if (dir_prev >= 0) corner = dir == 0 ? p0 : (dir == 1 ? p1 : (dir == 2 ? p2 : p3));
-                        p0 = c0; p1 = c1; p2 = c2; p3 = c3;
-                        c0 = c1 = c2 = c3 = 0xffffu;
-                        if (dir_prev >= 0) { const int q = dir_prev ^ 1; if (q == 0) c0 = corner; else if (q == 1) c1 = corner; else if (q == 2) c2 = corner; else c3 = corner; }
-                        { const int q = dir ^ 1; const uint32_t m = (uint32_t)min_sad & 0xffffu; if (q == 0) c0 = m; else if (q == 1) c1 = m; else if (q == 2) c2 = m; else c3 = m; }
+                        const uint32_t corner = dir_prev >= 0 ? CGET(pc, dir) : 0xffffu;
+                        pc = cc;
+                        cc = ~0ULL;
+                        if (dir_prev >= 0) CSET(cc, dir_prev ^ 1, corner);
+                        CSET(cc, dir ^ 1, (uint32_t)min_sad);
                         mv = mv_pack(mv_x(mv) + (dir == 0 ? 4 : (dir == 1 ? -4 : 0)), mv_y(mv) + (dir == 2 ? 4 : (dir == 3 ? -4 : 0)));
                         min_sad = cost;
                         dir_prev = dir;
@@ -806,15 +803,18 @@ HDN int me_search_par(const MBState &s, int ppx, int ppy, int *pmv, const int *r
             if (!moved) break;          /* the walk has settled on this centre; after a move its neighbours are costed anew */
         }
         {
-            const int pneg = c3 >= c2 ? 0 : 1, sneg = c1 >= c0 ? 0 : 1, kk = 4 + sneg + 2 * pneg;
+            const int pneg = CGET(cc, 3) >= CGET(cc, 2) ? 0 : 1, sneg = CGET(cc, 1) >= CGET(cc, 0) ? 0 : 1, kk = 4 + sneg + 2 * pneg;
             if ((inmask >> kk) & 1u)
             {
-                const int cost = kk == 4 ? nb4 : (kk == 5 ? nb5 : (kk == 6 ? nb6 : nb7));
+                const int cost = __shfl_sync(FULLM, cst, kk);
                 if (cost < min_sad) { mv = mv_pack(mv_x(mv) + (sneg ? -4 : 4), mv_y(mv) + (pneg ? -4 : 4)); min_sad = cost; continue; }
             }
         }
         break;
     }
+    const uint32_t c0 = CGET(cc, 0), c1 = CGET(cc, 1), c2 = CGET(cc, 2), c3 = CGET(cc, 3);
+#undef CGET
+#undef CSET
     if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
     {
         uint32_t minsad1 = c1, minsad2 = c3;
@@ -2078,7 +2078,7 @@ HDF_partition_tasks void partition_tasks(MBState &s, int slot)
 {
     MBWork *w = s.w;
     const int pref = w->ic[IC_PREF];
-    s.ss = &w->ss[slot];
+    s.ss = &w->ss[SS_SLOT(slot)];
     for (;;)
     {
         int k = 0;
@@ -2197,7 +2197,7 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
     s.fp = fp; s.w = w; s.mbx = mbx; s.mby = mby;
     s.avail = mb_avail(mbx, mby, fp->nmbx);
     s.type = 0; s.cost = 0x7FFFFFFF; s.i16_mode = 2; s.mv_skip_pred = 0;
-    s.pbest = w->skip_pred; s.ss = &w->ss[WARP_ID < 3 ? WARP_ID : 0];
+    s.pbest = w->skip_pred; s.ss = &w->ss[SS_SLOT(WARP_ID < 3 ? WARP_ID : 0)];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     s.map = 0; s.lut = 0;
     const int is_p = fp->slice_type == SLICE_P;

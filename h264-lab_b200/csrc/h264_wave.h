@@ -292,13 +292,13 @@ HDN int wave_cand_check(const FrameParams *fp, MBWork *w, int x, int y, const in
             {
                 ON_WARP(1)
                 {
-                    s.ss = &w->ss[1];
+                    s.ss = &w->ss[SS_SLOT(1)];
                     if (extra & 1) inter_mode_search(s, 1);
                     if (extra & 2) inter_mode_search(s, 2);
                 }
                 ON_WARP(2)
                 {
-                    s.ss = &w->ss[2];
+                    s.ss = &w->ss[SS_SLOT(2)];
                     if (extra & 4) inter_mode_search(s, 3);
                 }
                 CTA_SYNC();

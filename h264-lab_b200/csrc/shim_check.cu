@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(32) k_check1(const FrameParams *fps, int njobs
 /* Speculative motion estimation ahead of the wavefront (h264_wave.h, me_prepass_mb): one warp per macroblock, every
  * macroblock of every P frame of the submission, no dependencies between them.  round 0 predicts the context from the
  * previous frame's motion field, later rounds from the field the round before predicted. */
-__global__ void __launch_bounds__(32) k_me(const FrameParams *fps, int njobs, int round)
+#ifndef ME_MIN_BLOCKS
+#define ME_MIN_BLOCKS 20
+#endif
+__global__ void __launch_bounds__(32, ME_MIN_BLOCKS) k_me(const FrameParams *fps, int njobs, int round)
 {
     __shared__ MBWork work;
     __shared__ FrameParams sfp;

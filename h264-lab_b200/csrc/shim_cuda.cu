@@ -1607,6 +1607,17 @@ extern "C" int h264b200_get_recon(h264b200_ctx *c, unsigned char *const planes[3
     return 0;
 }
 
+/* test hook: the SAD-map / motion-estimation records (h264_sadmap.h) of the last P frame of ctx, [nmb][SM_WORDS] words */
+extern "C" int h264b200_debug_get_sadmap(h264b200_ctx *c, unsigned int *out, int max_words)
+{
+    if (!c || !out) return -3;
+    std::lock_guard<std::mutex> guard(lane_enter(c)->lock);
+    const int words = SM_WORDS * c->nmb;
+    if (max_words < words) return -3;
+    CK(cudaMemcpy(out, c->d_sadmap, sizeof(uint32_t) * (size_t)words, cudaMemcpyDeviceToHost));
+    return SM_WORDS;
+}
+
 extern "C" void h264b200_note_transparent(h264b200_ctx *c) { if (c) c->last_dec = c->cur ^ 1; }
 
 extern "C" int h264b200_last_timing_ex(float *out_ms, int n)

@@ -116,6 +116,11 @@ void h264b200_ctx_stats(h264b200_ctx *ctx, int out[4]);
  * (csrc/h264_fast.h), [5] macroblocks of those sweeps encoded by the complete path, [6], [7] reserved */
 int h264b200_ctx_stats_ex(h264b200_ctx *ctx, int *out, int n);
 
+/* Test hook: copies the SAD-map records of the last P frame of ctx (csrc/h264_sadmap.h: per macroblock the quadrant SADs
+ * at 15 x 15 full-sample offsets and 13 x 13 quarter-sample positions + the motion-estimation record) to out[]; returns
+ * the number of 32-bit words per macroblock, or a negative error. */
+int h264b200_debug_get_sadmap(h264b200_ctx *ctx, unsigned int *out, int max_words);
+
 /* Number of frames that found their input staged by h264b200_prefetch_input. */
 long h264b200_prefetch_hits(void);
 /* Number of kernel launches issued since the library was loaded. */

@@ -292,6 +292,13 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
     c->clip.assign(frames, frames + fs * nframes);
     return 0;
 }
+extern "C" int h264b200_debug_get_sadmap(h264b200_ctx *c, unsigned int *out, int max_words)
+{
+    const int words = SM_WORDS * c->nmbx * c->nmby;
+    if (max_words < words) return -3;
+    memcpy(out, c->sadmap.data(), sizeof(uint32_t) * (size_t)words);
+    return SM_WORDS;
+}
 extern "C" void h264b200_note_transparent(h264b200_ctx *c) { if (c) c->last_dec = c->cur ^ 1; }
 extern "C" int h264b200_last_timing_ex(float *out_ms, int n) { for (int i = 0; i < n; i++) out_ms[i] = 0; return 8; }
 extern "C" void h264b200_last_timing(float out_ms[4]) { out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0; }
