@@ -470,10 +470,14 @@ struct FrameParams
     /* 1: sweep 0 of this P frame decides every macroblock among the inter modes only; the intra costs of all macroblocks are
      * verified afterwards, in parallel, against the finished sweep (h264_wave.h, wave_mb_intra_check) */
     int spec_no_intra;
-    /* [0]: inter cost from which a macroblock of this frame evaluates its intra modes inside sweep 0 after all (11/8 of the
+    /* [0]: inter cost from which a macroblock of this frame evaluates its intra modes inside sweep 0 after all (13/8 of the
      * mean inter cost of the previous P frame, written by wave_replay(predict)); [1]: inter cost from which the
-     * motion-estimation pre-pass predicts an intra outcome (15/8 of that mean); only read when spec_from_prev */
+     * motion-estimation pre-pass predicts an intra outcome (15/8 of that mean); [2 + y]: the same threshold as [0] for the
+     * macroblocks of row y, but never below 13/8 of THAT ROW's mean (a row that is expensive as a whole -- the cropped
+     * bottom row of 1080p -- is not sent through the complete path macroblock after macroblock: its intra winners are
+     * found by the parallel verification and repaired in parallel rounds); only read when spec_from_prev */
     int *cost_stat;
+    int thr_eighths;            /* the "13" of the 13/8 above (developer knob H264B200_THR, A/B runs) */
     /* temporal noise suppressor (h264_denoise.h); dn_out[0] == NULL: not used for this frame */
     const pix_t *dn_src[3];     /* picture as submitted                                       */
     const pix_t *dn_prev[3];    /* previous output of the filter                              */

@@ -144,7 +144,7 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
         inter_decide(fp, w, &type, &cost, pmv, pmvd, &usp);
         /* an inter cost nearly twice the usual: the macroblock will most likely end up intra, i.e. without vectors
          * for its neighbours' context (only a prediction -- the wavefront checks every context) */
-        if (type != MBT_SKIP && fp->spec_from_prev && cost >= fp->cost_stat[1]) type = -3;
+        if (type != MBT_SKIP && fp->spec_from_prev && cost >= imax(fp->cost_stat[1], fp->cost_stat[2 + y] * 15 / fp->thr_eighths)) type = -3;
     } else
     {   /* no estimation by look-up here: no record; the field keeps the previous frame's vectors for the neighbours' context */
         IF_THREAD0 { mr[ME_KEY + 15] = 0; }
@@ -524,7 +524,16 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
         {
 #pragma unroll
             for (int o = 16; o; o >>= 1) { csum += __shfl_xor_sync(0xffffffffu, csum, o); ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o); }
-            if (lane == 0) { fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0; fp->cost_stat[1] = ccnt ? (int)((csum / ccnt) * 15 / 8) : 0x7FFFFFFF; }
+            const int thr = ccnt ? (int)((csum / ccnt) * fp->thr_eighths / 8) : 0;
+            if (lane == 0) { fp->cost_stat[0] = thr; fp->cost_stat[1] = ccnt ? (int)((csum / ccnt) * 15 / 8) : 0x7FFFFFFF; }
+            for (int y = 0; y < fp->nmby; y++)
+            {   /* per-row thresholds */
+                long long rs = 0; int rc = 0;
+                for (int x = lane; x < fp->nmbx; x += 32) { const MBSpec *sp = fp->spec + y * fp->nmbx + x; if (sp->flags & SPEC_USED_CL) { rs += sp->pad[0]; rc++; } }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rc += __shfl_xor_sync(0xffffffffu, rc, o); }
+                if (lane == 0) fp->cost_stat[2 + y] = imax(thr, rc ? (int)((rs / rc) * fp->thr_eighths / 8) : 0);
+            }
         }
     }
 #else
@@ -532,8 +541,14 @@ HDN int wave_replay(const FrameParams *fp, MBWork *w, int predict, int first_blo
     {
         long long csum = 0; int ccnt = 0;
         for (int n = 0; n < nmb; n++) if (fp->spec[n].flags & SPEC_USED_CL) { csum += fp->spec[n].pad[0]; ccnt++; }
-        fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * 11 / 8) : 0;
+        fp->cost_stat[0] = ccnt ? (int)((csum / ccnt) * fp->thr_eighths / 8) : 0;
         fp->cost_stat[1] = ccnt ? (int)((csum / ccnt) * 15 / 8) : 0x7FFFFFFF;
+        for (int y = 0; y < fp->nmby; y++)
+        {
+            long long rs = 0; int rc = 0;
+            for (int x = 0; x < fp->nmbx; x++) { const MBSpec *sp = fp->spec + y * fp->nmbx + x; if (sp->flags & SPEC_USED_CL) { rs += sp->pad[0]; rc++; } }
+            fp->cost_stat[2 + y] = imax(fp->cost_stat[0], rc ? (int)((rs / rc) * fp->thr_eighths / 8) : 0);
+        }
     }
     for (int base = 32 * first_block; base < nmb; base += 32)
     {

@@ -922,6 +922,7 @@ struct h264b200_ctx
     int out_cap_words;
     int *d_out_info;
     int32_t *d_clusters;
+    int *d_cost_stat;             /* [2 + nmby] inter-cost thresholds derived from the previous P frame (FrameParams::cost_stat) */
     MBSpec *d_spec; int32_t *d_cl_true; int32_t *d_cl_ckpt; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
     int have_traj; int stats[8]; long long dbg[8];
     int *d_prof;
@@ -993,12 +994,14 @@ static std::once_flag g_knob_once;
 static int g_no_sadmap = 0;        /* developer knob H264B200_NO_SADMAP: pixel flavour of the searches everywhere (A/B runs) */
 static int g_no_me = 0;            /* developer knob H264B200_NO_ME_PREPASS: no speculative motion estimation ahead of the wavefront */
 static int g_me_rounds = ME_ROUNDS; /* developer knob H264B200_ME_ROUNDS */
+static int g_thr_eighths = 13;     /* developer knob H264B200_THR: in-sweep intra evaluation from thr/8 of the mean inter cost */
 static int g_no_intra_spec = 0;    /* developer knob H264B200_NO_INTRA_SPEC: intra modes evaluated inside sweep 0 as the reference does */
 static int ensure_globals(int njobs)
 {
     std::call_once(g_knob_once, []() {
         g_no_sadmap = getenv("H264B200_NO_SADMAP") != NULL;
         g_no_me = getenv("H264B200_NO_ME_PREPASS") != NULL;
+        if (getenv("H264B200_THR")) g_thr_eighths = atoi(getenv("H264B200_THR"));
         g_no_intra_spec = getenv("H264B200_NO_INTRA_SPEC") != NULL;
         if (getenv("H264B200_NO_FAST")) { int one = 1; cudaMemcpyToSymbol(g_d_no_fast, &one, sizeof(one)); }
         if (getenv("H264B200_ME_ROUNDS")) g_me_rounds = atoi(getenv("H264B200_ME_ROUNDS"));
@@ -1080,6 +1083,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CKC(cudaMalloc(&c->d_out_info, 64));
     CKC(cudaMalloc(&c->d_clusters, 16));
     CKC(cudaMemset(c->d_clusters, 0, 16));
+    CKC(cudaMalloc(&c->d_cost_stat, sizeof(int) * (2 + c->nmby)));
+    CKC(cudaMemset(c->d_cost_stat, 0, sizeof(int) * (2 + c->nmby)));
     CKC(cudaMalloc(&c->d_progress, sizeof(int) * (4 * PROG_STRIDE + 1) * c->nmby));
     CKC(cudaMalloc(&c->d_spec, sizeof(MBSpec) * c->nmb));
     CKC(cudaMemset(c->d_spec, 0, sizeof(MBSpec) * c->nmb));
@@ -1120,7 +1125,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->d_clip) cudaFree(c->d_clip);
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
-    cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress);
+    cudaFree(c->d_out_words); cudaFree(c->d_out_info); cudaFree(c->d_clusters); cudaFree(c->d_progress); cudaFree(c->d_cost_stat);
     cudaFree(c->d_spec); cudaFree(c->d_cl_true); cudaFree(c->d_cl_ckpt); cudaFree(c->d_changed_pass); cudaFree(c->d_need_reenc); cudaFree(c->d_fsync);
     if (c->h_out_words) cudaFreeHost(c->h_out_words);
     if (c->h_out_info) cudaFreeHost(c->h_out_info);
@@ -1185,7 +1190,8 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->stride[0] = c->stride[0]; fp->stride[1] = c->stride[1];
     fp->mbi = c->d_mbi; fp->coef = c->d_coef;
     fp->clusters = c->d_clusters;
-    fp->cost_stat = c->d_clusters + 2;       /* the allocation holds 4 ints */
+    fp->cost_stat = c->d_cost_stat;
+    fp->thr_eighths = g_thr_eighths;
     fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_progress_mv = c->d_progress + 3 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 4 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;

@@ -53,7 +53,7 @@ struct h264b200_ctx
     int fsync[FS_WORDS];
     int stats[4];
     int32_t clusters[2];
-    int cost_stat[2];
+    std::vector<int> cost_stat;
     int have_traj;
 };
 
@@ -147,7 +147,9 @@ static void run_job(h264b200_job *job)
     fp.stride[0] = c->stride[0]; fp.stride[1] = c->stride[1];
     fp.mbi = c->mbi.data(); fp.coef = c->coef.data();
     fp.clusters = c->clusters;
-    fp.cost_stat = c->cost_stat;
+    if (c->cost_stat.empty()) c->cost_stat.assign(2 + c->nmby, 0);
+    fp.cost_stat = c->cost_stat.data();
+    fp.thr_eighths = getenv("H264B200_THR") ? atoi(getenv("H264B200_THR")) : 13;
     fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.cl_ckpt = c->cl_ckpt.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
     memset(c->fsync, 0, sizeof(c->fsync));
     fp.fsync = c->fsync;

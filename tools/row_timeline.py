@@ -9,10 +9,13 @@ L = B.Library(os.environ.get("H264B200_LIB"))
 L.lib.H264E_b200_ctx.restype = C.c_void_p
 w, h, n = 1920, 1080, 4
 fr = content.panning(w, h, n, seed=1000)
-enc = B.Encoder(L, w, h, 60); rp = enc.run_param(qp=28)
+nsess = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+encs = [B.Encoder(L, w, h, 60) for _ in range(nsess)]
+rps = [e.run_param(qp=28) for e in encs]
+enc = encs[0]
 nmb = 120 * 68
 for i in range(n):
-    enc.encode(fr[i].copy(), rp)
+    B.encode_batch(L, encs, [fr[i].copy() for _ in encs], rps)
 prof = np.zeros((nmb * 20,), np.int32)
 L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
 r = prof[:68 * 8].reshape(68, 8).astype(np.int64)
