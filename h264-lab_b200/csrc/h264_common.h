@@ -494,7 +494,7 @@ struct FrameParams
 /* SAD-map record of one macroblock (h264_sadmap.h) */
 #define SM_R 7
 #define SM_N (2 * SM_R + 1)
-#define SM_QR 6
+#define SM_QR 2
 #define SM_QN (2 * SM_QR + 1)
 #define SM_INT_ENTRIES (SM_N * SM_N)
 #define SM_Q_ENTRIES (SM_QN * SM_QN)

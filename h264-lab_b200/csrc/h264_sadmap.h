@@ -15,6 +15,9 @@
  *                     integer position with the smallest 16x16 SAD: every sub-sample probe of the reference's
  *                     refinement (H:5083-5174) is a standard quarter-sample position, i.e. one sample of one of the
  *                     planes {G, b, h, j} or the rounded average of two (interp_luma_planes, h264_pixel.h).
+ *                     SM_QR = 2 covers the seven probes around that position; measured on the bench content, 93 % of all
+ *                     sub-sample look-ups fall there, 0.6 % between 3 and 6 quarter samples away (a 13 x 13 map would
+ *                     catch those at seven times the work) and the rest further away than any small map reaches.
  *
  * The wavefront kernel then replays the reference's search with table look-ups (a few instructions per probe,
  * maps staged into shared memory by one bulk-copy (TMA) instruction per macroblock) instead of warp-wide pixel loops.
@@ -22,7 +25,7 @@
  * values, never an approximation, so the decisions are the reference's by construction; a macroblock whose
  * predictor points away from its map skips the look-ups altogether and runs the pixel path with its search window.
  *
- * Record of one macroblock, SM_WORDS 32-bit words (3488 bytes, a multiple of 16 for the bulk copy):
+ * Record of one macroblock, SM_WORDS 32-bit words (2336 bytes, a multiple of 16 for the bulk copy):
  *   [0] centre of the integer map, macroblock-relative full samples (x | y << 16)      [1] centre of the quarter map
  *   [2] 1 when the record is valid for the frame                                       [3] reserved
  *   [SM_INT_OFF + 2 k]     q0 | q1 << 16     k = (dy + SM_R) * SM_N + dx + SM_R        (q0 TL, q1 TR, q2 BL, q3 BR)
@@ -49,6 +52,9 @@ HD int sadmap_lookup(const uint32_t *map, int cx, int cy, int qcx, int qcy, int 
     if (!((x | y) & 3))
     {
         const int ix = (x >> 2) - cx + SM_R, iy = (y >> 2) - cy + SM_R;
+#if !H264_DEVICE && defined(SADMAP_STATS)
+        { extern long g_emu_ihist[16]; int m = imax(iabs((x >> 2) - cx), iabs((y >> 2) - cy)); g_emu_ihist[m > 15 ? 15 : m]++; }
+#endif
         if ((unsigned)ix < (unsigned)SM_N && (unsigned)iy < (unsigned)SM_N)
         {
             const uint32_t *e = map + SM_INT_OFF + 2 * (iy * SM_N + ix);
@@ -57,6 +63,9 @@ HD int sadmap_lookup(const uint32_t *map, int cx, int cy, int qcx, int qcy, int 
         }
     }
     const int qx = x - 4 * qcx + SM_QR, qy = y - 4 * qcy + SM_QR;
+#if !H264_DEVICE && defined(SADMAP_STATS)
+    { extern long g_emu_qhist[16]; int m = imax(iabs(x - 4 * qcx), iabs(y - 4 * qcy)); g_emu_qhist[m > 15 ? 15 : m]++; }
+#endif
     if ((unsigned)qx < (unsigned)SM_QN && (unsigned)qy < (unsigned)SM_QN)
     {
         const uint32_t *e = map + SM_Q_OFF + 2 * (qy * SM_QN + qx);

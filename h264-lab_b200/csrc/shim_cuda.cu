@@ -842,12 +842,16 @@ __global__ void __launch_bounds__(256) k_sadmap(const FrameParams *fps, int njob
             s_pl[pl][r * SMP_STRIDE + wd] = *(const uint32_t *)(plane + (long)y * st + x);
         }
         __syncthreads();
-        if (t < SM_Q_ENTRIES)
+        if ((t & ~31) < 4 * SM_Q_ENTRIES)              /* whole warps (the shuffles below): surplus lanes redo position 0 and store nothing */
         {
-            const int qyi = t / SM_QN, qxi = t - qyi * SM_QN, qx = qxi - SM_QR, qy = qyi - SM_QR;
+            /* quarter map: thread = (position, group of four rows); the four threads of a position sit in one warp and
+             * combine their partial quadrant sums with two shuffles */
+            const int act = t < 4 * SM_Q_ENTRIES;
+            const int pq = act ? t >> 2 : 0, g = t & 3;
+            const int qyi = pq / SM_QN, qxi = pq - qyi * SM_QN, qx = qxi - SM_QR, qy = qyi - SM_QR;
             const int aqx = (mbx * 16 + bx) * 4 + qx, aqy = (mby * 16 + by) * 4 + qy;
-            uint32_t lo = SM_INVALID, hi = SM_INVALID;
-            if (sadmap_block_inside(fp, aqx >> 2, aqy >> 2))
+            const int inside = sadmap_block_inside(fp, aqx >> 2, aqy >> 2);
+            int ql = 0, qr = 0;
             {
                 /* the two sources of the position (interp_luma_word): plane, column / row offset inside the staged windows */
                 const int dx = qx & 3, dy = qy & 3, fx = (qx >> 2) + 2, fy = (qy >> 2) + 2, pos = 1 << (dx + 4 * dy);
@@ -861,11 +865,10 @@ __global__ void __launch_bounds__(256) k_sadmap(const FrameParams *fps, int njob
                     if ((pos & 0xfafa) && pb < 0) { pb = 0; cb = fx + ((dx + 1) >> 2); rb = fy + ((dy + 1) >> 2); }
                 }
                 const int cola = psh0 + ca, sha = (cola & 3) * 8, colb = psh0 + cb, shb = (colb & 3) * 8;
-                const uint32_t *rowa = s_pl[pa] + ra * SMP_STRIDE + (cola >> 2);
-                const uint32_t *rowb = s_pl[pb < 0 ? 0 : pb] + rb * SMP_STRIDE + (colb >> 2);
-                int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-#pragma unroll 4
-                for (int r = 0; r < 16; r++)
+                const uint32_t *rowa = s_pl[pa] + (ra + 4 * g) * SMP_STRIDE + (cola >> 2);
+                const uint32_t *rowb = s_pl[pb < 0 ? 0 : pb] + (rb + 4 * g) * SMP_STRIDE + (colb >> 2);
+#pragma unroll
+                for (int r = 0; r < 4; r++)
                 {
                     uint32_t a0 = __funnelshift_r(rowa[0], rowa[1], sha), a1 = __funnelshift_r(rowa[1], rowa[2], sha);
                     uint32_t a2 = __funnelshift_r(rowa[2], rowa[3], sha), a3 = __funnelshift_r(rowa[3], rowa[4], sha);
@@ -874,14 +877,16 @@ __global__ void __launch_bounds__(256) k_sadmap(const FrameParams *fps, int njob
                         a0 = __vavgu4(a0, __funnelshift_r(rowb[0], rowb[1], shb)); a1 = __vavgu4(a1, __funnelshift_r(rowb[1], rowb[2], shb));
                         a2 = __vavgu4(a2, __funnelshift_r(rowb[2], rowb[3], shb)); a3 = __vavgu4(a3, __funnelshift_r(rowb[3], rowb[4], shb));
                     }
-                    const uint4 in = *(const uint4 *)(s_inp + 4 * r);
-                    const int l = (int)(__vsadu4(a0, in.x) + __vsadu4(a1, in.y)), rr = (int)(__vsadu4(a2, in.z) + __vsadu4(a3, in.w));
-                    if (r < 8) { q0 += l; q1 += rr; } else { q2 += l; q3 += rr; }
+                    const uint4 in = *(const uint4 *)(s_inp + 4 * (4 * g + r));
+                    ql += (int)(__vsadu4(a0, in.x) + __vsadu4(a1, in.y)); qr += (int)(__vsadu4(a2, in.z) + __vsadu4(a3, in.w));
                     rowa += SMP_STRIDE; rowb += SMP_STRIDE;
                 }
-                lo = (uint32_t)q0 | ((uint32_t)q1 << 16); hi = (uint32_t)q2 | ((uint32_t)q3 << 16);
             }
-            *(uint2 *)(rec + SM_Q_OFF + 2 * t) = make_uint2(lo, hi);
+            /* rows 0-7 (groups 0, 1): q0 | q1;  rows 8-15 (groups 2, 3): q2 | q3 */
+            uint32_t half = (uint32_t)ql | ((uint32_t)qr << 16);
+            half += __shfl_xor_sync(0xffffffffu, half, 1);
+            const uint32_t other = __shfl_down_sync(0xffffffffu, half, 2);
+            if (g == 0 && act) *(uint2 *)(rec + SM_Q_OFF + 2 * pq) = inside ? make_uint2(half, other) : make_uint2(SM_INVALID, SM_INVALID);
         }
         if (t == 0) { rec[0] = (uint32_t)mv_pack(cx, cy); rec[1] = (uint32_t)mv_pack(bx, by); rec[2] = 1; rec[3] = 0; rec[SM_ME_OFF + ME_KEY + 15] = 0; }
         __syncthreads();

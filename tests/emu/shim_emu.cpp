@@ -16,6 +16,10 @@
 int g_emu_dbg[8];
 long g_emu_lut[8];
 long g_emu_miss[20];
+long g_emu_qhist[16];
+long g_emu_ihist[16];
+extern "C" long *emu_ihist(void) { return g_emu_ihist; }
+extern "C" long *emu_qhist(void) { return g_emu_qhist; }
 extern "C" long *emu_miss_stats(void) { return g_emu_miss; }
 extern "C" long *emu_lut_stats(void) { return g_emu_lut; }
 extern "C" int *emu_dbg(void) { return g_emu_dbg; }

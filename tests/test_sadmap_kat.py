@@ -12,7 +12,7 @@ import pytest
 
 import cases
 
-SM_R, SM_QR = 7, 6
+SM_R, SM_QR = 7, 2
 SM_N, SM_QN = 2 * SM_R + 1, 2 * SM_QR + 1
 SM_INT_OFF = 4
 SM_Q_OFF = SM_INT_OFF + 2 * SM_N * SM_N
@@ -88,7 +88,7 @@ def _check(binding, lib, ref, w, h, every):
             want = quads(mbx, mby, 4 * qcx + qx, 4 * qcy + qy)
             assert [lo & 0xFFFF, lo >> 16, hi & 0xFFFF, hi >> 16] == want, ("quarter map", n, qx, qy)
             checked += 1
-    assert checked > 1000
+    assert checked > 500
     return checked
 
 
