@@ -467,6 +467,8 @@ struct FrameParams
      * me_field = [nmb][16] motion field the pre-pass predicts for THIS frame (input of its refinement rounds) */
     int use_me;
     int32_t *me_field;
+    int *me_list, *me_count;    /* refinement rounds: macroblocks whose record does not belong to the predicted context any more
+                                   (k_me_scan), [nmb] indices and the count per round [8] */
     /* 1: sweep 0 of this P frame decides every macroblock among the inter modes only; the intra costs of all macroblocks are
      * verified afterwards, in parallel, against the finished sweep (h264_wave.h, wave_mb_intra_check) */
     int spec_no_intra;
@@ -475,8 +477,10 @@ struct FrameParams
      * motion-estimation pre-pass predicts an intra outcome (15/8 of that mean); [2 + y]: the same threshold as [0] for the
      * macroblocks of row y, but never below 13/8 of THAT ROW's mean (a row that is expensive as a whole -- the cropped
      * bottom row of 1080p -- is not sent through the complete path macroblock after macroblock: its intra winners are
-     * found by the parallel verification and repaired in parallel rounds); only read when spec_from_prev */
+     * found by the parallel verification and repaired in parallel rounds); only read when have_cost_stat
+     * (a P frame of this session has been finished before -- the statistic survives IDR frames) */
     int *cost_stat;
+    int have_cost_stat;
     int thr_eighths;            /* the "13" of the 13/8 above (developer knob H264B200_THR, A/B runs) */
     /* temporal noise suppressor (h264_denoise.h); dn_out[0] == NULL: not used for this frame */
     const pix_t *dn_src[3];     /* picture as submitted                                       */

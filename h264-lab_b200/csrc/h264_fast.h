@@ -62,7 +62,7 @@ HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32
     const int best_type = inter_decide_p(fp, ic, mc, (const int32_t *)(mr + ME_MV), (const int32_t *)(mr + ME_MVD), &type, &cost, pmv, pmvd, &usp);
     const int searched = ic[IC_STATE] != 1;
     /* an inter cost this far above the usual: an intra mode probably wins, look at it now (encode_mb) rather than repair later */
-    if (searched && cost >= (fp->spec_from_prev ? fp->cost_stat[2 + y] : 0)) return 0;
+    if (searched && cost >= (fp->have_cost_stat ? fp->cost_stat[2 + y] : 0)) return 0;
     MBInfo *mi = fp->mbi + n;
     uint32_t *sp = (uint32_t *)(fp->spec + n);
     FOR_LANES(i, 32)

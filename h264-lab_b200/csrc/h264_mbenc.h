@@ -2248,7 +2248,7 @@ HDF_encode_mb void encode_mb(const FrameParams *fp, MBWork *w, int mbx, int mby,
         {
             int t_, c_, u_; int32_t m_[4], d_[4];
             inter_decide(fp, w, &t_, &c_, m_, d_, &u_);
-            do_intra = t_ != MBT_SKIP && c_ >= (fp->spec_from_prev ? fp->cost_stat[2 + mby] : 0);
+            do_intra = t_ != MBT_SKIP && c_ >= (fp->have_cost_stat ? fp->cost_stat[2 + mby] : 0);
         }
     }
     /* ---- concurrent tasks ---- */

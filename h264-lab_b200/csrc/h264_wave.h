@@ -66,6 +66,27 @@ HD void spec_store(const FrameParams *fp, int n, const MBSpec &sp)
  * different means the estimation runs in place, as before.  Nothing is ever trusted without that comparison, so the
  * decisions stay the reference's; only the critical path of the wavefront gets shorter.
  * ---------------------------------------------------------------------------- */
+/* one thread: does the record of macroblock n still belong to the context the predicted field gives it?  (refinement rounds) */
+HD int me_record_stale(const FrameParams *fp, int n)
+{
+    const int nmbx = fp->nmbx, y = n / nmbx, x = n - y * nmbx, av = mb_avail(x, y, nmbx);
+    const uint32_t *mr = fp->sadmap + (size_t)n * SM_WORDS + SM_ME_OFF;
+    if (mr[ME_KEY + 15] != 1u) return 1;
+    const int32_t *f = fp->me_field;
+    for (int i = 0; i < 15; i++)
+    {
+        int32_t have;
+        if (i < 4) have = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * i + 3] : MV_NA;
+        else if (i == 4) have = (av & AVAIL_TL) ? f[(n - nmbx - 1) * 16 + 15] : MV_NA;
+        else if (i < 8) have = (av & AVAIL_L) ? f[(n - 1) * 16 + 4 * (i - 5) + 3] : MV_NA;
+        else if (i < 12) have = (av & AVAIL_T) ? f[(n - nmbx) * 16 + 12 + (i - 8)] : MV_NA;
+        else if (i == 12) have = (av & AVAIL_TR) ? f[(n - nmbx + 1) * 16 + 12] : MV_NA;
+        else have = fp->spec_from_prev ? fp->cl_true[2 * n + (i - 13)] : mv_round_fullpel(fp->clusters[i - 13]);
+        if ((int32_t)mr[ME_KEY + i] != have) return 1;
+    }
+    return 0;
+}
+
 HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x;
@@ -144,7 +165,7 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
         inter_decide(fp, w, &type, &cost, pmv, pmvd, &usp);
         /* an inter cost nearly twice the usual: the macroblock will most likely end up intra, i.e. without vectors
          * for its neighbours' context (only a prediction -- the wavefront checks every context) */
-        if (type != MBT_SKIP && fp->spec_from_prev && cost >= imax(fp->cost_stat[1], fp->cost_stat[2 + y] * 15 / fp->thr_eighths)) type = -3;
+        if (type != MBT_SKIP && fp->have_cost_stat && cost >= imax(fp->cost_stat[1], fp->cost_stat[2 + y] * 15 / fp->thr_eighths)) type = -3;
     } else
     {   /* no estimation by look-up here: no record; the field keeps the previous frame's vectors for the neighbours' context */
         IF_THREAD0 { mr[ME_KEY + 15] = 0; }

@@ -48,11 +48,32 @@ __global__ void __launch_bounds__(32, ME_MIN_BLOCKS) k_me(const FrameParams *fps
     const FrameParams *fp = &sfp;
     if (!fp->use_me || fp->slice_type != SLICE_P) return;
     const int nmbx = fp->nmbx, nmb = fp->nmbx * fp->nmby;
-    for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+    if (round == 0)
     {
-        int y = n / nmbx;
+        for (int n = blockIdx.x; n < nmb; n += gridDim.x)
+        {
+            int y = n / nmbx;
+            me_prepass_mb(fp, &work, n - y * nmbx, y, 0);
+        }
+        return;
+    }
+    /* refinement rounds: only the macroblocks k_me_scan listed */
+    const int cnt = fp->me_count[round];
+    for (int i = blockIdx.x; i < cnt; i += gridDim.x)
+    {
+        const int n = fp->me_list[i], y = n / nmbx;
         me_prepass_mb(fp, &work, n - y * nmbx, y, round);
     }
+}
+
+/* one THREAD per macroblock: list the macroblocks whose record has to be recomputed in refinement round `round` */
+__global__ void __launch_bounds__(256) k_me_scan(const FrameParams *fps, int njobs, int round)
+{
+    const FrameParams *fp = fps + blockIdx.y;
+    if (!fp->use_me || fp->slice_type != SLICE_P) return;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= fp->nmbx * fp->nmby) return;
+    if (me_record_stale(fp, n)) fp->me_list[atomicAdd(fp->me_count + round, 1)] = n;
 }
 
 /* Intra modes of every macroblock of a finished sweep 0 (h264_wave.h, wave_mb_intra_check): one warp per macroblock,
@@ -82,7 +103,9 @@ void h264b200_launch_intra_check(const FrameParams *fps, int njobs, int max_nmb,
 
 void h264b200_launch_me(const FrameParams *fps, int njobs, int max_nmb, int round, cudaStream_t st)
 {
-    k_me<<<dim3((max_nmb + 3) / 4, njobs), 32, 0, st>>>(fps, njobs, round);
+    if (round == 0) { k_me<<<dim3((max_nmb + 3) / 4, njobs), 32, 0, st>>>(fps, njobs, 0); return; }
+    k_me_scan<<<dim3((max_nmb + 255) / 256, njobs), 256, 0, st>>>(fps, njobs, round);
+    k_me<<<dim3((max_nmb + 15) / 16, njobs), 32, 0, st>>>(fps, njobs, round);
 }
 
 void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st)

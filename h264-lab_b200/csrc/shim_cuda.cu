@@ -673,6 +673,7 @@ __global__ void __launch_bounds__(256) k_frame_init(const FrameParams *fps, int 
         if (threadIdx.x < 16) fp->out_info[threadIdx.x] = 0;
         if (threadIdx.x < FS_WORDS) fp->fsync[threadIdx.x] = (threadIdx.x == FS_LIVE || threadIdx.x == FS_LIVE + 1) ? fp->clusters[threadIdx.x - FS_LIVE] : 0;
         if (blockIdx.y == 0 && threadIdx.x < 16) tickets[threadIdx.x] = 0;
+        if (threadIdx.x < 8) fp->me_count[threadIdx.x] = 0;
     }
 }
 
@@ -927,12 +928,14 @@ struct h264b200_ctx
     int out_cap_words;
     int *d_out_info;
     int32_t *d_clusters;
+    int cost_stat_valid;          /* a P frame has been finished: d_cost_stat holds its statistic */
     int *d_cost_stat;             /* [2 + nmby] inter-cost thresholds derived from the previous P frame (FrameParams::cost_stat) */
     MBSpec *d_spec; int32_t *d_cl_true; int32_t *d_cl_ckpt; int *d_changed_pass; int *d_need_reenc; int *d_fsync;
     int have_traj; int stats[8]; long long dbg[8];
     int *d_prof;
     uint32_t *d_sadmap;           /* [nmb][SM_WORDS] SAD-map records of the frame being encoded (h264_sadmap.h) */
     int32_t *d_me_field;          /* [nmb][16] motion field predicted by the motion-estimation pre-pass (h264_wave.h) */
+    int *d_me_list;               /* [8 + nmb] per-round counters, then the list of macroblocks a refinement round recomputes */
     int *d_progress;              /* 2 * nmby */
     uint32_t *h_out_words;        /* pinned */
     int *h_out_info;              /* pinned */
@@ -1105,6 +1108,8 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     CKC(cudaMemset(c->d_sadmap, 0, sizeof(uint32_t) * SM_WORDS * (size_t)c->nmb + 256));
     CKC(cudaMalloc(&c->d_me_field, sizeof(int32_t) * 16 * (size_t)c->nmb));
     CKC(cudaMemset(c->d_me_field, 0, sizeof(int32_t) * 16 * (size_t)c->nmb));
+    CKC(cudaMalloc(&c->d_me_list, sizeof(int) * (8 + (size_t)c->nmb)));
+    CKC(cudaMemset(c->d_me_list, 0, sizeof(int) * (8 + (size_t)c->nmb)));
 #if defined(H264_PROFILE) || defined(H264_FASTPROF)
     CKC(cudaMalloc(&c->d_prof, sizeof(int) * 20 * c->nmb));
     CKC(cudaMemset(c->d_prof, 0, sizeof(int) * 20 * c->nmb));
@@ -1126,7 +1131,7 @@ extern "C" void h264b200_ctx_destroy(h264b200_ctx *c)
     if (c->stg.ev) cudaEventDestroy(c->stg.ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d_prof) cudaFree(c->d_prof);
-    cudaFree(c->d_sadmap); cudaFree(c->d_me_field);
+    cudaFree(c->d_sadmap); cudaFree(c->d_me_field); cudaFree(c->d_me_list);
     if (c->d_clip) cudaFree(c->d_clip);
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) cudaFree(c->d_dn[i]);
     cudaFree(c->d_mbi); cudaFree(c->d_coef); cudaFree(c->d_mb_bits); cudaFree(c->d_mb_nbits); cudaFree(c->d_mb_bitoff);
@@ -1143,7 +1148,7 @@ extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
     cudaSetDevice(c->device);
     cudaMemset(c->d_clusters, 0, 16);
     c->cur = 0; c->last_dec = 0;
-    c->have_traj = 0;
+    c->have_traj = 0; c->cost_stat_valid = 0;
     c->stg.ttl = 0; c->want_valid = 0;
     /* the noise suppressor starts from an all-zero "previous picture" (H:6345-6349) */
     for (int i = 0; i < 2; i++) if (c->d_dn[i]) { cudaFree(c->d_dn[i]); c->d_dn[i] = NULL; }
@@ -1197,6 +1202,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->clusters = c->d_clusters;
     fp->cost_stat = c->d_cost_stat;
     fp->thr_eighths = g_thr_eighths;
+    fp->have_cost_stat = c->cost_stat_valid;
     fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_progress_mv = c->d_progress + 3 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 4 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
     fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
@@ -1210,6 +1216,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->use_me = fp->use_sadmap && !g_no_me;
     fp->spec_no_intra = p.slice_type == SLICE_P && !g_no_intra_spec;
     fp->me_field = c->d_me_field;
+    fp->me_count = c->d_me_list; fp->me_list = c->d_me_list + 8;
 }
 
 extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned char *frames)
@@ -1376,7 +1383,7 @@ static int encode_chunk(int n, h264b200_job *jobs)
     /* ... and the motion estimation itself on predicted contexts (round 0 + refinement rounds); the wavefront verifies */
     int any_me = 0;
     for (int i = 0; i < n; i++) any_me |= g_h_fps[i].use_me;
-    if (any_me) for (int r = 0; r < g_me_rounds; r++) { h264b200_launch_me(g_d_fps, n, max_nmb, r, st); g_launches += 1; }
+    if (any_me) for (int r = 0; r < g_me_rounds && r < 8; r++) { h264b200_launch_me(g_d_fps, n, max_nmb, r, st); g_launches += r ? 2 : 1; }
     CK(cudaEventRecord(g_ev_x[4], st));
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
@@ -1474,6 +1481,7 @@ static int encode_chunk(int n, h264b200_job *jobs)
         c->stats[4] += c->h_out_info[12]; c->stats[5] += c->h_out_info[13];
         for (int k = 0; k < 5; k++) c->dbg[k] = c->h_out_info[14 + k];
         c->have_traj = jobs[i].p.slice_type == SLICE_P;
+        if (jobs[i].p.slice_type == SLICE_P && jobs[i].status == 0) c->cost_stat_valid = 1;
         if (jobs[i].status) { if (!rc) rc = jobs[i].status; continue; }
         if (c->h_out_info[1] & 4) { jobs[i].status = -4; if (!rc) rc = -4; continue; }
         if (c->h_out_info[1]) { jobs[i].status = -2; if (!rc) rc = -2; continue; }

@@ -57,7 +57,7 @@ struct h264b200_ctx
     int fsync[FS_WORDS];
     int stats[4];
     int32_t clusters[2];
-    std::vector<int> cost_stat;
+    std::vector<int> cost_stat; int cost_stat_valid = 0;
     int have_traj;
 };
 
@@ -95,7 +95,7 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
     return 0;
 }
 extern "C" void h264b200_ctx_destroy(h264b200_ctx *c) { delete c; }
-extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->last_dec = 0; c->have_traj = 0; c->dn[0].clear(); c->dn[1].clear(); c->dn_cur = 0; }
+extern "C" void h264b200_ctx_reset(h264b200_ctx *c) { c->clusters[0] = c->clusters[1] = 0; c->cur = 0; c->last_dec = 0; c->have_traj = 0; c->cost_stat_valid = 0; c->dn[0].clear(); c->dn[1].clear(); c->dn_cur = 0; }
 
 static void run_job(h264b200_job *job)
 {
@@ -154,6 +154,7 @@ static void run_job(h264b200_job *job)
     if (c->cost_stat.empty()) c->cost_stat.assign(2 + c->nmby, 0);
     fp.cost_stat = c->cost_stat.data();
     fp.thr_eighths = getenv("H264B200_THR") ? atoi(getenv("H264B200_THR")) : 13;
+    fp.have_cost_stat = c->cost_stat_valid;
     fp.spec = c->spec.data(); fp.cl_true = c->cl_true.data(); fp.cl_ckpt = c->cl_ckpt.data(); fp.changed_pass = c->changed_pass.data(); fp.need_reenc = c->need_reenc.data();
     memset(c->fsync, 0, sizeof(c->fsync));
     fp.fsync = c->fsync;
@@ -174,7 +175,7 @@ static void run_job(h264b200_job *job)
             for (int x = 0; x < c->nmbx; x++) sadmap_build_mb(&fp, x, y);
 
     MBWork *w = new MBWork();
-    if (fp.spec_from_prev) wave_replay(&fp, w, 1);
+    if (fp.spec_from_prev) { wave_replay(&fp, w, 1); c->cost_stat_valid = fp.have_cost_stat = 1; }
     /* speculative motion estimation ahead of the wavefront (h264_wave.h): round 0 + refinement rounds */
     fp.me_field = c->me_field.data();
     fp.use_me = fp.use_sadmap && !getenv("H264B200_NO_ME_PREPASS");
