@@ -238,49 +238,12 @@ HDF_mb_load void mb_load(MBState &s)
 #else
     lut_bind(s, (fp->use_sadmap && fp->slice_type == SLICE_P) ? fp->sadmap + (size_t)(mby * nmbx + mbx) * SM_WORDS : 0);
 #endif
-#if H264_DEVICE && MB_WARPS == 4
-    if (have_inp && inside)
-    {
-        /* Fast path: the input is already in shared memory (prefetched); every physical warp
-         * fetches one kind of neighbour data with lane-indexed addresses -- a few instructions
-         * per warp, all loads of the macroblock in flight together. */
-        const int pw = (int)(threadIdx.x >> 5) & 3, lane = LANE_ID;
-        if (lane < 24)
-        {
-            const uint32_t v = w->pf_inp[pw * 24 + lane];
-            const int k = pw * 24 + lane;
-            if (k < 64) *(uint32_t *)(w->inp_y + (k >> 2) * 16 + (k & 3) * 4) = v;
-            else { const int k2 = k - 64; *(uint32_t *)(w->inp_c + (k2 >> 2) * 16 + (k2 & 3) * 4) = v; }
-        }
-        if (pw == 0)
-        {   /* row above: 16 + 4 luma samples, top-left samples */
-            if (lane < 20) w->top_y[lane] = ((av & AVAIL_T) && (lane < 16 || (av & AVAIL_TR))) ? dy[-sy + lane] : 0;
-            else if (lane == 20) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
-            else if (lane == 21) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
-            else if (lane == 22) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
-            else if (lane == 23) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; w->predc_tag = 0; }
-        } else if (pw == 1)
-        {   /* left column: 16 luma + 8 + 8 chroma samples */
-            if (lane < 16) w->left_y[lane] = (av & AVAIL_L) ? dy[lane * sy - 1] : 0;
-            else { const int k = lane - 16; w->left_c[k] = (av & AVAIL_L) ? ((k < 8 ? du : dv)[(k & 7) * sc - 1]) : 0; }
-        } else if (pw == 2)
-        {   /* chroma row above, I4x4 modes of the neighbours */
-            if (lane < 16) w->top_c[lane] = (av & AVAIL_T) ? ((lane < 8 ? du : dv)[-sc + (lane & 7)]) : 0;
-            else if (lane < 20) w->nb_i4mode[lane - 16] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (lane - 16) + 3] : -1;
-            else if (lane < 24) w->nb_i4mode[4 + lane - 20] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (lane - 20)] : -1;
-        } else
-        {   /* motion vectors of the neighbours */
-            if (lane < 4) w->mvp0_left[lane] = (av & AVAIL_L) ? mbi[-1].mv[4 * lane + 3] : MV_NA;
-            else if (lane == 4) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
-            else if (lane < 8) w->mvp0_tl[lane - 4] = (av & AVAIL_L) ? mbi[-1].mv[4 * (lane - 5) + 3] : MV_NA;
-            else if (lane < 12) w->mvp0_top[lane - 8] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (lane - 8)] : MV_NA;
-            else if (lane == 12) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
-        }
-    } else
-#endif
     {
     /* one flat list of independent loads so that all of them are in flight together:
-     * [0,96) neighbour samples / MVs / modes, [96,192) input words (unless prefetched) */
+     * [0,96) neighbour samples / MVs / modes, [96,192) input words (unless prefetched).  A neighbour item first works
+     * out WHERE its value lies (a chain of cases, no memory access), then there is one load per item: lanes that
+     * take different cases still have their loads in flight together -- one memory round trip for the whole context
+     * instead of one per case. */
     FOR_THREADS(i, 192)
     {
         if (i >= 96)
@@ -317,23 +280,30 @@ HDF_mb_load void mb_load(MBState &s)
             /* unfiltered neighbour samples of the picture under construction (the reference's
              * top_line context, H:4693-4714), neighbours' MVs (enc->mv_pred, H:742) and I4x4 modes */
             const int j = i;
-            if (j < 20) w->top_y[j] = ((av & AVAIL_T) && (j < 16 || (av & AVAIL_TR))) ? dy[-sy + j] : 0;
-            else if (j < 36) w->left_y[j - 20] = (av & AVAIL_L) ? dy[(j - 20) * sy - 1] : 0;
-            else if (j < 44) w->top_c[j - 36] = (av & AVAIL_T) ? du[-sc + (j - 36)] : 0;
-            else if (j < 52) w->top_c[8 + j - 44] = (av & AVAIL_T) ? dv[-sc + (j - 44)] : 0;
-            else if (j < 60) w->left_c[j - 52] = (av & AVAIL_L) ? du[(j - 52) * sc - 1] : 0;
-            else if (j < 68) w->left_c[8 + j - 60] = (av & AVAIL_L) ? dv[(j - 60) * sc - 1] : 0;
-            else if (j == 68) w->tl[0] = (av & AVAIL_TL) ? dy[-sy - 1] : 0;
-            else if (j == 69) w->tl[1] = (av & AVAIL_TL) ? du[-sc - 1] : 0;
-            else if (j == 70) w->tl[2] = (av & AVAIL_TL) ? dv[-sc - 1] : 0;
+            const void *src = 0;       /* NULL: not available, the default value is stored */
+            void *dst = 0;
+            int kind = 0;              /* 0: sample (u8 -> u8), 1: vector (i32 -> i32), 2: mode (i8 -> i32) */
+            int def = 0;
+            if (j < 20) { dst = &w->top_y[j]; if ((av & AVAIL_T) && (j < 16 || (av & AVAIL_TR))) src = dy - sy + j; }
+            else if (j < 36) { dst = &w->left_y[j - 20]; if (av & AVAIL_L) src = dy + (j - 20) * sy - 1; }
+            else if (j < 44) { dst = &w->top_c[j - 36]; if (av & AVAIL_T) src = du - sc + (j - 36); }
+            else if (j < 52) { dst = &w->top_c[8 + j - 44]; if (av & AVAIL_T) src = dv - sc + (j - 44); }
+            else if (j < 60) { dst = &w->left_c[j - 52]; if (av & AVAIL_L) src = du + (j - 52) * sc - 1; }
+            else if (j < 68) { dst = &w->left_c[8 + j - 60]; if (av & AVAIL_L) src = dv + (j - 60) * sc - 1; }
+            else if (j == 68) { dst = &w->tl[0]; if (av & AVAIL_TL) src = dy - sy - 1; }
+            else if (j == 69) { dst = &w->tl[1]; if (av & AVAIL_TL) src = du - sc - 1; }
+            else if (j == 70) { dst = &w->tl[2]; if (av & AVAIL_TL) src = dv - sc - 1; }
             else if (j == 71) { w->ic[IC_STATE] = 0; w->ic[IC_COST0] = -1; w->task_next = 0; w->predc_tag = 0; }
-            else if (j < 76) w->mvp0_left[j - 72] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 72) + 3] : MV_NA;
-            else if (j == 76) w->mvp0_tl[0] = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
-            else if (j < 80) w->mvp0_tl[j - 76] = (av & AVAIL_L) ? mbi[-1].mv[4 * (j - 77) + 3] : MV_NA;
-            else if (j < 84) w->mvp0_top[j - 80] = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (j - 80)] : MV_NA;
-            else if (j == 84) w->mvp0_top[4] = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
-            else if (j < 89) w->nb_i4mode[j - 85] = (av & AVAIL_L) ? mbi[-1].i4_mode[4 * (j - 85) + 3] : -1;
-            else if (j < 93) w->nb_i4mode[4 + j - 89] = (av & AVAIL_T) ? mbi[-nmbx].i4_mode[12 + (j - 89)] : -1;
+            else if (j < 76) { kind = 1; def = MV_NA; dst = &w->mvp0_left[j - 72]; if (av & AVAIL_L) src = &mbi[-1].mv[4 * (j - 72) + 3]; }
+            else if (j == 76) { kind = 1; def = MV_NA; dst = &w->mvp0_tl[0]; if (av & AVAIL_TL) src = &mbi[-nmbx - 1].mv[15]; }
+            else if (j < 80) { kind = 1; def = MV_NA; dst = &w->mvp0_tl[j - 76]; if (av & AVAIL_L) src = &mbi[-1].mv[4 * (j - 77) + 3]; }
+            else if (j < 84) { kind = 1; def = MV_NA; dst = &w->mvp0_top[j - 80]; if (av & AVAIL_T) src = &mbi[-nmbx].mv[12 + (j - 80)]; }
+            else if (j == 84) { kind = 1; def = MV_NA; dst = &w->mvp0_top[4]; if (av & AVAIL_TR) src = &mbi[-nmbx + 1].mv[12]; }
+            else if (j < 89) { kind = 2; def = -1; dst = &w->nb_i4mode[j - 85]; if (av & AVAIL_L) src = &mbi[-1].i4_mode[4 * (j - 85) + 3]; }
+            else if (j < 93) { kind = 2; def = -1; dst = &w->nb_i4mode[4 + j - 89]; if (av & AVAIL_T) src = &mbi[-nmbx].i4_mode[12 + (j - 89)]; }
+            int v = def;
+            if (src) v = kind == 1 ? *(const int32_t *)src : (kind == 2 ? (int)*(const int8_t *)src : (int)*(const pix_t *)src);
+            if (dst) { if (kind == 0) *(pix_t *)dst = (pix_t)v; else *(int32_t *)dst = v; }
         }
     }
     }

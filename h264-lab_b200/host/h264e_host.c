@@ -238,6 +238,14 @@ static void write_slice_header(h264e_host_t *e, hbits_t *b, int slice_type, int 
 
 /* ------------------------------------------------------------------------------ */
 /* rate control (H:5815-6141)                                                       */
+/*                                                                                  */
+/* This section (mul_q16 / div_q16, rc_frame_start, rc_frame_end) is a RESTATEMENT of */
+/* the reference's frame-level rate control, H:3420-3440 and H:5924-6141, statement  */
+/* by statement: the Q16 fixed-point arithmetic with its truncations, the budget /   */
+/* VBV bookkeeping and the QP update ARE the contract (the QP trajectory must match  */
+/* the reference frame for frame), so there is no room to */
+/* write it differently.  Only the golden / long-term-frame branches are absent      */
+/* (unsupported features).  It runs on the host, outside the device hot path.        */
 /* ------------------------------------------------------------------------------ */
 static uint32_t mul_q16(uint32_t x, uint32_t y)        /* H:3420 */
 {
