@@ -28,7 +28,7 @@
 #if MB_WARPS != 1
 /* one warp.  mr = the macroblock's motion-estimation record (shared-memory copy or where it lies).  1 = decided: vectors,
  * speculation record and w->fd[slot] written (the caller publishes the progress); 0 = take the complete path. */
-HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32_t *mr, int slot)
+HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32_t *mr, int slot, int thr)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x, av = mb_avail(x, y, nmbx);
     if (mr[ME_KEY + 15] != 1u) return 0;
@@ -36,14 +36,18 @@ HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32
     int ok = 1;
     FOR_LANES(i, 16)
     {
-        int32_t have;
-        if (i < 4) have = (av & AVAIL_L) ? w->last_mv[4 * i + 3] : MV_NA;
-        else if (i == 4) have = (av & AVAIL_TL) ? mbi[-nmbx - 1].mv[15] : MV_NA;
-        else if (i < 8) have = (av & AVAIL_L) ? w->last_mv[4 * (i - 5) + 3] : MV_NA;
-        else if (i < 12) have = (av & AVAIL_T) ? mbi[-nmbx].mv[12 + (i - 8)] : MV_NA;
-        else if (i == 12) have = (av & AVAIL_TR) ? mbi[-nmbx + 1].mv[12] : MV_NA;
-        else if (i < 15) have = fp->spec_from_prev ? fp->cl_true[2 * n + (i - 13)] : mv_round_fullpel(fp->clusters[i - 13]);
+        /* where the lane's context word lies (no memory access in the cases), then ONE load: the lanes' loads of the row
+         * above and of the cluster candidates are in flight together */
+        int32_t have = MV_NA;
+        const int32_t *src = 0;
+        if (i < 4) { if (av & AVAIL_L) have = w->last_mv[4 * i + 3]; }
+        else if (i == 4) { if (av & AVAIL_TL) src = &mbi[-nmbx - 1].mv[15]; }
+        else if (i < 8) { if (av & AVAIL_L) have = w->last_mv[4 * (i - 5) + 3]; }
+        else if (i < 12) { if (av & AVAIL_T) src = &mbi[-nmbx].mv[12 + (i - 8)]; }
+        else if (i == 12) { if (av & AVAIL_TR) src = &mbi[-nmbx + 1].mv[12]; }
+        else if (i < 15) { if (fp->spec_from_prev) src = &fp->cl_true[2 * n + (i - 13)]; else have = mv_round_fullpel(fp->clusters[i - 13]); }
         else have = 1;
+        if (src) have = *src;
         if ((int32_t)mr[ME_KEY + i] != have)
         {
 #if !H264_DEVICE
@@ -62,7 +66,7 @@ HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32
     const int best_type = inter_decide_p(fp, ic, mc, (const int32_t *)(mr + ME_MV), (const int32_t *)(mr + ME_MVD), &type, &cost, pmv, pmvd, &usp);
     const int searched = ic[IC_STATE] != 1;
     /* an inter cost this far above the usual: an intra mode probably wins, look at it now (encode_mb) rather than repair later */
-    if (searched && cost >= (fp->have_cost_stat ? fp->cost_stat[2 + y] : 0)) return 0;
+    if (searched && cost >= thr) return 0;           /* thr: FrameParams::cost_stat of the row (the caller reads it once per row) */
     MBInfo *mi = fp->mbi + n;
     uint32_t *sp = (uint32_t *)(fp->spec + n);
     FOR_LANES(i, 32)

@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
         /* state of the deciding warp */
         int x = 0, q = 0, seen_mv = 0, x_base = 0, q_base = 0, pub_full = 0;
         int my = pw - 1;                                   /* next decision of a working warp */
+        const int row_thr = fp->have_cost_stat ? fp->cost_stat[2 + row] : 0;
 #ifdef H264_FASTPROF
         unsigned long long gt0, gt_poll = 0, gt_ring = 0, gt_dec = 0, gt_slow = 0, gt_tmp;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
 #ifdef H264_FASTPROF
                         GT(b_); gt_ring += b_ - a_; }
 #endif
-                        if (!fast_decide(fp, &work, x, row, work.me_stage[x - first], q % FAST_RING)) { go_slow = 1; break; }
+                        if (!fast_decide(fp, &work, x, row, work.me_stage[x - first], q % FAST_RING, row_thr)) { go_slow = 1; break; }
                         q++;
                         __threadfence_block();
                         if (lane == 0) *v_qdec = q;

@@ -199,7 +199,7 @@ static void run_job(h264b200_job *job)
                 {
                     /* fast path of P frames (h264_fast.h): decide from the motion-estimation record, then the pixel work */
                     const int n = y * c->nmbx + x;
-                    if (use_fast && fast_decide(&fp, w, x, y, fp.sadmap + (size_t)n * SM_WORDS + SM_ME_OFF, 0)) { fast_work(&fp, w, x, y, 0, 0); g_emu_lut[6]++; continue; }
+                    if (use_fast && fast_decide(&fp, w, x, y, fp.sadmap + (size_t)n * SM_WORDS + SM_ME_OFF, 0, fp.have_cost_stat ? fp.cost_stat[2 + y] : 0)) { fast_work(&fp, w, x, y, 0, 0); g_emu_lut[6]++; continue; }
                     wave_mb_first(&fp, w, x, y);
                     for (int i = 0; i < 16; i++) w->last_mv[i] = fp.mbi[n].mv[i];
                 }
