@@ -349,3 +349,27 @@ def test_batch_larger_than_one_submission(binding, cuda_lib, ref):
     outs, _, _ = _batch_units(binding, cuda_lib, clips, w, h, 60, qp=30)
     for s in range(nstreams):
         assert outs[s] == refs[s % 7], "stream %d" % s
+
+
+KNOBS = [{}, {"H264B200_NO_SADMAP": "1"}, {"H264B200_NO_ME_PREPASS": "1"}, {"H264B200_NO_INTRA_SPEC": "1"},
+         {"H264B200_NO_FAST": "1"}, {"H264B200_ME_ROUNDS": "1"}, {"H264B200_THR": "6"}, {"H264B200_THR": "40"},
+         {"H264B200_NO_PREV_TRAJ": "1"}]
+
+
+def test_speculation_layers_switched_off(ref):
+    """Every layer of DESIGN.md 5 (SAD maps, motion-estimation pre-pass, intra speculation, decide / work fast path,
+    trajectory prediction) only decides WHERE work happens: with any of them switched off, or with another threshold,
+    the bytes are the reference's."""
+    import subprocess
+    import sys
+    import knob_child
+    want = []
+    for kind, w, h, n, gop, kw in knob_child.CASES:
+        frames = cases.make(kind, w, h, n)
+        rbs, _, rrec, _ = ref.encode_sequence(frames, w, h, gop, **kw)
+        want.append(hashlib.md5(rbs + rrec.tobytes()).hexdigest())
+    for knob in KNOBS:
+        env = dict(os.environ, **knob)
+        out = subprocess.run([sys.executable, knob_child.__file__], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (knob, out.stderr[-2000:])
+        assert out.stdout.split() == want, knob
