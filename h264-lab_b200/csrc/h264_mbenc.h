@@ -700,8 +700,12 @@ HDN int me_search_lut(const MBState &s, int ppx, int ppy, int *pmv, const int *r
  * sub-sample probes and the start candidates are each costed by their own lane (look-up + MV cost), and only the
  * order-dependent replay of the reference's comparisons runs warp-uniform on the gathered costs.
  * ---------------------------------------------------------------------------- */
-/* SAD of the lane's own vector v (lanes with valid == 0 return 0); positions that are not tabulated are computed from
- * the pictures by the whole warp, one after the other (rare) */
+/* SAD of the lane's own vector v (lanes with valid == 0 return 0).  Positions that are not tabulated are computed from
+ * the pictures, eight of them at a time: four lanes per position, every lane a quarter of the block's words, each word
+ * predicted where it lies (interp_luma_word: the position table of H:2079-2130 over the half-sample planes), so that
+ * all loads of the batch are in flight together.  (Where the search leaves its maps -- flat content, whose vectors
+ * follow the predictors rather than the SAD minimum the quarter map is centred on -- all seven sub-sample probes miss:
+ * one after the other they were 40 % of such a macroblock's latency.) */
 HD int lut_sad_lanes(const MBState &s, int v, int valid, int ppx, int ppy, int bw, int bh)
 {
     const unsigned FULLM = 0xffffffffu;
@@ -712,10 +716,31 @@ HD int lut_sad_lanes(const MBState &s, int v, int valid, int ppx, int ppy, int b
     unsigned miss = __ballot_sync(FULLM, valid && !hit);
     while (miss)
     {
-        const int l = __ffs((int)miss) - 1;
-        miss &= miss - 1;
-        const int sv = part_sad_pixels(s, __shfl_sync(FULLM, v, l), ppx, ppy, bw, bh);
-        if (LANE_ID == l) sad = sv;
+        const int lane = LANE_ID, g = lane >> 2, sub = lane & 3;
+        /* lane that asked for the g-th missing position (31 + a dead group when there are fewer) */
+        int src = -1;
+        { unsigned m = miss; for (int k = 0; k < g; k++) m &= m - 1; if (m) src = __ffs((int)m) - 1; }
+        const int vg = __shfl_sync(FULLM, v, src & 31);
+        int part = 0;
+        if (src >= 0)
+        {
+            const FrameParams *fp = s.fp;
+            const int wsh = bw == 16 ? 2 : 1, nw = bh << wsh;
+            const int ax = mv_x(vg) + ppx * 4, ay = mv_y(vg) + ppy * 4;
+            const pix_t *inp = s.w->inp_y + ppy * 16 + ppx;
+#pragma unroll 4
+            for (int k = sub; k < nw; k += 4)
+            {
+                const int r = k >> wsh, c = k & ((1 << wsh) - 1);
+                part += sad4(interp_luma_word(fp, ax + 16 * c, ay + 4 * r), ld4_sm(inp + r * 16 + 4 * c));
+            }
+        }
+        part += __shfl_xor_sync(FULLM, part, 1);
+        part += __shfl_xor_sync(FULLM, part, 2);
+        const int rank = __popc(miss & ((1u << lane) - 1u));      /* this lane's position is the rank-th missing one */
+        const int got = __shfl_sync(FULLM, part, (rank & 7) * 4);
+        if (((miss >> lane) & 1u) && rank < 8) sad = got;
+        for (int k = 0; k < 8 && miss; k++) miss &= miss - 1;
     }
     return sad;
 }

@@ -48,6 +48,9 @@
 #include "h264_denoise.h"
 #include "../../include/h264b200_shim.h"
 
+#ifndef ENC_MIN_BLOCKS_I
+#define ENC_MIN_BLOCKS_I 3      /* k_encode_rows_i: submissions without a P frame */
+#endif
 #ifndef ENC_MIN_BLOCKS
 #define ENC_MIN_BLOCKS 2        /* 232 registers, no spills; with the decide / work fast path the latency of the complete path
                                    counts for more than resident row slots (3: 168 registers, -1 %; 4: 128 registers, -5 %) */
@@ -295,7 +298,7 @@ __device__ __forceinline__ void me_stage_issue(const FrameParams *fp, MBWork *w,
     w->me_cnt++;
 }
 
-__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
+static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, int njobs, int *tickets, int pass)
 {
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
@@ -562,6 +565,19 @@ __global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(c
         publish_row_cta(progress + row * PROG_STRIDE, base + x);
         mb_store_coefs(fp, &work);
     }
+}
+
+/* Two register budgets of the same row loop.  P frames: two CTAs per SM (232 registers, no spills) -- with the decide /
+ * work fast path the latency of the complete path counts for more than resident row slots (3 per SM: 168 registers,
+ * -1 %; 4: 128 registers, -5 %).  Submissions of I frames only (every macroblock takes the complete path, nothing
+ * waits on a vector chain): three per SM, +13 % on the all-intra configuration. */
+__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS) k_encode_rows(const FrameParams *fps, int njobs, int *tickets, int pass)
+{
+    encode_rows_body(fps, njobs, tickets, pass);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32, ENC_MIN_BLOCKS_I) k_encode_rows_i(const FrameParams *fps, int njobs, int *tickets, int pass)
+{
+    encode_rows_body(fps, njobs, tickets, pass);
 }
 
 /* parallel repair round r of pass `pass` (h264_wave.h): every CTA looks at a strip of macroblocks
@@ -1016,7 +1032,7 @@ static int ensure_globals(int njobs)
         if (getenv("H264B200_NO_FAST")) { int one = 1; cudaMemcpyToSymbol(g_d_no_fast, &one, sizeof(one)); }
         if (getenv("H264B200_ME_ROUNDS")) g_me_rounds = atoi(getenv("H264B200_ME_ROUNDS"));
         const char *e = getenv("H264B200_ENC_SMEM");
-        if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
+        if (e) { g_enc_dyn_smem = atoi(e); cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); cudaFuncSetAttribute(k_encode_rows_i, cudaFuncAttributeMaxDynamicSharedMemorySize, g_enc_dyn_smem); }
     });
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_d_tickets) CK(cudaMalloc(&g_d_tickets, 64));
@@ -1234,18 +1250,25 @@ extern "C" int h264b200_preload(h264b200_ctx *c, int nframes, const unsigned cha
     return 0;
 }
 
-/* kernels that follow the macroblock sweeps; frames that are not FS_DONE are skipped inside */
-static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nmb, int cap_words, cudaStream_t st,
-                       cudaEvent_t ev_mid)
+/* second stream of the lane (entropy coding beside the in-loop filter, intra verification beside the candidate re-check) */
+static int ensure_stream2(void)
 {
-    /* the entropy-coding kernels only read the macroblock records: they run on a second stream next to the
-     * in-loop filter (a latency-bound wavefront that leaves most of the chip idle) */
     if (!g_stream2)
     {
         CK(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
     }
+    return 0;
+}
+
+/* kernels that follow the macroblock sweeps; frames that are not FS_DONE are skipped inside */
+static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nmb, int cap_words, cudaStream_t st,
+                       cudaEvent_t ev_mid)
+{
+    /* the entropy-coding kernels only read the macroblock records: they run on a second stream next to the
+     * in-loop filter (a latency-bound wavefront that leaves most of the chip idle) */
+    if (ensure_stream2()) return -3;
     CK(cudaEventRecord(g_ev_fork, st));
     CK(cudaStreamWaitEvent(g_stream2, g_ev_fork, 0));
     if (ev_mid) CK(cudaEventRecord(g_ev_x[0], g_stream2));
@@ -1377,8 +1400,8 @@ static int encode_chunk(int n, h264b200_job *jobs)
     g_launches += 1;
     if (any_denoise) { k_denoise<<<dim3(296, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
     /* SAD maps of every macroblock of every P frame of the submission: dependency-free, ahead of the wavefront */
-    int any_p = 0;
-    for (int i = 0; i < n; i++) any_p |= g_h_fps[i].use_sadmap;
+    int any_p = 0, any_pslice = 0;
+    for (int i = 0; i < n; i++) { any_p |= g_h_fps[i].use_sadmap; any_pslice |= g_h_fps[i].slice_type == SLICE_P; }
     CK(cudaEventRecord(g_ev_x[2], st));
     if (any_p) { k_sadmap<<<dim3(max_nmb, n), 256, 0, st>>>(g_d_fps, n); g_launches += 1; }
     CK(cudaEventRecord(g_ev_x[3], st));
@@ -1389,7 +1412,7 @@ static int encode_chunk(int n, h264b200_job *jobs)
     CK(cudaEventRecord(g_ev_x[4], st));
     /* sweep 0 of every frame, then -- optimistically -- everything that follows it */
     CK(cudaEventRecord(g_ev[1], st));
-    k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
+    (any_pslice ? k_encode_rows : k_encode_rows_i)<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets, 0);
     {   /* inputs of the NEXT frames named by h264b200_prefetch_input: their copies start now, behind this submission's
          * own uploads, and run under its kernels */
         for (int i = 0; i < n; i++)
@@ -1407,11 +1430,18 @@ static int encode_chunk(int n, h264b200_job *jobs)
     {   /* P frames: sweep 0 decided among the inter modes only; the intra modes of every macroblock are verified now */
         int any_spec = 0;
         for (int i = 0; i < n; i++) any_spec |= g_h_fps[i].spec_no_intra;
-        CK(cudaEventRecord(g_ev_x[5], st));
-        if (any_spec) { h264b200_launch_intra_check(g_d_fps, n, max_nmb, st); g_launches += 1; }
-        CK(cudaEventRecord(g_ev_x[6], st));
+        /* ... on the second stream, beside the candidate re-check: the two read the finished sweep, tag disjoint causes
+         * (both write the same tag value, k_after_check looks at the sum) and are bound by different things */
+        if (ensure_stream2()) return -3;
+        CK(cudaEventRecord(g_ev_fork, st));
+        CK(cudaStreamWaitEvent(g_stream2, g_ev_fork, 0));
+        CK(cudaEventRecord(g_ev_x[5], g_stream2));
+        if (any_spec) { h264b200_launch_intra_check(g_d_fps, n, max_nmb, g_stream2); g_launches += 1; }
+        CK(cudaEventRecord(g_ev_x[6], g_stream2));
+        CK(cudaEventRecord(g_ev_join, g_stream2));
     }
     h264b200_launch_check1(g_d_fps, n, 1, st);
+    CK(cudaStreamWaitEvent(st, g_ev_join, 0));
     k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, 1);
     g_launches += 3;
     /* two repair rounds are queued unconditionally (frames that are already exact skip them on
@@ -1420,7 +1450,7 @@ static int encode_chunk(int n, h264b200_job *jobs)
     {
         for (int r = 0; r < REPAIR_ROUNDS; r++) k_repair_round<<<dim3(296, n), MB_WARPS * 32, 0, st>>>(g_d_fps, n, pass, r);
         /* ticket slots: [0] sweep 0, [1] in-loop filter, [2], [3] the two repair waves queued here, [4] host-driven passes */
-        k_encode_rows<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets + 1 + pass, pass);
+        (any_pslice ? k_encode_rows : k_encode_rows_i)<<<n * max_rows + n, MB_WARPS * 32, g_enc_dyn_smem, st>>>(g_d_fps, n, g_d_tickets + 1 + pass, pass);
         k_replay<<<n, 32, 0, st>>>(g_d_fps, n, pass);
         h264b200_launch_check1(g_d_fps, n, pass + 1, st);
         k_after_check<<<(n + 63) / 64, 64, 0, st>>>(g_d_fps, n, pass + 1);
