@@ -524,8 +524,13 @@ struct SearchScratch
 {
     pix_t store[4][256];         /* prediction variants, stride 16 (mb_pix_store, H:567)    */
     pix_t tmpblk[256];           /* second operand of quarter-sample averages               */
+    pix_t probe_pad[560];        /* store + tmpblk + this: the probe window of lut_sad_lanes (PROBE_* below) */
     int32_t mvp_left[4], mvp_tl[4], mvp_top[5];   /* rolling MV predictor context (H:742)   */
 };
+/* probe window: the samples of G, b, h, j that a batch of neighbouring untabulated search positions needs -- 4 planes x
+ * up to 19 rows x 24 bytes (+ one word that unaligned reads may touch) */
+#define PROBE_ROWS 19
+#define PROBE_PITCH 24
 
 /* What prediction + transform / quantisation / reconstruction of one macroblock work on.  MBWork starts with one (its
  * members are used as w->inp_y ... everywhere); the fast path of P frames (h264_fast.h) gives every warp a private one,

@@ -26,6 +26,31 @@
 #include "h264_wave.h"
 
 #if MB_WARPS != 1
+/* one warp: input samples of macroblock (x, y) into t->inp_y / t->inp_c, with the edge replication of cropped pictures
+ * (pix_copy_cropped_mb H:3536) */
+HD void fast_load_input(const FrameParams *fp, TQBuf *t, int x, int y)
+{
+    const int wv = fp->width, hv = fp->height;
+    FOR_LANES(i, 96)
+    {
+        if (i < 64) *(uint32_t *)(t->inp_y + (i >> 2) * 16 + (i & 3) * 4) = sadmap_inp_word(fp, x, y, i >> 2, i & 3);
+        else
+        {
+            const int k2 = i - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
+            const int cx = x * 8 + c, cy = y * 8 + r;
+            uint32_t v;
+            if (cx + 4 <= wv / 2 && cy < hv / 2) v = ld4u(fp->inp[1 + pl] + (long)cy * fp->inp_stride[1 + pl] + cx);
+            else
+            {
+                const pix_t *row = fp->inp[1 + pl] + (long)imin(cy, hv / 2 - 1) * fp->inp_stride[1 + pl];
+                v = 0;
+                for (int q2 = 0; q2 < 4; q2++) v |= (uint32_t)row[imin(cx + q2, wv / 2 - 1)] << (8 * q2);
+            }
+            *(uint32_t *)(t->inp_c + (k2 >> 2) * 16 + (k2 & 3) * 4) = v;
+        }
+    }
+}
+
 /* one warp.  mr = the macroblock's motion-estimation record (shared-memory copy or where it lies).  1 = decided: vectors,
  * speculation record and w->fd[slot] written (the caller publishes the progress); 0 = take the complete path. */
 HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32_t *mr, int slot, int thr)
@@ -118,25 +143,7 @@ HDN void fast_work(const FrameParams *fp, MBWork *w, int x, int y, int slot, int
     s.mbx = x; s.mby = y; s.avail = mb_avail(x, y, fp->nmbx);
     s.type = type; s.cost = 0; s.i16_mode = 2; s.mv_skip_pred = mv_skip;
     s.pbest = pred; s.ss = 0; s.win_ok = 0; s.win_x0 = s.win_y0 = 0; s.map = 0; s.lut = 0;
-    const int wv = fp->width, hv = fp->height;
-    FOR_LANES(i, 96)
-    {
-        if (i < 64) *(uint32_t *)(t->inp_y + (i >> 2) * 16 + (i & 3) * 4) = sadmap_inp_word(fp, x, y, i >> 2, i & 3);
-        else
-        {   /* chroma, same edge replication (pix_copy_cropped_mb H:3536) */
-            const int k2 = i - 64, r = k2 >> 2, q = k2 & 3, pl = q >> 1, c = (q & 1) * 4;
-            const int cx = x * 8 + c, cy = y * 8 + r;
-            uint32_t v;
-            if (cx + 4 <= wv / 2 && cy < hv / 2) v = ld4u(fp->inp[1 + pl] + (long)cy * fp->inp_stride[1 + pl] + cx);
-            else
-            {
-                const pix_t *row = fp->inp[1 + pl] + (long)imin(cy, hv / 2 - 1) * fp->inp_stride[1 + pl];
-                v = 0;
-                for (int q2 = 0; q2 < 4; q2++) v |= (uint32_t)row[imin(cx + q2, wv / 2 - 1)] << (8 * q2);
-            }
-            *(uint32_t *)(t->inp_c + (k2 >> 2) * 16 + (k2 & 3) * 4) = v;
-        }
-    }
+    fast_load_input(fp, t, x, y);
     luma_pred_half(s, 0, type, pmv, pred);
     luma_pred_half(s, 1, type, pmv, pred);
     mc_chroma_plane(s, 0, type, pmv);

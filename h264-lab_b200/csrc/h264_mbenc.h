@@ -702,10 +702,13 @@ HDN int me_search_lut(const MBState &s, int ppx, int ppy, int *pmv, const int *r
  * ---------------------------------------------------------------------------- */
 /* SAD of the lane's own vector v (lanes with valid == 0 return 0).  Positions that are not tabulated are computed from
  * the pictures, eight of them at a time: four lanes per position, every lane a quarter of the block's words, each word
- * predicted where it lies (interp_luma_word: the position table of H:2079-2130 over the half-sample planes), so that
- * all loads of the batch are in flight together.  (Where the search leaves its maps -- flat content, whose vectors
- * follow the predictors rather than the SAD minimum the quarter map is centred on -- all seven sub-sample probes miss:
- * one after the other they were 40 % of such a macroblock's latency.) */
+ * predicted where it lies (interp_luma_sel: the position table of H:2079-2130 over G and the half-sample planes).
+ * The eight neighbours of a search centre and the seven sub-sample probes lie within two integer samples of each
+ * other: the few rows of G, b, h, j they need (19 x 24 bytes per plane) are staged in the warp's scratch first, with
+ * coalesced loads that are all in flight together, and the positions are evaluated from there.  (Gathering the words
+ * of eight positions straight from the pictures makes every load instruction touch ~28 cache lines: for flat content,
+ * whose vectors follow the predictors rather than the SAD minimum the quarter map is centred on, all seven probes are
+ * untabulated and that gather was 30 % of such a macroblock's latency.) */
 HD int lut_sad_lanes(const MBState &s, int v, int valid, int ppx, int ppy, int bw, int bh)
 {
     const unsigned FULLM = 0xffffffffu;
@@ -716,25 +719,80 @@ HD int lut_sad_lanes(const MBState &s, int v, int valid, int ppx, int ppy, int b
     unsigned miss = __ballot_sync(FULLM, valid && !hit);
     while (miss)
     {
+        const FrameParams *fp = s.fp;
         const int lane = LANE_ID, g = lane >> 2, sub = lane & 3;
-        /* lane that asked for the g-th missing position (31 + a dead group when there are fewer) */
+        /* lane that asked for the g-th missing position (none: a dead group) */
         int src = -1;
         { unsigned m = miss; for (int k = 0; k < g; k++) m &= m - 1; if (m) src = __ffs((int)m) - 1; }
         const int vg = __shfl_sync(FULLM, v, src & 31);
+        const int wsh = bw == 16 ? 2 : 1, nw = bh << wsh;
+        const int st = fp->stride[0];
+        /* do the positions of this batch fit one window? */
+        const int bx = mv_x(vg) >> 2, by = mv_y(vg) >> 2;
+        const int xmin = __reduce_min_sync(FULLM, src >= 0 ? bx : 0x7fff), xmax = __reduce_max_sync(FULLM, src >= 0 ? bx : -0x7fff);
+        const int ymin = __reduce_min_sync(FULLM, src >= 0 ? by : 0x7fff), ymax = __reduce_max_sync(FULLM, src >= 0 ? by : -0x7fff);
+        const pix_t *pl0 = fp->ref[0], *pl1 = fp->hp[0], *pl2 = fp->hp[1], *pl3 = fp->hp[2];
+        int pst = st, ax = mv_x(vg) + ppx * 4, ay = mv_y(vg) + ppy * 4;
+        if (xmax - xmin <= 2 && ymax - ymin <= 2)
+        {
+            const int wx = (xmin + ppx) & ~3, wy = ymin + ppy, nitem = (ymax - ymin + bh + 1) * (PROBE_PITCH / 4);
+            uint32_t *pw = (uint32_t *)s.ss->store;
+            uint32_t t[16];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+            {
+                const uint32_t *srcw = (const uint32_t *)((p == 0 ? pl0 : (p == 1 ? pl1 : (p == 2 ? pl2 : pl3))) + (long)wy * st + wx);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int i = lane + 32 * u, r = i / (PROBE_PITCH / 4), c = i - r * (PROBE_PITCH / 4);
+                    t[p * 4 + u] = i < nitem ? srcw[r * (st >> 2) + c] : 0u;
+                }
+            }
+            WSYNC();                        /* earlier readers of the scratch */
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int i = lane + 32 * u;
+                    if (i < PROBE_ROWS * (PROBE_PITCH / 4)) pw[p * (PROBE_ROWS * PROBE_PITCH / 4) + i] = t[p * 4 + u];
+                }
+            WSYNC();
+            pl0 = (const pix_t *)pw; pl1 = pl0 + PROBE_ROWS * PROBE_PITCH; pl2 = pl1 + PROBE_ROWS * PROBE_PITCH; pl3 = pl2 + PROBE_ROWS * PROBE_PITCH;
+            pst = PROBE_PITCH; ax -= 4 * wx; ay -= 4 * wy;
+        }
         int part = 0;
         if (src >= 0)
         {
-            const FrameParams *fp = s.fp;
-            const int wsh = bw == 16 ? 2 : 1, nw = bh << wsh;
-            const int ax = mv_x(vg) + ppx * 4, ay = mv_y(vg) + ppy * 4;
             const pix_t *inp = s.w->inp_y + ppy * 16 + ppx;
-#pragma unroll 4
-            for (int k = sub; k < nw; k += 4)
+            /* a lane's share is nw / 4 = 4, 8 or 16 words: four at a time, their loads issued before the first use.
+             * Which planes a position averages and how its words are aligned is the same for every word of the block:
+             * worked out once, for word (0, 0) */
+            const pix_t *a0, *b0;
+            interp_luma_sel(pl0, pl1, pl2, pl3, pst, ax, ay, &a0, &b0);
+            const uint32_t *qa = (const uint32_t *)((uintptr_t)a0 & ~(uintptr_t)3), *qb = (const uint32_t *)((uintptr_t)b0 & ~(uintptr_t)3);
+            const unsigned sha = (unsigned)((uintptr_t)a0 & 3) * 8, shb = (unsigned)((uintptr_t)b0 & 3) * 8;
+            const int pw4 = pst >> 2;
+            for (int k0 = sub; k0 < nw; k0 += 16)
             {
-                const int r = k >> wsh, c = k & ((1 << wsh) - 1);
-                part += sad4(interp_luma_word(fp, ax + 16 * c, ay + 4 * r), ld4_sm(inp + r * 16 + 4 * c));
+                uint32_t va[4], vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int k = k0 + 4 * u, r = k >> wsh, c = k & ((1 << wsh) - 1), o = r * pw4 + c;
+                    va[u] = __funnelshift_r(qa[o], qa[o + 1], sha);
+                    vb[u] = __funnelshift_r(qb[o], qb[o + 1], shb);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int k = k0 + 4 * u, r = k >> wsh, c = k & ((1 << wsh) - 1);
+                    part += sad4(avg4(va[u], vb[u]), ld4_sm(inp + r * 16 + 4 * c));
+                }
             }
         }
+        WSYNC();                            /* the scratch may be staged again */
         part += __shfl_xor_sync(FULLM, part, 1);
         part += __shfl_xor_sync(FULLM, part, 2);
         const int rank = __popc(miss & ((1u << lane) - 1u));      /* this lane's position is the rank-th missing one */
@@ -808,6 +866,7 @@ HDN int me_search_par(const MBState &s, int ppx, int ppy, int *pmv, const int *r
         break;
     }
     const uint32_t c0 = CGET(cc, 0), c1 = CGET(cc, 1), c2 = CGET(cc, 2), c3 = CGET(cc, 3);
+    if (bw == 16 && bh == 16) PROF_SUB(s, 12);
 #undef CGET
 #undef CSET
     if (fp->speed < 9 && mv_in_rect(mv, fp->mvlim_x0 + 16, fp->mvlim_y0 + 16, fp->mvlim_x1 - 16, fp->mvlim_y1 - 16))
@@ -832,6 +891,7 @@ HDN int me_search_par(const MBState &s, int ppx, int ppy, int *pmv, const int *r
         key = __shfl_sync(FULLM, key, 0);
         if ((key >> 3) < min_sad) { min_sad = key >> 3; mv = __shfl_sync(FULLM, v, key & 7); }
     }
+    if (bw == 16 && bh == 16) PROF_SUB(s, 13);
     *pmv = mv;
     return min_sad;
 }

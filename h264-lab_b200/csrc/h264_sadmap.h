@@ -78,23 +78,36 @@ HD int sadmap_lookup(const uint32_t *map, int cx, int cy, int qcx, int qcy, int 
 /* four samples of the prediction at ABSOLUTE quarter-sample position (ax, ay) (first sample of the word): the position
  * table of h264e_qpel_interpolate_luma (H:2079-2130) on the half-sample planes, per word -- same values as
  * interp_luma_planes() */
-HD uint32_t interp_luma_word(const FrameParams *fp, int ax, int ay)
+HD void interp_luma_sel(const pix_t *pg, const pix_t *pb0, const pix_t *ph0, const pix_t *pj0, int st, int ax, int ay,
+                        const pix_t **pa, const pix_t **pb)
 {
-    const int st = fp->stride[0], dx = ax & 3, dy = ay & 3;
+    /* branch-free: the lanes of a warp ask for different positions (partitions, probes), and one instruction stream
+     * keeps all their loads in flight together.  Positions made of a single sample average it with itself.
+     * The four planes are given by the address of their sample (0, 0) and a common stride (the pictures, or a staged
+     * window of them). */
+    const int dx = ax & 3, dy = ay & 3;
     const long o = (long)(ay >> 2) * st + (ax >> 2);
     const int pos = 1 << (dx + 4 * dy);
-    const pix_t *a = fp->ref[0] + o, *b = 0;
-    if (pos != 1)
-    {
-        a = 0;
-        if (pos & 0xe0ee) a = fp->hp[0] + o + ((pos & 0xe000) ? st : 0);
-        if (pos & 0xbbb0) { const pix_t *q = fp->hp[1] + o + ((pos & 0x8880) ? 1 : 0); if (a) b = q; else a = q; }
-        if (pos & 0x4e40) { if (a) b = fp->hp[2] + o; else a = fp->hp[2] + o; }
-        if ((pos & 0xfafa) && !b) b = fp->ref[0] + o + ((dx + 1) >> 2) + ((dy + 1) >> 2) * st;
-    }
-    uint32_t v = ld4u(a);
-    if (b) v = avg4(v, ld4u(b));
-    return v;
+    const int m0 = (pos & 0xe0ee) != 0, m1 = (pos & 0xbbb0) != 0, m2 = (pos & 0x4e40) != 0, m3 = (pos & 0xfafa) != 0;
+    const pix_t *g = pg + o;
+    const pix_t *p0 = pb0 + o + ((pos & 0xe000) ? st : 0);
+    const pix_t *p1 = ph0 + o + ((pos & 0x8880) ? 1 : 0);
+    const pix_t *p2 = pj0 + o;
+    const pix_t *p3 = g + ((dx + 1) >> 2) + ((dy + 1) >> 2) * st;
+    const pix_t *a = m0 ? p0 : (m1 ? p1 : (m2 ? p2 : g));
+    const pix_t *b = m0 ? (m1 ? p1 : (m2 ? p2 : (const pix_t *)0)) : ((m1 && m2) ? p2 : (const pix_t *)0);
+    *pa = a;
+    *pb = b ? b : (m3 ? p3 : a);
+}
+HD void interp_luma_ptrs(const FrameParams *fp, int ax, int ay, const pix_t **pa, const pix_t **pb)
+{
+    interp_luma_sel(fp->ref[0], fp->hp[0], fp->hp[1], fp->hp[2], fp->stride[0], ax, ay, pa, pb);
+}
+HD uint32_t interp_luma_word(const FrameParams *fp, int ax, int ay)
+{
+    const pix_t *a, *b;
+    interp_luma_ptrs(fp, ax, ay, &a, &b);
+    return avg4(ld4u(a), ld4u(b));
 }
 
 /* word c4 of row r of the input macroblock (mbx, mby); samples beyond the visible picture replicate the last column / row

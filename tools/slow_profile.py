@@ -34,7 +34,7 @@ for i in range(n):
             m = ch & (prof[:, 16] == t)
             ph = prof[m][:, :12].mean(0)
             print("   type %2d: %5d MBs, mean %7.0f cyc | " % (t, m.sum(), tot[m].mean()) + " ".join("%s %.0f" % (names[k], ph[k]) for k in range(12))
-                  + " s16_int %.0f s16_fetch %.0f" % tuple(s16[m].mean(0)) + " | arrive w0..3 %s" % (prof[m][:, 12:16].mean(0).astype(int).tolist()))
+                  + " s16_walk %.0f s16_probes %.0f" % tuple(s16[m].mean(0)) + " | arrive w0..3 %s" % (prof[m][:, 12:16].mean(0).astype(int).tolist()))
         # the rectangle rows only
         yy = np.arange(nmb) // nmbx
         m = ch & (yy >= 17) & (yy <= 30)
