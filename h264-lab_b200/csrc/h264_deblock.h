@@ -94,35 +94,36 @@ struct DeblockTile
  * memory, filtered there (one lane per line crossing the edges, held in registers; vertical
  * edges left to right, then horizontal edges top to bottom -- the reference's per-macroblock
  * order) and written back as words. */
-HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
+/* boundary strength (df_strength H:5535) of item j of macroblock (mbx, mby): j -> edge e, 4-sample segment seg.
+ * Everything an item may need is fetched up front with independent loads (one memory round trip instead of a
+ * chain of dependent ones), the decision is taken afterwards. */
+HD int deblock_bs_item(const FrameParams *fp, int mbx, int mby, int j)
 {
     const MBInfo *mi = fp->mbi + mby * fp->nmbx + mbx;
     const MBInfo *ml = mi - 1, *mt = mi - fp->nmbx;
-    /* boundary strengths (df_strength H:5535): lane j -> edge e, 4-sample segment seg.  Everything a lane
-     * may need is fetched up front with independent loads (one memory round trip instead of a chain of
-     * dependent ones), the decision is taken afterwards. */
-    FOR_LANES(j, 32)
+    const int horiz = j >> 4, e = (j >> 2) & 3, seg = j & 3;
+    const int at_border = (horiz ? mby : mbx) == 0;
+    /* p side: the neighbouring macroblock for edge 0 (this macroblock again at a picture border: unused) */
+    const MBInfo *mp = e ? mi : (at_border ? mi : (horiz ? mt : ml));
+    const int ip = e ? (horiz ? (e - 1) * 4 + seg : seg * 4 + e - 1) : (horiz ? 12 + seg : seg * 4 + 3);
+    const int iq = horiz ? e * 4 + seg : seg * 4 + e;
+    const int type_q = mi->type, type_p = mp->type;
+    const unsigned nz_p = mp->nz_mask, nz_q = mi->nz_mask;
+    const int mv_p = mp->mv[ip], mv_q = mi->mv[iq];
+    const int intra = type_q >= 5;
+    int bs;
+    if (e == 0)
     {
-        const int horiz = j >> 4, e = (j >> 2) & 3, seg = j & 3;
-        const int at_border = (horiz ? mby : mbx) == 0;
-        /* p side: the neighbouring macroblock for edge 0 (this macroblock again at a picture border: unused) */
-        const MBInfo *mp = e ? mi : (at_border ? mi : (horiz ? mt : ml));
-        const int ip = e ? (horiz ? (e - 1) * 4 + seg : seg * 4 + e - 1) : (horiz ? 12 + seg : seg * 4 + 3);
-        const int iq = horiz ? e * 4 + seg : seg * 4 + e;
-        const int type_q = mi->type, type_p = mp->type;
-        const unsigned nz_p = mp->nz_mask, nz_q = mi->nz_mask;
-        const int mv_p = mp->mv[ip], mv_q = mi->mv[iq];
-        const int intra = type_q >= 5;
-        int bs;
-        if (e == 0)
-        {
-            if (at_border) bs = 0;
-            else if (intra || type_p >= 5) bs = 4;
-            else bs = ((nz_p & (0x8000u >> ip)) || (nz_q & (0x8000u >> iq))) ? 2 : (mv_far(mv_p, mv_q) ? 1 : 0);
-        } else if (intra) bs = 3;
+        if (at_border) bs = 0;
+        else if (intra || type_p >= 5) bs = 4;
         else bs = ((nz_p & (0x8000u >> ip)) || (nz_q & (0x8000u >> iq))) ? 2 : (mv_far(mv_p, mv_q) ? 1 : 0);
-        t->bs[j] = (uint8_t)bs;
-    }
+    } else if (intra) bs = 3;
+    else bs = ((nz_p & (0x8000u >> ip)) || (nz_q & (0x8000u >> iq))) ? 2 : (mv_far(mv_p, mv_q) ? 1 : 0);
+    return bs;
+}
+HD void deblock_bs(const FrameParams *fp, DeblockTile *t, int mbx, int mby)
+{
+    FOR_LANES(j, 32) { t->bs[j] = (uint8_t)deblock_bs_item(fp, mbx, mby, j); }
 }
 
 /* phase 0: everything that does not depend on the row above -- the macroblock's own rows (with the 4
@@ -140,7 +141,7 @@ HD void df_cp_async_wait()
 }
 /* GPU software pipeline (k_deblock_rows): while macroblock x is being filtered, the samples of macroblock x + 1
  * that nothing can touch before its own filtering (its 16x16 / 8x8 samples, not the 4 columns to its left) are
- * already on their way into the other tile, and its boundary strengths are computed. */
+ * already on their way into the other tile. */
 HD void deblock_prefetch(const FrameParams *fp, DeblockTile *t, int mbx, int mby, int part)
 {
     const int sy = fp->stride[0], sc = fp->stride[1];
@@ -157,7 +158,7 @@ HD void deblock_prefetch(const FrameParams *fp, DeblockTile *t, int mbx, int mby
             df_cp_async4(&t->c[pl][(r + 4) * 3 + c], pc + r * sc + c * 4 - 4);
         }
     }
-    deblock_bs(fp, t, mbx, mby);
+    /* its boundary strengths: k_deblock_rows (deblock_bs_item before, the store after the current macroblock's filters) */
 }
 /* the 4 columns to the left of macroblock x + 1 = the last 4 columns of macroblock x, final in tile `cur` */
 HD void deblock_handover(const DeblockTile *cur, DeblockTile *nxt, int part)

@@ -656,12 +656,24 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     int *progress = part ? fp->row_progress_dfc : fp->row_progress_df;
     /* software pipeline over the macroblocks of the row: tile[x & 1] is filtered while tile[(x + 1) & 1] fills */
     deblock_mb(fp, &tile[0], 0, row, part, 0);
+    int seen = 0;                              /* progress of the row above as far as this warp has acquired it */
     for (int x = 0; x < nmbx; x++)
     {
         DeblockTile *cur = &tile[x & 1], *nxt = &tile[(x + 1) & 1];
-        if (x + 1 < nmbx) deblock_prefetch(fp, nxt, x + 1, row, part);
-        if (row > 0) wait_row(progress + (row - 1) * PROG_STRIDE, min(x + 2, nmbx));
+        /* the progress of the row above is asked for BEFORE the next tile's prefetch and looked at after it: in the steady
+         * state of the wavefront the row above is exactly far enough, and the round trip hides behind the prefetch */
+        const int need = min(x + 2, nmbx), must = row > 0 && seen < need;
+        int p = seen;
+        if (must && LANE_ID == 0) p = ld_relaxed(progress + (row - 1) * PROG_STRIDE);
+        int bs_next = 0;                       /* the next macroblock's boundary strengths: loads now, store after the filters */
+        if (x + 1 < nmbx) { deblock_prefetch(fp, nxt, x + 1, row, part); bs_next = deblock_bs_item(fp, x + 1, row, LANE_ID); }
+        if (must)
+        {
+            if (LANE_ID == 0) { while (p < need) { __nanosleep(32); p = ld_relaxed(progress + (row - 1) * PROG_STRIDE); } fence_acquire(); }
+            seen = __shfl_sync(0xffffffffu, p, 0);
+        }
         deblock_mb(fp, cur, x, row, part, 1);
+        nxt->bs[LANE_ID] = (uint8_t)bs_next;
         if (x + 1 < nmbx) deblock_handover(cur, nxt, part);
         publish_row(progress + row * PROG_STRIDE, x + 1);
     }
