@@ -89,13 +89,17 @@ __device__ __forceinline__ int ld_relaxed(const int *p)
     return v;
 }
 __device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+/* After relaxed polls have seen the awaited value: ONE acquiring load of the same counter (it reads that value or a later
+ * one, so it synchronises with a release that covers everything awaited).  Unlike a fence it does not wait for the
+ * polling thread's own outstanding stores -- the write-back of the macroblock it has just finished. */
+__device__ __forceinline__ void acquire_counter(const int *p) { (void)ld_acquire(p); }
 __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void wait_row(const int *progress_above, int need)      /* one warp */
 {
-    if (LANE_ID == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(32); fence_acquire(); }
+    if (LANE_ID == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(32); acquire_counter(progress_above); }
     __syncwarp();
 }
 __device__ __forceinline__ void publish_row(int *progress, int done)               /* one warp */
@@ -105,7 +109,7 @@ __device__ __forceinline__ void publish_row(int *progress, int done)            
 }
 __device__ __forceinline__ void wait_row_cta(const int *progress_above, int need)  /* whole CTA */
 {
-    if (threadIdx.x == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(POLL_NS); fence_acquire(); }
+    if (threadIdx.x == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(POLL_NS); acquire_counter(progress_above); }
     __syncthreads();
 }
 __device__ __forceinline__ void publish_row_cta(int *progress, int done)
@@ -187,7 +191,7 @@ __device__ void trajectory_follower(const FrameParams *fp)
         {
             int p;
             while ((p = ld_relaxed(prog + row * PROG_STRIDE)) <= x) __nanosleep(200);
-            fence_acquire();
+            acquire_counter(prog + row * PROG_STRIDE);
             avail = min(p - x, 32 - (n & 31));       /* chunks end at multiples of 32 (checkpoints) */
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
@@ -251,7 +255,7 @@ __device__ void repair_follower(const FrameParams *fp, int pass)
         {
             int p;
             while ((p = ld_relaxed(fp->row_progress + row * PROG_STRIDE) - base) <= x) __nanosleep(100);
-            fence_acquire();
+            acquire_counter(fp->row_progress + row * PROG_STRIDE);
             avail = min(p - x, 32 - (n & 31));
         }
         avail = __shfl_sync(0xffffffffu, avail, 0);
@@ -423,7 +427,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
                                 if (lane == 0) p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                                 p = __shfl_sync(0xffffffffu, p, 0);
                             }
-                            if (lane == 0) fence_acquire();
+                            if (lane == 0) acquire_counter(prog_mv + (row - 1) * PROG_STRIDE);
                             __syncwarp();
                             seen_mv = p;
 #ifdef H264_FASTPROF
@@ -530,7 +534,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
             {
                 const int need = base + min(x + 2, nmbx);
                 while ((p = ld_relaxed(progress + (row - 1) * PROG_STRIDE)) < need) __nanosleep(20);
-                fence_acquire();
+                acquire_counter(progress + (row - 1) * PROG_STRIDE);
                 p -= base;
             }
             s_above = p;
@@ -669,7 +673,9 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
         if (x + 1 < nmbx) { deblock_prefetch(fp, nxt, x + 1, row, part); bs_next = deblock_bs_item(fp, x + 1, row, LANE_ID); }
         if (must)
         {
-            if (LANE_ID == 0) { while (p < need) { __nanosleep(32); p = ld_relaxed(progress + (row - 1) * PROG_STRIDE); } fence_acquire(); }
+            /* relaxed polls, then ONE acquiring load of the counter: unlike a fence it does not wait for this lane's own
+             * write-back stores of the previous macroblock */
+            if (LANE_ID == 0) { while (p < need) { __nanosleep(32); p = ld_relaxed(progress + (row - 1) * PROG_STRIDE); } acquire_counter(progress + (row - 1) * PROG_STRIDE); }
             seen = __shfl_sync(0xffffffffu, p, 0);
         }
         deblock_mb(fp, cur, x, row, part, 1);
