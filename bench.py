@@ -281,6 +281,23 @@ def clip_frames(cfg, steps, warmup):
 # --------------------------------------------------------------------------------------
 # roofline inputs measured elsewhere and committed under profiles/
 # --------------------------------------------------------------------------------------
+def l2_policy(nseg, W, H, frame_bytes):
+    """What a step touches: every step reads input frames that were never read before (the clip is resident, frame t of
+    every unit) and re-writes the per-step state of every unit -- two padded pictures, three half-sample planes,
+    SAD-map / motion-estimation records (2336 B per macroblock), levels, bit strings, macroblock records."""
+    w16, h16 = (W + 15) // 16 * 16, (H + 15) // 16 * 16
+    pad = (w16 + 32) * (h16 + 32)
+    nmb = (w16 // 16) * (h16 // 16)
+    per_unit = frame_bytes + 2 * pad * 3 // 2 + 3 * pad + nmb * (2336 + 832 + 2048 + 144 + 64 + 64)
+    ws = nseg * per_unit
+    l2 = 126 * 2**20
+    if ws > l2:
+        return ("no flush needed: %d MB of fresh input per step (never re-read) and a per-step working set of %d MB "
+                "(pictures, half-sample planes, SAD-map records, levels, bit strings) > 126 MB of L2" % (nseg * frame_bytes // 2**20, ws // 2**20))
+    return ("per-step working set %d MB < 126 MB of L2 and no flush: %d MB of fresh input per step (never re-read); what stays "
+            "in L2 between steps is the previous reconstruction, as in the encoder's real operation" % (ws // 2**20, nseg * frame_bytes // 2**20))
+
+
 def load_json(path, default=None):
     try:
         return json.load(open(path))
@@ -349,8 +366,7 @@ def main():
               "config": args.config, "width": W, "height": H, "gop": GOP, "qp": cfg["qp"], "kbps": cfg["kbps"],
               "units_per_gpu": nseg if args.scaling == "weak" else None, "units_total": total_units, "speed": 0,
               "timed_frames_per_unit": "t = %d..%d of an endless IPPP stream with GOP %d (IDR whenever t %% GOP == 0)" % (Wm, Wm + K - 1, GOP),
-              "l2_policy": "inputs larger than L2: %d MB of fresh input + %d MB of reference pictures per step"
-                           % (nseg * FRAME_BYTES // 2**20, nseg * FRAME_BYTES // 2**20)}
+              "l2_policy": l2_policy(nseg, W, H, FRAME_BYTES)}
 
     if args.impl == "reference":
         if rank != 0:
