@@ -386,11 +386,11 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
         if (threadIdx.x == 0) { work.pf_enable = 0; work.q_dec = 0; work.cmd = 0; work.slow_x = 0; for (int k = 0; k < MB_WARPS; k++) work.q_done[k] = 0; }
         __syncthreads();
         /* state of the deciding warp */
-        int x = 0, q = 0, seen_mv = 0, x_base = 0, q_base = 0, pub_full = 0;
+        int x = 0, q = 0, seen_mv = 0, x_base = 0, q_base = 0, pub_full = 0, p_early = -1;
         int my = pw - 1;                                   /* next decision of a working warp */
         const int row_thr = fp->have_cost_stat ? fp->cost_stat[2 + row] : 0;
 #ifdef H264_FASTPROF
-        unsigned long long gt0, gt_poll = 0, gt_ring = 0, gt_dec = 0, gt_slow = 0, gt_tmp;
+        unsigned long long gt0, gt_poll = 0, gt_ring = 0, gt_dec = 0, gt_slow = 0, gt_pub = 0, gt_stage = 0, gt_tmp;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
 #define GT(v) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v))
 #else
@@ -402,13 +402,22 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
             {
                 /* decisions worked off completely: everything below the smallest decision still open at one of the three warps */
 #define FAST_PREFIX() min(q, min(min(0 + 3 * v_done[1], 1 + 3 * v_done[2]), 2 + 3 * v_done[3]))
-#define FAST_PUBLISH_FULL() do { const int xf_ = x_base + (FAST_PREFIX() - q_base); if (xf_ > pub_full) { pub_full = xf_; __threadfence(); if (lane == 0) st_release(progress + row * PROG_STRIDE, xf_); } } while (0)
+/* the working warps make their stores visible device-wide (__threadfence) BEFORE they count a decision as done; the
+ * deciding warp only has to order its reads of those counters before its own release (a CTA-scope fence: both sides
+ * are in this CTA), the release store is cumulative */
+#define FAST_PUBLISH_FULL() do { const int xf_ = x_base + (FAST_PREFIX() - q_base); if (xf_ > pub_full) { pub_full = xf_; __threadfence_block(); if (lane == 0) st_release(progress + row * PROG_STRIDE, xf_); } } while (0)
                 int go_slow = 0;
                 while (x < nmbx && !go_slow)
                 {
                     if (x < work.me_first || x >= work.me_first + work.me_num) { if (lane == 0) me_stage_issue(fp, &work, x, row); __syncwarp(); }
                     const int first = work.me_first, num = work.me_num;
+#ifdef H264_FASTPROF
+                    { unsigned long long a_, b_; GT(a_);
+#endif
                     mbar_wait(&work.me_bar, (unsigned)(work.me_cnt - 1) & 1u);
+#ifdef H264_FASTPROF
+                    GT(b_); gt_stage += b_ - a_; gt_ring += 0; }
+#endif
                     for (int nb = x - first; nb < num; nb++)
                     {
                         const int need = min(x + 2, nmbx);
@@ -418,7 +427,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
 #ifdef H264_FASTPROF
                             unsigned long long a_, b_; GT(a_);
 #endif
-                            if (lane == 0) p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
+                            if (lane == 0) p = p_early >= 0 ? p_early : ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                             p = __shfl_sync(0xffffffffu, p, 0);
                             while (p < need)
                             {
@@ -441,13 +450,26 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
 #ifdef H264_FASTPROF
                         GT(b_); gt_ring += b_ - a_; }
 #endif
+#ifdef H264_FASTPROF
+                        unsigned long long d0_, d1_, d2_; GT(d0_);
+#endif
                         if (!fast_decide(fp, &work, x, row, work.me_stage[x - first], q % FAST_RING, row_thr)) { go_slow = 1; break; }
+#ifdef H264_FASTPROF
+                        GT(d1_); gt_dec += d1_ - d0_;
+#endif
                         q++;
                         __threadfence_block();
                         if (lane == 0) *v_qdec = q;
                         x++;
+                        /* the progress of the row above that the NEXT macroblock needs is asked for before this one is
+                         * published: the release waits for this warp's stores, the load's round trip runs beside it */
+                        p_early = -1;
+                        if (row > 0 && seen_mv < min(x + 2, nmbx) && lane == 0) p_early = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                         publish_row(prog_mv + row * PROG_STRIDE, x);
                         FAST_PUBLISH_FULL();
+#ifdef H264_FASTPROF
+                        GT(d2_); gt_pub += d2_ - d1_;
+#endif
                     }
                 }
                 /* drain the ring: the complete path (or the end of the row) needs every earlier macroblock finished */
@@ -501,7 +523,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
         {
             unsigned long long b_; GT(b_);
             int *pr = fp->prof + row * 8;
-            pr[0] = (int)(gt0 & 0x7fffffff); pr[1] = (int)(b_ - gt0); pr[2] = (int)gt_poll; pr[3] = (int)gt_ring; pr[4] = (int)gt_slow; pr[5] = q;
+            pr[0] = (int)(gt0 & 0x7fffffff); pr[1] = (int)(b_ - gt0); pr[2] = (int)gt_poll; pr[3] = (int)gt_ring; pr[4] = (int)gt_slow; pr[5] = q; pr[6] = (int)gt_dec; pr[7] = (int)gt_pub; pr[3] = (int)gt_ring + 0; pr[2] = (int)gt_poll; if (fp->prof) fp->prof[68 * 8 + 300 + row] = (int)gt_stage;
         }
 #endif
         if (threadIdx.x == 0) { st_release(progress + row * PROG_STRIDE, nmbx); atomicAdd(fp->fsync + FS_FAST, q); }

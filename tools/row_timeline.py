@@ -20,8 +20,8 @@ prof = np.zeros((nmb * 20,), np.int32)
 L.lib.h264b200_get_profile(C.c_void_p(L.lib.H264E_b200_ctx(C.c_void_p(enc.persist))), prof.ctypes.data_as(C.c_void_p))
 r = prof[:68 * 8].reshape(68, 8).astype(np.int64)
 t0 = r[:, 0].min()
-print("row  start_us  dur_us  poll_us  ring_us  slow_us  fast")
+print("row  start_us  dur_us  poll_us  ring_us  slow_us  fast  decide_us  publish_us  stage_us")
 for y in range(68):
-    print("%3d %9.1f %7.1f %8.1f %8.1f %8.1f %5d" % (y, ((r[y, 0] - t0) & 0x7fffffff) / 1e3, r[y, 1] / 1e3, r[y, 2] / 1e3, r[y, 3] / 1e3, r[y, 4] / 1e3, r[y, 5]))
+    print("%3d %9.1f %7.1f %8.1f %8.1f %8.1f %5d %9.1f %9.1f %9.1f" % (y, ((r[y, 0] - t0) & 0x7fffffff) / 1e3, r[y, 1] / 1e3, r[y, 2] / 1e3, r[y, 3] / 1e3, r[y, 4] / 1e3, r[y, 5], r[y, 6] / 1e3, r[y, 7] / 1e3, prof[68 * 8 + 300 + y] / 1e3))
 f = prof[68 * 8:68 * 8 + 210].astype(np.int64)
 print("follower: end %.1f us, waiting %.1f us; reaches row r at (us):" % (f[200] / 1e3, f[201] / 1e3), " ".join("%d:%.0f" % (y, f[2 * y] / 1e3) for y in range(0, 68, 6)))
