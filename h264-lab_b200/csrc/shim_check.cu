@@ -13,7 +13,10 @@
 #include "h264_mbenc.h"
 #include "h264_wave.h"
 
-__global__ void __launch_bounds__(32) k_check1(const FrameParams *fps, int njobs, int pass)
+#ifndef CHECK_MIN_BLOCKS
+#define CHECK_MIN_BLOCKS 24
+#endif
+__global__ void __launch_bounds__(32, CHECK_MIN_BLOCKS) k_check1(const FrameParams *fps, int njobs, int pass)
 {
     __shared__ MBWork work;
     __shared__ FrameParams sfp;
@@ -110,5 +113,5 @@ void h264b200_launch_me(const FrameParams *fps, int njobs, int max_nmb, int roun
 
 void h264b200_launch_check1(const FrameParams *fps, int njobs, int pass, cudaStream_t st)
 {
-    k_check1<<<dim3(148 * 4, njobs), 32, 0, st>>>(fps, njobs, pass);
+    k_check1<<<dim3(148 * 8, njobs), 32, 0, st>>>(fps, njobs, pass);
 }
