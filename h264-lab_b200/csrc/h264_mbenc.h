@@ -206,7 +206,9 @@ HD void map_prefetch(const FrameParams *fp, MBWork *w, int mbx, int mby)
 }
 #endif
 
-HDF_mb_load void mb_load(MBState &s)
+/* me_only: what the motion-estimation pre-pass needs of it (input samples, SAD maps, MV context) -- no neighbour samples
+ * of the picture under construction, no Intra4x4 modes */
+HDF_mb_load void mb_load(MBState &s, int me_only = 0)
 {
     const FrameParams *fp = s.fp;
     MBWork *w = s.w;
@@ -244,11 +246,12 @@ HDF_mb_load void mb_load(MBState &s)
      * out WHERE its value lies (a chain of cases, no memory access), then there is one load per item: lanes that
      * take different cases still have their loads in flight together -- one memory round trip for the whole context
      * instead of one per case. */
-    FOR_THREADS(i, 192)
+    const int nb_lo = me_only ? 71 : 0, nb_n = me_only ? 14 : 96;
+    FOR_THREADS(i, nb_n + 96)
     {
-        if (i >= 96)
+        if (i >= nb_n)
         {
-            const int k = i - 96;
+            const int k = i - nb_n;
             uint32_t v;
             if (have_inp) v = w->pf_inp[k];
             else if (k < 64)
@@ -279,7 +282,7 @@ HDF_mb_load void mb_load(MBState &s)
         {
             /* unfiltered neighbour samples of the picture under construction (the reference's
              * top_line context, H:4693-4714), neighbours' MVs (enc->mv_pred, H:742) and I4x4 modes */
-            const int j = i;
+            const int j = nb_lo + i;
             const void *src = 0;       /* NULL: not available, the default value is stored */
             void *dst = 0;
             int kind = 0;              /* 0: sample (u8 -> u8), 1: vector (i32 -> i32), 2: mode (i8 -> i32) */

@@ -120,7 +120,7 @@ HDN void me_prepass_mb(const FrameParams *fp, MBWork *w, int x, int y, int round
     s.pbest = w->skip_pred; s.ss = &w->ss[0];
     s.win_ok = 0; s.win_x0 = s.win_y0 = 0;
     s.map = 0; s.lut = 0;
-    mb_load(s);                                  /* input samples, SAD maps, MV context from the record array = the PREVIOUS frame's field */
+    mb_load(s, 1);                               /* input samples, SAD maps, MV context from the record array = the PREVIOUS frame's field */
     if (round > 0)
     {   /* context from the field predicted for this frame (same availability rules as mb_load) */
         const int av = s.avail;
