@@ -56,6 +56,11 @@ HD void fast_load_input(const FrameParams *fp, TQBuf *t, int x, int y)
 HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32_t *mr, int slot, int thr)
 {
     const int nmbx = fp->nmbx, n = y * nmbx + x, av = mb_avail(x, y, nmbx);
+#if !H264_DEVICE
+    extern int g_emu_reason;            /* emulation statistics: why the macroblock leaves the fast path (0: it does not) */
+    g_emu_reason = 0;
+    if (mr[ME_KEY + 15] != 1u) g_emu_reason = 1;
+#endif
     if (mr[ME_KEY + 15] != 1u) return 0;
     const MBInfo *mbi = fp->mbi + n;
     int ok = 1;
@@ -76,7 +81,7 @@ HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32
         if ((int32_t)mr[ME_KEY + i] != have)
         {
 #if !H264_DEVICE
-            { extern long g_emu_miss[20]; if (ok) { g_emu_miss[i]++; if ((int32_t)mr[ME_KEY + i] == MV_NA || have == MV_NA) g_emu_miss[16]++; } }
+            { extern long g_emu_miss[20]; if (ok) { g_emu_miss[i]++; g_emu_reason = 2 + i + (((int32_t)mr[ME_KEY + i] == MV_NA) ? 100 : (have == MV_NA ? 200 : 0)); if ((int32_t)mr[ME_KEY + i] == MV_NA || have == MV_NA) g_emu_miss[16]++; } }
 #endif
             ok = 0;
         }
@@ -91,6 +96,9 @@ HDN int fast_decide(const FrameParams *fp, MBWork *w, int x, int y, const uint32
     const int best_type = inter_decide_p(fp, ic, mc, (const int32_t *)(mr + ME_MV), (const int32_t *)(mr + ME_MVD), &type, &cost, pmv, pmvd, &usp);
     const int searched = ic[IC_STATE] != 1;
     /* an inter cost this far above the usual: an intra mode probably wins, look at it now (encode_mb) rather than repair later */
+#if !H264_DEVICE
+    if (searched && cost >= thr) g_emu_reason = 20;
+#endif
     if (searched && cost >= thr) return 0;           /* thr: FrameParams::cost_stat of the row (the caller reads it once per row) */
     MBInfo *mi = fp->mbi + n;
     uint32_t *sp = (uint32_t *)(fp->spec + n);

@@ -20,6 +20,7 @@ long g_emu_qhist[16];
 long g_emu_ihist[16];
 extern "C" long *emu_ihist(void) { return g_emu_ihist; }
 extern "C" long *emu_qhist(void) { return g_emu_qhist; }
+int g_emu_reason = 0;
 extern "C" long *emu_miss_stats(void) { return g_emu_miss; }
 extern "C" long *emu_lut_stats(void) { return g_emu_lut; }
 extern "C" int *emu_dbg(void) { return g_emu_dbg; }
@@ -200,6 +201,7 @@ static void run_job(h264b200_job *job)
                     /* fast path of P frames (h264_fast.h): decide from the motion-estimation record, then the pixel work */
                     const int n = y * c->nmbx + x;
                     if (use_fast && fast_decide(&fp, w, x, y, fp.sadmap + (size_t)n * SM_WORDS + SM_ME_OFF, 0, fp.have_cost_stat ? fp.cost_stat[2 + y] : 0)) { fast_work(&fp, w, x, y, 0, 0); g_emu_lut[6]++; continue; }
+                    if (use_fast && getenv("H264B200_DUMP_SLOW")) fprintf(stderr, "slow y %d x %d reason %d\n", y, x, g_emu_reason);
                     wave_mb_first(&fp, w, x, y);
                     for (int i = 0; i < 16; i++) w->last_mv[i] = fp.mbi[n].mv[i];
                 }
