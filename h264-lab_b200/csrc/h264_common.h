@@ -398,6 +398,7 @@ struct MBSpec
 #define FS_WAVE_TAGS 16    /* macroblocks tagged for the repair WAVE of the current pass (successors of changes of the last parallel round) */
 #define FS_FAST 17         /* statistics: macroblocks of sweep 0 taken by the decide / work fast path (h264_fast.h) */
 #define FS_SLOW 18         /* statistics: macroblocks of sweep 0 encoded by the complete path */
+#define FS_WAVE_REENC 19   /* statistics: macroblocks the repair WAVES looked at one after the other (h264b200_ctx_stats_ex [8]) */
 #define FS_WORDS 24
 #define FS_DONE 0x40000000
 

@@ -18,7 +18,4 @@ for i in range(n):
     cur = list(st)[:8]
     d = [a - b for a, b in zip(cur, prev)]; prev = cur
     dbg = list(st)[8:13]
-    if any(dbg):
-        rows = (h + 15) // 16
-        print("   per row CTA (K cycles): decide %.0f work %.0f slow %.0f poll %.0f | batches/row %.1f" % tuple([v * 64 / rows / 1e3 for v in dbg[:4]] + [dbg[4] / rows]))
-    print("frame %d: passes %d reenc %d checks %d fast %d slow %d | ms total %.2f sweep %.2f deblock %.2f sadmap %.2f me %.2f intra_check %.2f" % (i, d[0], d[1], d[2], d[4], d[5], tm[0], tm[1], tm[2], tm[4], tm[5], tm[6]))
+    print("frame %d: passes %d reenc %d (in the waves, one after the other: %d) checks %d fast %d slow %d | ms total %.2f sweep %.2f deblock %.2f sadmap %.2f me %.2f intra_check %.2f" % (i, d[0], d[1], dbg[0], d[2], d[4], d[5], tm[0], tm[1], tm[2], tm[4], tm[5], tm[6]))
