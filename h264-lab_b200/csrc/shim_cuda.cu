@@ -427,18 +427,16 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
 #ifdef H264_FASTPROF
                             unsigned long long a_, b_; GT(a_);
 #endif
-                            int acq = 0;                   /* lane 0: the value in p comes from an acquiring load */
-                            if (lane == 0) { if (p_early >= 0) { p = p_early; acq = 1; } else p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE); }
+                            if (lane == 0) p = p_early >= 0 ? p_early : ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                             p = __shfl_sync(0xffffffffu, p, 0);
                             while (p < need)
                             {
                                 FAST_PUBLISH_FULL();
                                 __nanosleep(POLL_NS);
-                                acq = 0;
                                 if (lane == 0) p = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                                 p = __shfl_sync(0xffffffffu, p, 0);
                             }
-                            if (lane == 0 && !acq) acquire_counter(prog_mv + (row - 1) * PROG_STRIDE);
+                            if (lane == 0) acquire_counter(prog_mv + (row - 1) * PROG_STRIDE);
                             __syncwarp();
                             seen_mv = p;
 #ifdef H264_FASTPROF
@@ -463,11 +461,10 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
                         __threadfence_block();
                         if (lane == 0) *v_qdec = q;
                         x++;
-                        /* the progress of the row above that the NEXT macroblock needs is sampled (acquiring load) before
-                         * this one is published: the release waits for this warp's stores, the load's round trip runs
-                         * beside it, and when the row above is far enough the sample is all the synchronisation needed */
+                        /* the progress of the row above that the NEXT macroblock needs is asked for before this one is
+                         * published: the release waits for this warp's stores, the load's round trip runs beside it */
                         p_early = -1;
-                        if (row > 0 && seen_mv < min(x + 2, nmbx) && lane == 0) p_early = ld_acquire(prog_mv + (row - 1) * PROG_STRIDE);
+                        if (row > 0 && seen_mv < min(x + 2, nmbx) && lane == 0) p_early = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                         publish_row(prog_mv + row * PROG_STRIDE, x);
                         FAST_PUBLISH_FULL();
 #ifdef H264_FASTPROF
@@ -687,35 +684,26 @@ __global__ void __launch_bounds__(32) k_deblock_rows(const FrameParams *fps, int
     /* software pipeline over the macroblocks of the row: tile[x & 1] is filtered while tile[(x + 1) & 1] fills */
     deblock_mb(fp, &tile[0], 0, row, part, 0);
     int seen = 0;                              /* progress of the row above as far as this warp has acquired it */
-    int p_early = -1;                          /* lane 0: acquiring sample of that counter taken ahead of time */
-    if (row > 0 && LANE_ID == 0) p_early = ld_acquire(progress + (row - 1) * PROG_STRIDE);
     for (int x = 0; x < nmbx; x++)
     {
         DeblockTile *cur = &tile[x & 1], *nxt = &tile[(x + 1) & 1];
-        /* The progress of the row above is sampled (with an acquiring load) BEFORE the previous macroblock's release and
-         * the next tile's prefetch, and looked at after them: in the steady state of the wavefront the row above is
-         * exactly far enough, so the sample is all the synchronisation this macroblock needs and its round trip hides
-         * behind the release's wait for the write-back stores.  Otherwise: relaxed polls, then one acquiring load --
-         * unlike a fence it does not wait for this lane's own stores. */
+        /* the progress of the row above is asked for BEFORE the next tile's prefetch and looked at after it: in the steady
+         * state of the wavefront the row above is exactly far enough, and the round trip hides behind the prefetch */
         const int need = min(x + 2, nmbx), must = row > 0 && seen < need;
         int p = seen;
-        if (must && LANE_ID == 0) p = p_early >= 0 ? p_early : ld_acquire(progress + (row - 1) * PROG_STRIDE);
+        if (must && LANE_ID == 0) p = ld_relaxed(progress + (row - 1) * PROG_STRIDE);
         int bs_next = 0;                       /* the next macroblock's boundary strengths: loads now, store after the filters */
         if (x + 1 < nmbx) { deblock_prefetch(fp, nxt, x + 1, row, part); bs_next = deblock_bs_item(fp, x + 1, row, LANE_ID); }
         if (must)
         {
-            if (LANE_ID == 0 && p < need)
-            {
-                do { __nanosleep(32); p = ld_relaxed(progress + (row - 1) * PROG_STRIDE); } while (p < need);
-                acquire_counter(progress + (row - 1) * PROG_STRIDE);
-            }
+            /* relaxed polls, then ONE acquiring load of the counter: unlike a fence it does not wait for this lane's own
+             * write-back stores of the previous macroblock */
+            if (LANE_ID == 0) { while (p < need) { __nanosleep(32); p = ld_relaxed(progress + (row - 1) * PROG_STRIDE); } acquire_counter(progress + (row - 1) * PROG_STRIDE); }
             seen = __shfl_sync(0xffffffffu, p, 0);
         }
         deblock_mb(fp, cur, x, row, part, 1);
         nxt->bs[LANE_ID] = (uint8_t)bs_next;
         if (x + 1 < nmbx) deblock_handover(cur, nxt, part);
-        p_early = -1;
-        if (row > 0 && x + 1 < nmbx && seen < min(x + 3, nmbx) && LANE_ID == 0) p_early = ld_acquire(progress + (row - 1) * PROG_STRIDE);
         publish_row(progress + row * PROG_STRIDE, x + 1);
     }
 }
