@@ -940,6 +940,9 @@ HD void inter_partition_hint(const int sad[4], int mode[4])
     if (iabs(skew) > (sum >> 4) && iabs(slope) <= (sum >> 4)) mode[3] = 1;
 }
 
+/* does macroblock (mbx, mby) cross the picture edge (cropped sizes)? */
+HD int mb_crosses_edge(const FrameParams *fp, int mbx, int mby) { return (mbx + 1) * 16 > fp->width || (mby + 1) * 16 > fp->height; }
+
 /* chroma motion compensation of plane pl for every partition of the current MB type
  * (interpolate_chroma H:4915). mvs: per-partition MVs relative to the MB.  Warp-level. */
 HDF_mc_chroma_plane void mc_chroma_plane(const MBState &s, int pl, int type, const int32_t *mvs)
@@ -1013,6 +1016,12 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
         {
             int32_t one_mv = mv_skip;
             int ok = 1;
+            /* A macroblock that crosses the picture edge: the reference copies its replicated chroma input (8 x 8, stride 8)
+             * to the START of mb_pix_store (H:5333) -- where, after the swap of H:5316, the chroma prediction it is about
+             * to be compared with lies (stride 16, U | V) -- so rows 0..3 of the "prediction" are input rows 2r (U) /
+             * 2r + 1 (V) of the plane under test.  Reproduced, not fixed.  Only the TEST sees the damage: the chroma
+             * prediction of an accepted skip is interpolated again before it becomes the reconstruction (H:5786). */
+            const int crosses = mb_crosses_edge(fp, s.mbx, s.mby);
             for (int pl = 0; pl < 2 && ok; pl++)
             {
                 mc_chroma_plane(s, pl, MBT_SKIP, &one_mv);
@@ -1020,7 +1029,8 @@ HDF_inter_stage_a void inter_stage_a(MBState &s, const int32_t cl[2])
                 FOR_LANES(i, 16)
                 {
                     int r = i >> 1, c = (i & 1) * 4;
-                    acc += sad4(ld4_sm(w->inp_c + r * 16 + pl * 8 + c), ld4_sm(w->predc + r * 16 + pl * 8 + c));
+                    const uint32_t pr = (crosses && r < 4) ? ld4_sm(w->inp_c + (2 * r + pl) * 16 + pl * 8 + c) : ld4_sm(w->predc + r * 16 + pl * 8 + c);
+                    acc += sad4(ld4_sm(w->inp_c + r * 16 + pl * 8 + c), pr);
                 }
                 acc = wsum(acc);
                 if (acc >= fp->skip_thr_inter) ok = 0;

@@ -13,7 +13,7 @@ import refenc  # noqa: E402
 
 GOLD = [c for c in cases.SMALL if c[0] in (
     "cif_i_only", "cif_ipp_qp28", "cif_speed2", "cif_speed10", "cif_kbps300", "noise_qp12", "crop_366x250",
-    "small_48x32_inf_gop", "cif_denoise", "crop_denoise_366x250", "vbv_empty_denoise")] + cases.CIF_FOREMAN_SUBSTITUTE[:1] + [("1080p_ipp", "panning", 1920, 1080, 3, 3, dict(qp=28))]
+    "small_48x32_inf_gop", "cif_denoise", "crop_denoise_366x250", "vbv_empty_denoise", "crop_skip_480x50_qp44", "crop_skip_640x50_rc")] + cases.CIF_FOREMAN_SUBSTITUTE[:1] + [("1080p_ipp", "panning", 1920, 1080, 3, 3, dict(qp=28))]
 
 out = {"generator": "tests/golden/make_golden.py", "reference": "l646773422/h264-lab src/h264-lab.h via oracle/ref_harness.c, gcc -O2",
        "cases": []}
