@@ -12,7 +12,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 t0 = time.time(); n = 0; fails = 0
 while time.time() - t0 < budget:
-    kind = rng.choice(["panning", "multi", "noise", "chess", "panning", "multi"])
+    kind = rng.choice(["panning", "multi", "noise", "chess", "panning", "multi", "flat", "static", "static", "slow"])
     w = rng.choice([16, 32, 48, 100, 176, 200, 320, 352, 366, 640, 854, 1280, 1920])
     h = rng.choice([16, 32, 50, 120, 144, 180, 250, 288, 360, 480, 720, 1080])
     if w * h > 1280 * 720 and rng.random() < 0.7: continue
@@ -21,14 +21,26 @@ while time.time() - t0 < budget:
     kw = dict(qp=rng.choice([10, 20, 28, 33, 40, 51])) if rng.random() < 0.7 else dict(kbps=rng.choice([100, 500, 3000]))
     if rng.random() < 0.15: kw["denoise"] = 1
     if rng.random() < 0.2: kw["speed"] = rng.choice([1, 2, 5, 9, 10])
+    if rng.random() < 0.15: kw["empty_frames"] = 1
+    if rng.random() < 0.1: kw["stuffing"] = 1
     try:
-        frames = cases.make(kind, w, h, nf)
+        if kind == "static":       # the same picture again and again (+ a little noise now and then): early skips everywhere
+            base = cases.make("panning", w, h, 2)[0]
+            frames = np.stack([base] * nf)
+            if rng.random() < 0.5:
+                nz = np.random.default_rng(rng.randint(0, 1 << 30)).integers(-1, 2, size=frames.shape)
+                frames = np.clip(frames.astype(np.int16) + nz * (np.arange(nf)[:, None] % 2), 0, 255).astype(np.uint8)
+        elif kind == "slow":       # every picture twice: skips and motion alternate
+            base = cases.make("multi", w, h, (nf + 1) // 2)
+            frames = np.repeat(base, 2, axis=0)[:nf]
+        else:
+            frames = cases.make(kind, w, h, nf)
         rbs, rsz, rrec, _ = refenc.encode_sequence(frames, w, h, gop, **kw)
     except Exception as e:          # a combination the reference itself refuses
         continue
     bs, sz, rec = B.encode_sequence(L, frames, w, h, gop, **kw)
     ok = bs == rbs and np.array_equal(rec, rrec)
-    if ok and rng.random() < 0.3 and "denoise" not in kw:
+    if ok and rng.random() < 0.3 and not (set(kw) & {"denoise", "empty_frames", "stuffing"}):
         # the same clip as a batch of 3 sessions in one submission
         encs = [B.Encoder(L, w, h, gop) for _ in range(3)]
         rps = [e.run_param(**{k: v for k, v in kw.items() if k in ("qp", "kbps", "speed")}) for e in encs]
