@@ -688,7 +688,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
         h264b200_note_transparent(e->ctx);
         hb_ue(&pl->hdr, (uint32_t)e->nmb);
         hb_trailing(&pl->hdr);
-        if ((int)e->out_pos + 4 + 2 * pl->hdr.nbytes + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+        if ((int)e->out_pos + 4 + 2 * pl->hdr.nbytes + 64 > e->out_cap) return H264E_STATUS_OUTPUT_OVERFLOW;
         emit_nal(e, pl->hdr.buf, pl->hdr.nbytes);
         if (pl->inplace.yuv[0])
         {   /* in-place mode: the caller's frame receives the reconstruction = the unchanged reference picture */
@@ -718,7 +718,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
      * add the RBSP stop bit and convert MSB-first words to escaped bytes */
     nbits = job->out_bits + 1;
     nbytes = (nbits + 7) >> 3;
-    if ((int)e->out_pos + 4 + nbytes + 64 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+    if ((int)e->out_pos + 4 + nbytes + 64 > e->out_cap) return H264E_STATUS_OUTPUT_OVERFLOW;
     d = e->out + e->out_pos;
     d[0] = d[1] = d[2] = 0; d[3] = 1;
     nal = d + 4;
@@ -742,7 +742,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
                     const uint32_t be = __builtin_bswap32(wv);
                     memcpy(nal + j, &be, 4);
                     j += 4; i += 3; zeros = 0;
-                    if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+                    if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_OUTPUT_OVERFLOW;
                     continue;
                 }
             }
@@ -753,7 +753,7 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
             if (zeros == 2 && byte <= 3) { nal[j++] = 3; zeros = 0; }
             zeros = byte ? 0 : zeros + 1;
             nal[j++] = byte;
-            if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_DEVICE_ERROR;
+            if (!roomy && (int)e->out_pos + 4 + j + 8 > e->out_cap) return H264E_STATUS_OUTPUT_OVERFLOW;
         }
     }
     if (e->run.nalu_callback) e->run.nalu_callback(nal, j, e->run.nalu_callback_token);
@@ -762,7 +762,9 @@ static int finish_frame(frame_plan_t *pl, h264b200_job *job)
     filler = rc_frame_end(e, pl->long_term_idx_use == -1, job->trailing_skip_run == e->nmb);
 after_rc:
     if (filler)
-    {   /* filler_data NAL (H:6113-6122) */
+    {   /* filler_data NAL (H:6113-6122).  0xFF bytes need no escapes: 4 + filler + 2 bytes.  The reference does not look at
+         * the room left in the scratch buffer here (tiny pictures at high bit rates overrun it); this layer reports it. */
+        if ((long)e->out_pos + 4 + (long)filler + 2 > (long)e->out_cap) return H264E_STATUS_OUTPUT_OVERFLOW;
         uint8_t *f = (uint8_t *)malloc((size_t)filler + 2);
         if (f)
         {

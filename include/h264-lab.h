@@ -43,6 +43,8 @@ extern "C" {
 #define H264E_STATUS_NO_DEVICE              100  /* CUDA device or kernels unavailable     */
 #define H264E_STATUS_UNSUPPORTED            101  /* feature outside the B200 hot path */
 #define H264E_STATUS_DEVICE_ERROR           102
+#define H264E_STATUS_OUTPUT_OVERFLOW        103  /* the coded frame (with its filler-data NAL) does not fit the caller's scratch buffer;
+                                                    the reference writes past the buffer in that case */
 
 /* ---- frame types (reference H:63-70) ---- */
 #define H264E_FRAME_TYPE_DEFAULT    0    /* by GOP position: KEY when frame.num == 0, else P */

@@ -68,3 +68,12 @@ def _droppable_sequence(binding, lib, ref):
 
 def test_emu_droppable_frames(binding, emu_lib, ref):
     _droppable_sequence(binding, emu_lib, ref)
+
+
+def test_filler_nal_larger_than_the_scratch_buffer_is_an_error(binding, emu_lib):
+    """vbv_underflow_stuffing_flag on a tiny picture at a high bit rate asks for a filler-data NAL that does not fit the
+    caller's scratch buffer.  The reference writes past the buffer (heap corruption, found by tools/stress_parity.py);
+    this layer returns H264E_STATUS_OUTPUT_OVERFLOW (103) and touches nothing beyond the buffer."""
+    frames = cases.make("noise", 32, 32, 3)
+    with pytest.raises(RuntimeError, match="error 103"):
+        binding.encode_sequence(emu_lib, frames, 32, 32, 3, kbps=3000, empty_frames=1, stuffing=1)

@@ -12,7 +12,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 t0 = time.time(); n = 0; fails = 0
 while time.time() - t0 < budget:
-    kind = rng.choice(["panning", "multi", "noise", "chess", "panning", "multi", "flat", "static", "static", "slow"])
+    kind = rng.choice(["panning", "multi", "noise", "chess", "panning", "multi", "flat", "static", "static", "slow", "fastpan", "fastpan"])
     w = rng.choice([16, 32, 48, 100, 176, 200, 320, 352, 366, 640, 854, 1280, 1920])
     h = rng.choice([16, 32, 50, 120, 144, 180, 250, 288, 360, 480, 720, 1080])
     if w * h > 1280 * 720 and rng.random() < 0.7: continue
@@ -22,7 +22,8 @@ while time.time() - t0 < budget:
     if rng.random() < 0.15: kw["denoise"] = 1
     if rng.random() < 0.2: kw["speed"] = rng.choice([1, 2, 5, 9, 10])
     if rng.random() < 0.15: kw["empty_frames"] = 1
-    if rng.random() < 0.1: kw["stuffing"] = 1
+    if rng.random() < 0.1 and kw.get("kbps", 0) * 1000 // 240 < w * h // 4: kw["stuffing"] = 1      # (the reference writes past its scratch buffer when a filler NAL outgrows a tiny picture)
+    if os.environ.get("STRESS_VERBOSE"): print("case", kind, w, h, nf, gop, kw, flush=True)
     try:
         if kind == "static":       # the same picture again and again (+ a little noise now and then): early skips everywhere
             base = cases.make("panning", w, h, 2)[0]
@@ -30,6 +31,14 @@ while time.time() - t0 < budget:
             if rng.random() < 0.5:
                 nz = np.random.default_rng(rng.randint(0, 1 << 30)).integers(-1, 2, size=frames.shape)
                 frames = np.clip(frames.astype(np.int16) + nz * (np.arange(nf)[:, None] % 2), 0, 255).astype(np.uint8)
+        elif kind == "fastpan":    # large global motion (up to +-24 samples per frame): search range, vector limits, untabulated positions
+            base = cases.make("panning", w, h, 2)[0]
+            y0 = base[:w * h].reshape(h, w); u0 = base[w * h:w * h + (w // 2) * (h // 2)].reshape(h // 2, w // 2); v0 = base[w * h + (w // 2) * (h // 2):].reshape(h // 2, w // 2)
+            dx, dy = rng.randint(-24, 24) & ~1, rng.randint(-24, 24) & ~1
+            fl = []
+            for t in range(nf):
+                fl.append(np.concatenate([np.roll(y0, (dy * t, dx * t), (0, 1)).ravel(), np.roll(u0, (dy * t // 2, dx * t // 2), (0, 1)).ravel(), np.roll(v0, (dy * t // 2, dx * t // 2), (0, 1)).ravel()]))
+            frames = np.stack(fl).astype(np.uint8)
         elif kind == "slow":       # every picture twice: skips and motion alternate
             base = cases.make("multi", w, h, (nf + 1) // 2)
             frames = np.repeat(base, 2, axis=0)[:nf]
