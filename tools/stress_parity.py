@@ -1,6 +1,6 @@
 """Developer tool (GPU box): randomised parity sweep -- random picture sizes (incl. cropped ones), contents, GOP lengths,
 fixed QP or rate control, single sessions and batches, every run compared byte for byte with the compiled reference
-(oracle/_ref).  usage: stress_parity.py <seconds> [seed]"""
+(oracle/_ref).  usage: stress_parity.py <seconds> [seed] [big]"""
 import os, sys, time, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,12 +10,14 @@ B = conftest.load_binding()
 L = B.Library(os.environ.get("H264B200_LIB") or os.path.join(ROOT, "h264-lab_b200", "libh264lab_b200.so"))
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+big = len(sys.argv) > 3 and sys.argv[3] == "big"
 t0 = time.time(); n = 0; fails = 0
 while time.time() - t0 < budget:
     kind = rng.choice(["panning", "multi", "noise", "chess", "panning", "multi", "flat", "static", "static", "slow", "fastpan", "fastpan"])
     w = rng.choice([16, 32, 48, 100, 176, 200, 320, 352, 366, 640, 854, 1280, 1920])
     h = rng.choice([16, 32, 50, 120, 144, 180, 250, 288, 360, 480, 720, 1080])
-    if w * h > 1280 * 720 and rng.random() < 0.7: continue
+    if big and w * h < 320 * 240: continue           # "big": pictures with many macroblock rows (the wavefront at scale)
+    if not big and w * h > 1280 * 720 and rng.random() < 0.7: continue
     nf = rng.randint(2, 7) if w * h < 400 * 300 else rng.randint(2, 4)
     gop = rng.choice([1, 2, 3, nf, nf, 60])
     kw = dict(qp=rng.choice([10, 20, 28, 33, 40, 51])) if rng.random() < 0.7 else dict(kbps=rng.choice([100, 500, 3000]))
