@@ -456,6 +456,7 @@ struct FrameParams
     int *mb_nbits;              /* [nmb + 1]                                                */
     int *mb_bitoff;             /* [nmb + 1] exclusive prefix sum of mb_nbits + hdr_bits    */
     uint32_t *out_words;        /* packed slice payload                                     */
+    int out_cap_words;          /* its capacity (this session's: the jobs of a submission may differ in picture size) */
     int *out_info;              /* [0] total bits, [1] error flags, [2] trailing skip run   */
     int hdr_bits;               /* bit offset at which the slice data starts                */
     int *prof;                  /* developer builds: per-MB phase cycle counts [nmb][10]    */

@@ -776,7 +776,7 @@ __global__ void k_cavlc(const FrameParams *fps, int njobs)
 }
 
 /* one block per frame: exclusive scan of mb_nbits -> mb_bitoff, totals, and zero the payload */
-__global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs, int out_cap_words)
+__global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs)
 {
     const FrameParams *fp = fps + blockIdx.x;
     if (fp->fsync[FS_STATE] != FS_DONE) return;
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs
     for (int i = lo; i < hi; i++) { int b = fp->mb_nbits[i]; fp->mb_bitoff[i] = base; base += b; }
     const int total = fp->hdr_bits + part[1023];
     if (maxb > MB_BITS_WORDS * 32 - 64) atomicOr(&fp->out_info[1], 1);
-    if ((total + 95) / 32 > out_cap_words) atomicOr(&fp->out_info[1], 2);
+    if ((total + 95) / 32 > fp->out_cap_words) atomicOr(&fp->out_info[1], 2);
     if (tid == 0)
     {
         fp->out_info[0] = total;
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(1024) k_scan(const FrameParams *fps, int njobs
         if (fp->slice_type == SLICE_P) for (int k = cnt - 2; k >= 0 && fp->mbi[k].type == MBT_SKIP; k--) run++;
         fp->out_info[2] = run;
     }
-    const int nw = min((total + 95) / 32, out_cap_words);
+    const int nw = min((total + 95) / 32, fp->out_cap_words);
     for (int i = tid; i < nw; i += 1024) fp->out_words[i] = 0;
 }
 
@@ -1264,7 +1264,7 @@ static void build_fp(const h264b200_job *job, FrameParams *fp)
     fp->have_cost_stat = c->cost_stat_valid;
     fp->row_progress = c->d_progress; fp->row_progress_df = c->d_progress + PROG_STRIDE * c->nmby; fp->row_progress_dfc = c->d_progress + 2 * PROG_STRIDE * c->nmby; fp->row_progress_mv = c->d_progress + 3 * PROG_STRIDE * c->nmby; fp->row_clean = c->d_progress + 4 * PROG_STRIDE * c->nmby;
     fp->mb_bits = c->d_mb_bits; fp->mb_nbits = c->d_mb_nbits; fp->mb_bitoff = c->d_mb_bitoff;
-    fp->out_words = c->d_out_words; fp->out_info = c->d_out_info;
+    fp->out_words = c->d_out_words; fp->out_cap_words = c->out_cap_words; fp->out_info = c->d_out_info;
     fp->hdr_bits = p.hdr_bits;
     fp->spec = c->d_spec; fp->cl_true = c->d_cl_true; fp->cl_ckpt = c->d_cl_ckpt; fp->changed_pass = c->d_changed_pass; fp->need_reenc = c->d_need_reenc; fp->fsync = c->d_fsync;
     fp->max_passes = 4096;
@@ -1309,12 +1309,13 @@ static int launch_post(const FrameParams *d_fps, int n, int max_rows, int max_nm
 {
     /* the entropy-coding kernels only read the macroblock records: they run on a second stream next to the
      * in-loop filter (a latency-bound wavefront that leaves most of the chip idle) */
+    (void)cap_words;            /* every job carries its own capacity (FrameParams::out_cap_words): pictures of a batch may differ in size */
     if (ensure_stream2()) return -3;
     CK(cudaEventRecord(g_ev_fork, st));
     CK(cudaStreamWaitEvent(g_stream2, g_ev_fork, 0));
     if (ev_mid) CK(cudaEventRecord(g_ev_x[0], g_stream2));
     k_cavlc<<<dim3((max_nmb + 1 + 63) / 64, n), 64, 0, g_stream2>>>(d_fps, n);
-    k_scan<<<n, 1024, 0, g_stream2>>>(d_fps, n, cap_words);
+    k_scan<<<n, 1024, 0, g_stream2>>>(d_fps, n);
     k_pack<<<dim3((max_nmb + 1 + 127) / 128, n), 128, 0, g_stream2>>>(d_fps, n);
     if (ev_mid) CK(cudaEventRecord(g_ev_x[1], g_stream2));
     CK(cudaEventRecord(g_ev_join, g_stream2));

@@ -373,3 +373,25 @@ def test_speculation_layers_switched_off(ref):
         out = subprocess.run([sys.executable, knob_child.__file__], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, (knob, out.stderr[-2000:])
         assert out.stdout.split() == want, knob
+
+
+def test_heterogeneous_batch(binding, cuda_lib, ref):
+    """Sessions of different picture sizes, GOP lengths (I and P frames in one submission) and quantisers in one
+    H264E_encode_batch: every job has its own geometry and payload capacity (a batch-wide capacity -- the smallest
+    picture's -- once failed the large ones; found by tools/stress_batch.py)."""
+    specs = [("panning", 1280, 720, 3, 60, dict(qp=22)), ("noise", 32, 32, 4, 2, dict(qp=12)), ("multi", 366, 250, 4, 3, dict(qp=33)),
+             ("chess", 176, 144, 2, 1, dict(kbps=200))]
+    sess = []
+    for kind, w, h, n, gop, kw in specs:
+        frames = cases.make(kind, w, h, n)
+        rbs, _, _, _ = ref.encode_sequence(frames, w, h, gop, want_recon=False, **kw)
+        enc = binding.Encoder(cuda_lib, w, h, gop)
+        sess.append(dict(frames=frames, n=n, ref=rbs, enc=enc, rp=enc.run_param(**kw), out=b""))
+    for t in range(max(s["n"] for s in sess)):
+        act = [s for s in sess if t < s["n"]]
+        res = binding.encode_batch(cuda_lib, [s["enc"] for s in act], [s["frames"][t].copy() for s in act], [s["rp"] for s in act])
+        for s, r in zip(act, res):
+            s["out"] += r
+    for i, s in enumerate(sess):
+        assert s["out"] == s["ref"], specs[i]
+        s["enc"].close()
