@@ -1,0 +1,44 @@
+"""Developer tool (GPU box): several host threads, each encoding its own random sessions (sizes, contents, QPs; single
+sessions and small batches) at the same time -- every thread has its own lane (stream pair, staging) in the shim -- each
+result compared with the compiled reference.  usage: stress_threads.py <seconds> [threads] [seed]"""
+import os, sys, time, random, threading
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import conftest, cases, refenc
+B = conftest.load_binding()
+L = B.Library(os.environ.get("H264B200_LIB") or os.path.join(ROOT, "h264-lab_b200", "libh264lab_b200.so"))
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+res = [None] * T
+def work(k):
+    rng = random.Random(seed * 100 + k)
+    t0 = time.time(); n = 0; fails = 0
+    while time.time() - t0 < budget:
+        kind = rng.choice(["panning", "multi", "noise", "chess"])
+        w = rng.choice([48, 176, 352, 366, 640, 1280]); h = rng.choice([50, 144, 250, 288, 360, 720])
+        nf = rng.randint(2, 5); gop = rng.choice([1, 3, 60]); kw = dict(qp=rng.choice([20, 28, 40])) if rng.random() < 0.7 else dict(kbps=500)
+        try:
+            frames = cases.make(kind, w, h, nf)
+            rbs, _, _, _ = refenc.encode_sequence(frames, w, h, gop, want_recon=False, **kw)
+        except Exception:
+            continue
+        m = rng.choice([1, 1, 2, 3])
+        encs = [B.Encoder(L, w, h, gop) for _ in range(m)]
+        rps = [e.run_param(**kw) for e in encs]
+        outs = [b""] * m
+        for t in range(nf):
+            r = B.encode_batch(L, encs, [frames[t].copy() for _ in encs], rps)
+            for i in range(m): outs[i] += r[i]
+        for e in encs: e.close()
+        n += 1
+        if any(o != rbs for o in outs):
+            fails += 1
+            print("MISMATCH thread", k, kind, w, h, nf, gop, kw, "batch", m, flush=True)
+    res[k] = (n, fails)
+th = [threading.Thread(target=work, args=(k,)) for k in range(T)]
+for t in th: t.start()
+for t in th: t.join()
+print("%d threads: %s cases, %d mismatches" % (T, [r[0] for r in res], sum(r[1] for r in res)))
+sys.exit(1 if any(r[1] for r in res) else 0)
