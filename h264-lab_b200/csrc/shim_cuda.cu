@@ -1175,6 +1175,10 @@ extern "C" int h264b200_ctx_create(h264b200_ctx **out, int width, int height, in
 #endif
     CKC(cudaMallocHost(&c->h_out_words, sizeof(uint32_t) * (size_t)c->out_cap_words));
     CKC(cudaMallocHost(&c->h_out_info, 128));
+    /* The clears above run on the legacy default stream, which does not order itself against the lanes' NON-BLOCKING
+     * streams: without this wait the first submission could start before (or while) they execute -- seen as rare wrong
+     * first frames when several host threads create and drive encoders at the same time (tools/stress_threads.py). */
+    CKC(cudaStreamSynchronize(0));
 #undef CKC
     *out = c;
     return 0;
@@ -1206,6 +1210,7 @@ extern "C" void h264b200_ctx_reset(h264b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaMemset(c->d_clusters, 0, 16);
+    cudaStreamSynchronize(0);           /* default-stream clear before anything a lane's non-blocking stream does with it */
     c->cur = 0; c->last_dec = 0;
     c->have_traj = 0; c->cost_stat_valid = 0;
     c->stg.ttl = 0; c->want_valid = 0;
@@ -1400,7 +1405,7 @@ static int encode_chunk(int n, h264b200_job *jobs)
                 {
                     const size_t sz = (size_t)c->inp_stride[0] * c->height + 2 * (size_t)c->inp_stride[1] * (c->height / 2) + 256;
                     CK(cudaMalloc(&c->d_dn[k], sz));
-                    CK(cudaMemset(c->d_dn[k], 0, sz));
+                    CK(cudaMemsetAsync(c->d_dn[k], 0, sz, st));      /* on the lane's stream: ordered before the kernels that read it */
                 }
         }
         jobs[i].status = 0;
@@ -1599,7 +1604,7 @@ static int denoise_only_chunk(int n, h264b200_job *jobs)
             {
                 const size_t sz = (size_t)c->inp_stride[0] * c->height + 2 * (size_t)c->inp_stride[1] * (c->height / 2) + 256;
                 CK(cudaMalloc(&c->d_dn[k], sz));
-                CK(cudaMemset(c->d_dn[k], 0, sz));
+                CK(cudaMemsetAsync(c->d_dn[k], 0, sz, st));      /* on the lane's stream: ordered before the kernels that read it */
             }
         if (c->stg.ttl > 0) { c->stg.ttl = 0; CK(cudaStreamWaitEvent(st, c->stg.ev, 0)); }    /* a staged copy is not used here */
         if (jobs[i].preloaded_index >= 0) { if (jobs[i].preloaded_index >= c->clip_frames) return -3; }

@@ -16,7 +16,7 @@ def work(k):
     rng = random.Random(seed * 100 + k)
     t0 = time.time(); n = 0; fails = 0
     while time.time() - t0 < budget:
-        kind = rng.choice(["panning", "multi", "noise", "chess"])
+        kind = rng.choice(os.environ.get("STRESS_KINDS", "panning,multi,noise,chess").split(","))
         w = rng.choice([48, 176, 352, 366, 640, 1280]); h = rng.choice([50, 144, 250, 288, 360, 720])
         nf = rng.randint(2, 5); gop = rng.choice([1, 3, 60]); kw = dict(qp=rng.choice([20, 28, 40])) if rng.random() < 0.7 else dict(kbps=500)
         try:
@@ -35,7 +35,12 @@ def work(k):
         n += 1
         if any(o != rbs for o in outs):
             fails += 1
-            print("MISMATCH thread", k, kind, w, h, nf, gop, kw, "batch", m, flush=True)
+            # which side is not reproducible?  run both again (the other threads keep going)
+            rbs2, _, _, _ = refenc.encode_sequence(frames, w, h, gop, want_recon=False, **kw)
+            out2, _, _ = B.encode_sequence(L, frames, w, h, gop, want_recon=False, **kw)
+            print("MISMATCH thread", k, kind, w, h, nf, gop, kw, "batch", m, "| reference repeatable:", rbs2 == rbs,
+                  "| ours repeatable:", [o == out2 for o in outs], "| second runs agree:", out2 == rbs2,
+                  "| first differing byte", [next((i for i in range(min(len(o), len(rbs))) if o[i] != rbs[i]), -1) for o in outs], "of", len(rbs), flush=True)
     res[k] = (n, fails)
 th = [threading.Thread(target=work, args=(k,)) for k in range(T)]
 for t in th: t.start()
