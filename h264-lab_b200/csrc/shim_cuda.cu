@@ -405,7 +405,8 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
 /* the working warps make their stores visible device-wide (__threadfence) BEFORE they count a decision as done; the
  * deciding warp only has to order its reads of those counters before its own release (a CTA-scope fence: both sides
  * are in this CTA), the release store is cumulative */
-#define FAST_PUBLISH_FULL() do { const int xf_ = x_base + (FAST_PREFIX() - q_base); if (xf_ > pub_full) { pub_full = xf_; __threadfence_block(); if (lane == 0) st_release(progress + row * PROG_STRIDE, xf_); } } while (0)
+#define FAST_PUBLISH_FULL_IF(k_) do { const int xf_ = x_base + (FAST_PREFIX() - q_base); if (xf_ >= pub_full + (k_)) { pub_full = xf_; __threadfence_block(); if (lane == 0) st_release(progress + row * PROG_STRIDE, xf_); } } while (0)
+#define FAST_PUBLISH_FULL() FAST_PUBLISH_FULL_IF(1)
                 int go_slow = 0;
                 while (x < nmbx && !go_slow)
                 {
@@ -466,7 +467,9 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
                         p_early = -1;
                         if (row > 0 && seen_mv < min(x + 2, nmbx) && lane == 0) p_early = ld_relaxed(prog_mv + (row - 1) * PROG_STRIDE);
                         publish_row(prog_mv + row * PROG_STRIDE, x);
-                        FAST_PUBLISH_FULL();
+                        /* complete progress (what slow macroblocks and intra neighbours of the row below wait for) costs a
+                         * release of its own: while deciding, only every second step; every wait of this warp publishes at once */
+                        FAST_PUBLISH_FULL_IF(2);
 #ifdef H264_FASTPROF
                         GT(d2_); gt_pub += d2_ - d1_;
 #endif
