@@ -6,14 +6,21 @@
  * (a CUDA stream pair; see `Lane`):
  *
  *   H2D inputs [-> k_denoise     : optional temporal noise suppressor in front of the encoder]
- *              -> k_encode_rows  : sweep 0: macroblock decisions + transform/quant/recon.
+ *              -> k_sadmap       : P frames: per macroblock, quadrant SADs at 15 x 15 full-sample offsets and 5 x 5
+ *                                  quarter-sample positions (h264_sadmap.h) -- what the motion search looks up
+ *              -> k_me (x3, + k_me_scan; shim_check.cu): speculative motion estimation of every macroblock on a
+ *                                  PREDICTED context, result stored with the context as its key (h264_wave.h)
+ *              -> k_encode_rows  : sweep 0: macroblock decisions + transform/quant/recon.  P frames: decide / work
+ *                                  pipeline inside the row's CTA (h264_fast.h; records staged by TMA bulk copies).
  *                                  Persistent-style wavefront: one CTA of 4 warps per macroblock
  *                                  ROW; rows are claimed from an atomic ticket so that a
  *                                  claimed row's predecessor is always running; a row may
  *                                  process macroblock x when the row above has finished
  *                                  x+2 macroblocks (acquire/release on per-row counters).
  *                                  The first n tickets follow the mv_clusters trajectory.
- *              -> k_check1, k_after_check, k_repair_round x3, k_encode_rows (repair wave),
+ *              -> k_intra_check (second stream) || k_check1: intra modes of the macroblocks the sweep decided without
+ *                                  them / candidate stage of those whose speculated cluster candidates were wrong
+ *              -> k_after_check, k_repair_round x3, k_encode_rows (repair wave),
  *                 k_replay       : the exact-wavefront machinery of h264_wave.h (twice, more
  *                                  passes only after a host check)
  *              -> k_deblock_rows : in-loop filter, same wavefront on its own counters, luma and
@@ -25,8 +32,8 @@
  *              -> k_hpel         : its three half-sample planes.
  *   D2H payload.
  *
- * Build-time knobs (A/B-tested on B200): ENC_MIN_BLOCKS (CTAs per SM of k_encode_rows,
- * i.e. its register budget), H264_INL (h264_common.h: which big leaves are inlined), PROG_STRIDE, POLL_NS.
+ * Build-time knobs (A/B-tested on B200): ENC_MIN_BLOCKS / ENC_MIN_BLOCKS_I (CTAs per SM of k_encode_rows /
+ * k_encode_rows_i, i.e. their register budgets), H264_INL (h264_common.h: which big leaves are inlined), PROG_STRIDE, POLL_NS.
  *
  * The per-macroblock code is in h264_*.h (shared with the test-only host emulation).
  */
