@@ -104,6 +104,11 @@ __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+/* two counters published together: ONE release fence, then two relaxed stores (each of them a release pattern with it) */
+__device__ __forceinline__ void st_release2(int *p, int v, int *q, int u)
+{
+    asm volatile("fence.acq_rel.gpu;\n\tst.relaxed.gpu.global.s32 [%0], %1;\n\tst.relaxed.gpu.global.s32 [%2], %3;" ::"l"(p), "r"(v), "l"(q), "r"(u) : "memory");
+}
 __device__ __forceinline__ void wait_row(const int *progress_above, int need)      /* one warp */
 {
     if (LANE_ID == 0) { while (ld_relaxed(progress_above) < need) __nanosleep(32); acquire_counter(progress_above); }
@@ -518,7 +523,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
             __syncthreads();
             if (threadIdx.x == 0)
             {
-                st_release(prog_mv + row * PROG_STRIDE, sx + 1); st_release(progress + row * PROG_STRIDE, sx + 1);
+                st_release2(prog_mv + row * PROG_STRIDE, sx + 1, progress + row * PROG_STRIDE, sx + 1);
                 work.cmd = 0;
                 atomicAdd(fp->fsync + FS_SLOW, 1);
             }
@@ -546,7 +551,7 @@ static __device__ __forceinline__ void encode_rows_body(const FrameParams *fps, 
             if (row > 0) wait_row_cta(progress + (row - 1) * PROG_STRIDE, base + min(x + 2, nmbx));
             wave_mb_first(fp, &work, x, row);
             __syncthreads();
-            if (threadIdx.x == 0) { st_release(fp->row_progress_mv + row * PROG_STRIDE, x + 1); st_release(progress + row * PROG_STRIDE, base + x + 1); }
+            if (threadIdx.x == 0) st_release2(fp->row_progress_mv + row * PROG_STRIDE, x + 1, progress + row * PROG_STRIDE, base + x + 1);
             mb_store_coefs(fp, &work);
         }
         return;
