@@ -538,7 +538,11 @@ struct SearchScratch
  * members are used as w->inp_y ... everywhere); the fast path of P frames (h264_fast.h) gives every warp a private one,
  * and the functions that only touch these members (luma_tq_*, chroma_tq_*, mc_chroma_plane) are handed such a buffer
  * through MBState::w. */
+#if H264_DEVICE
 struct TQBuf
+#else
+struct alignas(16) TQBuf         /* host emulation: keeps the (MBWork *) view of a private buffer (h264_fast.h) aligned for the sanitizers */
+#endif
 {
     pix_t inp_y[256];            /* input MB, stride 16 (mb_pix_inp, H:566)                 */
     pix_t inp_c[128];            /* U at +0, V at +8, stride 16                             */
